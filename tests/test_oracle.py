@@ -1,0 +1,212 @@
+"""Pins oracle/osvos_oracle.py against outputs of the unmodified reference
+(tests/golden/reference_outputs.npz, made by tests/golden/make_golden.py) and
+against the analytic known-answer values of SURVEY.md section 8c."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import osvos_oracle as oc
+
+
+def maxrel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+@pytest.fixture(scope="module")
+def params():
+    return oc.he_params(seed=0)
+
+
+# ---- KAT 1/2: bilinear taps and interp_surgery ------------------------------
+def test_upsample_filt_kat(golden):
+    np.testing.assert_allclose(oc.upsample_filt(4), np.outer([.25, .75, .75, .25], [.25, .75, .75, .25]))
+    np.testing.assert_allclose(oc.upsample_filt(8)[3] / oc.upsample_filt(8)[3].max() * .765625,
+                               [.109375, .328125, .546875, .765625, .765625, .546875, .328125, .109375])
+    for s in (4, 8, 16, 32):
+        np.testing.assert_array_equal(oc.upsample_filt(s), golden[f"upsample_filt.{s}"])
+        np.testing.assert_allclose(np.outer(oc.upsample_taps_1d(s // 2), oc.upsample_taps_1d(s // 2)),
+                                   golden[f"upsample_filt.{s}"], rtol=0, atol=1e-15)
+
+
+def test_interp_weight_is_diagonal():
+    w = oc.interp_weight(16, 4)
+    assert tuple(w.shape) == (16, 16, 8, 8)
+    for i in range(16):
+        for j in range(16):
+            if i == j:
+                np.testing.assert_allclose(w[i, j].numpy(), oc.upsample_filt(8).astype(np.float32))
+            else:
+                assert float(w[i, j].abs().max()) == 0.0
+
+
+def test_upsample_closed_form_matches_conv_transpose():
+    g = torch.Generator().manual_seed(3)
+    for s, (h, w) in ((2, (5, 7)), (4, (3, 4)), (8, (2, 3)), (16, (2, 2))):
+        x = torch.randn(2, 3, h, w, generator=g, dtype=torch.float64)
+        ref = torch.nn.functional.conv_transpose2d(x, oc.interp_weight(3, s, torch.float64), stride=s)
+        got = oc.upsample_zero_padded(x, s)
+        assert got.shape == ref.shape == (2, 3, (h + 1) * s, (w + 1) * s)
+        assert maxrel(got, ref) < 1e-14
+    # border attenuation of a constant-1 input
+    for s, corner in ((2, .5625), (4, .390625), (8, .31640625), (16, .2822265625)):
+        one = torch.ones(1, 1, 4, 4, dtype=torch.float64)
+        up = oc.upsample_zero_padded(one, s)
+        crop = up[0, 0, s // 2:, s // 2:]
+        assert abs(float(crop[0, 0]) - corner) < 1e-12
+        assert abs(float(up[0, 0, 2 * s, 2 * s]) - 1.0) < 1e-12
+
+
+# ---- KAT 6: crop offsets / pooled sizes --------------------------------------
+def test_crop_table_and_pooled_sizes(golden):
+    for row in golden["crop_table"]:
+        h, w = int(row[0]), int(row[1])
+        hh, ww = h, w
+        for i in range(4):
+            hh, ww = oc.pooled_size(hh), oc.pooled_size(ww)
+            s = 2 ** (i + 1)
+            top, _ = oc.crop_offsets((hh + 1) * s, h)
+            left, _ = oc.crop_offsets((ww + 1) * s, w)
+            assert (top, left) == (int(row[2 + 2 * i]), int(row[3 + 2 * i]))
+    sizes = [854]
+    for _ in range(4):
+        sizes.append(oc.pooled_size(sizes[-1]))
+    assert sizes == [854, 427, 214, 107, 54]
+    assert oc.pooled_size(54) == 27
+    # the table of SURVEY.md 8a a7
+    t = {(int(r[0]), int(r[1])): [(int(r[2 + 2 * i]), int(r[3 + 2 * i])) for i in range(4)] for r in golden["crop_table"]}
+    assert t[(240, 427)] == [(1, 1), (2, 2), (4, 6), (8, 10)]
+    assert t[(480, 854)] == [(1, 1), (2, 3), (4, 5), (8, 13)]
+    assert t[(1080, 1920)] == [(1, 1), (2, 2), (4, 4), (12, 8)]
+
+
+# ---- KAT 3/4/5/8: the loss ---------------------------------------------------
+def test_loss_known_answers(golden):
+    z = torch.zeros(1, 1, 4, 5)
+    lab = torch.zeros(1, 1, 4, 5)
+    lab.view(-1)[:10] = 1
+    v = float(oc.class_balanced_cross_entropy_loss(z, lab, size_average=False))
+    assert abs(v - 2 * 10 * 10 * math.log(2) / 20) < 1e-5 and abs(v - 6.931472) < 1e-5
+    assert abs(v - float(golden["loss.zero.ba"])) < 1e-5
+    assert abs(float(oc.class_balanced_cross_entropy_loss(z, lab)) - 0.3465736) < 1e-6
+    m = oc.class_balanced_cross_entropy_loss(torch.full((1, 1, 2, 2), -100.0),
+                                             torch.tensor([1.0, 0, 0, 0]).view(1, 1, 2, 2), size_average=False)
+    assert abs(float(m) - 75.0) < 1e-4 and abs(float(golden["loss.m100"]) - 75.0) < 1e-4
+    p = oc.class_balanced_cross_entropy_loss(torch.full((1, 1, 2, 2), 100.0), torch.ones(1, 1, 2, 2), size_average=False)
+    assert float(p) == 0.0 == float(golden["loss.p100"])
+    assert float(golden["loss.nopos"]) == 0.0
+    assert float(oc.class_balanced_cross_entropy_loss(torch.randn(1, 1, 3, 3), torch.zeros(1, 1, 3, 3),
+                                                      size_average=False)) == 0.0
+
+
+def test_loss_matches_reference_on_random(golden):
+    g = torch.Generator().manual_seed(5)
+    lo = torch.randn(2, 1, 9, 13, generator=g) * 4.0
+    la = torch.rand(2, 1, 9, 13, generator=g)
+    for key, kw in (("sa", {}), ("ba", dict(size_average=False)),
+                    ("none", dict(size_average=False, batch_average=False))):
+        got = float(oc.class_balanced_cross_entropy_loss(lo, la, **kw))
+        assert abs(got - float(golden[f"loss.rand.{key}"])) <= 2e-6 * abs(float(golden[f"loss.rand.{key}"]))
+    grad = oc.class_balanced_cross_entropy_grad(lo, la, size_average=False)
+    assert maxrel(grad.numpy(), golden["loss.rand.grad"]) < 2e-6
+    # closed-form gradient == autograd of the closed-form loss (fp64)
+    lo64 = lo.double().requires_grad_(True)
+    oc.class_balanced_cross_entropy_loss(lo64, la.double(), size_average=False).backward()
+    assert maxrel(oc.class_balanced_cross_entropy_grad(lo.double(), la.double(), size_average=False), lo64.grad) < 1e-12
+
+
+# ---- forward parity with the reference ---------------------------------------
+@pytest.mark.parametrize("tag,n,h,w,seed", [("fwd_48x70", 1, 48, 70, 11), ("fwd_33x45_n2", 2, 33, 45, 12),
+                                            ("fwd_240x427", 1, 240, 427, 1234)])
+def test_forward_matches_reference(golden, params, tag, n, h, w, seed):
+    x, _ = oc.synthetic_frame(n, h, w, seed)
+    with torch.no_grad():
+        outs = oc.osvos_forward(params, x)
+    assert len(outs) == 5
+    for i, o in enumerate(outs):
+        ref = golden[f"{tag}.out{i}"]
+        assert tuple(o.shape) == ref.shape == (n, 1, h, w)
+        assert maxrel(o.numpy(), ref) < 2e-5, (tag, i)
+        # masks bit-exact except where |logit| is at the fp32 noise floor
+        flips = ((o.numpy() > 0) != (ref > 0)) & (np.abs(ref) > 1e-3 * np.abs(ref).max())
+        assert int(flips.sum()) == 0
+
+
+def test_fusion_identity_vs_literal_route(params):
+    """SURVEY.md 8a a8 / KAT 7: the linearity rewrite equals cat + 1x1 conv."""
+    x, _ = oc.synthetic_frame(1, 40, 56, 21)
+    p64 = {k: v.double() for k, v in params.items()}
+    with torch.no_grad():
+        a = oc.osvos_forward(p64, x.double())
+        b = oc.osvos_forward_literal(p64, x.double())
+    for u, v in zip(a, b):
+        assert maxrel(u, v) < 1e-12
+
+
+def test_config1_plumbing(golden):
+    """BASELINE.json configs[0]: 240x427 frame, stock-scale init, CPU: shapes and a finite loss."""
+    assert golden["cfg1.shapes"].tolist() == [[1, 1, 240, 427]] * 5
+    assert np.isfinite(golden["cfg1.loss"]) and float(golden["cfg1.absmax"].max()) < 1e-6
+    g = torch.Generator().manual_seed(7)
+    p = {k: (torch.randn(v.shape, generator=g) * 0.001 if k.endswith("weight") else torch.zeros(v.shape))
+         for k, v in oc.he_params(0).items()}
+    x, gt = oc.synthetic_frame(1, 240, 427, 1234)
+    with torch.no_grad():
+        outs = oc.osvos_forward(p, x)
+    assert [tuple(o.shape) for o in outs] == [(1, 1, 240, 427)] * 5
+    loss = oc.class_balanced_cross_entropy_loss(outs[-1], gt, size_average=False)
+    assert torch.isfinite(loss)
+    # logits ~ 0  ->  loss == 2 P Nn ln2 / N, which is what the reference printed too
+    assert abs(float(loss) - float(golden["cfg1.loss"])) < 1e-3 * float(golden["cfg1.loss"])
+
+
+# ---- backward parity ----------------------------------------------------------
+@pytest.mark.parametrize("tag", ["online", "parent"])
+def test_backward_matches_reference(golden, params, tag):
+    x, gt = oc.synthetic_frame(1, 40, 56, 21)
+    loss, outs, grads = oc.forward_backward(params, x, gt, objective=tag, side_weight=0.75)
+    assert abs(float(loss) - float(golden[f"bwd.{tag}.loss"])) < 2e-5 * abs(float(golden[f"bwd.{tag}.loss"]))
+    none_ref = sorted(k.split("none.")[1] for k in golden if k.startswith(f"bwd.{tag}.none."))
+    if tag == "online":   # KAT 9
+        assert none_ref == sorted([f"score_dsn.{i}.{p}" for i in range(4) for p in ("weight", "bias")]
+                                  + [f"upscale_.{i}.weight" for i in range(4)])
+    else:
+        assert none_ref == []
+    for name in oc.param_shapes():
+        if name.startswith("upscale"):
+            continue
+        if name in none_ref:
+            assert name not in grads
+            continue
+        gsum = grads[name].double()
+        ref_norm = float(golden[f"bwd.{tag}.norm.{name}"])
+        assert abs(float(gsum.norm()) - ref_norm) < 1e-4 * ref_norm, name
+        idx = golden[f"bwd.{tag}.idx.{name}"]
+        val = golden[f"bwd.{tag}.val.{name}"]
+        got = gsum.flatten()[torch.from_numpy(idx)].numpy()
+        assert np.abs(got - val).max() < 2e-4 * max(np.abs(val).max(), ref_norm / math.sqrt(gsum.numel())), name
+
+
+def test_batch_semantics(golden, params):
+    """KAT 8: P / Nn are counted over the whole batch tensor (layers/osvos_layers.py:30-32)."""
+    x, gt = oc.synthetic_frame(3, 24, 40, 31)
+    with torch.no_grad():
+        o = oc.osvos_forward(params, x)[-1]
+    whole = float(oc.class_balanced_cross_entropy_loss(o, gt, size_average=False))
+    per = [float(oc.class_balanced_cross_entropy_loss(o[i:i + 1], gt[i:i + 1], size_average=False)) for i in range(3)]
+    assert abs(whole - float(golden["batch3.loss"])) < 1e-4 * abs(whole)
+    np.testing.assert_allclose(per, golden["batch3.per_sample"], rtol=1e-4)
+    assert abs(whole - float(np.mean(per))) > 1e-6 * abs(whole)      # NOT the mean of per-sample losses
+
+
+def test_param_inventory():
+    shapes = oc.param_shapes()
+    assert len(shapes) == 52      # (SURVEY.md says 50; the reference state_dict has 52)
+    total = sum(int(np.prod(s)) for s in shapes.values())
+    assert total == 15267157
+    frozen = sum(int(np.prod(s)) for k, s in shapes.items() if k.startswith("upscale"))
+    assert frozen == 349520 and total - frozen == 14917637
+    assert abs(oc.conv_flops(480, 854) / 1e9 - 258.23) < 0.01
+    assert abs(oc.conv_flops(240, 427) / 1e9 - 64.77) < 0.01

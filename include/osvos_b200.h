@@ -1,0 +1,154 @@
+/* libosvos_b200 - C ABI of the B200-native OSVOS hot path.
+ *
+ * The reference (kmaninis/OSVOS-PyTorch) has no FFI of its own: its hot path is
+ * Python calling torch.nn modules.  This header is the native
+ * boundary introduced underneath the unchanged Python API; each entry point
+ * names the reference call it replaces (file:line relative to the reference
+ * repo).  The binding a maintainer adds on the reference side is the ctypes
+ * stub shown in INTEGRATION.md (osvos_pytorch_b200/_native.py is that stub).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name says host;
+ *   - no allocation inside: outputs and workspaces are caller-provided;
+ *   - every function enqueues on `stream` and returns immediately with an
+ *     OSVOS_* status (0 = ok); no exceptions cross the boundary;
+ *     osvos_last_error() returns a thread-local message for the last failure;
+ *   - "act" = activation tensor, NHWC, stored as split bf16: value ~= hi + lo,
+ *     two planes of shape [N,H,W,C] (C a multiple of 64 for 3x3 conv inputs,
+ *     16 for the side-branch gradient).  In OSVOS_FLAG_FAST mode only `hi`
+ *     exists (lo pointers may be NULL) and a single tensor-core pass is issued;
+ *     the default (exact) mode issues the three passes hi*hi + hi*lo + lo*hi
+ *     with fp32 accumulation in TMEM.
+ */
+#ifndef OSVOS_B200_H_
+#define OSVOS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OSVOS_B200_VERSION 100 /* major*10000 + minor*100 + patch */
+
+#if defined(__GNUC__)
+#define OSVOS_API __attribute__((visibility("default")))
+#else
+#define OSVOS_API
+#endif
+
+enum {
+  OSVOS_OK = 0,
+  OSVOS_ERR_INVALID_ARGUMENT = 1,
+  OSVOS_ERR_CUDA = 2,
+  OSVOS_ERR_UNSUPPORTED = 3
+};
+
+enum {
+  OSVOS_FLAG_RELU = 1,       /* fwd: y = max(y, 0)            (networks/vgg_osvos.py:143) */
+  OSVOS_FLAG_FAST = 2,       /* single-pass bf16 operands (hi planes only)               */
+  OSVOS_FLAG_RELU_MASK = 4,  /* dgrad: dx *= (mask_hi > 0)    (autograd of :143)          */
+  OSVOS_FLAG_ACCUMULATE = 8  /* add into the existing output instead of overwriting it    */
+};
+
+typedef void* osvos_stream_t; /* cudaStream_t */
+
+OSVOS_API int osvos_version(void);
+OSVOS_API const char* osvos_last_error(void);
+
+/* ---- weight packing ------------------------------------------------------
+ * nn.Conv2d weight, OIHW fp32 (networks/vgg_osvos.py:41,142) -> split-bf16
+ * K-major GEMM operand [plane(hi,lo)][tap = 3*r+s][rows][cols]:
+ *   transpose_flip == 0 (forward):  rows = Cout, cols = Cin, element = w[co][ci][r][s]
+ *   transpose_flip == 1 (dgrad):    rows = Cin,  cols = Cout, element = w[co][ci][2-r][2-s]
+ * cols is padded up to a multiple of `col_pad` (64 or 16) with zeros.
+ * Bytes needed: osvos_packed_weight_bytes(rows, cols_padded).                      */
+OSVOS_API size_t osvos_packed_weight_bytes(int rows, int cols_padded);
+OSVOS_API int osvos_pack_conv3x3_weights(const float* w_oihw, void* packed, int cout, int cin, int transpose_flip,
+                               int col_pad, osvos_stream_t stream);
+
+/* ---- layout conversion (test / boundary helpers) -------------------------- */
+OSVOS_API int osvos_nchw_to_act(const float* x_nchw, void* act_hi, void* act_lo, int n, int c, int h, int w,
+                      osvos_stream_t stream);
+OSVOS_API int osvos_act_to_nchw(const void* act_hi, const void* act_lo, float* y_nchw, int n, int c, int h, int w,
+                      osvos_stream_t stream);
+
+/* ---- conv1_1: nn.Conv2d(3, 64, 3, padding=1) + ReLU ------------------------
+ * Replaces stages[0][0..1] (networks/vgg_osvos.py:61,142-143).  Reads the
+ * caller's NCHW fp32 frame directly (no layout pass), fp32 CUDA-core math
+ * (K = 27 is bandwidth bound), writes an act [N,H,W,64].                       */
+OSVOS_API int osvos_conv_first_fwd(const float* x_nchw, const float* w_oihw, const float* bias, void* y_hi, void* y_lo,
+                         int n, int h, int w, int flags, osvos_stream_t stream);
+
+/* ---- 3x3 convolution, padding 1, stride 1, as a tcgen05 implicit GEMM -------
+ * Replaces every other nn.Conv2d(k=3, p=1) on the path: the 12 remaining trunk
+ * convs (+ReLU, networks/vgg_osvos.py:142-143, run at :61,:66) and the four
+ * side_prep convs (:41, run at :67, no ReLU); with transpose-flipped packed
+ * weights it is also their data gradient (autograd of the same lines).
+ *   M = N*H*W pixels (tiles of 16 rows x 8 px), N = cout, K = 9 * cin.         */
+typedef struct {
+  const void* x_hi;      /* act [n,h,w,cin]                                     */
+  const void* x_lo;      /* NULL in FAST mode                                   */
+  const void* w_packed;  /* osvos_pack_conv3x3_weights output, rows = cout      */
+  const float* bias;     /* [cout] or NULL                                      */
+  void* y_hi;            /* act [n,h,w,cout] or NULL                            */
+  void* y_lo;            /* NULL in FAST mode / when y_hi is NULL               */
+  float* y_f32;          /* optional fp32 NHWC copy of the output [n,h,w,cout]  */
+  const void* mask_hi;   /* RELU_MASK: act hi plane [n,h,w,cout] of the fwd output this gradient flows into */
+  /* side_prep only (cout == 16): fused 1x1 projections of the 16 features
+   *   pq[px][0] = <y, proj_w[0:16]>  + proj_b[0]   score_dsn (networks/vgg_osvos.py:44,69)
+   *   pq[px][1] = <y, proj_w[16:32]>               this scale's slice of fuse (:54,72)  */
+  const float* proj_w;   /* [32] or NULL */
+  const float* proj_b;   /* [1]  or NULL */
+  float* pq;             /* [n,h,w,2] or NULL */
+  int n, h, w, cin, cout;
+  int flags;
+} osvos_conv3x3_args;
+OSVOS_API int osvos_conv3x3(const osvos_conv3x3_args* args /* host */, osvos_stream_t stream);
+/* Same contract on CUDA cores (fp32 FMA over hi+lo); debugging cross-check only. */
+OSVOS_API int osvos_conv3x3_simt(const osvos_conv3x3_args* args /* host */, osvos_stream_t stream);
+
+/* ---- MaxPool2d(2, 2, ceil_mode=True) on an act (networks/vgg_osvos.py:140) --- */
+OSVOS_API int osvos_maxpool2x2_fwd(const void* x_hi, const void* x_lo, void* y_hi, void* y_lo, int n, int h, int w, int c,
+                         osvos_stream_t stream);
+
+/* ---- side-branch tail ----------------------------------------------------------
+ * Replaces, in one bandwidth-bound kernel, upscale_[i](score_dsn[i](.)) + center_crop
+ * (networks/vgg_osvos.py:69), upscale[i] + center_crop + cat + fuse (:68,:71-72), the
+ * interp_surgery bilinear taps (layers/osvos_layers.py:59-85), the crop offsets
+ * (layers/osvos_layers.py:51-56) and, when `label` is given, the per-pixel terms and
+ * reductions of class_balanced_cross_entropy_loss (layers/osvos_layers.py:28-41).
+ *   out[k][n,0,y,x], k<4 = sum over the <=2x2 low-res taps of scale k of p_k
+ *   out[4]               = sum_k (same taps of q_k) + fuse_bias
+ *   sums[k] = {sum_{y=1} (softplus(x)-x), sum_{y=0} softplus(x)} for the 5 maps,
+ *   sums[10] = P = #(label >= .5), sums[11] = number of pixels        (12 doubles, zeroed by the call) */
+typedef struct {
+  const float* pq[4];      /* [n, h_k, w_k, 2], h_k = ceil-halved k+1 times          */
+  const float* fuse_bias;  /* [1] */
+  float* out[5];           /* each [n,1,h,w] fp32, any may be NULL                   */
+  const float* label;      /* [n,1,h,w] or NULL */
+  double* sums;            /* [12] or NULL */
+  int n, h, w;
+} osvos_tail_fwd_args;
+OSVOS_API int osvos_tail_fwd(const osvos_tail_fwd_args* args /* host */, osvos_stream_t stream);
+
+/* Standalone 1x1 projections of a side feature map (used when the features do
+ * not come from osvos_conv3x3's fused epilogue): pq as above.                       */
+OSVOS_API int osvos_side_project(const float* feat /* [n,h,w,16] */, const float* proj_w, const float* proj_b, float* pq,
+                       int n, int h, int w, osvos_stream_t stream);
+
+/* ---- class_balanced_cross_entropy_loss (layers/osvos_layers.py:19-48) -----------
+ * forward: sums[0..3] = {S_pos, S_neg, P, N} (fp64, zeroed by the call), loss[0] =
+ * (Nn/N*S_pos + P/N*S_neg)/divisor with divisor = numel (size_average), batch
+ * (batch_average) or 1.  backward: grad_in = grad_out[0] * w * (sigmoid(x) - y) / divisor
+ * (grad_out == NULL means 1).                                                        */
+OSVOS_API int osvos_cbce_fwd(const float* output, const float* label, size_t numel, double divisor, double* sums,
+                             float* loss, osvos_stream_t stream);
+OSVOS_API int osvos_cbce_bwd(const float* output, const float* label, const double* sums, const float* grad_out,
+                             double divisor, size_t numel, float* grad_in, osvos_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OSVOS_B200_H_ */

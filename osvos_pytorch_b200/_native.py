@@ -1,0 +1,87 @@
+"""ctypes binding of libosvos_b200.so (the C ABI declared in include/osvos_b200.h).
+
+This is the stub a maintainer of the reference would add to call the native hot
+path from Python.  There is deliberately NO fallback: if the
+library cannot be loaded, or a call fails, an exception is raised.
+"""
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_size_t, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libosvos_b200.so")
+
+FLAG_RELU = 1
+FLAG_FAST = 2
+FLAG_RELU_MASK = 4
+FLAG_ACCUMULATE = 8
+
+
+class NativeLibraryError(RuntimeError):
+    pass
+
+
+class Conv3x3Args(Structure):
+    _fields_ = [("x_hi", c_void_p), ("x_lo", c_void_p), ("w_packed", c_void_p), ("bias", c_void_p),
+                ("y_hi", c_void_p), ("y_lo", c_void_p), ("y_f32", c_void_p), ("mask_hi", c_void_p),
+                ("proj_w", c_void_p), ("proj_b", c_void_p), ("pq", c_void_p),
+                ("n", c_int), ("h", c_int), ("w", c_int), ("cin", c_int), ("cout", c_int), ("flags", c_int)]
+
+
+class TailFwdArgs(Structure):
+    _fields_ = [("pq", c_void_p * 4), ("fuse_bias", c_void_p), ("out", c_void_p * 5), ("label", c_void_p),
+                ("sums", c_void_p), ("n", c_int), ("h", c_int), ("w", c_int)]
+
+
+# name -> (restype, argtypes); mirrors include/osvos_b200.h one to one (tests/test_abi.py checks it)
+SIGNATURES = {
+    "osvos_version": (c_int, []),
+    "osvos_last_error": (c_char_p, []),
+    "osvos_packed_weight_bytes": (c_size_t, [c_int, c_int]),
+    "osvos_pack_conv3x3_weights": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "osvos_nchw_to_act": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "osvos_act_to_nchw": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "osvos_conv_first_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                     c_void_p]),
+    "osvos_conv3x3": (c_int, [POINTER(Conv3x3Args), c_void_p]),
+    "osvos_conv3x3_simt": (c_int, [POINTER(Conv3x3Args), c_void_p]),
+    "osvos_maxpool2x2_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "osvos_tail_fwd": (c_int, [POINTER(TailFwdArgs), c_void_p]),
+    "osvos_cbce_fwd": (c_int, [c_void_p, c_void_p, c_size_t, c_double, c_void_p, c_void_p, c_void_p]),
+    "osvos_cbce_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_size_t, c_void_p, c_void_p]),
+    "osvos_side_project": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library once; raise NativeLibraryError if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NativeLibraryError(
+            f"{LIB_PATH} not found: build it with `python -m osvos_pytorch_b200.build` "
+            "(or __graft_entry__.build()).  There is no CPU / PyTorch fallback for the OSVOS hot path.")
+    try:
+        lib = ctypes.CDLL(LIB_PATH)
+    except OSError as e:  # pragma: no cover
+        raise NativeLibraryError(f"cannot load {LIB_PATH}: {e}") from e
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(status, what):
+    if status != 0:
+        msg = load().osvos_last_error()
+        raise NativeLibraryError(f"{what} failed with status {status}: {msg.decode() if msg else ''}")
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()

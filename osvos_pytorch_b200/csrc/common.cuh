@@ -1,0 +1,53 @@
+// Shared host/device helpers for libosvos_b200: status codes, the driver entry
+// point for cuTensorMapEncodeTiled (resolved at run time so the library loads on
+// a box without libcuda), split-bf16 arithmetic.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/osvos_b200.h"
+
+namespace osvos {
+
+#define OSVOS_CHECK_ARG(cond)                                                              \
+  do {                                                                                     \
+    if (!(cond)) {                                                                         \
+      set_last_error("%s:%d: invalid argument: %s", __FILE__, __LINE__, #cond);            \
+      return OSVOS_ERR_INVALID_ARGUMENT;                                                   \
+    }                                                                                      \
+  } while (0)
+
+#define OSVOS_CHECK_CUDA(expr)                                                             \
+  do {                                                                                     \
+    cudaError_t e__ = (expr);                                                              \
+    if (e__ != cudaSuccess) {                                                              \
+      set_last_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__)); \
+      return OSVOS_ERR_CUDA;                                                               \
+    }                                                                                      \
+  } while (0)
+
+void set_last_error(const char* fmt, ...);
+
+// Encodes a tiled tensor map over a bf16 / fp32 tensor. dims/strides innermost first;
+// strides[0] is implied by the element size. Returns an OSVOS_* status.
+int encode_tensor_map(CUtensorMap* map, CUtensorMapDataType dtype, int elem_bytes, int rank, const void* base,
+                      const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
+                      CUtensorMapSwizzle swizzle);
+
+int device_sm_count();
+
+// ---- split-bf16 ("bf16x2") representation of an fp32 value: v ~= hi + lo ------
+__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(v);
+  lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b) {
+  return static_cast<uint32_t>(__bfloat16_as_ushort(a)) | (static_cast<uint32_t>(__bfloat16_as_ushort(b)) << 16);
+}
+__device__ __forceinline__ float bf16_lo_to_float(uint32_t packed) { return __uint_as_float(packed << 16); }
+__device__ __forceinline__ float bf16_hi_to_float(uint32_t packed) { return __uint_as_float(packed & 0xFFFF0000u); }
+
+}  // namespace osvos

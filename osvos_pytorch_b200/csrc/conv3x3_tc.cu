@@ -1,0 +1,415 @@
+// 3x3 / pad 1 / stride 1 convolution as a tcgen05 implicit GEMM (sm_100a).
+//
+//   D[pixel, co] = sum_{tap, ci} X[pixel + tap, ci] * Wt[tap][co][ci]
+//
+// M = pixels, tiled as patches of 16 rows x 8 px of one image (128 GEMM rows);
+// N = BLOCK_N output channels; K = 9 taps x cin, consumed in blocks of 64
+// channels of one tap.  The A operand of a K block is the input patch shifted by
+// the tap: one 4-D TMA box {64 ch, 8 px, 16 rows, 1 image} whose out-of-image
+// part (the conv zero padding, and ragged right/bottom tiles) is zero-filled by
+// the TMA unit, so im2col never exists in memory.  The box lands in shared
+// memory as 128 rows x 128 B with the 128-byte swizzle, which is exactly the
+// canonical K-major SWIZZLE_128B UMMA operand.  B is the packed weight slab
+// [tap][co][ci] (box {64, BLOCK_N, 1}).
+//
+// Precision: activations/weights are split bf16 (v ~= hi + lo).  Exact mode
+// (PLANES == 2) issues hi*hi + hi*lo + lo*hi into one fp32 TMEM accumulator
+// (~2^-17 relative operand error, i.e. fp32-class results); fast mode
+// (PLANES == 1) issues hi*hi only.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM
+// alloc/dealloc), warps 2..5 = epilogue (TMEM -> registers -> bias / ReLU /
+// mask / split -> global).  Persistent CTAs walk tiles round-robin; two TMEM
+// accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.
+//
+// Replaces nn.Conv2d(k=3, p=1)[+ReLU] of the reference
+// (networks/vgg_osvos.py:41,142-143) and, with flipped weights, its dgrad.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace osvos {
+
+constexpr int kTileW = 8;     // pixels per patch row  (= one 8-row swizzle atom)
+constexpr int kTileH = 16;    // patch rows
+constexpr int kBlockM = 128;  // kTileW * kTileH
+constexpr int kBlockK = 64;   // channels per K block (128 B of bf16)
+constexpr int kConvThreads = 192;
+constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KiB per plane
+
+struct ConvParams {
+  const float* bias;
+  __nv_bfloat16* y_hi;
+  __nv_bfloat16* y_lo;
+  float* y_f32;
+  const __nv_bfloat16* mask_hi;
+  const float* proj_w;
+  const float* proj_b;
+  float* pq;
+  int n, h, w, cin, cout;
+  int tiles_x, tiles_y, n_blocks, total_tiles, k_chunks;
+  int flags;
+};
+
+template <int BLOCK_N, int PLANES>
+struct ConvCfg {
+  static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+  static constexpr int kStageBytes = PLANES * (kABytes + kBBytes);
+  static constexpr int kStagesRaw = (212 * 1024) / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kTmemCols = (2 * BLOCK_N) < 32 ? 32 : 2 * BLOCK_N;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static_assert(kStages >= 2, "pipeline too shallow");
+  static_assert(kBBytes % 1024 == 0, "B stage must keep 1024-byte alignment");
+};
+
+__device__ __forceinline__ void decode_tile(const ConvParams& p, int tile, int& nb, int& tx, int& ty, int& img) {
+  nb = tile % p.n_blocks;
+  int m = tile / p.n_blocks;
+  tx = m % p.tiles_x;
+  m /= p.tiles_x;
+  ty = m % p.tiles_y;
+  img = m / p.tiles_y;
+}
+
+template <int BLOCK_N, int PLANES>
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo,
+                  const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
+                  const ConvParams p) {
+  using Cfg = ConvCfg<BLOCK_N, PLANES>;
+  constexpr int kStages = Cfg::kStages;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kStages;
+  uint64_t* tfull_bar = bars + 2 * kStages;
+  uint64_t* tempty_bar = bars + 2 * kStages + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_x_hi);
+    tma_prefetch_desc(&map_w_hi);
+    if (PLANES == 2) {
+      tma_prefetch_desc(&map_x_lo);
+      tma_prefetch_desc(&map_w_lo);
+    }
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_kb = 9 * p.k_chunks;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        int nb, tx, ty, img;
+        decode_tile(p, tile, nb, tx, ty, img);
+        for (int kc = 0; kc < p.k_chunks; ++kc) {
+          for (int tap = 0; tap < 9; ++tap) {
+            const int r = tap / 3, s = tap - 3 * r;
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* st = smem + stage * Cfg::kStageBytes;
+            mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            tma_load_4d(&map_x_hi, &full_bar[stage], st, kc * kBlockK, tx * kTileW + s - 1, ty * kTileH + r - 1, img);
+            tma_load_3d(&map_w_hi, &full_bar[stage], st + PLANES * kABytes, kc * kBlockK, nb * BLOCK_N, tap);
+            if (PLANES == 2) {
+              tma_load_4d(&map_x_lo, &full_bar[stage], st + kABytes, kc * kBlockK, tx * kTileW + s - 1,
+                          ty * kTileH + r - 1, img);
+              tma_load_3d(&map_w_lo, &full_bar[stage], st + 2 * kABytes + Cfg::kBBytes, kc * kBlockK, nb * BLOCK_N,
+                          tap);
+            }
+            if (++stage == kStages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // -------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(kBlockM, BLOCK_N, /*bf16=*/true);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t aph = (it >> 1) & 1;
+        mbar_wait(&tempty_bar[as], aph ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_hi = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t b_hi = a_hi + PLANES * kABytes;
+          const uint64_t da_hi = make_smem_desc(a_hi, 16, 1024, kLayoutSW128);
+          const uint64_t db_hi = make_smem_desc(b_hi, 16, 1024, kLayoutSW128);
+          const uint64_t da_lo = make_smem_desc(a_hi + kABytes, 16, 1024, kLayoutSW128);
+          const uint64_t db_lo = make_smem_desc(b_hi + Cfg::kBBytes, 16, 1024, kLayoutSW128);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            const uint64_t adv = static_cast<uint64_t>(k * 2);  // 32 bytes >> 4
+            if (PLANES == 2) {
+              umma_f16(tmem_d, da_lo + adv, db_hi + adv, idesc, (kb | k) != 0);
+              umma_f16(tmem_d, da_hi + adv, db_lo + adv, idesc, 1);
+              umma_f16(tmem_d, da_hi + adv, db_hi + adv, idesc, 1);
+            } else {
+              umma_f16(tmem_d, da_hi + adv, db_hi + adv, idesc, (kb | k) != 0);
+            }
+          }
+          umma_commit(&empty_bar[stage]);
+          if (kb == num_kb - 1) umma_commit(&tfull_bar[as]);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue
+    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    const int row = q * 32 + lane;
+    const int ly = row / kTileW, lx = row % kTileW;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      int nb, tx, ty, img;
+      decode_tile(p, tile, nb, tx, ty, img);
+      const int as = it & 1;
+      const uint32_t aph = (it >> 1) & 1;
+      const int y = ty * kTileH + ly, x = tx * kTileW + lx;
+      const bool valid = (y < p.h) && (x < p.w);
+      const size_t pix = (static_cast<size_t>(img) * p.h + y) * p.w + x;
+
+      mbar_wait(&tfull_bar[as], aph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + as * BLOCK_N + (static_cast<uint32_t>(q * 32) << 16);
+
+      if constexpr (BLOCK_N == 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr, v);
+        tmem_ld_wait();
+        if (valid) {
+          float f[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            f[j] = __uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + j) : 0.f);
+            if (p.flags & OSVOS_FLAG_RELU) f[j] = fmaxf(f[j], 0.f);
+          }
+          if (p.y_f32) {
+            float4* dst = reinterpret_cast<float4*>(p.y_f32 + pix * 16);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+          }
+          if (p.y_hi) {
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              __nv_bfloat16 h0, l0, h1, l1;
+              split_bf16(f[2 * j], h0, l0);
+              split_bf16(f[2 * j + 1], h1, l1);
+              hi[j] = pack_bf16x2(h0, h1);
+              lo[j] = pack_bf16x2(l0, l1);
+            }
+            uint4* dh = reinterpret_cast<uint4*>(p.y_hi + pix * 16);
+            dh[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            dh[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+            if (p.y_lo) {
+              uint4* dl = reinterpret_cast<uint4*>(p.y_lo + pix * 16);
+              dl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+              dl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+            }
+          }
+          if (p.pq) {
+            float sp = p.proj_b ? __ldg(p.proj_b) : 0.f, sq = 0.f;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              sp = fmaf(f[j], __ldg(p.proj_w + j), sp);
+              sq = fmaf(f[j], __ldg(p.proj_w + 16 + j), sq);
+            }
+            *reinterpret_cast<float2*>(p.pq + pix * 2) = make_float2(sp, sq);
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(taddr + c0, v);
+          tmem_ld_wait();
+          if (valid) {
+            const int ch = nb * BLOCK_N + c0;
+            float f[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              f[j] = __uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + ch + j) : 0.f);
+              if (p.flags & OSVOS_FLAG_RELU) f[j] = fmaxf(f[j], 0.f);
+            }
+            if (p.flags & OSVOS_FLAG_RELU_MASK) {
+              const uint4* mk = reinterpret_cast<const uint4*>(p.mask_hi + pix * p.cout + ch);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint4 m = __ldg(mk + j);
+                const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                  if (!(bf16_lo_to_float(mw[t]) > 0.f)) f[8 * j + 2 * t] = 0.f;
+                  if (!(bf16_hi_to_float(mw[t]) > 0.f)) f[8 * j + 2 * t + 1] = 0.f;
+                }
+              }
+            }
+            if (p.y_f32) {
+              float4* dst = reinterpret_cast<float4*>(p.y_f32 + pix * p.cout + ch);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+            }
+            if (p.y_hi) {
+              uint32_t hi[16], lo[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                __nv_bfloat16 h0, l0, h1, l1;
+                split_bf16(f[2 * j], h0, l0);
+                split_bf16(f[2 * j + 1], h1, l1);
+                hi[j] = pack_bf16x2(h0, h1);
+                lo[j] = pack_bf16x2(l0, l1);
+              }
+              uint4* dh = reinterpret_cast<uint4*>(p.y_hi + pix * p.cout + ch);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) dh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+              if (p.y_lo) {
+                uint4* dl = reinterpret_cast<uint4*>(p.y_lo + pix * p.cout + ch);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  dl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// --------------------------------------------------------------------- host
+template <int BLOCK_N, int PLANES>
+static int launch_conv(const osvos_conv3x3_args* a, cudaStream_t stream) {
+  using Cfg = ConvCfg<BLOCK_N, PLANES>;
+  ConvParams p;
+  p.bias = a->bias;
+  p.y_hi = static_cast<__nv_bfloat16*>(a->y_hi);
+  p.y_lo = static_cast<__nv_bfloat16*>(a->y_lo);
+  p.y_f32 = a->y_f32;
+  p.mask_hi = static_cast<const __nv_bfloat16*>(a->mask_hi);
+  p.proj_w = a->proj_w;
+  p.proj_b = a->proj_b;
+  p.pq = a->pq;
+  p.n = a->n;
+  p.h = a->h;
+  p.w = a->w;
+  p.cin = a->cin;
+  p.cout = a->cout;
+  p.tiles_x = (a->w + kTileW - 1) / kTileW;
+  p.tiles_y = (a->h + kTileH - 1) / kTileH;
+  p.n_blocks = a->cout / BLOCK_N;
+  p.total_tiles = p.tiles_x * p.tiles_y * a->n * p.n_blocks;
+  p.k_chunks = a->cin / kBlockK;
+  p.flags = a->flags;
+
+  CUtensorMap mx_hi, mx_lo, mw_hi, mw_lo;
+  {
+    const uint64_t dims[4] = {(uint64_t)a->cin, (uint64_t)a->w, (uint64_t)a->h, (uint64_t)a->n};
+    const uint64_t strides[3] = {(uint64_t)a->cin * 2, (uint64_t)a->w * a->cin * 2,
+                                 (uint64_t)a->h * a->w * a->cin * 2};
+    const uint32_t box[4] = {kBlockK, kTileW, kTileH, 1};
+    int rc = encode_tensor_map(&mx_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 4, a->x_hi, dims, strides, box,
+                               CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    rc = encode_tensor_map(&mx_lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 4, PLANES == 2 ? a->x_lo : a->x_hi, dims,
+                           strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  {
+    const size_t plane = static_cast<size_t>(9) * a->cout * a->cin;  // elements
+    const uint64_t dims[3] = {(uint64_t)a->cin, (uint64_t)a->cout, 9};
+    const uint64_t strides[2] = {(uint64_t)a->cin * 2, (uint64_t)a->cout * a->cin * 2};
+    const uint32_t box[3] = {kBlockK, BLOCK_N, 1};
+    const __nv_bfloat16* wp = static_cast<const __nv_bfloat16*>(a->w_packed);
+    int rc = encode_tensor_map(&mw_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 3, wp, dims, strides, box,
+                               CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    rc = encode_tensor_map(&mw_lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 3, wp + plane, dims, strides, box,
+                           CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+
+  auto kern = conv3x3_tc_kernel<BLOCK_N, PLANES>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    OSVOS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_done = true;
+  }
+  const int sms = device_sm_count();
+  const int grid = p.total_tiles < sms ? p.total_tiles : sms;
+  kern<<<grid, kConvThreads, Cfg::kSmemBytes, stream>>>(mx_hi, mx_lo, mw_hi, mw_lo, p);
+  OSVOS_CHECK_CUDA(cudaGetLastError());
+  return OSVOS_OK;
+}
+
+static int check_conv_args(const osvos_conv3x3_args* a) {
+  OSVOS_CHECK_ARG(a != nullptr);
+  OSVOS_CHECK_ARG(a->x_hi != nullptr && a->w_packed != nullptr);
+  OSVOS_CHECK_ARG(a->n > 0 && a->h > 0 && a->w > 0);
+  OSVOS_CHECK_ARG(a->cin > 0 && a->cin % 64 == 0);
+  OSVOS_CHECK_ARG(a->cout == 16 || a->cout % 64 == 0);
+  OSVOS_CHECK_ARG((a->flags & OSVOS_FLAG_FAST) || a->x_lo != nullptr);
+  OSVOS_CHECK_ARG(a->y_hi != nullptr || a->y_f32 != nullptr || a->pq != nullptr);
+  OSVOS_CHECK_ARG(!(a->flags & OSVOS_FLAG_RELU_MASK) || a->mask_hi != nullptr);
+  OSVOS_CHECK_ARG(a->pq == nullptr || (a->cout == 16 && a->proj_w != nullptr));
+  OSVOS_CHECK_ARG((reinterpret_cast<uintptr_t>(a->x_hi) & 15) == 0);
+  OSVOS_CHECK_ARG((reinterpret_cast<uintptr_t>(a->w_packed) & 15) == 0);
+  return OSVOS_OK;
+}
+
+}  // namespace osvos
+
+using namespace osvos;
+
+extern "C" int osvos_conv3x3(const osvos_conv3x3_args* a, osvos_stream_t stream_) {
+  int rc = check_conv_args(a);
+  if (rc) return rc;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const bool fast = (a->flags & OSVOS_FLAG_FAST) != 0;
+  if (a->cout == 16) return fast ? launch_conv<16, 1>(a, stream) : launch_conv<16, 2>(a, stream);
+  if (a->cout == 64) return fast ? launch_conv<64, 1>(a, stream) : launch_conv<64, 2>(a, stream);
+  return fast ? launch_conv<128, 1>(a, stream) : launch_conv<128, 2>(a, stream);
+}

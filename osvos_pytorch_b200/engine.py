@@ -1,0 +1,115 @@
+"""Execution engine behind ``OSVOS.forward``: walks the module's parameter
+containers and enqueues the native kernels (include/osvos_b200.h).  Python here
+is plumbing - packing caches keyed on parameter versions, buffer allocation,
+stream handling; all arithmetic is in csrc/.
+
+Call graph replaced: reference networks/vgg_osvos.py:59-74 (forward) and, in
+training, the autograd graph PyTorch builds for it.
+"""
+import torch
+import torch.nn as nn
+
+from . import ops
+from .layers.osvos_layers import bilinear_deconv_weight
+
+
+class OSVOSEngine:
+    def __init__(self, module):
+        # no reference cycle through nn.Module registration: keep a plain attribute
+        object.__setattr__(self, "m", module)
+        self._pack_cache = {}
+        self._deconv_checked = {}
+
+    # ------------------------------------------------------------ weight caches
+    def _cached(self, key, params, make):
+        ver = tuple((p.data_ptr(), p._version) for p in params)
+        hit = self._pack_cache.get(key)
+        if hit is not None and hit[0] == ver:
+            return hit[1]
+        val = make()
+        self._pack_cache[key] = (ver, val)
+        return val
+
+    def _packed(self, conv, key, transpose_flip=False, col_pad=64):
+        return self._cached((key, transpose_flip), [conv.weight],
+                            lambda: ops.pack_conv3x3_weights(conv.weight, transpose_flip, col_pad))
+
+    def _proj(self, i):
+        m = self.m
+        sd, fu = m.score_dsn[i], m.fuse
+        return self._cached(("proj", i), [sd.weight, fu.weight],
+                            lambda: torch.cat([sd.weight.detach().reshape(16),
+                                               fu.weight.detach().reshape(64)[16 * i:16 * i + 16]]).float().contiguous())
+
+    def _check_deconvs(self):
+        """The native tail implements the bilinear deconvolution in closed form; both entry points of
+        the reference keep these weights fixed (lr = 0, train_online.py:84-85, train_parent.py:99-100).
+        Anything else is refused loudly rather than computed wrongly."""
+        m = self.m
+        for name, lst in (("upscale", m.upscale), ("upscale_", m.upscale_)):
+            for i, lay in enumerate(lst):
+                w = lay.weight
+                key = (name, i)
+                ver = (w.data_ptr(), w._version)
+                if self._deconv_checked.get(key) == ver:
+                    continue
+                ref = bilinear_deconv_weight(w.shape[0], w.shape[1], w.shape[2]).to(w.device)
+                if tuple(w.shape[2:]) != (2 ** (i + 2),) * 2 or not torch.equal(w.detach().float(), ref):
+                    raise NotImplementedError(
+                        f"{name}.{i}.weight is not the fixed bilinear interpolation kernel written by interp_surgery; "
+                        "the B200 path only implements that (reference layers/osvos_layers.py:72-85)")
+                self._deconv_checked[key] = ver
+
+    # ----------------------------------------------------------------- forward
+    def forward(self, x):
+        if not isinstance(x, torch.Tensor) or x.dim() != 4 or x.size(1) != 3:
+            raise ValueError("OSVOS.forward expects a [N, 3, H, W] tensor")
+        if not x.is_cuda:
+            raise RuntimeError("osvos_pytorch_b200.OSVOS runs on CUDA (sm_100a) only: move the module and the input "
+                               "to the GPU.  There is no CPU fallback for the hot path.")
+        needs_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.m.parameters()))
+        if needs_grad:
+            from .autograd import osvos_apply
+            return osvos_apply(self, x)
+        return self.forward_inference(x)
+
+    @torch.no_grad()
+    def forward_inference(self, x, simt=False, return_intermediates=False):
+        m = self.m
+        fast = m.precision == "fast"
+        self._check_deconvs()
+        x = x.detach().contiguous().float()
+        n, _, h, w = (int(v) for v in x.shape)
+        inter = {}
+        convs0 = [c for c in m.stages[0] if isinstance(c, nn.Conv2d)]
+        a = ops.conv_first(x, convs0[0].weight.detach(), convs0[0].bias.detach(), relu=True, fast=fast)
+        a, _, _ = ops.conv3x3(a, self._packed(convs0[1], "s0c1"), convs0[1].bias.detach(), convs0[1].out_channels,
+                              relu=True, fast=fast, simt=simt)
+        if return_intermediates:
+            inter["stage0"] = a
+        pqs = []
+        for i in range(1, 5):
+            a = ops.maxpool2x2(a)
+            for j, conv in enumerate(c for c in m.stages[i] if isinstance(c, nn.Conv2d)):
+                a, _, _ = ops.conv3x3(a, self._packed(conv, f"s{i}c{j}"), conv.bias.detach(), conv.out_channels,
+                                      relu=True, fast=fast, simt=simt)
+            if return_intermediates:
+                inter[f"stage{i}"] = a
+            sp = m.side_prep[i - 1]
+            if simt:
+                _, feat, _ = ops.conv3x3(a, self._packed(sp, f"sp{i}"), sp.bias.detach(), 16, relu=False, fast=fast,
+                                         out_act=False, out_f32=True, simt=True)
+                pq = ops.side_project(feat, self._proj(i - 1), m.score_dsn[i - 1].bias.detach())
+            else:
+                _, feat, pq = ops.conv3x3(a, self._packed(sp, f"sp{i}"), sp.bias.detach(), 16, relu=False, fast=fast,
+                                          out_act=False, out_f32=return_intermediates, proj_w=self._proj(i - 1),
+                                          proj_b=m.score_dsn[i - 1].bias.detach())
+            if return_intermediates:
+                inter[f"side{i}"] = feat
+                inter[f"pq{i}"] = pq
+            pqs.append(pq)
+        out, _ = ops.tail_fwd(pqs, m.fuse.bias.detach(), n, h, w)
+        outs = [out[k] for k in range(5)]
+        if return_intermediates:
+            return outs, inter
+        return outs

@@ -1,0 +1,149 @@
+"""Tensor-level wrappers over the C ABI: they allocate outputs with torch (device
+memory + stream plumbing only) and enqueue the native kernels on the current
+torch stream.  No arithmetic happens in Python / PyTorch here."""
+from ctypes import byref
+
+import torch
+
+from . import _native as nat
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+class Act:
+    """Split-bf16 NHWC activation tensor: value ~= hi + lo (lo is None in fast mode)."""
+    __slots__ = ("hi", "lo")
+
+    def __init__(self, hi, lo):
+        self.hi = hi
+        self.lo = lo
+
+    @property
+    def shape(self):
+        return tuple(self.hi.shape)
+
+    @staticmethod
+    def empty(n, h, w, c, device, fast=False):
+        hi = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=device)
+        lo = None if fast else torch.empty((n, h, w, c), dtype=torch.bfloat16, device=device)
+        return Act(hi, lo)
+
+
+def _require_cuda(t, name):
+    if not t.is_cuda:
+        raise RuntimeError(f"osvos_pytorch_b200: {name} must be a CUDA tensor; the OSVOS hot path has no CPU fallback "
+                           "(the CPU restatement under oracle/ is test infrastructure only)")
+
+
+def pack_conv3x3_weights(weight, transpose_flip=False, col_pad=64):
+    """nn.Conv2d weight (OIHW fp32) -> packed split-bf16 GEMM operand (see include/osvos_b200.h)."""
+    _require_cuda(weight, "weight")
+    lib = nat.load()
+    w = weight.detach().contiguous().float()
+    cout, cin = int(w.shape[0]), int(w.shape[1])
+    rows, cols = (cin, cout) if transpose_flip else (cout, cin)
+    colp = (cols + col_pad - 1) // col_pad * col_pad
+    nbytes = lib.osvos_packed_weight_bytes(rows, colp)
+    packed = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=w.device)
+    nat.check(lib.osvos_pack_conv3x3_weights(w.data_ptr(), packed.data_ptr(), cout, cin, int(transpose_flip), col_pad,
+                                             _stream()), "osvos_pack_conv3x3_weights")
+    return packed
+
+
+def nchw_to_act(x, fast=False):
+    _require_cuda(x, "x")
+    lib = nat.load()
+    x = x.contiguous().float()
+    n, c, h, w = (int(v) for v in x.shape)
+    a = Act.empty(n, h, w, c, x.device, fast)
+    nat.check(lib.osvos_nchw_to_act(x.data_ptr(), a.hi.data_ptr(), nat.ptr(a.lo), n, c, h, w, _stream()),
+              "osvos_nchw_to_act")
+    return a
+
+
+def act_to_nchw(a):
+    lib = nat.load()
+    n, h, w, c = a.shape
+    y = torch.empty((n, c, h, w), dtype=torch.float32, device=a.hi.device)
+    nat.check(lib.osvos_act_to_nchw(a.hi.data_ptr(), nat.ptr(a.lo), y.data_ptr(), n, c, h, w, _stream()),
+              "osvos_act_to_nchw")
+    return y
+
+
+def conv_first(x, weight, bias, relu=True, fast=False):
+    """conv1_1 (+ReLU) straight from the NCHW fp32 frame."""
+    _require_cuda(x, "x")
+    lib = nat.load()
+    n, c, h, w = (int(v) for v in x.shape)
+    assert c == 3 and tuple(weight.shape) == (64, 3, 3, 3)
+    y = Act.empty(n, h, w, 64, x.device, fast)
+    flags = (nat.FLAG_RELU if relu else 0) | (nat.FLAG_FAST if fast else 0)
+    nat.check(lib.osvos_conv_first_fwd(x.data_ptr(), weight.data_ptr(), nat.ptr(bias), y.hi.data_ptr(), nat.ptr(y.lo),
+                                       n, h, w, flags, _stream()), "osvos_conv_first_fwd")
+    return y
+
+
+def conv3x3(x, w_packed, bias, cout, relu=False, fast=False, out_act=True, out_f32=False, mask=None,
+            proj_w=None, proj_b=None, simt=False):
+    """3x3 / pad 1 conv of an Act through the tcgen05 kernel.  Returns (Act|None, f32|None, pq|None)."""
+    lib = nat.load()
+    n, h, w, cin = x.shape
+    dev = x.hi.device
+    y = Act.empty(n, h, w, cout, dev, fast) if out_act else None
+    yf = torch.empty((n, h, w, cout), dtype=torch.float32, device=dev) if out_f32 else None
+    pq = torch.empty((n, h, w, 2), dtype=torch.float32, device=dev) if proj_w is not None else None
+    a = nat.Conv3x3Args()
+    a.x_hi, a.x_lo = x.hi.data_ptr(), nat.ptr(x.lo)
+    a.w_packed, a.bias = w_packed.data_ptr(), nat.ptr(bias)
+    a.y_hi = nat.ptr(y.hi) if y is not None else None
+    a.y_lo = nat.ptr(y.lo) if y is not None else None
+    a.y_f32 = nat.ptr(yf)
+    a.mask_hi = nat.ptr(mask)
+    a.proj_w, a.proj_b, a.pq = nat.ptr(proj_w), nat.ptr(proj_b), nat.ptr(pq)
+    a.n, a.h, a.w, a.cin, a.cout = n, h, w, cin, cout
+    a.flags = (nat.FLAG_RELU if relu else 0) | (nat.FLAG_FAST if fast else 0) | \
+              (nat.FLAG_RELU_MASK if mask is not None else 0)
+    fn = lib.osvos_conv3x3_simt if simt else lib.osvos_conv3x3
+    nat.check(fn(byref(a), _stream()), "osvos_conv3x3")
+    return y, yf, pq
+
+
+def maxpool2x2(x):
+    lib = nat.load()
+    n, h, w, c = x.shape
+    y = Act.empty(n, (h + 1) // 2, (w + 1) // 2, c, x.hi.device, x.lo is None)
+    nat.check(lib.osvos_maxpool2x2_fwd(x.hi.data_ptr(), nat.ptr(x.lo), y.hi.data_ptr(), nat.ptr(y.lo), n, h, w, c,
+                                       _stream()), "osvos_maxpool2x2_fwd")
+    return y
+
+
+def side_project(feat, proj_w, proj_b):
+    lib = nat.load()
+    n, h, w, c = (int(v) for v in feat.shape)
+    assert c == 16
+    pq = torch.empty((n, h, w, 2), dtype=torch.float32, device=feat.device)
+    nat.check(lib.osvos_side_project(feat.data_ptr(), proj_w.data_ptr(), nat.ptr(proj_b), pq.data_ptr(), n, h, w,
+                                     _stream()), "osvos_side_project")
+    return pq
+
+
+def tail_fwd(pqs, fuse_bias, n, h, w, label=None, out=None):
+    """Upsample + crop + fuse (+ loss sums).  Returns (out [5,n,1,h,w] fp32, sums [12] f64 | None)."""
+    lib = nat.load()
+    dev = pqs[0].device
+    if out is None:
+        out = torch.empty((5, n, 1, h, w), dtype=torch.float32, device=dev)
+    sums = torch.empty(12, dtype=torch.float64, device=dev) if label is not None else None
+    a = nat.TailFwdArgs()
+    for k in range(4):
+        a.pq[k] = pqs[k].data_ptr()
+    for k in range(5):
+        a.out[k] = out[k].data_ptr()
+    a.fuse_bias = nat.ptr(fuse_bias)
+    a.label = nat.ptr(label)
+    a.sums = nat.ptr(sums)
+    a.n, a.h, a.w = n, h, w
+    nat.check(lib.osvos_tail_fwd(byref(a), _stream()), "osvos_tail_fwd")
+    return out, sums

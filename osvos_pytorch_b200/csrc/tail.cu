@@ -29,6 +29,7 @@ struct TailParams {
   const float* label;
   double* sums;
   int n, h, w;
+  int vec_mask;  // bit k: out[k] is 16-byte aligned; bit 5: label is
 };
 
 constexpr int kTailThreads = 256;
@@ -51,7 +52,7 @@ __global__ void __launch_bounds__(kTailThreads) tail_fwd_kernel(const TailParams
     float lab[4] = {0, 0, 0, 0};
     const bool full = (e0 + 3 < total);
     if (p.label) {
-      if (full) {
+      if (full && (p.vec_mask & 32)) {
         const float4 l4 = __ldg(reinterpret_cast<const float4*>(p.label + e0));
         lab[0] = l4.x, lab[1] = l4.y, lab[2] = l4.z, lab[3] = l4.w;
       } else {
@@ -116,7 +117,7 @@ __global__ void __launch_bounds__(kTailThreads) tail_fwd_kernel(const TailParams
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
       if (!p.out[k]) continue;
-      if (full) {
+      if (full && (p.vec_mask & (1 << k))) {
         *reinterpret_cast<float4*>(p.out[k] + e0) = make_float4(o[k][0], o[k][1], o[k][2], o[k][3]);
       } else {
         for (int j = 0; j < 4; ++j)
@@ -177,17 +178,19 @@ extern "C" int osvos_tail_fwd(const osvos_tail_fwd_args* a, osvos_stream_t strea
     p.sc[k].top = ((hk + 1) * s - a->h) / 2;   // layers/osvos_layers.py:52-56: floor(d/2) rows cropped on top
     p.sc[k].left = ((wk + 1) * s - a->w) / 2;
   }
+  p.vec_mask = 0;
   for (int k = 0; k < 5; ++k) {
     p.out[k] = a->out[k];
-    OSVOS_CHECK_ARG(a->out[k] == nullptr || (reinterpret_cast<uintptr_t>(a->out[k]) & 15) == 0);
+    OSVOS_CHECK_ARG((reinterpret_cast<uintptr_t>(a->out[k]) & 3) == 0);
+    if ((reinterpret_cast<uintptr_t>(a->out[k]) & 15) == 0) p.vec_mask |= 1 << k;
   }
+  if ((reinterpret_cast<uintptr_t>(a->label) & 15) == 0) p.vec_mask |= 32;
   p.fuse_bias = a->fuse_bias;
   p.label = a->label;
   p.sums = a->sums;
   p.n = a->n;
   p.h = a->h;
   p.w = a->w;
-  OSVOS_CHECK_ARG(a->label == nullptr || (reinterpret_cast<uintptr_t>(a->label) & 15) == 0);
   if (a->sums) OSVOS_CHECK_CUDA(cudaMemsetAsync(a->sums, 0, 12 * sizeof(double), stream));
   const size_t nvec = (static_cast<size_t>(a->n) * a->h * a->w + 3) / 4;
   size_t blocks = (nvec + kTailThreads - 1) / kTailThreads;

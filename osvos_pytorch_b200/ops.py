@@ -134,7 +134,9 @@ def tail_fwd(pqs, fuse_bias, n, h, w, label=None, out=None):
     lib = nat.load()
     dev = pqs[0].device
     if out is None:
-        out = torch.empty((5, n, 1, h, w), dtype=torch.float32, device=dev)
+        # each map starts on a 16-byte boundary so the kernel can use 128-bit stores
+        per = (n * h * w + 3) // 4 * 4
+        out = torch.empty((5, per), dtype=torch.float32, device=dev)[:, :n * h * w].view(5, n, 1, h, w)
     sums = torch.empty(12, dtype=torch.float64, device=dev) if label is not None else None
     a = nat.TailFwdArgs()
     for k in range(4):

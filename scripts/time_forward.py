@@ -2,6 +2,7 @@
 import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
+torch.set_grad_enabled(False)
 from oracle import osvos_oracle as oc
 from osvos_pytorch_b200 import ops
 from osvos_pytorch_b200.networks.vgg_osvos import OSVOS, he_init_

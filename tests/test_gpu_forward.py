@@ -92,8 +92,9 @@ def test_forward_full_resolution_480p(net):
     # input must not be mutated, outputs are fresh tensors
     x2 = x.cuda()
     keep = x2.clone()
-    o1 = net(x2)
-    o2 = net(x2)
+    with torch.no_grad():
+        o1 = net(x2)
+        o2 = net(x2)
     assert torch.equal(x2, keep) and o1[4].data_ptr() != o2[4].data_ptr() and torch.equal(o1[4], o2[4])
 
 

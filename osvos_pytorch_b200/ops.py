@@ -8,8 +8,16 @@ import torch
 from . import _native as nat
 
 
+# number of native kernels enqueued since import (bench.py reports the per-step delta)
+KERNEL_LAUNCHES = [0]
+
+
 def _stream():
     return torch.cuda.current_stream().cuda_stream
+
+
+def _count(n=1):
+    KERNEL_LAUNCHES[0] += n
 
 
 class Act:
@@ -47,6 +55,7 @@ def pack_conv3x3_weights(weight, transpose_flip=False, col_pad=64):
     colp = (cols + col_pad - 1) // col_pad * col_pad
     nbytes = lib.osvos_packed_weight_bytes(rows, colp)
     packed = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=w.device)
+    _count()
     nat.check(lib.osvos_pack_conv3x3_weights(w.data_ptr(), packed.data_ptr(), cout, cin, int(transpose_flip), col_pad,
                                              _stream()), "osvos_pack_conv3x3_weights")
     return packed
@@ -58,6 +67,7 @@ def nchw_to_act(x, fast=False):
     x = x.contiguous().float()
     n, c, h, w = (int(v) for v in x.shape)
     a = Act.empty(n, h, w, c, x.device, fast)
+    _count()
     nat.check(lib.osvos_nchw_to_act(x.data_ptr(), a.hi.data_ptr(), nat.ptr(a.lo), n, c, h, w, _stream()),
               "osvos_nchw_to_act")
     return a
@@ -67,6 +77,7 @@ def act_to_nchw(a):
     lib = nat.load()
     n, h, w, c = a.shape
     y = torch.empty((n, c, h, w), dtype=torch.float32, device=a.hi.device)
+    _count()
     nat.check(lib.osvos_act_to_nchw(a.hi.data_ptr(), nat.ptr(a.lo), y.data_ptr(), n, c, h, w, _stream()),
               "osvos_act_to_nchw")
     return y
@@ -80,6 +91,7 @@ def conv_first(x, weight, bias, relu=True, fast=False):
     assert c == 3 and tuple(weight.shape) == (64, 3, 3, 3)
     y = Act.empty(n, h, w, 64, x.device, fast)
     flags = (nat.FLAG_RELU if relu else 0) | (nat.FLAG_FAST if fast else 0)
+    _count()
     nat.check(lib.osvos_conv_first_fwd(x.data_ptr(), weight.data_ptr(), nat.ptr(bias), y.hi.data_ptr(), nat.ptr(y.lo),
                                        n, h, w, flags, _stream()), "osvos_conv_first_fwd")
     return y
@@ -106,6 +118,7 @@ def conv3x3(x, w_packed, bias, cout, relu=False, fast=False, out_act=True, out_f
     a.flags = (nat.FLAG_RELU if relu else 0) | (nat.FLAG_FAST if fast else 0) | \
               (nat.FLAG_RELU_MASK if mask is not None else 0)
     fn = lib.osvos_conv3x3_simt if simt else lib.osvos_conv3x3
+    _count()
     nat.check(fn(byref(a), _stream()), "osvos_conv3x3")
     return y, yf, pq
 
@@ -114,6 +127,7 @@ def maxpool2x2(x):
     lib = nat.load()
     n, h, w, c = x.shape
     y = Act.empty(n, (h + 1) // 2, (w + 1) // 2, c, x.hi.device, x.lo is None)
+    _count()
     nat.check(lib.osvos_maxpool2x2_fwd(x.hi.data_ptr(), nat.ptr(x.lo), y.hi.data_ptr(), nat.ptr(y.lo), n, h, w, c,
                                        _stream()), "osvos_maxpool2x2_fwd")
     return y
@@ -124,6 +138,7 @@ def side_project(feat, proj_w, proj_b):
     n, h, w, c = (int(v) for v in feat.shape)
     assert c == 16
     pq = torch.empty((n, h, w, 2), dtype=torch.float32, device=feat.device)
+    _count()
     nat.check(lib.osvos_side_project(feat.data_ptr(), proj_w.data_ptr(), nat.ptr(proj_b), pq.data_ptr(), n, h, w,
                                      _stream()), "osvos_side_project")
     return pq
@@ -147,5 +162,6 @@ def tail_fwd(pqs, fuse_bias, n, h, w, label=None, out=None):
     a.label = nat.ptr(label)
     a.sums = nat.ptr(sums)
     a.n, a.h, a.w = n, h, w
+    _count()
     nat.check(lib.osvos_tail_fwd(byref(a), _stream()), "osvos_tail_fwd")
     return out, sums

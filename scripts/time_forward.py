@@ -36,7 +36,7 @@ def wrap(name):
         s.record(); r = f(*a, **k); e.record()
         desc = name
         if name == "conv3x3":
-            desc += f" {a[0].shape}->{a[3]}"
+            desc += " " + "x".join(str(v) for v in a[0].shape) + f"->{a[3]}"
         rec.append((desc, s, e))
         return r
     setattr(O, name, g)
@@ -49,7 +49,7 @@ for d, s, e in rec:
     t = s.elapsed_time(e); tot += t
     extra = ""
     if d.startswith("conv3x3"):
-        n_, hh, ww, ci = eval(d.split(" ")[1].split("->")[0]); co = int(d.split("->")[1])
+        n_, hh, ww, ci = (int(v) for v in d.split(" ")[1].split("->")[0].split("x")); co = int(d.split("->")[1])
         fl = 2.0 * n_ * hh * ww * co * 9 * ci
         extra = f"  {fl/t/1e9:8.1f} TFLOP/s"
     print(f"  {d:45s} {t*1000:9.1f} us{extra}")

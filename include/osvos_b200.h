@@ -148,6 +148,66 @@ OSVOS_API int osvos_cbce_fwd(const float* output, const float* label, size_t num
 OSVOS_API int osvos_cbce_bwd(const float* output, const float* label, const double* sums, const float* grad_out,
                              double divisor, size_t numel, float* grad_in, osvos_stream_t stream);
 
+/* ======================= backward (training) entry points ======================= */
+
+/* ---- weight gradient of a 3x3 conv (tcgen05 GEMM over the pixel axis) -----------
+ * Replaces autograd's weight gradient of nn.Conv2d(k=3,p=1) (reference
+ * networks/vgg_osvos.py:41,142; backward at train_online.py:141 / train_parent.py:164):
+ *   dw[co][ci][r][s] = sum_px dz[px][co] * x[px + (r-1, s-1)][ci]
+ * swapped == 0: trunk conv, dz has `cout` channels (dz_channels == cout, a multiple of 64).
+ * swapped == 1: side_prep, dz is the 16-channel feature gradient stored with
+ *               dz_channels == 64 (channels >= cout are zero).
+ * workspace: osvos_wgrad_workspace_bytes(dz_channels, cin) bytes, contents destroyed.  */
+typedef struct {
+  const void* x_hi;   /* layer input act [n,h,w,cin]        */
+  const void* x_lo;
+  const void* dz_hi;  /* output-gradient act [n,h,w,dz_channels] */
+  const void* dz_lo;
+  float* dw;          /* [cout][cin][3][3] fp32, overwritten */
+  float* workspace;
+  int n, h, w, cin, cout, dz_channels;
+  int swapped;
+  int flags;          /* OSVOS_FLAG_FAST */
+} osvos_wgrad_args;
+OSVOS_API size_t osvos_wgrad_workspace_bytes(int dz_channels, int cin);
+OSVOS_API int osvos_conv3x3_wgrad(const osvos_wgrad_args* args /* host */, osvos_stream_t stream);
+
+/* ---- adjoint of the tail: gradients of the five maps -> low-res dp/dq ------------
+ * Backward of osvos_tail_fwd (autograd of networks/vgg_osvos.py:68-72): strided bilinear
+ * DOWN-sampling of grad_out[k] (-> dpq[k][..,0]) and of grad_out[4] (-> dpq[k][..,1])
+ * through the crop window.  NULL grad_out entries count as zero.                       */
+typedef struct {
+  const float* grad_out[5]; /* each [n,1,h,w] or NULL */
+  float* dpq[4];            /* [n,h_k,w_k,2] */
+  int n, h, w;
+} osvos_tail_bwd_args;
+OSVOS_API int osvos_tail_bwd(const osvos_tail_bwd_args* args /* host */, osvos_stream_t stream);
+
+/* out[0] = sum(x[0:n]) (fuse.bias gradient); scratch: 1 double.                          */
+OSVOS_API int osvos_sum_f32(const float* x, size_t n, double* scratch, float* out, osvos_stream_t stream);
+
+/* ---- backward of score_dsn / the fuse slice (1x1 convs, networks/vgg_osvos.py:44,54) --
+ * dfeat = dp*w_score + dq*w_fuse_slice as an act with 64 channels (16..63 zero);
+ * param_grads[0:16] = d score_dsn.weight, [16] = d score_dsn.bias,
+ * [17:33] = d fuse.weight slice, [33] = sum dq.  scratch: 34 doubles.  feat may be NULL
+ * (then only dfeat and the two plain sums are produced).                                */
+OSVOS_API int osvos_side_bwd(const float* feat, const float* dpq, const float* proj_w, void* dfeat_hi, void* dfeat_lo,
+                             double* scratch, float* param_grads, int n, int h, int w, osvos_stream_t stream);
+
+/* ---- max-unpool + side-branch add + ReLU mask (autograd of networks/vgg_osvos.py:140,143) */
+OSVOS_API int osvos_unpool_add_mask(const void* dpool_hi, const void* dpool_lo, const void* x_hi, const void* x_lo,
+                                    const float* dside /* [n,h,w,c] fp32 or NULL */, void* dz_hi, void* dz_lo, int n,
+                                    int h, int w, int c, osvos_stream_t stream);
+
+/* ---- bias gradient: out[c] = sum over pixels of an act ----------------------------- */
+OSVOS_API int osvos_channel_sum(const void* act_hi, const void* act_lo, float* out, size_t npix, int c,
+                                osvos_stream_t stream);
+
+/* ---- conv1_1 backward: dw [64][3][3][3] and (optionally) dx [n,3,h,w] --------------- */
+OSVOS_API int osvos_conv_first_bwd(const float* x_nchw, const void* dz_hi, const void* dz_lo, const float* w_oihw,
+                                   float* dw, float* dx_nchw /* or NULL */, int n, int h, int w,
+                                   osvos_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

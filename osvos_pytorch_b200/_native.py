@@ -33,6 +33,16 @@ class TailFwdArgs(Structure):
                 ("sums", c_void_p), ("n", c_int), ("h", c_int), ("w", c_int)]
 
 
+class WgradArgs(Structure):
+    _fields_ = [("x_hi", c_void_p), ("x_lo", c_void_p), ("dz_hi", c_void_p), ("dz_lo", c_void_p), ("dw", c_void_p),
+                ("workspace", c_void_p), ("n", c_int), ("h", c_int), ("w", c_int), ("cin", c_int), ("cout", c_int),
+                ("dz_channels", c_int), ("swapped", c_int), ("flags", c_int)]
+
+
+class TailBwdArgs(Structure):
+    _fields_ = [("grad_out", c_void_p * 5), ("dpq", c_void_p * 4), ("n", c_int), ("h", c_int), ("w", c_int)]
+
+
 # name -> (restype, argtypes); mirrors include/osvos_b200.h one to one (tests/test_abi.py checks it)
 SIGNATURES = {
     "osvos_version": (c_int, []),
@@ -49,6 +59,17 @@ SIGNATURES = {
     "osvos_tail_fwd": (c_int, [POINTER(TailFwdArgs), c_void_p]),
     "osvos_cbce_fwd": (c_int, [c_void_p, c_void_p, c_size_t, c_double, c_void_p, c_void_p, c_void_p]),
     "osvos_cbce_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_size_t, c_void_p, c_void_p]),
+    "osvos_wgrad_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "osvos_conv3x3_wgrad": (c_int, [POINTER(WgradArgs), c_void_p]),
+    "osvos_tail_bwd": (c_int, [POINTER(TailBwdArgs), c_void_p]),
+    "osvos_sum_f32": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
+    "osvos_side_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                               c_int, c_void_p]),
+    "osvos_unpool_add_mask": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                      c_int, c_int, c_int, c_void_p]),
+    "osvos_channel_sum": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
+    "osvos_conv_first_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                     c_void_p]),
     "osvos_side_project": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
 }
 

@@ -1,0 +1,130 @@
+"""Training path: one torch.autograd.Function spanning the whole network, so that autograd sees
+a single node whose forward/backward are sequences of native kernels (no PyTorch op does
+arithmetic).  Replaces the autograd graph of reference networks/vgg_osvos.py:59-74 built at
+train_online.py:124 / train_parent.py:140 and walked at :141 / :164.
+
+Gradient bookkeeping mirrors the reference: parameters that do not influence the objective get
+``None`` (e.g. score_dsn.* under the fuse-only online loss); the fixed
+bilinear deconvolution weights (lr = 0 in both scripts) receive no gradient.
+"""
+import torch
+import torch.nn as nn
+
+from . import ops
+
+
+def _trunk_convs(m):
+    return [[c for c in stage if isinstance(c, nn.Conv2d)] for stage in m.stages]
+
+
+class _OSVOSFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, engine, x, *params):
+        m = engine.m
+        fast = m.precision == "fast"
+        engine._check_deconvs()
+        ctx.set_materialize_grads(False)
+        xin = x.detach().contiguous().float()
+        n, _, h, w = (int(v) for v in xin.shape)
+        convs = _trunk_convs(m)
+        acts = []      # acts[i][j] = output act of conv j of stage i
+        pooled = [None]
+        a = ops.conv_first(xin, convs[0][0].weight.detach(), convs[0][0].bias.detach(), relu=True, fast=fast)
+        stage_acts = [a]
+        a, _, _ = ops.conv3x3(a, engine._packed(convs[0][1], "s0c1"), convs[0][1].bias.detach(), 64, relu=True, fast=fast)
+        stage_acts.append(a)
+        acts.append(stage_acts)
+        feats, pqs = [], []
+        for i in range(1, 5):
+            a = ops.maxpool2x2(a)
+            pooled.append(a)
+            stage_acts = []
+            for j, conv in enumerate(convs[i]):
+                a, _, _ = ops.conv3x3(a, engine._packed(conv, f"s{i}c{j}"), conv.bias.detach(), conv.out_channels,
+                                      relu=True, fast=fast)
+                stage_acts.append(a)
+            acts.append(stage_acts)
+            sp = m.side_prep[i - 1]
+            _, feat, pq = ops.conv3x3(a, engine._packed(sp, f"sp{i}"), sp.bias.detach(), 16, relu=False, fast=fast,
+                                      out_act=False, out_f32=True, proj_w=engine._proj(i - 1),
+                                      proj_b=m.score_dsn[i - 1].bias.detach())
+            feats.append(feat)
+            pqs.append(pq)
+        out, _ = ops.tail_fwd(pqs, m.fuse.bias.detach(), n, h, w)
+        ctx.engine = engine
+        ctx.saved = (xin, acts, pooled, feats)
+        ctx.dims = (n, h, w)
+        ctx.fast = fast
+        outs = tuple(out[k] for k in range(5))
+        return outs
+
+    @staticmethod
+    def backward(ctx, *grads):
+        engine = ctx.engine
+        m = engine.m
+        fast = ctx.fast
+        xin, acts, pooled, feats = ctx.saved
+        n, h, w = ctx.dims
+        convs = _trunk_convs(m)
+        pg = {}                                   # parameter -> gradient tensor
+        if all(g is None for g in grads):
+            return (None, None) + tuple(None for _ in engine._param_list())
+        dpq = ops.tail_bwd(list(grads), n, h, w)
+        if grads[4] is not None:
+            pg[m.fuse.bias] = ops.sum_f32(grads[4]).reshape(m.fuse.bias.shape)
+        fuse_w_grad = torch.zeros(64, dtype=torch.float32, device=xin.device) if grads[4] is not None else None
+        dfeats = []
+        for i in range(4):
+            d, g34 = ops.side_bwd(feats[i], dpq[i], engine._proj(i), fast)
+            dfeats.append(d)
+            if grads[i] is not None:
+                pg[m.score_dsn[i].weight] = g34[0:16].reshape(m.score_dsn[i].weight.shape)
+                pg[m.score_dsn[i].bias] = g34[16:17].reshape(m.score_dsn[i].bias.shape)
+            if fuse_w_grad is not None:
+                fuse_w_grad[16 * i:16 * i + 16] = g34[17:33]           # slice copy (plumbing)
+            sp = m.side_prep[i]
+            s_out = acts[i + 1][-1]
+            pg[sp.weight] = ops.conv3x3_wgrad(s_out, d, 16, swapped=True, fast=fast)
+            pg[sp.bias] = ops.channel_sum(d)[:16]
+        if fuse_w_grad is not None:
+            pg[m.fuse.weight] = fuse_w_grad.reshape(m.fuse.weight.shape)
+
+        dpool = None
+        for i in range(4, 0, -1):
+            s_out = acts[i][-1]
+            sp = m.side_prep[i - 1]
+            wt_side = engine._packed(sp, f"sp{i}", transpose_flip=True, col_pad=64)
+            cst = s_out.shape[3]
+            if dpool is None:        # deepest stage: the side branch is the only consumer
+                dz, _, _ = ops.conv3x3(dfeats[i - 1], wt_side, None, cst, fast=fast, mask=s_out.hi)
+            else:
+                _, dside, _ = ops.conv3x3(dfeats[i - 1], wt_side, None, cst, fast=fast, out_act=False, out_f32=True)
+                dz = ops.unpool_add_mask(dpool, s_out, dside)
+            for j in range(len(convs[i]) - 1, -1, -1):
+                conv = convs[i][j]
+                inp = acts[i][j - 1] if j > 0 else pooled[i]
+                pg[conv.weight] = ops.conv3x3_wgrad(inp, dz, conv.out_channels, fast=fast)
+                pg[conv.bias] = ops.channel_sum(dz)
+                wt = engine._packed(conv, f"s{i}c{j}", transpose_flip=True)
+                if j > 0:
+                    dz, _, _ = ops.conv3x3(dz, wt, None, conv.in_channels, fast=fast, mask=inp.hi)
+                else:
+                    dpool, _, _ = ops.conv3x3(dz, wt, None, conv.in_channels, fast=fast)
+        # stage 1 (no side branch)
+        dz = ops.unpool_add_mask(dpool, acts[0][1], None)
+        c12, c11 = convs[0][1], convs[0][0]
+        pg[c12.weight] = ops.conv3x3_wgrad(acts[0][0], dz, 64, fast=fast)
+        pg[c12.bias] = ops.channel_sum(dz)
+        dz, _, _ = ops.conv3x3(dz, engine._packed(c12, "s0c1", transpose_flip=True), None, 64, fast=fast,
+                               mask=acts[0][0].hi)
+        dw0, dx = ops.conv_first_bwd(xin, dz, c11.weight.detach(), ctx.needs_input_grad[1])
+        pg[c11.weight] = dw0
+        pg[c11.bias] = ops.channel_sum(dz)
+        ctx.saved = None
+        return (None, dx) + tuple(pg.get(p) for p in engine._param_list())
+
+
+def osvos_apply(engine, x):
+    params = engine._param_list()
+    outs = _OSVOSFunction.apply(engine, x, *params)
+    return list(outs)

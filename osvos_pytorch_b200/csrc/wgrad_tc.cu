@@ -1,0 +1,340 @@
+// Weight gradient of the 3x3 convolutions as a tcgen05 GEMM whose reduction
+// dimension is the PIXEL axis:
+//
+//   ws[tap][m][n] += sum_px P[px (+tap)][m] * Q[px (+tap)][n]
+//
+// For a trunk conv P = dZ (gradient of the conv output, unshifted, m = co) and
+// Q = the layer's input activation shifted by the tap (n = ci); for side_prep the
+// roles are swapped (P = shifted input, m = ci; Q = the 16-channel feature
+// gradient padded to 64, n = co) so that M stays 128-wide.  Both operands are
+// NHWC acts, i.e. the reduction index (pixel) is the strided one: they are
+// "MN-major" UMMA operands.  A K block is a patch of 8 x 8 pixels; its TMA box
+// {64 ch, 8 px, 8 rows, 1} lands as 64 rows x 128 B (SWIZZLE_128B), which is the
+// canonical MN-major SW128 atom layout (64 MN elements x 8 K rows per atom,
+// SBO = 1024 B between K groups, LBO = 8192 B between 64-wide MN atoms).
+// Out-of-image pixels are zero-filled by TMA: they are both the conv padding of
+// the shifted operand and the ragged-edge mask of the unshifted one.
+//
+// Work item = (m block of 128, n block, tap, pixel-range split); the fp32 TMEM
+// accumulator is flushed with vector atomics (red.global.add.v4.f32) into the
+// zero-initialised workspace, which a small kernel then transposes into the
+// OIHW gradient.  Same warp roles / mbarrier pipeline as conv3x3_tc.cu.
+//
+// Replaces autograd's weight gradient of nn.Conv2d(k=3, p=1)
+// (reference networks/vgg_osvos.py:41,142; backward triggered at train_online.py:141).
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace osvos {
+
+constexpr int kWgThreads = 192;
+constexpr int kWgPatchW = 8, kWgPatchH = 8;
+constexpr int kWgBlockK = 64;                  // pixels per K block
+constexpr int kWgBoxBytes = kWgBlockK * 128;   // 8 KiB: 64 pixels x 64 channels of bf16
+
+struct WgradParams {
+  float* ws;  // [9][m_total][n_total]
+  int n_img, h, w;
+  int m_total, n_total, m_valid;
+  int m_blocks, n_blocks, splits;
+  int patches_x, patches_y, patches_total, patches_per_split;
+  int total_items;
+  int p_shifted;  // 1: P is the shifted operand, 0: Q is
+};
+
+template <int BLOCK_N, int PLANES>
+struct WgCfg {
+  static constexpr int kPBytes = 2 * kWgBoxBytes;               // 128 m
+  static constexpr int kQBytes = (BLOCK_N / 64) * kWgBoxBytes;  // BLOCK_N n
+  static constexpr int kStageBytes = PLANES * (kPBytes + kQBytes);
+  static constexpr int kStagesRaw = (212 * 1024) / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+};
+
+__device__ __forceinline__ void wg_decode_item(const WgradParams& p, int item, int& mb, int& nb, int& tap, int& split) {
+  nb = item % p.n_blocks;
+  int t = item / p.n_blocks;
+  mb = t % p.m_blocks;
+  t /= p.m_blocks;
+  tap = t % 9;
+  split = t / 9;
+}
+
+template <int BLOCK_N, int PLANES>
+__global__ void __launch_bounds__(kWgThreads, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_p_hi, const __grid_constant__ CUtensorMap map_p_lo,
+                const __grid_constant__ CUtensorMap map_q_hi, const __grid_constant__ CUtensorMap map_q_lo,
+                const WgradParams p) {
+  using Cfg = WgCfg<BLOCK_N, PLANES>;
+  constexpr int kStages = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kStages;
+  uint64_t* tfull_bar = bars + 2 * kStages;
+  uint64_t* tempty_bar = bars + 2 * kStages + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_p_hi);
+    tma_prefetch_desc(&map_q_hi);
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+        int mb, nb, tap, split;
+        wg_decode_item(p, item, mb, nb, tap, split);
+        const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+        const int pdy = p.p_shifted ? dy : 0, pdx = p.p_shifted ? dx : 0;
+        const int qdy = p.p_shifted ? 0 : dy, qdx = p.p_shifted ? 0 : dx;
+        const int pb = split * p.patches_per_split;
+        int pe = pb + p.patches_per_split;
+        if (pe > p.patches_total) pe = p.patches_total;
+        for (int patch = pb; patch < pe; ++patch) {
+          const int px = patch % p.patches_x;
+          const int t = patch / p.patches_x;
+          const int py = t % p.patches_y;
+          const int img = t / p.patches_y;
+          const int x0 = px * kWgPatchW, y0 = py * kWgPatchH;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* st = smem + stage * Cfg::kStageBytes;
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+#pragma unroll
+          for (int pl = 0; pl < PLANES; ++pl) {
+            const CUtensorMap* mp = pl == 0 ? &map_p_hi : &map_p_lo;
+            const CUtensorMap* mq = pl == 0 ? &map_q_hi : &map_q_lo;
+            uint8_t* sp = st + pl * Cfg::kPBytes;
+            uint8_t* sq = st + PLANES * Cfg::kPBytes + pl * Cfg::kQBytes;
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+              tma_load_4d(mp, &full_bar[stage], sp + j * kWgBoxBytes, mb * 128 + j * 64, x0 + pdx, y0 + pdy, img);
+#pragma unroll
+            for (int j = 0; j < BLOCK_N / 64; ++j)
+              tma_load_4d(mq, &full_bar[stage], sq + j * kWgBoxBytes, nb * BLOCK_N + j * 64, x0 + qdx, y0 + qdy, img);
+          }
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(128, BLOCK_N, true, /*a_mn=*/true, /*b_mn=*/true);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
+        int mb, nb, tap, split;
+        wg_decode_item(p, item, mb, nb, tap, split);
+        const int pb = split * p.patches_per_split;
+        int pe = pb + p.patches_per_split;
+        if (pe > p.patches_total) pe = p.patches_total;
+        const int as = it & 1;
+        const uint32_t aph = (it >> 1) & 1;
+        mbar_wait(&tempty_bar[as], aph ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * BLOCK_N;
+        for (int patch = pb; patch < pe; ++patch) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sp = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t sq = sp + PLANES * Cfg::kPBytes;
+          // MN-major SW128: LBO = bytes between 64-wide MN atoms, SBO = bytes between 8-row K groups
+          const uint64_t dp_hi = make_smem_desc(sp, kWgBoxBytes, 1024, kLayoutSW128);
+          const uint64_t dq_hi = make_smem_desc(sq, kWgBoxBytes, 1024, kLayoutSW128);
+          const uint64_t dp_lo = make_smem_desc(sp + Cfg::kPBytes, kWgBoxBytes, 1024, kLayoutSW128);
+          const uint64_t dq_lo = make_smem_desc(sq + Cfg::kQBytes, kWgBoxBytes, 1024, kLayoutSW128);
+#pragma unroll
+          for (int k = 0; k < kWgBlockK / 16; ++k) {
+            const uint64_t adv = static_cast<uint64_t>(k * (2048 >> 4));  // 16 pixel rows x 128 B
+            const uint32_t acc = (patch != pb || k != 0) ? 1u : 0u;
+            if (PLANES == 2) {
+              umma_f16(tmem_d, dp_lo + adv, dq_hi + adv, idesc, acc);
+              umma_f16(tmem_d, dp_hi + adv, dq_lo + adv, idesc, 1);
+              umma_f16(tmem_d, dp_hi + adv, dq_hi + adv, idesc, 1);
+            } else {
+              umma_f16(tmem_d, dp_hi + adv, dq_hi + adv, idesc, acc);
+            }
+          }
+          umma_commit(&empty_bar[stage]);
+          if (patch == pe - 1) umma_commit(&tfull_bar[as]);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    int it = 0;
+    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
+      int mb, nb, tap, split;
+      wg_decode_item(p, item, mb, nb, tap, split);
+      const int as = it & 1;
+      const uint32_t aph = (it >> 1) & 1;
+      const int m = mb * 128 + row;
+      mbar_wait(&tfull_bar[as], aph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + as * BLOCK_N + (static_cast<uint32_t>(q * 32) << 16);
+      float* dst = p.ws + (static_cast<size_t>(tap) * p.m_total + m) * p.n_total + nb * BLOCK_N;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + c0, v);
+        tmem_ld_wait();
+        if (m < p.m_valid) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 val = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                     __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+            atomicAdd(reinterpret_cast<float4*>(dst + c0 + 4 * j), val);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ws[tap][a][b] (+ optional existing grad) -> OIHW gradient.
+//   swapped == 0: a = co, b = ci ; swapped == 1: a = ci, b = co (b padded to ld_b)
+__global__ void wgrad_finish_kernel(const float* __restrict__ ws, float* __restrict__ dw, int cout, int cin, int ld_a,
+                                    int ld_b, int swapped, float scale, int accumulate) {
+  const int total = cout * cin * 9;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int tap = i % 9;
+    const int ci = (i / 9) % cin;
+    const int co = i / (9 * cin);
+    const int a = swapped ? ci : co, b = swapped ? co : ci;
+    const float v = ws[(static_cast<size_t>(tap) * ld_a + a) * ld_b + b] * scale;
+    dw[i] = accumulate ? dw[i] + v : v;
+  }
+}
+
+template <int BLOCK_N, int PLANES>
+static int launch_wgrad(const osvos_wgrad_args* a, cudaStream_t stream) {
+  using Cfg = WgCfg<BLOCK_N, PLANES>;
+  const bool swapped = a->swapped != 0;
+  // operand roles
+  const void* p_hi = swapped ? a->x_hi : a->dz_hi;
+  const void* p_lo = swapped ? a->x_lo : a->dz_lo;
+  const void* q_hi = swapped ? a->dz_hi : a->x_hi;
+  const void* q_lo = swapped ? a->dz_lo : a->x_lo;
+  const int cp = swapped ? a->cin : a->dz_channels;   // channels of the P tensor
+  const int cq = swapped ? a->dz_channels : a->cin;   // channels of the Q tensor
+
+  WgradParams p;
+  p.ws = a->workspace;
+  p.n_img = a->n;
+  p.h = a->h;
+  p.w = a->w;
+  p.m_total = (cp + 127) / 128 * 128;
+  if (p.m_total != cp && cp != 64) return OSVOS_ERR_UNSUPPORTED;
+  p.m_total = cp;  // rows actually stored in the workspace
+  p.m_valid = cp;
+  p.n_total = cq;
+  p.m_blocks = (cp + 127) / 128;
+  p.n_blocks = cq / BLOCK_N;
+  p.patches_x = (a->w + kWgPatchW - 1) / kWgPatchW;
+  p.patches_y = (a->h + kWgPatchH - 1) / kWgPatchH;
+  p.patches_total = p.patches_x * p.patches_y * a->n;
+  const int tiles = p.m_blocks * p.n_blocks * 9;
+  const int sms = device_sm_count();
+  int splits = (2 * sms + tiles - 1) / tiles;
+  const int max_splits = (p.patches_total + 3) / 4;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  p.patches_per_split = (p.patches_total + splits - 1) / splits;
+  p.splits = (p.patches_total + p.patches_per_split - 1) / p.patches_per_split;
+  p.total_items = tiles * p.splits;
+  p.p_shifted = swapped ? 1 : 0;
+
+  CUtensorMap mp_hi, mp_lo, mq_hi, mq_lo;
+  auto enc = [&](CUtensorMap* m, const void* base, int c) {
+    const uint64_t dims[4] = {(uint64_t)c, (uint64_t)a->w, (uint64_t)a->h, (uint64_t)a->n};
+    const uint64_t strides[3] = {(uint64_t)c * 2, (uint64_t)a->w * c * 2, (uint64_t)a->h * a->w * c * 2};
+    const uint32_t box[4] = {64, kWgPatchW, kWgPatchH, 1};
+    return encode_tensor_map(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 4, base, dims, strides, box,
+                             CU_TENSOR_MAP_SWIZZLE_128B);
+  };
+  int rc;
+  if ((rc = enc(&mp_hi, p_hi, cp))) return rc;
+  if ((rc = enc(&mp_lo, PLANES == 2 ? p_lo : p_hi, cp))) return rc;
+  if ((rc = enc(&mq_hi, q_hi, cq))) return rc;
+  if ((rc = enc(&mq_lo, PLANES == 2 ? q_lo : q_hi, cq))) return rc;
+
+  const size_t ws_bytes = static_cast<size_t>(9) * p.m_total * p.n_total * sizeof(float);
+  OSVOS_CHECK_CUDA(cudaMemsetAsync(a->workspace, 0, ws_bytes, stream));
+  auto kern = wgrad_tc_kernel<BLOCK_N, PLANES>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    OSVOS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_done = true;
+  }
+  const int grid = p.total_items < sms ? p.total_items : sms;
+  kern<<<grid, kWgThreads, Cfg::kSmemBytes, stream>>>(mp_hi, mp_lo, mq_hi, mq_lo, p);
+  OSVOS_CHECK_CUDA(cudaGetLastError());
+  const int total = a->cout * a->cin * 9;
+  wgrad_finish_kernel<<<(total + 255) / 256, 256, 0, stream>>>(a->workspace, a->dw, a->cout, a->cin, p.m_total,
+                                                                p.n_total, swapped ? 1 : 0, 1.0f, 0);
+  OSVOS_CHECK_CUDA(cudaGetLastError());
+  return OSVOS_OK;
+}
+
+}  // namespace osvos
+
+using namespace osvos;
+
+extern "C" size_t osvos_wgrad_workspace_bytes(int cout_or_padded, int cin) {
+  return static_cast<size_t>(9) * cout_or_padded * cin * sizeof(float);
+}
+
+extern "C" int osvos_conv3x3_wgrad(const osvos_wgrad_args* a, osvos_stream_t stream_) {
+  OSVOS_CHECK_ARG(a != nullptr && a->x_hi != nullptr && a->dz_hi != nullptr && a->dw != nullptr &&
+                  a->workspace != nullptr);
+  OSVOS_CHECK_ARG(a->n > 0 && a->h > 0 && a->w > 0 && a->cin % 64 == 0 && a->dz_channels % 64 == 0);
+  OSVOS_CHECK_ARG(a->cout <= a->dz_channels);
+  OSVOS_CHECK_ARG((a->flags & OSVOS_FLAG_FAST) || (a->x_lo != nullptr && a->dz_lo != nullptr));
+  OSVOS_CHECK_ARG(!a->swapped || a->dz_channels == 64);
+  OSVOS_CHECK_ARG(a->swapped || a->cout == a->dz_channels);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const bool fast = (a->flags & OSVOS_FLAG_FAST) != 0;
+  const int cq = a->swapped ? a->dz_channels : a->cin;
+  if (cq % 128 == 0) return fast ? launch_wgrad<128, 1>(a, stream) : launch_wgrad<128, 2>(a, stream);
+  return fast ? launch_wgrad<64, 1>(a, stream) : launch_wgrad<64, 2>(a, stream);
+}

@@ -31,8 +31,14 @@ class OSVOSEngine:
         return val
 
     def _packed(self, conv, key, transpose_flip=False, col_pad=64):
-        return self._cached((key, transpose_flip), [conv.weight],
+        return self._cached((key, transpose_flip, col_pad), [conv.weight],
                             lambda: ops.pack_conv3x3_weights(conv.weight, transpose_flip, col_pad))
+
+    def _param_list(self):
+        """Parameters the native path differentiates (everything except the fixed deconvolution taps)."""
+        m = self.m
+        return ([p for p in m.stages.parameters()] + [p for p in m.side_prep.parameters()]
+                + [p for p in m.score_dsn.parameters()] + [m.fuse.weight, m.fuse.bias])
 
     def _proj(self, i):
         m = self.m

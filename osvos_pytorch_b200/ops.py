@@ -165,3 +165,104 @@ def tail_fwd(pqs, fuse_bias, n, h, w, label=None, out=None):
     _count()
     nat.check(lib.osvos_tail_fwd(byref(a), _stream()), "osvos_tail_fwd")
     return out, sums
+
+
+# ------------------------------------------------------------------ backward ops
+def conv3x3_wgrad(x, dz, cout, swapped=False, fast=False):
+    """dW [cout, cin, 3, 3] of a 3x3 conv from its input act `x` and output-gradient act `dz`."""
+    lib = nat.load()
+    n, h, w, cin = x.shape
+    dzc = dz.shape[3]
+    dev = x.hi.device
+    dw = torch.empty((cout, cin, 3, 3), dtype=torch.float32, device=dev)
+    ws = torch.empty(lib.osvos_wgrad_workspace_bytes(dzc, cin) // 4, dtype=torch.float32, device=dev)
+    a = nat.WgradArgs()
+    a.x_hi, a.x_lo, a.dz_hi, a.dz_lo = x.hi.data_ptr(), nat.ptr(x.lo), dz.hi.data_ptr(), nat.ptr(dz.lo)
+    a.dw, a.workspace = dw.data_ptr(), ws.data_ptr()
+    a.n, a.h, a.w, a.cin, a.cout, a.dz_channels = n, h, w, cin, cout, dzc
+    a.swapped = int(swapped)
+    a.flags = nat.FLAG_FAST if fast else 0
+    _count(3)
+    nat.check(lib.osvos_conv3x3_wgrad(byref(a), _stream()), "osvos_conv3x3_wgrad")
+    return dw
+
+
+def tail_bwd(grads, n, h, w):
+    """grads: list of 5 tensors [n,1,h,w] or None -> list of 4 dpq tensors [n,hk,wk,2]."""
+    lib = nat.load()
+    dev = next(g for g in grads if g is not None).device
+    a = nat.TailBwdArgs()
+    keep = []
+    for k in range(5):
+        g = grads[k]
+        if g is not None:
+            g = g.contiguous().float()
+            keep.append(g)
+        a.grad_out[k] = nat.ptr(g)
+    dpq, hk, wk = [], h, w
+    for k in range(4):
+        hk, wk = (hk + 1) // 2, (wk + 1) // 2
+        t = torch.empty((n, hk, wk, 2), dtype=torch.float32, device=dev)
+        dpq.append(t)
+        a.dpq[k] = t.data_ptr()
+    a.n, a.h, a.w = n, h, w
+    _count(4)
+    nat.check(lib.osvos_tail_bwd(byref(a), _stream()), "osvos_tail_bwd")
+    return dpq
+
+
+def sum_f32(x):
+    lib = nat.load()
+    x = x.contiguous().float()
+    scratch = torch.empty(1, dtype=torch.float64, device=x.device)
+    out = torch.empty(1, dtype=torch.float32, device=x.device)
+    _count(2)
+    nat.check(lib.osvos_sum_f32(x.data_ptr(), x.numel(), scratch.data_ptr(), out.data_ptr(), _stream()),
+              "osvos_sum_f32")
+    return out
+
+
+def side_bwd(feat, dpq, proj_w, fast=False):
+    """-> (dfeat Act [n,h,w,64], param_grads [34] fp32)."""
+    lib = nat.load()
+    n, h, w, _ = (int(v) for v in dpq.shape)
+    dev = dpq.device
+    d = Act.empty(n, h, w, 64, dev, fast)
+    scratch = torch.empty(34, dtype=torch.float64, device=dev)
+    pg = torch.empty(34, dtype=torch.float32, device=dev)
+    _count(2)
+    nat.check(lib.osvos_side_bwd(nat.ptr(feat), dpq.data_ptr(), proj_w.data_ptr(), d.hi.data_ptr(), nat.ptr(d.lo),
+                                 scratch.data_ptr(), pg.data_ptr(), n, h, w, _stream()), "osvos_side_bwd")
+    return d, pg
+
+
+def unpool_add_mask(dpool, x, dside):
+    lib = nat.load()
+    n, h, w, c = x.shape
+    dz = Act.empty(n, h, w, c, x.hi.device, x.lo is None)
+    _count()
+    nat.check(lib.osvos_unpool_add_mask(dpool.hi.data_ptr(), nat.ptr(dpool.lo), x.hi.data_ptr(), nat.ptr(x.lo),
+                                        nat.ptr(dside), dz.hi.data_ptr(), nat.ptr(dz.lo), n, h, w, c, _stream()),
+              "osvos_unpool_add_mask")
+    return dz
+
+
+def channel_sum(a):
+    lib = nat.load()
+    n, h, w, c = a.shape
+    out = torch.empty(c, dtype=torch.float32, device=a.hi.device)
+    _count()
+    nat.check(lib.osvos_channel_sum(a.hi.data_ptr(), nat.ptr(a.lo), out.data_ptr(), n * h * w, c, _stream()),
+              "osvos_channel_sum")
+    return out
+
+
+def conv_first_bwd(x, dz, weight, need_dx):
+    lib = nat.load()
+    n, _, h, w = (int(v) for v in x.shape)
+    dw = torch.empty((64, 3, 3, 3), dtype=torch.float32, device=x.device)
+    dx = torch.empty_like(x) if need_dx else None
+    _count(2 if need_dx else 1)
+    nat.check(lib.osvos_conv_first_bwd(x.data_ptr(), dz.hi.data_ptr(), nat.ptr(dz.lo), weight.data_ptr(),
+                                       dw.data_ptr(), nat.ptr(dx), n, h, w, _stream()), "osvos_conv_first_bwd")
+    return dw, dx

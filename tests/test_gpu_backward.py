@@ -1,0 +1,230 @@
+"""Backward parity of the CUDA path: per-kernel adjoint checks against torch CPU fp64 autograd, and the
+whole fwd+bwd (online and parent objectives) against the golden gradients of the unmodified reference
+and against the oracle.  Tolerances: per-parameter ||g - g_ref|| / ||g_ref|| <= 2e-3, loss rel 1e-4."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import osvos_oracle as oc
+from gpu_util import maxrel, split_round
+
+pytestmark = pytest.mark.gpu
+GRAD_TOL = 2e-3
+
+
+def relnorm(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / b.norm().clamp(min=1e-30))
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda:0")
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", [(1, 8, 8, 64, 64), (1, 20, 13, 64, 64), (2, 17, 9, 128, 128),
+                                            (1, 9, 11, 256, 128), (1, 33, 45, 64, 128), (1, 5, 3, 512, 512)])
+@pytest.mark.parametrize("fast", [False, True])
+def test_wgrad_tensor_core(dev, n, h, w, cin, cout, fast):
+    from osvos_pytorch_b200 import ops
+    g = torch.Generator().manual_seed(h * w + cin)
+    x = torch.randn(n, cin, h, w, generator=g)
+    dz = torch.randn(n, cout, h, w, generator=g) * 0.1
+    wt = torch.zeros(cout, cin, 3, 3, dtype=torch.float64, requires_grad=True)
+    F.conv2d(x.double(), wt, None, padding=1).backward(dz.double())
+    got = ops.conv3x3_wgrad(ops.nchw_to_act(x.to(dev), fast), ops.nchw_to_act(dz.to(dev), fast), cout, fast=fast)
+    assert tuple(got.shape) == (cout, cin, 3, 3)
+    assert maxrel(got, wt.grad) < (3e-2 if fast else 3e-5), maxrel(got, wt.grad)
+
+
+def test_wgrad_side_prep_swapped(dev):
+    from osvos_pytorch_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    n, h, w, cin = 1, 19, 21, 128
+    x = torch.randn(n, cin, h, w, generator=g)
+    dz16 = torch.randn(n, 16, h, w, generator=g) * 0.1
+    dz = torch.cat([dz16, torch.zeros(n, 48, h, w)], 1)
+    wt = torch.zeros(16, cin, 3, 3, dtype=torch.float64, requires_grad=True)
+    F.conv2d(x.double(), wt, None, padding=1).backward(dz16.double())
+    got = ops.conv3x3_wgrad(ops.nchw_to_act(x.to(dev)), ops.nchw_to_act(dz.to(dev)), 16, swapped=True)
+    assert maxrel(got, wt.grad) < 3e-5
+
+
+def test_dgrad_is_the_adjoint(dev):
+    from osvos_pytorch_b200 import ops
+    g = torch.Generator().manual_seed(4)
+    n, h, w, cin, cout = 1, 18, 11, 64, 128
+    wt = torch.randn(cout, cin, 3, 3, generator=g) * 0.05
+    dz = torch.randn(n, cout, h, w, generator=g)
+    xin = torch.zeros(n, cin, h, w, dtype=torch.float64, requires_grad=True)
+    F.conv2d(xin, wt.double(), None, padding=1).backward(dz.double())
+    wp = ops.pack_conv3x3_weights(wt.to(dev), transpose_flip=True)
+    _, dx, _ = ops.conv3x3(ops.nchw_to_act(dz.to(dev)), wp, None, cin, out_act=False, out_f32=True)
+    assert maxrel(dx.permute(0, 3, 1, 2), xin.grad) < 3e-5
+
+
+@pytest.mark.parametrize("n,h,w", [(1, 48, 70), (2, 33, 45), (1, 17, 3)])
+def test_tail_bwd_is_the_adjoint(dev, n, h, w):
+    from osvos_pytorch_b200 import ops
+    g = torch.Generator().manual_seed(6)
+    grads = [torch.randn(n, 1, h, w, generator=g) for _ in range(5)]
+    pqs, hk, wk = [], h, w
+    for k in range(4):
+        hk, wk = oc.pooled_size(hk), oc.pooled_size(wk)
+        pqs.append(torch.zeros(n, hk, wk, 2, dtype=torch.float64, requires_grad=True))
+    tot = 0
+    for k in range(4):
+        s = 2 ** (k + 1)
+        p = pqs[k][..., 0].unsqueeze(1)
+        q = pqs[k][..., 1].unsqueeze(1)
+        tot = tot + (oc.center_crop(oc.upsample_zero_padded(p, s), h, w) * grads[k].double()).sum()
+        tot = tot + (oc.center_crop(oc.upsample_zero_padded(q, s), h, w) * grads[4].double()).sum()
+    tot.backward()
+    got = ops.tail_bwd([t.to(dev) for t in grads], n, h, w)
+    for k in range(4):
+        assert maxrel(got[k], pqs[k].grad) < 2e-6
+    # missing side gradients (online objective): dp == 0, dq unchanged
+    got2 = ops.tail_bwd([None, None, None, None, grads[4].to(dev)], n, h, w)
+    for k in range(4):
+        assert float(got2[k][..., 0].abs().max()) == 0.0
+        assert maxrel(got2[k][..., 1], pqs[k].grad[..., 1]) < 2e-6
+
+
+@pytest.mark.parametrize("n,h,w,c,with_side", [(1, 8, 8, 64, True), (2, 7, 5, 64, False), (1, 33, 45, 128, True)])
+def test_unpool_add_mask(dev, n, h, w, c, with_side):
+    from osvos_pytorch_b200 import ops
+    g = torch.Generator().manual_seed(8)
+    x = split_round(torch.randn(n, c, h, w, generator=g).clamp(min=0) * 3)
+    dpool = split_round(torch.randn(n, c, (h + 1) // 2, (w + 1) // 2, generator=g))
+    dside = torch.randn(n, c, h, w, generator=g) if with_side else None
+    xr = x.clone().double().requires_grad_(True)
+    F.max_pool2d(xr, 2, 2, ceil_mode=True).backward(dpool.double())
+    want = xr.grad + (dside.double() if with_side else 0)
+    want = want * (x > 0)
+    ds = dside.permute(0, 2, 3, 1).contiguous().to(dev) if with_side else None
+    got = ops.act_to_nchw(ops.unpool_add_mask(ops.nchw_to_act(dpool.to(dev)), ops.nchw_to_act(x.to(dev)), ds)).cpu()
+    assert maxrel(got, want) < 2e-5
+
+
+def test_channel_sum_side_bwd_and_first_layer(dev):
+    from osvos_pytorch_b200 import ops
+    g = torch.Generator().manual_seed(9)
+    a = split_round(torch.randn(2, 128, 13, 11, generator=g))
+    got = ops.channel_sum(ops.nchw_to_act(a.to(dev))).cpu()
+    assert maxrel(got, a.double().sum((0, 2, 3))) < 1e-5
+    # side_bwd
+    n, h, w = 1, 9, 14
+    feat = torch.randn(n, h, w, 16, generator=g)
+    dpq = torch.randn(n, h, w, 2, generator=g)
+    pw = torch.randn(32, generator=g)
+    d, pg = ops.side_bwd(feat.to(dev), dpq.to(dev), pw.to(dev))
+    dn = ops.act_to_nchw(d).cpu()
+    want = dpq[..., 0:1] * pw[:16] + dpq[..., 1:2] * pw[16:]
+    assert maxrel(dn[:, :16].permute(0, 2, 3, 1), want) < 2e-5 and float(dn[:, 16:].abs().max()) == 0.0
+    pg = pg.cpu()
+    assert maxrel(pg[:16], (dpq[..., 0:1] * feat).double().sum((0, 1, 2))) < 1e-5
+    assert maxrel(pg[17:33], (dpq[..., 1:2] * feat).double().sum((0, 1, 2))) < 1e-5
+    assert abs(float(pg[16]) - float(dpq[..., 0].double().sum())) < 1e-4
+    # conv1_1 backward
+    x, _ = oc.synthetic_frame(2, 13, 37, 5)
+    wt = torch.randn(64, 3, 3, 3, generator=g) * 0.2
+    dz = torch.randn(2, 64, 13, 37, generator=g)
+    xr = x.double().requires_grad_(True)
+    wr = wt.double().requires_grad_(True)
+    F.conv2d(xr, wr, None, padding=1).backward(dz.double())
+    dw, dx = ops.conv_first_bwd(x.to(dev), ops.nchw_to_act(dz.to(dev)), wt.to(dev), True)
+    assert maxrel(dw, wr.grad) < 3e-5 and maxrel(dx, xr.grad) < 3e-5
+    assert abs(float(ops.sum_f32(dz.to(dev))) - float(dz.double().sum())) < 1e-2
+
+
+@pytest.fixture(scope="module")
+def net():
+    from osvos_pytorch_b200.networks.vgg_osvos import OSVOS
+    m = OSVOS(pretrained=0, verbose=False)
+    m.load_state_dict(oc.he_params(seed=0), strict=False)
+    return m.cuda().train()
+
+
+@pytest.mark.parametrize("tag", ["online", "parent"])
+def test_forward_backward_vs_reference_golden(net, golden, tag):
+    from osvos_pytorch_b200.layers.osvos_layers import class_balanced_cross_entropy_loss as cbce
+    x, gt = oc.synthetic_frame(1, 40, 56, 21)
+    net.zero_grad()
+    xin = x.cuda().requires_grad_(True)            # train_online.py:121
+    outs = net(xin)
+    if tag == "online":
+        loss = cbce(outs[-1], gt.cuda(), size_average=False)
+    else:
+        ls = [cbce(o, gt.cuda(), size_average=False) for o in outs]
+        loss = 0.75 * sum(ls[:-1]) + ls[-1]
+    loss.backward()
+    ref_loss = float(golden[f"bwd.{tag}.loss"])
+    assert abs(float(loss) - ref_loss) < 1e-4 * abs(ref_loss)
+    assert maxrel(xin.grad, golden[f"bwd.{tag}.xgrad"]) < GRAD_TOL
+    _, _, ograds = oc.forward_backward(oc.he_params(seed=0), x, gt, objective=tag, side_weight=0.75)
+    worst = 0.0
+    for name, p in net.named_parameters():
+        if name.startswith("upscale"):
+            assert p.grad is None
+            continue
+        if f"bwd.{tag}.none.{name}" in golden:
+            assert p.grad is None, name
+            continue
+        assert p.grad is not None, name
+        gn = float(p.grad.double().norm())
+        ref_norm = float(golden[f"bwd.{tag}.norm.{name}"])
+        assert abs(gn - ref_norm) < GRAD_TOL * ref_norm, (name, gn, ref_norm)
+        idx = torch.from_numpy(golden[f"bwd.{tag}.idx.{name}"])
+        got = p.grad.detach().double().flatten().cpu()[idx].numpy()
+        val = golden[f"bwd.{tag}.val.{name}"]
+        assert np.abs(got - val).max() < GRAD_TOL * max(np.abs(val).max(), ref_norm / math.sqrt(p.numel())), name
+        err = relnorm(p.grad, ograds[name])
+        worst = max(worst, err)
+        assert err < GRAD_TOL, (name, err)
+    print(f"{tag}: loss {float(loss):.6f} (ref {ref_loss:.6f}); worst per-parameter gradient error {worst:.2e}")
+
+
+def test_gradient_accumulation_and_sgd_step(net):
+    """nAveGrad semantics (train_online.py:140-149): grads accumulate over backward calls; an SGD step
+    changes the weights and the packed-weight cache follows."""
+    from osvos_pytorch_b200.layers.osvos_layers import class_balanced_cross_entropy_loss as cbce
+    x, gt = oc.synthetic_frame(1, 32, 40, 41)
+    net.zero_grad()
+    for _ in range(2):
+        loss = cbce(net(x.cuda())[-1], gt.cuda(), size_average=False)
+        loss /= 2
+        loss.backward()
+    g2 = net.fuse.weight.grad.clone()
+    net.zero_grad()
+    cbce(net(x.cuda())[-1], gt.cuda(), size_average=False).backward()
+    assert relnorm(g2, net.fuse.weight.grad) < 1e-5
+    before = [o.clone() for o in net(x.cuda())]
+    opt = torch.optim.SGD(net.parameters(), lr=1e-7, momentum=0.9)
+    opt.step()
+    after = net(x.cuda())
+    assert float((after[-1] - before[-1]).abs().max()) > 0
+    # the same step on the oracle
+    net.zero_grad()
+
+
+def test_backward_480p_vs_oracle(net):
+    from osvos_pytorch_b200.layers.osvos_layers import class_balanced_cross_entropy_loss as cbce
+    x, gt = oc.synthetic_frame(1, 480, 854, 1234)
+    params = {k: v.detach().cpu() for k, v in net.state_dict().items() if not k.startswith("upscale")}
+    net.zero_grad()
+    loss = cbce(net(x.cuda())[-1], gt.cuda(), size_average=False)
+    loss.backward()
+    ref_loss, _, ograds = oc.forward_backward(params, x, gt, objective="online")
+    assert abs(float(loss) - float(ref_loss)) < 1e-4 * abs(float(ref_loss))
+    worst = ("", 0.0)
+    for name, p in net.named_parameters():
+        if name in ograds:
+            err = relnorm(p.grad, ograds[name])
+            if err > worst[1]:
+                worst = (name, err)
+    print(f"480p online fwd+bwd: loss {float(loss):.4f}; worst per-parameter gradient error {worst[1]:.2e} ({worst[0]})")
+    assert worst[1] < GRAD_TOL

@@ -71,14 +71,14 @@ class _ClassBalancedBCE(torch.autograd.Function):
         y = label.detach().to(x.device).contiguous().float()
         assert x.numel() == y.numel()
         sums = torch.empty(4, dtype=torch.float64, device=x.device)
-        loss = torch.empty(1, dtype=torch.float32, device=x.device)
+        loss = torch.empty((), dtype=torch.float32, device=x.device)   # 0-dim, not a view: `loss /= k` must work
         stream = torch.cuda.current_stream().cuda_stream
         nat.check(lib.osvos_cbce_fwd(x.data_ptr(), y.data_ptr(), x.numel(), float(divisor), sums.data_ptr(),
                                      loss.data_ptr(), stream), "osvos_cbce_fwd")
         ctx.save_for_backward(x, y, sums)
         ctx.divisor = float(divisor)
         ctx.shape = output.shape
-        return loss.reshape(())
+        return loss
 
     @staticmethod
     def backward(ctx, grad_out):

@@ -1,0 +1,18 @@
+"""Site configuration (reference mypath.py): override with OSVOS_DB_ROOT / OSVOS_SAVE_ROOT / OSVOS_MODELS_DIR."""
+import os
+
+from util.path_abstract import PathAbstract
+
+
+class Path(PathAbstract):
+    @staticmethod
+    def db_root_dir():
+        return os.environ.get("OSVOS_DB_ROOT", "/path/to/DAVIS-2016")
+
+    @staticmethod
+    def save_root_dir():
+        return os.environ.get("OSVOS_SAVE_ROOT", "./models")
+
+    @staticmethod
+    def models_dir():
+        return os.environ.get("OSVOS_MODELS_DIR", "./models")

@@ -1,0 +1,114 @@
+"""Loop bodies of the two entry points, factored so that train_online.py / train_parent.py stay thin:
+optimizer construction with the reference's per-group learning rates, synthetic DAVIS-shaped data,
+the online fine-tune loop (train_online.py:112-149 of the reference) and the parent loop with the new
+data-parallel exchange step (train_parent.py:129-176 + parallel.py)."""
+import time
+
+import torch
+
+from .layers.osvos_layers import class_balanced_cross_entropy_loss
+from .parallel import GradientBucket, trainable_parameters
+
+MEANVAL = (104.00699, 116.66877, 122.67892)      # dataloaders/davis_2016.py:19 of the reference
+
+
+def _named(module, key):
+    return [p for n, p in module.named_parameters() if key in n]
+
+
+def make_optimizer(net, mode, lr=1e-8, wd=0.0002, momentum=0.9):
+    """SGD with the reference's parameter groups.
+    online (train_online.py:77-88): stages / side_prep weights (wd) and biases (2 lr), deconvs lr 0,
+    fuse at lr/100; score_dsn is NOT optimised.  parent (train_parent.py:85-103): additionally score_dsn at lr/10."""
+    groups = [
+        {"params": _named(net.stages, "weight"), "weight_decay": wd, "initial_lr": lr},
+        {"params": _named(net.stages, "bias"), "lr": 2 * lr, "initial_lr": 2 * lr},
+        {"params": _named(net.side_prep, "weight"), "weight_decay": wd, "initial_lr": lr},
+        {"params": _named(net.side_prep, "bias"), "lr": 2 * lr, "initial_lr": 2 * lr},
+    ]
+    if mode == "parent":
+        groups += [
+            {"params": _named(net.score_dsn, "weight"), "lr": lr / 10, "weight_decay": wd, "initial_lr": lr / 10},
+            {"params": _named(net.score_dsn, "bias"), "lr": 2 * lr / 10, "initial_lr": 2 * lr / 10},
+        ]
+    groups += [
+        {"params": _named(net.upscale, "weight"), "lr": 0, "initial_lr": 0},
+        {"params": _named(net.upscale_, "weight"), "lr": 0, "initial_lr": 0},
+        {"params": [net.fuse.weight], "lr": lr / 100, "initial_lr": lr / 100, "weight_decay": wd},
+        {"params": [net.fuse.bias], "lr": 2 * lr / 100, "initial_lr": 2 * lr / 100},
+    ]
+    return torch.optim.SGD(groups, lr=lr, momentum=momentum)
+
+
+def synthetic_batch(n, h, w, seed, device):
+    """DAVIS-shaped synthetic sample: BGR 0..255 mean-subtracted image, ~30 % positive mask."""
+    g = torch.Generator().manual_seed(seed)
+    img = torch.rand(n, 3, h, w, generator=g) * 255.0 - torch.tensor(MEANVAL).view(1, 3, 1, 1)
+    gt = (torch.rand(n, 1, h, w, generator=g) > 0.7).float()
+    return {"image": img.to(device), "gt": gt.to(device)}
+
+
+def online_finetune(net, sample_fn, iters, n_ave_grad=5, lr=1e-8, wd=0.0002, log_every=0, log=print):
+    """`iters` forward/backward passes on the annotated frame, SGD step every `n_ave_grad` (reference
+    train_online.py:112-149).  Losses are kept on the device; one host read per `log_every` iterations
+    instead of the reference's per-iteration .item() sync.  Returns the list of logged losses."""
+    net.train()
+    opt = make_optimizer(net, "online", lr, wd)
+    opt.zero_grad()
+    history, running = [], None
+    for it in range(iters):
+        sample = sample_fn(it)
+        inputs, gts = sample["image"], sample["gt"]
+        outputs = net.forward(inputs)
+        loss = class_balanced_cross_entropy_loss(outputs[-1], gts, size_average=False)
+        running = loss.detach() if running is None else running + loss.detach()
+        loss /= n_ave_grad
+        loss.backward()
+        if (it + 1) % n_ave_grad == 0:
+            opt.step()
+            opt.zero_grad()
+        if log_every and (it + 1) % log_every == 0:
+            val = float(running) / log_every
+            history.append(val)
+            running = None
+            log(f"[iter {it + 1:6d}] loss {val:.6f}")
+    return history
+
+
+def parent_epoch(net, opt, bucket, batches, epoch, n_epochs, n_ave_grad=1, group=None):
+    """One epoch of the parent objective on this rank's shard: deep-supervision loss
+    (1 - epoch/nEpochs) * sum_{k<4} L_k + L_fuse (train_parent.py:143-147), gradient accumulation over
+    `n_ave_grad` local micro-batches, then ONE allreduce(mean) and one SGD step."""
+    net.train()
+    side_w = 1.0 - epoch / n_epochs
+    totals = torch.zeros(5, device=bucket.flat.device)
+    count = 0
+    for it, sample in enumerate(batches):
+        outputs = net.forward(sample["image"])
+        losses = [class_balanced_cross_entropy_loss(o, sample["gt"], size_average=False) for o in outputs]
+        totals += torch.stack([l.detach() for l in losses])
+        count += 1
+        loss = side_w * sum(losses[:-1]) + losses[-1]
+        loss /= n_ave_grad
+        loss.backward()
+        if (it + 1) % n_ave_grad == 0:
+            bucket.allreduce_mean(group)
+            opt.step()
+            bucket.zero_()
+    return (totals / max(count, 1)).tolist()
+
+
+def timed_parent_steps(net, opt, bucket, make_batch, steps, warmup, epoch=0, n_epochs=240, group=None):
+    """Benchmark helper: `steps` optimizer steps (1 micro-batch each); device time via CUDA events."""
+    def one(i):
+        parent_epoch(net, opt, bucket, [make_batch(i)], epoch, n_epochs, 1, group)
+    for i in range(warmup):
+        one(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        one(warmup + i)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps

@@ -1,0 +1,115 @@
+#!/usr/bin/env python
+"""Online (per-sequence) fine-tuning entry point - same role and defaults as the reference's
+train_online.py: load the parent model, run nAveGrad x 2000 forward/backward passes on the annotated
+first frame with SGD(lr 1e-8, momentum .9), save the weights, then segment the sequence.
+
+    SEQ_NAME=blackswan python train_online.py                 # DAVIS on disk (needs cv2 + the dataset)
+    python train_online.py --synthetic --iters 200            # synthetic 480x854 frame, no dataset
+
+Single GPU by design (BASELINE.json: online fine-tune stays single-GPU; run one sequence per GPU)."""
+import argparse
+import os
+import timeit
+
+import numpy as np
+import torch
+
+import networks.vgg_osvos as vo
+from mypath import Path
+from osvos_pytorch_b200 import training
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--seq-name", default=os.environ.get("SEQ_NAME", "blackswan"))
+    ap.add_argument("--n-ave-grad", type=int, default=5)
+    ap.add_argument("--iters", type=int, default=None, help="forward/backward passes (default 2000 * nAveGrad)")
+    ap.add_argument("--parent-epoch", type=int, default=240)
+    ap.add_argument("--parent-name", default="parent")
+    ap.add_argument("--lr", type=float, default=1e-8)
+    ap.add_argument("--wd", type=float, default=0.0002)
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--gpu-id", type=int, default=0)
+    ap.add_argument("--precision", default="exact", choices=["exact", "fast"])
+    ap.add_argument("--synthetic", action="store_true", help="synthetic frame + He-init weights instead of DAVIS + parent model")
+    ap.add_argument("--height", type=int, default=480)
+    ap.add_argument("--width", type=int, default=854)
+    ap.add_argument("--log-every", type=int, default=None)
+    ap.add_argument("--no-save", action="store_true")
+    return ap.parse_args()
+
+
+def main():
+    a = parse()
+    iters = a.iters if a.iters is not None else 2000 * a.n_ave_grad
+    log_every = a.log_every if a.log_every is not None else max(1, iters // 20)
+    save_dir = Path.save_root_dir()
+    os.makedirs(save_dir, exist_ok=True)
+    device = torch.device(f"cuda:{a.gpu_id}")
+    torch.cuda.set_device(device)
+
+    net = vo.OSVOS(pretrained=0, precision=a.precision)
+    if a.synthetic:
+        vo.he_init_(net, seed=a.seed)
+    else:
+        ckpt = os.path.join(save_dir, f"{a.parent_name}_epoch-{a.parent_epoch - 1}.pth")
+        net.load_state_dict(torch.load(ckpt, map_location="cpu"))
+    net.to(device)
+
+    if a.synthetic:
+        fixed = training.synthetic_batch(1, a.height, a.width, 1234 + a.seed, device)
+
+        def sample_fn(it):
+            return fixed
+        test_frames = [fixed]
+    else:
+        from dataloaders import davis_2016 as db
+        from dataloaders import custom_transforms as tr
+        from torch.utils.data import DataLoader
+        from torchvision import transforms
+        aug = transforms.Compose([tr.RandomHorizontalFlip(), tr.ScaleNRotate(rots=(-30, 30), scales=(.75, 1.25)),
+                                  tr.ToTensor()])
+        db_train = db.DAVIS2016(train=True, db_root_dir=Path.db_root_dir(), transform=aug, seq_name=a.seq_name)
+        db_test = db.DAVIS2016(train=False, db_root_dir=Path.db_root_dir(), transform=tr.ToTensor(), seq_name=a.seq_name)
+        loader = DataLoader(db_train, batch_size=1, shuffle=True, num_workers=1, persistent_workers=True)
+        state = {"it": iter(loader)}
+
+        def sample_fn(it):
+            np.random.seed(a.seed + it)
+            try:
+                s = next(state["it"])
+            except StopIteration:
+                state["it"] = iter(loader)
+                s = next(state["it"])
+            return {"image": s["image"].to(device, non_blocking=True), "gt": s["gt"].to(device, non_blocking=True)}
+        test_frames = DataLoader(db_test, batch_size=1, shuffle=False, num_workers=1)
+
+    print("Start of Online Training, sequence: " + a.seq_name)
+    t0 = timeit.default_timer()
+    history = training.online_finetune(net, sample_fn, iters, a.n_ave_grad, a.lr, a.wd, log_every)
+    torch.cuda.synchronize()
+    dt = timeit.default_timer() - t0
+    print(f"Online training time: {dt:.2f} s ({iters / dt:.1f} fwd+bwd/s, {iters / a.n_ave_grad / dt:.1f} SGD steps/s)")
+    if not a.no_save:
+        torch.save(net.state_dict(), os.path.join(save_dir, f"{a.seq_name}_epoch-{iters - 1}.pth"))
+
+    print("Testing Network")
+    out_dir = os.path.join(save_dir, "Results", a.seq_name)
+    os.makedirs(out_dir, exist_ok=True)
+    net.eval()
+    with torch.no_grad():
+        for ii, s in enumerate(test_frames):
+            outputs = net.forward(s["image"].to(device))
+            pred = torch.sigmoid(outputs[-1]).mul(255).byte().cpu().numpy()
+            for jj in range(pred.shape[0]):
+                name = os.path.basename(s["fname"][jj]) if "fname" in s else f"{ii:05d}"
+                try:
+                    import cv2
+                    cv2.imwrite(os.path.join(out_dir, name + ".png"), pred[jj, 0])
+                except ImportError:
+                    np.save(os.path.join(out_dir, name + ".npy"), pred[jj, 0])
+    return history
+
+
+if __name__ == "__main__":
+    main()

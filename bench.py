@@ -124,13 +124,80 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def run_parent(args, rank, world, local, dev):
+    """BASELINE.json configs[3]: parent training, per-GPU batch 12 at 480x854, 5-loss objective, one
+    gradient allreduce(mean) + SGD step per step; weak scaling (per-GPU work fixed)."""
+    import torch
+    import torch.distributed as dist
+    from osvos_pytorch_b200 import ops, parallel, training
+    from osvos_pytorch_b200.networks.vgg_osvos import OSVOS, he_init_
+    steps, warmup = max(1, args.steps), max(3, args.warmup)
+    net = he_init_(OSVOS(pretrained=0, verbose=False, precision=args.precision), seed=0).to(dev)
+    opt = training.make_optimizer(net, "parent")
+    bucket = parallel.GradientBucket(parallel.trainable_parameters(net), dev)
+    batches = [training.synthetic_batch(args.batch, H, W, 1000 * rank + i, dev) for i in range(2)]
+
+    def one(i):
+        training.parent_epoch(net, opt, bucket, [batches[i % 2]], 0, 240, 1)
+    for i in range(warmup):
+        one(i)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = ops.KERNEL_LAUNCHES[0]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        one(i)
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t) / steps
+    launches = (ops.KERNEL_LAUNCHES[0] - l0) // steps
+    clocks = sampler.stop() if rank == 0 else None
+    # allreduce alone (device time), for the share of the step
+    ar_ms = 0.0
+    if world > 1:
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(10):
+            bucket.allreduce_mean()
+        a1.record()
+        torch.cuda.synchronize()
+        ar_ms = a0.elapsed_time(a1) / 10
+    if rank == 0:
+        line = {"metric": "frames/sec at 480x854 fwd+bwd, parent training (5-loss objective, SGD step, DP allreduce)",
+                "value": world * args.batch * 1000.0 / ms, "unit": "frames/s", "n_gpus": world, "steps": steps,
+                "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16x3 (split-bf16 operands, fp32 accumulate)" if args.precision == "exact" else "bf16",
+                "data": "synthetic",
+                "config": {"workload": f"parent480: per-GPU batch {args.batch} x 3x{H}x{W} synthetic frames, global batch "
+                                       f"{world * args.batch}, parent objective, SGD(lr 1e-8, mom .9, wd 2e-4)",
+                           "parallelism": f"dp{world}: allreduce(mean) of a 59.7 MB flat fp32 gradient bucket per step (NCCL)",
+                           "l2": "per-step working set (>10 GB) exceeds L2", "timing": "CUDA events, max over ranks"},
+                "allreduce_ms": ar_ms, "allreduce_share": ar_ms / ms if ms else None,
+                "gpu_launches": int(launches), "clocks": clocks}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--workload", default="infer480", choices=["infer480", "train480"])
+    ap.add_argument("--workload", default="infer480", choices=["infer480", "train480", "parent480"])
+    ap.add_argument("--batch", type=int, default=12, help="parent480: frames per GPU per optimizer step")
     ap.add_argument("--precision", default="exact", choices=["exact", "fast"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -153,6 +220,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     steps, warmup = max(1, args.steps), max(3, args.warmup)
+    if args.workload == "parent480":
+        return run_parent(args, rank, world, local, dev)
     train = args.workload == "train480"
 
     net = he_init_(OSVOS(pretrained=0, verbose=False, precision=args.precision), seed=0).to(dev)

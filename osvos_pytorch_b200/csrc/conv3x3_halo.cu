@@ -1,0 +1,251 @@
+// 3x3 convolution as a tcgen05 implicit GEMM with HALO REUSE (sm_100a).
+//
+// Same GEMM view, tile geometry, precision scheme, warp roles and epilogue as conv3x3_tc.cu, but the
+// activation operand is loaded ONCE per (tile, 64-channel chunk) as the 18-row x 10-px halo patch and the
+// nine taps are nine UMMA smem descriptors into it: tap (r, s) starts at smem row (r * PITCH + s); the 16
+// tile rows are the sixteen 8-row swizzle groups at stride SBO = PITCH * 128 B.  That divides the
+// activation traffic through L2 -> smem by ~6 relative to one shifted box per tap, which is what bounded
+// the per-tap kernel.  The weight slabs stream through their own, deeper ring
+// (one stage per tap), and the next chunk's halo is prefetched while the current one is being consumed.
+//
+// PITCH is the smem row pitch in pixels: 16 keeps every 8-row group 1 KiB-periodic (2 KiB per patch row,
+// 6 pad pixels loaded); 10 packs the rows (1280 B) and relies on the swizzle being a function of the
+// absolute smem address.  OSVOS_HALO_BO=1 additionally sets the descriptor's base-offset field to
+// (start >> 7) & 7.  (Both knobs exist to validate the descriptor semantics on hardware.)
+#include <stdlib.h>
+
+#include "conv_common.cuh"
+
+namespace osvos {
+
+constexpr int kHaloRows = kTileH + 2;  // 18
+
+template <int BLOCK_N, int PLANES, int PITCH>
+struct HaloCfg {
+  static constexpr int kABoxBytes = kHaloRows * PITCH * 128;                // one plane, one chunk
+  static constexpr int kAPlaneBytes = (kABoxBytes + 1023) / 1024 * 1024;    // keep 1 KiB alignment
+  static constexpr int kAStageBytes = PLANES * kAPlaneBytes;
+  static constexpr int kAStages = 2;
+  static constexpr int kBPlaneBytes = BLOCK_N * 128;
+  static constexpr int kBStageBytes = PLANES * kBPlaneBytes;
+  static constexpr int kBudget = 214 * 1024 - kAStages * kAStageBytes;
+  static constexpr int kBStagesRaw = kBudget / kBStageBytes;
+  static constexpr int kBStages = kBStagesRaw > 9 ? 9 : kBStagesRaw;
+  static constexpr int kTmemCols = (2 * BLOCK_N) < 32 ? 32 : 2 * BLOCK_N;
+  static constexpr int kSmemBytes = kAStages * kAStageBytes + kBStages * kBStageBytes + 1024 + 512;
+  static_assert(kBStages >= 2, "weight ring too shallow");
+  static_assert(kBStageBytes % 1024 == 0, "B stage must keep 1024-byte alignment");
+};
+
+template <int BLOCK_N, int PLANES, int PITCH>
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo,
+                    const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
+                    const ConvParams p, const int use_base_offset) {
+  using Cfg = HaloCfg<BLOCK_N, PLANES, PITCH>;
+  constexpr int SA = Cfg::kAStages, SB = Cfg::kBStages;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + SA * Cfg::kAStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + SB * Cfg::kBStageBytes);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = bars + SA;
+  uint64_t* b_full = bars + 2 * SA;
+  uint64_t* b_empty = bars + 2 * SA + SB;
+  uint64_t* tfull_bar = bars + 2 * SA + 2 * SB;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_x_hi);
+    tma_prefetch_desc(&map_w_hi);
+    if (PLANES == 2) {
+      tma_prefetch_desc(&map_x_lo);
+      tma_prefetch_desc(&map_w_lo);
+    }
+    for (int i = 0; i < SA; ++i) {
+      mbar_init(&a_full[i], 1);
+      mbar_init(&a_empty[i], 1);
+    }
+    for (int i = 0; i < SB; ++i) {
+      mbar_init(&b_full[i], 1);
+      mbar_init(&b_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int a_stage = 0, b_stage = 0;
+      uint32_t a_phase = 0, b_phase = 0;
+      auto issue_a = [&](int tile, int kc) {
+        int nb, tx, ty, img;
+        decode_tile(p, tile, nb, tx, ty, img);
+        mbar_wait(&a_empty[a_stage], a_phase ^ 1);
+        uint8_t* st = smem_a + a_stage * Cfg::kAStageBytes;
+        mbar_arrive_expect_tx(&a_full[a_stage], PLANES * Cfg::kABoxBytes);
+        tma_load_4d(&map_x_hi, &a_full[a_stage], st, kc * kBlockK, tx * kTileW - 1, ty * kTileH - 1, img);
+        if (PLANES == 2)
+          tma_load_4d(&map_x_lo, &a_full[a_stage], st + Cfg::kAPlaneBytes, kc * kBlockK, tx * kTileW - 1,
+                      ty * kTileH - 1, img);
+        if (++a_stage == SA) {
+          a_stage = 0;
+          a_phase ^= 1;
+        }
+      };
+      if (static_cast<int>(blockIdx.x) < p.total_tiles) issue_a(blockIdx.x, 0);
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        int nb, tx, ty, img;
+        decode_tile(p, tile, nb, tx, ty, img);
+        for (int kc = 0; kc < p.k_chunks; ++kc) {
+          for (int tap = 0; tap < 9; ++tap) {
+            if (tap == 3) {  // prefetch the next chunk's halo while this one is being consumed
+              if (kc + 1 < p.k_chunks) issue_a(tile, kc + 1);
+              else if (tile + static_cast<int>(gridDim.x) < p.total_tiles) issue_a(tile + gridDim.x, 0);
+            }
+            mbar_wait(&b_empty[b_stage], b_phase ^ 1);
+            uint8_t* st = smem_b + b_stage * Cfg::kBStageBytes;
+            mbar_arrive_expect_tx(&b_full[b_stage], Cfg::kBStageBytes);
+            tma_load_3d(&map_w_hi, &b_full[b_stage], st, kc * kBlockK, nb * BLOCK_N, tap);
+            if (PLANES == 2)
+              tma_load_3d(&map_w_lo, &b_full[b_stage], st + Cfg::kBPlaneBytes, kc * kBlockK, nb * BLOCK_N, tap);
+            if (++b_stage == SB) {
+              b_stage = 0;
+              b_phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // -------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(kBlockM, BLOCK_N, /*bf16=*/true);
+      int a_stage = 0, b_stage = 0;
+      uint32_t a_phase = 0, b_phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t aph = (it >> 1) & 1;
+        mbar_wait(&tempty_bar[as], aph ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * BLOCK_N;
+        for (int kc = 0; kc < p.k_chunks; ++kc) {
+          mbar_wait(&a_full[a_stage], a_phase);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(smem_a + a_stage * Cfg::kAStageBytes);
+#pragma unroll 1
+          for (int tap = 0; tap < 9; ++tap) {
+            const int r = tap / 3, s = tap - 3 * r;
+            mbar_wait(&b_full[b_stage], b_phase);
+            tc_fence_after();
+            const uint32_t a_hi = a_base + (r * PITCH + s) * 128;
+            const uint32_t a_lo = a_hi + Cfg::kAPlaneBytes;
+            const uint32_t b_hi = smem_u32(smem_b + b_stage * Cfg::kBStageBytes);
+            const uint32_t bo_hi = use_base_offset ? ((a_hi >> 7) & 7) : 0;
+            const uint32_t bo_lo = use_base_offset ? ((a_lo >> 7) & 7) : 0;
+            const uint64_t da_hi = make_smem_desc(a_hi, 16, PITCH * 128, kLayoutSW128, bo_hi);
+            const uint64_t da_lo = make_smem_desc(a_lo, 16, PITCH * 128, kLayoutSW128, bo_lo);
+            const uint64_t db_hi = make_smem_desc(b_hi, 16, 1024, kLayoutSW128);
+            const uint64_t db_lo = make_smem_desc(b_hi + Cfg::kBPlaneBytes, 16, 1024, kLayoutSW128);
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k) {
+              const uint64_t adv = static_cast<uint64_t>(k * 2);
+              const uint32_t first = (kc | tap | k) != 0;
+              if (PLANES == 2) {
+                umma_f16(tmem_d, da_lo + adv, db_hi + adv, idesc, first);
+                umma_f16(tmem_d, da_hi + adv, db_lo + adv, idesc, 1);
+                umma_f16(tmem_d, da_hi + adv, db_hi + adv, idesc, 1);
+              } else {
+                umma_f16(tmem_d, da_hi + adv, db_hi + adv, idesc, first);
+              }
+            }
+            umma_commit(&b_empty[b_stage]);
+            if (++b_stage == SB) {
+              b_stage = 0;
+              b_phase ^= 1;
+            }
+          }
+          umma_commit(&a_empty[a_stage]);
+          if (kc == p.k_chunks - 1) umma_commit(&tfull_bar[as]);
+          if (++a_stage == SA) {
+            a_stage = 0;
+            a_phase ^= 1;
+          }
+        }
+      }
+    }
+  } else {
+    conv_epilogue_loop<BLOCK_N>(p, tmem_base, tfull_bar, tempty_bar, warp, lane);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+template <int BLOCK_N, int PLANES, int PITCH>
+static int launch_halo(const osvos_conv3x3_args* a, cudaStream_t stream, int use_bo) {
+  using Cfg = HaloCfg<BLOCK_N, PLANES, PITCH>;
+  ConvParams p;
+  fill_conv_params(p, a, BLOCK_N);
+  CUtensorMap mx_hi, mx_lo, mw_hi, mw_lo;
+  {
+    const uint64_t dims[4] = {(uint64_t)a->cin, (uint64_t)a->w, (uint64_t)a->h, (uint64_t)a->n};
+    const uint64_t strides[3] = {(uint64_t)a->cin * 2, (uint64_t)a->w * a->cin * 2,
+                                 (uint64_t)a->h * a->w * a->cin * 2};
+    const uint32_t box[4] = {kBlockK, PITCH, kHaloRows, 1};
+    int rc = encode_tensor_map(&mx_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 4, a->x_hi, dims, strides, box,
+                               CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    rc = encode_tensor_map(&mx_lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 4, PLANES == 2 ? a->x_lo : a->x_hi, dims,
+                           strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  int rc = encode_weight_maps(&mw_hi, &mw_lo, a, BLOCK_N);
+  if (rc) return rc;
+  auto kern = conv3x3_halo_kernel<BLOCK_N, PLANES, PITCH>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    OSVOS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_done = true;
+  }
+  const int sms = device_sm_count();
+  const int grid = p.total_tiles < sms ? p.total_tiles : sms;
+  kern<<<grid, kConvThreads, Cfg::kSmemBytes, stream>>>(mx_hi, mx_lo, mw_hi, mw_lo, p, use_bo);
+  OSVOS_CHECK_CUDA(cudaGetLastError());
+  return OSVOS_OK;
+}
+
+template <int PITCH>
+static int dispatch_halo(const osvos_conv3x3_args* a, cudaStream_t stream, int use_bo) {
+  const bool fast = (a->flags & OSVOS_FLAG_FAST) != 0;
+  if (a->cout == 16) return fast ? launch_halo<16, 1, PITCH>(a, stream, use_bo) : launch_halo<16, 2, PITCH>(a, stream, use_bo);
+  if (a->cout == 64) return fast ? launch_halo<64, 1, PITCH>(a, stream, use_bo) : launch_halo<64, 2, PITCH>(a, stream, use_bo);
+  return fast ? launch_halo<128, 1, PITCH>(a, stream, use_bo) : launch_halo<128, 2, PITCH>(a, stream, use_bo);
+}
+
+int conv3x3_halo_dispatch(const osvos_conv3x3_args* a, cudaStream_t stream, int pitch, int use_bo) {
+  if (pitch == 10) return dispatch_halo<10>(a, stream, use_bo);
+  return dispatch_halo<16>(a, stream, use_bo);
+}
+
+}  // namespace osvos

@@ -1,0 +1,205 @@
+// Shared pieces of the tcgen05 implicit-GEMM convolution kernels (conv3x3_tc.cu: per-tap TMA loads;
+// conv3x3_halo.cu: halo patch loaded once per channel chunk): tile geometry, parameters, tile decode and
+// the epilogue (TMEM -> registers -> bias / ReLU / mask / split-bf16 / projections -> global).
+#pragma once
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace osvos {
+
+constexpr int kTileW = 8;     // pixels per patch row  (= one 8-row swizzle atom)
+constexpr int kTileH = 16;    // patch rows
+constexpr int kBlockM = 128;  // kTileW * kTileH
+constexpr int kBlockK = 64;   // channels per K block (128 B of bf16)
+constexpr int kConvThreads = 192;
+constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KiB per plane
+
+struct ConvParams {
+  const float* bias;
+  __nv_bfloat16* y_hi;
+  __nv_bfloat16* y_lo;
+  float* y_f32;
+  const __nv_bfloat16* mask_hi;
+  const float* proj_w;
+  const float* proj_b;
+  float* pq;
+  int n, h, w, cin, cout;
+  int tiles_x, tiles_y, n_blocks, total_tiles, k_chunks;
+  int flags;
+};
+
+__device__ __forceinline__ void decode_tile(const ConvParams& p, int tile, int& nb, int& tx, int& ty, int& img) {
+  nb = tile % p.n_blocks;
+  int m = tile / p.n_blocks;
+  tx = m % p.tiles_x;
+  m /= p.tiles_x;
+  ty = m % p.tiles_y;
+  img = m / p.tiles_y;
+}
+
+// Epilogue of one warp (TMEM lane quarter q = warp & 3) over all tiles of this CTA.
+template <int BLOCK_N>
+__device__ __forceinline__ void conv_epilogue_loop(const ConvParams& p, uint32_t tmem_base, uint64_t* tfull_bar,
+                                                   uint64_t* tempty_bar, int warp, int lane) {
+    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    const int row = q * 32 + lane;
+    const int ly = row / kTileW, lx = row % kTileW;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      int nb, tx, ty, img;
+      decode_tile(p, tile, nb, tx, ty, img);
+      const int as = it & 1;
+      const uint32_t aph = (it >> 1) & 1;
+      const int y = ty * kTileH + ly, x = tx * kTileW + lx;
+      const bool valid = (y < p.h) && (x < p.w);
+      const size_t pix = (static_cast<size_t>(img) * p.h + y) * p.w + x;
+
+      mbar_wait(&tfull_bar[as], aph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + as * BLOCK_N + (static_cast<uint32_t>(q * 32) << 16);
+
+      if constexpr (BLOCK_N == 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr, v);
+        tmem_ld_wait();
+        if (valid) {
+          float f[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            f[j] = __uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + j) : 0.f);
+            if (p.flags & OSVOS_FLAG_RELU) f[j] = fmaxf(f[j], 0.f);
+          }
+          if (p.y_f32) {
+            float4* dst = reinterpret_cast<float4*>(p.y_f32 + pix * 16);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+          }
+          if (p.y_hi) {
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              __nv_bfloat16 h0, l0, h1, l1;
+              split_bf16(f[2 * j], h0, l0);
+              split_bf16(f[2 * j + 1], h1, l1);
+              hi[j] = pack_bf16x2(h0, h1);
+              lo[j] = pack_bf16x2(l0, l1);
+            }
+            uint4* dh = reinterpret_cast<uint4*>(p.y_hi + pix * 16);
+            dh[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            dh[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+            if (p.y_lo) {
+              uint4* dl = reinterpret_cast<uint4*>(p.y_lo + pix * 16);
+              dl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+              dl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+            }
+          }
+          if (p.pq) {
+            float sp = p.proj_b ? __ldg(p.proj_b) : 0.f, sq = 0.f;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              sp = fmaf(f[j], __ldg(p.proj_w + j), sp);
+              sq = fmaf(f[j], __ldg(p.proj_w + 16 + j), sq);
+            }
+            *reinterpret_cast<float2*>(p.pq + pix * 2) = make_float2(sp, sq);
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(taddr + c0, v);
+          tmem_ld_wait();
+          if (valid) {
+            const int ch = nb * BLOCK_N + c0;
+            float f[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              f[j] = __uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + ch + j) : 0.f);
+              if (p.flags & OSVOS_FLAG_RELU) f[j] = fmaxf(f[j], 0.f);
+            }
+            if (p.flags & OSVOS_FLAG_RELU_MASK) {
+              const uint4* mk = reinterpret_cast<const uint4*>(p.mask_hi + pix * p.cout + ch);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint4 m = __ldg(mk + j);
+                const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                  if (!(bf16_lo_to_float(mw[t]) > 0.f)) f[8 * j + 2 * t] = 0.f;
+                  if (!(bf16_hi_to_float(mw[t]) > 0.f)) f[8 * j + 2 * t + 1] = 0.f;
+                }
+              }
+            }
+            if (p.y_f32) {
+              float4* dst = reinterpret_cast<float4*>(p.y_f32 + pix * p.cout + ch);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+            }
+            if (p.y_hi) {
+              uint32_t hi[16], lo[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                __nv_bfloat16 h0, l0, h1, l1;
+                split_bf16(f[2 * j], h0, l0);
+                split_bf16(f[2 * j + 1], h1, l1);
+                hi[j] = pack_bf16x2(h0, h1);
+                lo[j] = pack_bf16x2(l0, l1);
+              }
+              uint4* dh = reinterpret_cast<uint4*>(p.y_hi + pix * p.cout + ch);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) dh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+              if (p.y_lo) {
+                uint4* dl = reinterpret_cast<uint4*>(p.y_lo + pix * p.cout + ch);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  dl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[as]);
+    }
+}
+
+// ---- host helpers shared by the launchers ------------------------------------------------
+static inline void fill_conv_params(ConvParams& p, const osvos_conv3x3_args* a, int block_n) {
+  p.bias = a->bias;
+  p.y_hi = static_cast<__nv_bfloat16*>(a->y_hi);
+  p.y_lo = static_cast<__nv_bfloat16*>(a->y_lo);
+  p.y_f32 = a->y_f32;
+  p.mask_hi = static_cast<const __nv_bfloat16*>(a->mask_hi);
+  p.proj_w = a->proj_w;
+  p.proj_b = a->proj_b;
+  p.pq = a->pq;
+  p.n = a->n;
+  p.h = a->h;
+  p.w = a->w;
+  p.cin = a->cin;
+  p.cout = a->cout;
+  p.tiles_x = (a->w + kTileW - 1) / kTileW;
+  p.tiles_y = (a->h + kTileH - 1) / kTileH;
+  p.n_blocks = a->cout / block_n;
+  p.total_tiles = p.tiles_x * p.tiles_y * a->n * p.n_blocks;
+  p.k_chunks = a->cin / kBlockK;
+  p.flags = a->flags;
+}
+
+// Packed weights [plane][tap][cout][cin] -> two 3-D maps with box {64, block_n, 1}.
+static inline int encode_weight_maps(CUtensorMap* hi, CUtensorMap* lo, const osvos_conv3x3_args* a, int block_n) {
+  const size_t plane = static_cast<size_t>(9) * a->cout * a->cin;  // elements
+  const uint64_t dims[3] = {(uint64_t)a->cin, (uint64_t)a->cout, 9};
+  const uint64_t strides[2] = {(uint64_t)a->cin * 2, (uint64_t)a->cout * a->cin * 2};
+  const uint32_t box[3] = {kBlockK, (uint32_t)block_n, 1};
+  const __nv_bfloat16* wp = static_cast<const __nv_bfloat16*>(a->w_packed);
+  int rc = encode_tensor_map(hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 3, wp, dims, strides, box,
+                             CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+  return encode_tensor_map(lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 3, wp + plane, dims, strides, box,
+                           CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+int conv3x3_halo_dispatch(const osvos_conv3x3_args* a, cudaStream_t stream, int pitch, int use_bo);
+
+}  // namespace osvos

@@ -89,20 +89,23 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_c
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // ------------------------------------------------------------ TMA producer (warp-uniform, elected lane issues)
+    {
       int a_stage = 0, b_stage = 0;
       uint32_t a_phase = 0, b_phase = 0;
       auto issue_a = [&](int tile, int kc) {
         int nb, tx, ty, img;
         decode_tile(p, tile, nb, tx, ty, img);
         mbar_wait(&a_empty[a_stage], a_phase ^ 1);
-        uint8_t* st = smem_a + a_stage * Cfg::kAStageBytes;
-        mbar_arrive_expect_tx(&a_full[a_stage], PLANES * Cfg::kABoxBytes);
-        tma_load_4d(&map_x_hi, &a_full[a_stage], st, kc * kBlockK, tx * kTileW - 1, ty * kTileH - 1, img);
-        if (PLANES == 2)
-          tma_load_4d(&map_x_lo, &a_full[a_stage], st + Cfg::kAPlaneBytes, kc * kBlockK, tx * kTileW - 1,
-                      ty * kTileH - 1, img);
+        if (elect_one()) {
+          uint8_t* st = smem_a + a_stage * Cfg::kAStageBytes;
+          mbar_arrive_expect_tx(&a_full[a_stage], PLANES * Cfg::kABoxBytes);
+          tma_load_4d(&map_x_hi, &a_full[a_stage], st, kc * kBlockK, tx * kTileW - 1, ty * kTileH - 1, img);
+          if (PLANES == 2)
+            tma_load_4d(&map_x_lo, &a_full[a_stage], st + Cfg::kAPlaneBytes, kc * kBlockK, tx * kTileW - 1,
+                        ty * kTileH - 1, img);
+        }
+        __syncwarp();
         if (++a_stage == SA) {
           a_stage = 0;
           a_phase ^= 1;
@@ -119,11 +122,14 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_c
               else if (tile + static_cast<int>(gridDim.x) < p.total_tiles) issue_a(tile + gridDim.x, 0);
             }
             mbar_wait(&b_empty[b_stage], b_phase ^ 1);
-            uint8_t* st = smem_b + b_stage * Cfg::kBStageBytes;
-            mbar_arrive_expect_tx(&b_full[b_stage], Cfg::kBStageBytes);
-            tma_load_3d(&map_w_hi, &b_full[b_stage], st, kc * kBlockK, nb * BLOCK_N, tap);
-            if (PLANES == 2)
-              tma_load_3d(&map_w_lo, &b_full[b_stage], st + Cfg::kBPlaneBytes, kc * kBlockK, nb * BLOCK_N, tap);
+            if (elect_one()) {
+              uint8_t* st = smem_b + b_stage * Cfg::kBStageBytes;
+              mbar_arrive_expect_tx(&b_full[b_stage], Cfg::kBStageBytes);
+              tma_load_3d(&map_w_hi, &b_full[b_stage], st, kc * kBlockK, nb * BLOCK_N, tap);
+              if (PLANES == 2)
+                tma_load_3d(&map_w_lo, &b_full[b_stage], st + Cfg::kBPlaneBytes, kc * kBlockK, nb * BLOCK_N, tap);
+            }
+            __syncwarp();
             if (++b_stage == SB) {
               b_stage = 0;
               b_phase ^= 1;
@@ -133,8 +139,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_c
       }
     }
   } else if (warp == 1) {
-    // -------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
+    // -------------------------------------------------------------- MMA issuer (warp-uniform, elected lane issues)
+    {
       constexpr uint32_t idesc = make_idesc_f16(kBlockM, BLOCK_N, /*bf16=*/true);
       int a_stage = 0, b_stage = 0;
       uint32_t a_phase = 0, b_phase = 0;
@@ -154,6 +160,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_c
             const int r = tap / 3, s = tap - 3 * r;
             mbar_wait(&b_full[b_stage], b_phase);
             tc_fence_after();
+            if (elect_one()) {
             const uint32_t a_hi = a_base + (r * PITCH + s) * 128;
             const uint32_t a_lo = a_hi + Cfg::kAPlaneBytes;
             const uint32_t b_hi = smem_u32(smem_b + b_stage * Cfg::kBStageBytes);
@@ -176,13 +183,17 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_c
               }
             }
             umma_commit(&b_empty[b_stage]);
+            if (tap == 8) {
+              umma_commit(&a_empty[a_stage]);
+              if (kc == p.k_chunks - 1) umma_commit(&tfull_bar[as]);
+            }
+            }
+            __syncwarp();
             if (++b_stage == SB) {
               b_stage = 0;
               b_phase ^= 1;
             }
           }
-          umma_commit(&a_empty[a_stage]);
-          if (kc == p.k_chunks - 1) umma_commit(&tfull_bar[as]);
           if (++a_stage == SA) {
             a_stage = 0;
             a_phase ^= 1;

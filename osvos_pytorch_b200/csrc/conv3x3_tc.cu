@@ -90,7 +90,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_con
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // Warp-uniform control flow; one elected lane issues.  (Issuing from a divergent `if (lane == 0)` branch
+    // makes the compiler wrap every UTMALDG / UTCHMMA in an ELECT/R2UR/BRA.U.ANY loop: ~350 cycles per step.)
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -100,16 +102,19 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_con
           for (int tap = 0; tap < 9; ++tap) {
             const int r = tap / 3, s = tap - 3 * r;
             mbar_wait(&empty_bar[stage], phase ^ 1);
-            uint8_t* st = smem + stage * Cfg::kStageBytes;
-            mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-            tma_load_4d(&map_x_hi, &full_bar[stage], st, kc * kBlockK, tx * kTileW + s - 1, ty * kTileH + r - 1, img);
-            tma_load_3d(&map_w_hi, &full_bar[stage], st + PLANES * kABytes, kc * kBlockK, nb * BLOCK_N, tap);
-            if (PLANES == 2) {
-              tma_load_4d(&map_x_lo, &full_bar[stage], st + kABytes, kc * kBlockK, tx * kTileW + s - 1,
-                          ty * kTileH + r - 1, img);
-              tma_load_3d(&map_w_lo, &full_bar[stage], st + 2 * kABytes + Cfg::kBBytes, kc * kBlockK, nb * BLOCK_N,
-                          tap);
+            if (elect_one()) {
+              uint8_t* st = smem + stage * Cfg::kStageBytes;
+              mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+              tma_load_4d(&map_x_hi, &full_bar[stage], st, kc * kBlockK, tx * kTileW + s - 1, ty * kTileH + r - 1, img);
+              tma_load_3d(&map_w_hi, &full_bar[stage], st + PLANES * kABytes, kc * kBlockK, nb * BLOCK_N, tap);
+              if (PLANES == 2) {
+                tma_load_4d(&map_x_lo, &full_bar[stage], st + kABytes, kc * kBlockK, tx * kTileW + s - 1,
+                            ty * kTileH + r - 1, img);
+                tma_load_3d(&map_w_lo, &full_bar[stage], st + 2 * kABytes + Cfg::kBBytes, kc * kBlockK,
+                            nb * BLOCK_N, tap);
+              }
             }
+            __syncwarp();
             if (++stage == kStages) {
               stage = 0;
               phase ^= 1;
@@ -120,7 +125,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_con
     }
   } else if (warp == 1) {
     // -------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
+    {
       constexpr uint32_t idesc = make_idesc_f16(kBlockM, BLOCK_N, /*bf16=*/true);
       int stage = 0;
       uint32_t phase = 0;
@@ -134,25 +139,28 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_con
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t a_hi = smem_u32(smem + stage * Cfg::kStageBytes);
-          const uint32_t b_hi = a_hi + PLANES * kABytes;
-          const uint64_t da_hi = make_smem_desc(a_hi, 16, 1024, kLayoutSW128);
-          const uint64_t db_hi = make_smem_desc(b_hi, 16, 1024, kLayoutSW128);
-          const uint64_t da_lo = make_smem_desc(a_hi + kABytes, 16, 1024, kLayoutSW128);
-          const uint64_t db_lo = make_smem_desc(b_hi + Cfg::kBBytes, 16, 1024, kLayoutSW128);
+          if (elect_one()) {
+            const uint32_t a_hi = smem_u32(smem + stage * Cfg::kStageBytes);
+            const uint32_t b_hi = a_hi + PLANES * kABytes;
+            const uint64_t da_hi = make_smem_desc(a_hi, 16, 1024, kLayoutSW128);
+            const uint64_t db_hi = make_smem_desc(b_hi, 16, 1024, kLayoutSW128);
+            const uint64_t da_lo = make_smem_desc(a_hi + kABytes, 16, 1024, kLayoutSW128);
+            const uint64_t db_lo = make_smem_desc(b_hi + Cfg::kBBytes, 16, 1024, kLayoutSW128);
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            const uint64_t adv = static_cast<uint64_t>(k * 2);  // 32 bytes >> 4
-            if (PLANES == 2) {
-              umma_f16(tmem_d, da_lo + adv, db_hi + adv, idesc, (kb | k) != 0);
-              umma_f16(tmem_d, da_hi + adv, db_lo + adv, idesc, 1);
-              umma_f16(tmem_d, da_hi + adv, db_hi + adv, idesc, 1);
-            } else {
-              umma_f16(tmem_d, da_hi + adv, db_hi + adv, idesc, (kb | k) != 0);
+            for (int k = 0; k < kBlockK / 16; ++k) {
+              const uint64_t adv = static_cast<uint64_t>(k * 2);  // 32 bytes >> 4
+              if (PLANES == 2) {
+                umma_f16(tmem_d, da_lo + adv, db_hi + adv, idesc, (kb | k) != 0);
+                umma_f16(tmem_d, da_hi + adv, db_lo + adv, idesc, 1);
+                umma_f16(tmem_d, da_hi + adv, db_hi + adv, idesc, 1);
+              } else {
+                umma_f16(tmem_d, da_hi + adv, db_hi + adv, idesc, (kb | k) != 0);
+              }
             }
+            umma_commit(&empty_bar[stage]);
+            if (kb == num_kb - 1) umma_commit(&tfull_bar[as]);
           }
-          umma_commit(&empty_bar[stage]);
-          if (kb == num_kb - 1) umma_commit(&tfull_bar[as]);
+          __syncwarp();
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
@@ -234,14 +242,15 @@ extern "C" int osvos_conv3x3(const osvos_conv3x3_args* a, osvos_stream_t stream_
   if (rc) return rc;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const bool fast = (a->flags & OSVOS_FLAG_FAST) != 0;
-  // Implementation switch (development / validation): OSVOS_CONV_IMPL = halo | tap.
+  // Default: halo-reuse kernel (conv3x3_halo.cu) with packed rows (pitch 10) - validated on B200: the UMMA
+  // swizzle is a function of the absolute smem address, so shifted descriptor starts need no base offset.
+  // OSVOS_CONV_IMPL=tap selects the one-box-per-tap kernel below (kept as a cross-check).
   const char* impl = getenv("OSVOS_CONV_IMPL");
   if (impl == nullptr || strcmp(impl, "tap") != 0) {
     const char* ps = getenv("OSVOS_HALO_PITCH");
     const char* bo = getenv("OSVOS_HALO_BO");
-    const int pitch = (ps && atoi(ps) == 10) ? 10 : 16;
-    if (impl != nullptr && strcmp(impl, "halo") == 0)
-      return conv3x3_halo_dispatch(a, stream, pitch, bo ? atoi(bo) : 0);
+    const int pitch = (ps && atoi(ps) == 16) ? 16 : 10;
+    return conv3x3_halo_dispatch(a, stream, pitch, bo ? atoi(bo) : 0);
   }
   if (a->cout == 16) return fast ? launch_conv<16, 1>(a, stream) : launch_conv<16, 2>(a, stream);
   if (a->cout == 64) return fast ? launch_conv<64, 1>(a, stream) : launch_conv<64, 2>(a, stream);

@@ -101,7 +101,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_p_hi, const __grid_const
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {  // warp-uniform control flow, one elected lane issues (see conv3x3_tc.cu)
       int stage = 0;
       uint32_t phase = 0;
       for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
@@ -120,6 +120,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_p_hi, const __grid_const
           const int img = t / p.patches_y;
           const int x0 = px * kWgPatchW, y0 = py * kWgPatchH;
           mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (elect_one()) {
           uint8_t* st = smem + stage * Cfg::kStageBytes;
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
 #pragma unroll
@@ -135,6 +136,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_p_hi, const __grid_const
             for (int j = 0; j < BLOCK_N / 64; ++j)
               tma_load_4d(mq, &full_bar[stage], sq + j * kWgBoxBytes, nb * BLOCK_N + j * 64, x0 + qdx, y0 + qdy, img);
           }
+          }
+          __syncwarp();
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
@@ -143,7 +146,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_p_hi, const __grid_const
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       constexpr uint32_t idesc = make_idesc_f16(128, BLOCK_N, true, /*a_mn=*/true, /*b_mn=*/true);
       int stage = 0;
       uint32_t phase = 0;
@@ -162,6 +165,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_p_hi, const __grid_const
         for (int patch = pb; patch < pe; ++patch) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
+          if (elect_one()) {
           const uint32_t sp = smem_u32(smem + stage * Cfg::kStageBytes);
           const uint32_t sq = sp + PLANES * Cfg::kPBytes;
           // MN-major SW128: LBO = bytes between 64-wide MN atoms, SBO = bytes between 8-row K groups
@@ -183,6 +187,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_p_hi, const __grid_const
           }
           umma_commit(&empty_bar[stage]);
           if (patch == pe - 1) umma_commit(&tfull_bar[as]);
+          }
+          __syncwarp();
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;

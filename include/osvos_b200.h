@@ -102,6 +102,13 @@ typedef struct {
   const float* proj_w;   /* [32] or NULL */
   const float* proj_b;   /* [1]  or NULL */
   float* pq;             /* [n,h,w,2] or NULL */
+  /* fused MaxPool2d(2,2,ceil_mode=True) of the output (networks/vgg_osvos.py:140): act
+   * [n, ceil(h/2), ceil(w/2), cout], written in addition to y (cout >= 64 only) */
+  void* pool_hi;
+  void* pool_lo;
+  /* fused per-channel sum of the (masked) output over all pixels = bias gradient of the layer this
+   * gradient belongs to; [cout] fp32, ACCUMULATED with atomics (caller zeroes); cout >= 64 only */
+  float* colsum;
   int n, h, w, cin, cout;
   int flags;
 } osvos_conv3x3_args;
@@ -189,14 +196,16 @@ OSVOS_API int osvos_sum_f32(const float* x, size_t n, double* scratch, float* ou
 /* ---- backward of score_dsn / the fuse slice (1x1 convs, networks/vgg_osvos.py:44,54) --
  * dfeat = dp*w_score + dq*w_fuse_slice as an act with 64 channels (16..63 zero);
  * param_grads[0:16] = d score_dsn.weight, [16] = d score_dsn.bias,
- * [17:33] = d fuse.weight slice, [33] = sum dq.  scratch: 34 doubles.  feat may be NULL
- * (then only dfeat and the two plain sums are produced).                                */
+ * [17:33] = d fuse.weight slice, [33] = sum dq, [34:50] = d side_prep.bias (= w_score*sum dp +
+ * w_fuse*sum dq).  param_grads: 50 floats; scratch: 34 doubles.  feat may be NULL (then only
+ * dfeat, the plain sums and the bias gradient are produced).                              */
 OSVOS_API int osvos_side_bwd(const float* feat, const float* dpq, const float* proj_w, void* dfeat_hi, void* dfeat_lo,
                              double* scratch, float* param_grads, int n, int h, int w, osvos_stream_t stream);
 
 /* ---- max-unpool + side-branch add + ReLU mask (autograd of networks/vgg_osvos.py:140,143) */
 OSVOS_API int osvos_unpool_add_mask(const void* dpool_hi, const void* dpool_lo, const void* x_hi, const void* x_lo,
-                                    const float* dside /* [n,h,w,c] fp32 or NULL */, void* dz_hi, void* dz_lo, int n,
+                                    const float* dside /* [n,h,w,c] fp32 or NULL */, void* dz_hi, void* dz_lo,
+                                    float* colsum /* [c] accumulated per-channel sum of dz, or NULL */, int n,
                                     int h, int w, int c, osvos_stream_t stream);
 
 /* ---- bias gradient: out[c] = sum over pixels of an act ----------------------------- */

@@ -31,21 +31,26 @@ class _OSVOSFunction(torch.autograd.Function):
         pooled = [None]
         a = ops.conv_first(xin, convs[0][0].weight.detach(), convs[0][0].bias.detach(), relu=True, fast=fast)
         stage_acts = [a]
-        a, _, _ = ops.conv3x3(a, engine._packed(convs[0][1], "s0c1"), convs[0][1].bias.detach(), 64, relu=True, fast=fast)
-        stage_acts.append(a)
+        full, a = ops.conv3x3(a, engine._packed(convs[0][1], "s0c1"), convs[0][1].bias.detach(), 64, relu=True,
+                              fast=fast, pool=True)               # 2x2 max pool fused into the epilogue
+        stage_acts.append(full)
         acts.append(stage_acts)
         feats, pqs = [], []
         for i in range(1, 5):
-            a = ops.maxpool2x2(a)
             pooled.append(a)
             stage_acts = []
             for j, conv in enumerate(convs[i]):
-                a, _, _ = ops.conv3x3(a, engine._packed(conv, f"s{i}c{j}"), conv.bias.detach(), conv.out_channels,
-                                      relu=True, fast=fast)
-                stage_acts.append(a)
+                if j == len(convs[i]) - 1 and i < 4:
+                    full, a = ops.conv3x3(a, engine._packed(conv, f"s{i}c{j}"), conv.bias.detach(), conv.out_channels,
+                                          relu=True, fast=fast, pool=True)
+                else:
+                    a, _, _ = ops.conv3x3(a, engine._packed(conv, f"s{i}c{j}"), conv.bias.detach(), conv.out_channels,
+                                          relu=True, fast=fast)
+                    full = a
+                stage_acts.append(full)
             acts.append(stage_acts)
             sp = m.side_prep[i - 1]
-            _, feat, pq = ops.conv3x3(a, engine._packed(sp, f"sp{i}"), sp.bias.detach(), 16, relu=False, fast=fast,
+            _, feat, pq = ops.conv3x3(full, engine._packed(sp, f"sp{i}"), sp.bias.detach(), 16, relu=False, fast=fast,
                                       out_act=False, out_f32=True, proj_w=engine._proj(i - 1),
                                       proj_b=m.score_dsn[i - 1].bias.detach())
             feats.append(feat)
@@ -73,19 +78,25 @@ class _OSVOSFunction(torch.autograd.Function):
         if grads[4] is not None:
             pg[m.fuse.bias] = ops.sum_f32(grads[4]).reshape(m.fuse.bias.shape)
         fuse_w_grad = torch.zeros(64, dtype=torch.float32, device=xin.device) if grads[4] is not None else None
+        # one zeroed buffer for all 13 trunk bias gradients; the dgrad / unpool epilogues accumulate into its slices
+        flat_convs = [c for stage in convs for c in stage]
+        bias_buf = torch.zeros(sum(c.out_channels for c in flat_convs), dtype=torch.float32, device=xin.device)
+        bias_slices, off = {}, 0
+        for c in flat_convs:
+            bias_slices[c] = bias_buf[off:off + c.out_channels]
+            off += c.out_channels
         dfeats = []
         for i in range(4):
-            d, g34 = ops.side_bwd(feats[i], dpq[i], engine._proj(i), fast)
+            d, g50 = ops.side_bwd(feats[i], dpq[i], engine._proj(i), fast)
             dfeats.append(d)
             if grads[i] is not None:
-                pg[m.score_dsn[i].weight] = g34[0:16].reshape(m.score_dsn[i].weight.shape)
-                pg[m.score_dsn[i].bias] = g34[16:17].reshape(m.score_dsn[i].bias.shape)
+                pg[m.score_dsn[i].weight] = g50[0:16].reshape(m.score_dsn[i].weight.shape)
+                pg[m.score_dsn[i].bias] = g50[16:17].reshape(m.score_dsn[i].bias.shape)
             if fuse_w_grad is not None:
-                fuse_w_grad[16 * i:16 * i + 16] = g34[17:33]           # slice copy (plumbing)
+                fuse_w_grad[16 * i:16 * i + 16] = g50[17:33]           # slice copy (plumbing)
             sp = m.side_prep[i]
-            s_out = acts[i + 1][-1]
-            pg[sp.weight] = ops.conv3x3_wgrad(s_out, d, 16, swapped=True, fast=fast)
-            pg[sp.bias] = ops.channel_sum(d)[:16]
+            pg[sp.weight] = ops.conv3x3_wgrad(acts[i + 1][-1], d, 16, swapped=True, fast=fast)
+            pg[sp.bias] = g50[34:50]
         if fuse_w_grad is not None:
             pg[m.fuse.weight] = fuse_w_grad.reshape(m.fuse.weight.shape)
 
@@ -95,31 +106,33 @@ class _OSVOSFunction(torch.autograd.Function):
             sp = m.side_prep[i - 1]
             wt_side = engine._packed(sp, f"sp{i}", transpose_flip=True, col_pad=64)
             cst = s_out.shape[3]
+            last_bias = bias_slices[convs[i][-1]]
             if dpool is None:        # deepest stage: the side branch is the only consumer
-                dz, _, _ = ops.conv3x3(dfeats[i - 1], wt_side, None, cst, fast=fast, mask=s_out.hi)
+                dz, _, _ = ops.conv3x3(dfeats[i - 1], wt_side, None, cst, fast=fast, mask=s_out.hi, colsum=last_bias)
             else:
                 _, dside, _ = ops.conv3x3(dfeats[i - 1], wt_side, None, cst, fast=fast, out_act=False, out_f32=True)
-                dz = ops.unpool_add_mask(dpool, s_out, dside)
+                dz = ops.unpool_add_mask(dpool, s_out, dside, colsum=last_bias)
             for j in range(len(convs[i]) - 1, -1, -1):
                 conv = convs[i][j]
                 inp = acts[i][j - 1] if j > 0 else pooled[i]
                 pg[conv.weight] = ops.conv3x3_wgrad(inp, dz, conv.out_channels, fast=fast)
-                pg[conv.bias] = ops.channel_sum(dz)
+                pg[conv.bias] = bias_slices[conv]
                 wt = engine._packed(conv, f"s{i}c{j}", transpose_flip=True)
                 if j > 0:
-                    dz, _, _ = ops.conv3x3(dz, wt, None, conv.in_channels, fast=fast, mask=inp.hi)
+                    dz, _, _ = ops.conv3x3(dz, wt, None, conv.in_channels, fast=fast, mask=inp.hi,
+                                           colsum=bias_slices[convs[i][j - 1]])
                 else:
                     dpool, _, _ = ops.conv3x3(dz, wt, None, conv.in_channels, fast=fast)
         # stage 1 (no side branch)
-        dz = ops.unpool_add_mask(dpool, acts[0][1], None)
         c12, c11 = convs[0][1], convs[0][0]
+        dz = ops.unpool_add_mask(dpool, acts[0][1], None, colsum=bias_slices[c12])
         pg[c12.weight] = ops.conv3x3_wgrad(acts[0][0], dz, 64, fast=fast)
-        pg[c12.bias] = ops.channel_sum(dz)
+        pg[c12.bias] = bias_slices[c12]
         dz, _, _ = ops.conv3x3(dz, engine._packed(c12, "s0c1", transpose_flip=True), None, 64, fast=fast,
-                               mask=acts[0][0].hi)
+                               mask=acts[0][0].hi, colsum=bias_slices[c11])
         dw0, dx = ops.conv_first_bwd(xin, dz, c11.weight.detach(), ctx.needs_input_grad[1])
         pg[c11.weight] = dw0
-        pg[c11.bias] = ops.channel_sum(dz)
+        pg[c11.bias] = bias_slices[c11]
         ctx.saved = None
         return (None, dx) + tuple(pg.get(p) for p in engine._param_list())
 

@@ -71,6 +71,12 @@ __global__ void f64_to_f32_kernel(const double* __restrict__ in, float* __restri
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = static_cast<float>(in[i]);
 }
+// side_bwd finalize: out[0:34] = sums; out[34+c] = d side_prep.bias[c] = w_score[c]*sum(dp) + w_fuse[c]*sum(dq)
+__global__ void side_finalize_kernel(const double* __restrict__ in, const float* __restrict__ pw, float* __restrict__ out) {
+  const int i = threadIdx.x;
+  if (i < 34) out[i] = static_cast<float>(in[i]);
+  else if (i < 50) out[i] = static_cast<float>(static_cast<double>(pw[i - 34]) * in[16] + static_cast<double>(pw[i - 18]) * in[33]);
+}
 
 // ------------------------------------------------------------------ side bwd
 // feat [npix][16] fp32, dpq [npix][2], pw[32] = {score_dsn w, fuse slice}:
@@ -151,7 +157,13 @@ side_bwd_kernel(const float* __restrict__ feat, const float* __restrict__ dpq, c
 __global__ void unpool_add_mask_kernel(const __nv_bfloat16* __restrict__ dp_hi, const __nv_bfloat16* __restrict__ dp_lo,
                                        const __nv_bfloat16* __restrict__ x_hi, const __nv_bfloat16* __restrict__ x_lo,
                                        const float* __restrict__ dside, __nv_bfloat16* __restrict__ dz_hi,
-                                       __nv_bfloat16* __restrict__ dz_lo, int n, int h, int w, int c, int oh, int ow) {
+                                       __nv_bfloat16* __restrict__ dz_lo, float* __restrict__ colsum, int n, int h,
+                                       int w, int c, int oh, int ow) {
+  extern __shared__ float cs[];  // [c] block-local channel sums (fused bias gradient)
+  if (colsum) {
+    for (int i = threadIdx.x; i < c; i += blockDim.x) cs[i] = 0.f;
+    __syncthreads();
+  }
   const int groups = c / 8;
   const size_t total = static_cast<size_t>(n) * oh * ow * groups;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
@@ -196,6 +208,7 @@ __global__ void unpool_add_mask_kernel(const __nv_bfloat16* __restrict__ dp_hi, 
         dpv[2 * t + 1] = bf16_hi_to_float(hw[t]) + bf16_hi_to_float(lw[t]);
       }
     }
+    float csum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int arg[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -227,6 +240,8 @@ __global__ void unpool_add_mask_kernel(const __nv_bfloat16* __restrict__ dp_hi, 
         float v1 = ds[2 * t + 1] + (arg[2 * t + 1] == q ? dpv[2 * t + 1] : 0.f);
         if (!(xv[q][2 * t] > 0.f)) v0 = 0.f;
         if (!(xv[q][2 * t + 1] > 0.f)) v1 = 0.f;
+        csum[2 * t] += v0;
+        csum[2 * t + 1] += v1;
         __nv_bfloat16 h0, l0, h1, l1;
         split_bf16(v0, h0, l0);
         split_bf16(v1, h1, l1);
@@ -236,6 +251,14 @@ __global__ void unpool_add_mask_kernel(const __nv_bfloat16* __restrict__ dp_hi, 
       *reinterpret_cast<uint4*>(dz_hi + dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
       if (dz_lo) *reinterpret_cast<uint4*>(dz_lo + dst) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
     }
+    if (colsum) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(&cs[g * 8 + j], csum[j]);
+    }
+  }
+  if (colsum) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < c; i += blockDim.x) atomicAdd(colsum + i, cs[i]);
   }
 }
 
@@ -432,21 +455,21 @@ extern "C" int osvos_side_bwd(const float* feat, const float* dpq, const float* 
   OSVOS_CHECK_CUDA(cudaMemsetAsync(scratch, 0, 34 * sizeof(double), stream));
   side_bwd_kernel<<<grid_cap((npix + 255) / 256, 4), 256, 0, stream>>>(
       feat, dpq, proj_w, static_cast<__nv_bfloat16*>(dfeat_hi), static_cast<__nv_bfloat16*>(dfeat_lo), scratch, npix);
-  f64_to_f32_kernel<<<1, 64, 0, stream>>>(scratch, param_grads, 34);
+  side_finalize_kernel<<<1, 64, 0, stream>>>(scratch, proj_w, param_grads);
   OSVOS_CHECK_CUDA(cudaGetLastError());
   return OSVOS_OK;
 }
 
 extern "C" int osvos_unpool_add_mask(const void* dpool_hi, const void* dpool_lo, const void* x_hi, const void* x_lo,
-                                     const float* dside, void* dz_hi, void* dz_lo, int n, int h, int w, int c,
-                                     osvos_stream_t stream_) {
+                                     const float* dside, void* dz_hi, void* dz_lo, float* colsum, int n, int h, int w,
+                                     int c, osvos_stream_t stream_) {
   OSVOS_CHECK_ARG(dpool_hi != nullptr && x_hi != nullptr && dz_hi != nullptr && n > 0 && h > 0 && w > 0 && c % 8 == 0);
   const int oh = (h + 1) / 2, ow = (w + 1) / 2;
   const size_t total = static_cast<size_t>(n) * oh * ow * (c / 8);
-  unpool_add_mask_kernel<<<grid_cap((total + 255) / 256, 16), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+  unpool_add_mask_kernel<<<grid_cap((total + 255) / 256, 8), 256, c * sizeof(float), static_cast<cudaStream_t>(stream_)>>>(
       static_cast<const __nv_bfloat16*>(dpool_hi), static_cast<const __nv_bfloat16*>(dpool_lo),
       static_cast<const __nv_bfloat16*>(x_hi), static_cast<const __nv_bfloat16*>(x_lo), dside,
-      static_cast<__nv_bfloat16*>(dz_hi), static_cast<__nv_bfloat16*>(dz_lo), n, h, w, c, oh, ow);
+      static_cast<__nv_bfloat16*>(dz_hi), static_cast<__nv_bfloat16*>(dz_lo), colsum, n, h, w, c, oh, ow);
   OSVOS_CHECK_CUDA(cudaGetLastError());
   return OSVOS_OK;
 }

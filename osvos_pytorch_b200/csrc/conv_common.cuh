@@ -23,6 +23,9 @@ struct ConvParams {
   const float* proj_w;
   const float* proj_b;
   float* pq;
+  __nv_bfloat16* pool_hi;  // optional fused 2x2 ceil-mode max pool of the output
+  __nv_bfloat16* pool_lo;
+  float* colsum;           // optional fused per-channel sum of the output (bias gradient), atomically accumulated
   int n, h, w, cin, cout;
   int tiles_x, tiles_y, n_blocks, total_tiles, k_chunks;
   int flags;
@@ -109,14 +112,14 @@ __device__ __forceinline__ void conv_epilogue_loop(const ConvParams& p, uint32_t
           uint32_t v[32];
           tmem_ld32(taddr + c0, v);
           tmem_ld_wait();
-          if (valid) {
-            const int ch = nb * BLOCK_N + c0;
-            float f[32];
+          const int ch = nb * BLOCK_N + c0;
+          float f[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              f[j] = __uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + ch + j) : 0.f);
-              if (p.flags & OSVOS_FLAG_RELU) f[j] = fmaxf(f[j], 0.f);
-            }
+          for (int j = 0; j < 32; ++j) {
+            f[j] = __uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + ch + j) : 0.f);
+            if (p.flags & OSVOS_FLAG_RELU) f[j] = fmaxf(f[j], 0.f);
+          }
+          if (valid) {
             if (p.flags & OSVOS_FLAG_RELU_MASK) {
               const uint4* mk = reinterpret_cast<const uint4*>(p.mask_hi + pix * p.cout + ch);
 #pragma unroll
@@ -156,6 +159,50 @@ __device__ __forceinline__ void conv_epilogue_loop(const ConvParams& p, uint32_t
               }
             }
           }
+          if (p.colsum) {
+            // fused bias gradient: per-channel sum of this warp's 32 pixels (butterfly), one atomic per lane
+            float mine = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float sj = valid ? f[j] : 0.f;
+#pragma unroll
+              for (int off = 16; off > 0; off >>= 1) sj += __shfl_xor_sync(0xffffffffu, sj, off);
+              if (lane == j) mine = sj;
+            }
+            atomicAdd(p.colsum + ch + lane, mine);
+          }
+          if (p.pool_hi) {
+            // fused MaxPool2d(2, 2, ceil_mode=True): the 2x2 partners are lanes ^1 (x) and ^8 (y) of this warp;
+            // out-of-image partners are excluded (ceil mode clips the window).
+            const int oh = (p.h + 1) >> 1, ow = (p.w + 1) >> 1;
+            const bool writer = valid && !(lx & 1) && !(ly & 1);
+            const size_t opix = (static_cast<size_t>(img) * oh + (y >> 1)) * ow + (x >> 1);
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float m0 = valid ? f[2 * j] : -INFINITY, m1 = valid ? f[2 * j + 1] : -INFINITY;
+              m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
+              m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+              m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 8));
+              m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 8));
+              __nv_bfloat16 h0, l0, h1, l1;
+              split_bf16(m0, h0, l0);
+              split_bf16(m1, h1, l1);
+              hi[j] = pack_bf16x2(h0, h1);
+              lo[j] = pack_bf16x2(l0, l1);
+            }
+            if (writer) {
+              uint4* dh = reinterpret_cast<uint4*>(p.pool_hi + opix * p.cout + ch);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) dh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+              if (p.pool_lo) {
+                uint4* dl = reinterpret_cast<uint4*>(p.pool_lo + opix * p.cout + ch);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  dl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+              }
+            }
+          }
         }
       }
       tc_fence_before();
@@ -173,6 +220,9 @@ static inline void fill_conv_params(ConvParams& p, const osvos_conv3x3_args* a, 
   p.proj_w = a->proj_w;
   p.proj_b = a->proj_b;
   p.pq = a->pq;
+  p.pool_hi = static_cast<__nv_bfloat16*>(a->pool_hi);
+  p.pool_lo = static_cast<__nv_bfloat16*>(a->pool_lo);
+  p.colsum = a->colsum;
   p.n = a->n;
   p.h = a->h;
   p.w = a->w;
@@ -200,6 +250,8 @@ static inline int encode_weight_maps(CUtensorMap* hi, CUtensorMap* lo, const osv
                            CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
+int conv_first_tc_launch(const float* x, const float* w_oihw, const float* bias, void* y_hi, void* y_lo, int n, int h,
+                         int w, int flags, cudaStream_t stream);
 int conv3x3_halo_dispatch(const osvos_conv3x3_args* a, cudaStream_t stream, int pitch, int use_bo);
 
 }  // namespace osvos

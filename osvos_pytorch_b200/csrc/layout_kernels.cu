@@ -2,9 +2,15 @@
 // weight packing, NCHW<->act conversion, conv1_1 (Cin = 3), 2x2 ceil-mode max
 // pooling, a CUDA-core reference conv (debug cross-check) and the standalone
 // side-feature projection.
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 
 namespace osvos {
+
+int conv_first_tc_launch(const float* x, const float* w_oihw, const float* bias, void* y_hi, void* y_lo, int n, int h,
+                         int w, int flags, cudaStream_t stream);
 
 // ------------------------------------------------------------ weight packing
 // out[plane][tap][row][colp]; see include/osvos_b200.h.
@@ -321,6 +327,11 @@ extern "C" int osvos_conv_first_fwd(const float* x, const float* w_oihw, const f
                                     int n, int h, int w, int flags, osvos_stream_t stream) {
   OSVOS_CHECK_ARG(x != nullptr && w_oihw != nullptr && y_hi != nullptr && n > 0 && h > 0 && w > 0);
   OSVOS_CHECK_ARG(h <= 65535 && n <= 65535);
+  {  // default: tensor-core kernel (conv_first_tc.cu); OSVOS_FIRST_IMPL=simt keeps the CUDA-core one as a cross-check
+    const char* impl = getenv("OSVOS_FIRST_IMPL");
+    if (impl == nullptr || strcmp(impl, "simt") != 0)
+      return conv_first_tc_launch(x, w_oihw, bias, y_hi, y_lo, n, h, w, flags, static_cast<cudaStream_t>(stream));
+  }
   dim3 grid((w + kFirstThreads - 1) / kFirstThreads, h, n);
   conv_first_kernel<<<grid, kFirstThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       x, w_oihw, bias, static_cast<__nv_bfloat16*>(y_hi),
@@ -346,7 +357,7 @@ extern "C" int osvos_maxpool2x2_fwd(const void* x_hi, const void* x_lo, void* y_
 extern "C" int osvos_conv3x3_simt(const osvos_conv3x3_args* a, osvos_stream_t stream) {
   OSVOS_CHECK_ARG(a != nullptr && a->x_hi != nullptr && a->w_packed != nullptr);
   OSVOS_CHECK_ARG((a->flags & OSVOS_FLAG_FAST) || a->x_lo != nullptr);
-  OSVOS_CHECK_ARG(a->pq == nullptr);
+  OSVOS_CHECK_ARG(a->pq == nullptr && a->pool_hi == nullptr && a->colsum == nullptr);
   const size_t total = static_cast<size_t>(a->n) * a->h * a->w * a->cout;
   conv3x3_simt_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(a->x_hi), static_cast<const __nv_bfloat16*>(a->x_lo),

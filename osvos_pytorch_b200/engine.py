@@ -89,25 +89,33 @@ class OSVOSEngine:
         inter = {}
         convs0 = [c for c in m.stages[0] if isinstance(c, nn.Conv2d)]
         a = ops.conv_first(x, convs0[0].weight.detach(), convs0[0].bias.detach(), relu=True, fast=fast)
-        a, _, _ = ops.conv3x3(a, self._packed(convs0[1], "s0c1"), convs0[1].bias.detach(), convs0[1].out_channels,
-                              relu=True, fast=fast, simt=simt)
+        # conv1_2 with the 2x2 max pool fused into its epilogue; the full-resolution map is only kept on request
+        full, a = ops.conv3x3(a, self._packed(convs0[1], "s0c1"), convs0[1].bias.detach(), convs0[1].out_channels,
+                              relu=True, fast=fast, simt=False, pool=True, out_act=return_intermediates)
         if return_intermediates:
-            inter["stage0"] = a
+            inter["stage0"] = full
         pqs = []
         for i in range(1, 5):
-            a = ops.maxpool2x2(a)
-            for j, conv in enumerate(c for c in m.stages[i] if isinstance(c, nn.Conv2d)):
-                a, _, _ = ops.conv3x3(a, self._packed(conv, f"s{i}c{j}"), conv.bias.detach(), conv.out_channels,
-                                      relu=True, fast=fast, simt=simt)
+            convs = [c for c in m.stages[i] if isinstance(c, nn.Conv2d)]
+            for j, conv in enumerate(convs):
+                if j == len(convs) - 1 and i < 4 and not simt:
+                    full, a = ops.conv3x3(a, self._packed(conv, f"s{i}c{j}"), conv.bias.detach(), conv.out_channels,
+                                          relu=True, fast=fast, pool=True)
+                else:
+                    a, _, _ = ops.conv3x3(a, self._packed(conv, f"s{i}c{j}"), conv.bias.detach(), conv.out_channels,
+                                          relu=True, fast=fast, simt=simt)
+                    full = a
+            if simt and i < 4:
+                a = ops.maxpool2x2(full)
             if return_intermediates:
-                inter[f"stage{i}"] = a
+                inter[f"stage{i}"] = full
             sp = m.side_prep[i - 1]
             if simt:
-                _, feat, _ = ops.conv3x3(a, self._packed(sp, f"sp{i}"), sp.bias.detach(), 16, relu=False, fast=fast,
+                _, feat, _ = ops.conv3x3(full, self._packed(sp, f"sp{i}"), sp.bias.detach(), 16, relu=False, fast=fast,
                                          out_act=False, out_f32=True, simt=True)
                 pq = ops.side_project(feat, self._proj(i - 1), m.score_dsn[i - 1].bias.detach())
             else:
-                _, feat, pq = ops.conv3x3(a, self._packed(sp, f"sp{i}"), sp.bias.detach(), 16, relu=False, fast=fast,
+                _, feat, pq = ops.conv3x3(full, self._packed(sp, f"sp{i}"), sp.bias.detach(), 16, relu=False, fast=fast,
                                           out_act=False, out_f32=return_intermediates, proj_w=self._proj(i - 1),
                                           proj_b=m.score_dsn[i - 1].bias.detach())
             if return_intermediates:

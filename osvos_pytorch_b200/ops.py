@@ -98,8 +98,10 @@ def conv_first(x, weight, bias, relu=True, fast=False):
 
 
 def conv3x3(x, w_packed, bias, cout, relu=False, fast=False, out_act=True, out_f32=False, mask=None,
-            proj_w=None, proj_b=None, simt=False):
-    """3x3 / pad 1 conv of an Act through the tcgen05 kernel.  Returns (Act|None, f32|None, pq|None)."""
+            proj_w=None, proj_b=None, simt=False, pool=False, colsum=None):
+    """3x3 / pad 1 conv of an Act through the tcgen05 kernel.  Returns (Act|None, f32|None, pq|None), or
+    (Act, pooled Act) when pool=True (fused MaxPool2d(2,2,ceil_mode)).  `colsum` ([cout] fp32, pre-zeroed)
+    receives the per-channel sum of the output (fused bias gradient)."""
     lib = nat.load()
     n, h, w, cin = x.shape
     dev = x.hi.device
@@ -114,12 +116,18 @@ def conv3x3(x, w_packed, bias, cout, relu=False, fast=False, out_act=True, out_f
     a.y_f32 = nat.ptr(yf)
     a.mask_hi = nat.ptr(mask)
     a.proj_w, a.proj_b, a.pq = nat.ptr(proj_w), nat.ptr(proj_b), nat.ptr(pq)
+    yp = Act.empty(n, (h + 1) // 2, (w + 1) // 2, cout, dev, fast) if pool else None
+    a.pool_hi = nat.ptr(yp.hi) if pool else None
+    a.pool_lo = nat.ptr(yp.lo) if pool else None
+    a.colsum = nat.ptr(colsum)
     a.n, a.h, a.w, a.cin, a.cout = n, h, w, cin, cout
     a.flags = (nat.FLAG_RELU if relu else 0) | (nat.FLAG_FAST if fast else 0) | \
               (nat.FLAG_RELU_MASK if mask is not None else 0)
     fn = lib.osvos_conv3x3_simt if simt else lib.osvos_conv3x3
     _count()
     nat.check(fn(byref(a), _stream()), "osvos_conv3x3")
+    if pool:
+        return y, yp
     return y, yf, pq
 
 
@@ -229,20 +237,21 @@ def side_bwd(feat, dpq, proj_w, fast=False):
     dev = dpq.device
     d = Act.empty(n, h, w, 64, dev, fast)
     scratch = torch.empty(34, dtype=torch.float64, device=dev)
-    pg = torch.empty(34, dtype=torch.float32, device=dev)
+    pg = torch.empty(50, dtype=torch.float32, device=dev)
     _count(2)
     nat.check(lib.osvos_side_bwd(nat.ptr(feat), dpq.data_ptr(), proj_w.data_ptr(), d.hi.data_ptr(), nat.ptr(d.lo),
                                  scratch.data_ptr(), pg.data_ptr(), n, h, w, _stream()), "osvos_side_bwd")
     return d, pg
 
 
-def unpool_add_mask(dpool, x, dside):
+def unpool_add_mask(dpool, x, dside, colsum=None):
     lib = nat.load()
     n, h, w, c = x.shape
     dz = Act.empty(n, h, w, c, x.hi.device, x.lo is None)
     _count()
     nat.check(lib.osvos_unpool_add_mask(dpool.hi.data_ptr(), nat.ptr(dpool.lo), x.hi.data_ptr(), nat.ptr(x.lo),
-                                        nat.ptr(dside), dz.hi.data_ptr(), nat.ptr(dz.lo), n, h, w, c, _stream()),
+                                        nat.ptr(dside), dz.hi.data_ptr(), nat.ptr(dz.lo), nat.ptr(colsum), n, h, w, c,
+                                        _stream()),
               "osvos_unpool_add_mask")
     return dz
 

@@ -113,8 +113,11 @@ def test_unpool_add_mask(dev, n, h, w, c, with_side):
     want = xr.grad + (dside.double() if with_side else 0)
     want = want * (x > 0)
     ds = dside.permute(0, 2, 3, 1).contiguous().to(dev) if with_side else None
-    got = ops.act_to_nchw(ops.unpool_add_mask(ops.nchw_to_act(dpool.to(dev)), ops.nchw_to_act(x.to(dev)), ds)).cpu()
+    colsum = torch.zeros(c, device=dev)
+    got = ops.act_to_nchw(ops.unpool_add_mask(ops.nchw_to_act(dpool.to(dev)), ops.nchw_to_act(x.to(dev)), ds,
+                                              colsum=colsum)).cpu()
     assert maxrel(got, want) < 2e-5
+    assert maxrel(colsum.cpu(), want.sum((0, 2, 3))) < 2e-5
 
 
 def test_channel_sum_side_bwd_and_first_layer(dev):
@@ -136,6 +139,7 @@ def test_channel_sum_side_bwd_and_first_layer(dev):
     assert maxrel(pg[:16], (dpq[..., 0:1] * feat).double().sum((0, 1, 2))) < 1e-5
     assert maxrel(pg[17:33], (dpq[..., 1:2] * feat).double().sum((0, 1, 2))) < 1e-5
     assert abs(float(pg[16]) - float(dpq[..., 0].double().sum())) < 1e-4
+    assert maxrel(pg[34:50], want.double().sum((0, 1, 2))) < 1e-5          # side_prep bias gradient
     # conv1_1 backward
     x, _ = oc.synthetic_frame(2, 13, 37, 5)
     wt = torch.randn(64, 3, 3, 3, generator=g) * 0.2

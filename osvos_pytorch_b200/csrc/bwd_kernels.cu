@@ -166,9 +166,11 @@ __global__ void unpool_add_mask_kernel(const __nv_bfloat16* __restrict__ dp_hi, 
   }
   const int groups = c / 8;
   const size_t total = static_cast<size_t>(n) * oh * ow * groups;
+  // blockDim (256) is a multiple of `groups`, so a thread keeps the same channel group over the whole loop
+  const int g = static_cast<int>(threadIdx.x % groups);
+  float csum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int g = static_cast<int>(i % groups);
     size_t r = i / groups;
     const int ox = static_cast<int>(r % ow);
     r /= ow;
@@ -208,7 +210,6 @@ __global__ void unpool_add_mask_kernel(const __nv_bfloat16* __restrict__ dp_hi, 
         dpv[2 * t + 1] = bf16_hi_to_float(hw[t]) + bf16_hi_to_float(lw[t]);
       }
     }
-    float csum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int arg[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -251,12 +252,10 @@ __global__ void unpool_add_mask_kernel(const __nv_bfloat16* __restrict__ dp_hi, 
       *reinterpret_cast<uint4*>(dz_hi + dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
       if (dz_lo) *reinterpret_cast<uint4*>(dz_lo + dst) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
     }
-    if (colsum) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) atomicAdd(&cs[g * 8 + j], csum[j]);
-    }
   }
   if (colsum) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(&cs[g * 8 + j], csum[j]);
     __syncthreads();
     for (int i = threadIdx.x; i < c; i += blockDim.x) atomicAdd(colsum + i, cs[i]);
   }

@@ -28,11 +28,12 @@ struct HaloCfg {
   static constexpr int kAStages = 2;
   static constexpr int kBPlaneBytes = BLOCK_N * 128;
   static constexpr int kBStageBytes = PLANES * kBPlaneBytes;
-  static constexpr int kBudget = 214 * 1024 - kAStages * kAStageBytes;
+  static constexpr int kStagingBytes = BLOCK_N >= 64 ? 2 * kABytes : 0;   // TMA-store staging (hi + lo slab)
+  static constexpr int kBudget = 214 * 1024 - kAStages * kAStageBytes - kStagingBytes;
   static constexpr int kBStagesRaw = kBudget / kBStageBytes;
   static constexpr int kBStages = kBStagesRaw > 9 ? 9 : kBStagesRaw;
   static constexpr int kTmemCols = (2 * BLOCK_N) < 32 ? 32 : 2 * BLOCK_N;
-  static constexpr int kSmemBytes = kAStages * kAStageBytes + kBStages * kBStageBytes + 1024 + 512;
+  static constexpr int kSmemBytes = kAStages * kAStageBytes + kBStages * kBStageBytes + kStagingBytes + 1024 + 512;
   static_assert(kBStages >= 2, "weight ring too shallow");
   static_assert(kBStageBytes % 1024 == 0, "B stage must keep 1024-byte alignment");
 };
@@ -41,6 +42,7 @@ template <int BLOCK_N, int PLANES, int PITCH>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo,
                     const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
+                    const __grid_constant__ CUtensorMap map_y_hi, const __grid_constant__ CUtensorMap map_y_lo,
                     const ConvParams p, const int use_base_offset) {
   using Cfg = HaloCfg<BLOCK_N, PLANES, PITCH>;
   constexpr int SA = Cfg::kAStages, SB = Cfg::kBStages;
@@ -49,7 +51,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_c
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + SA * Cfg::kAStageBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + SB * Cfg::kBStageBytes);
+  uint8_t* staging = smem_b + SB * Cfg::kBStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + Cfg::kStagingBytes);
   uint64_t* a_full = bars;
   uint64_t* a_empty = bars + SA;
   uint64_t* b_full = bars + 2 * SA;
@@ -202,7 +205,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_c
       }
     }
   } else {
-    conv_epilogue_loop<BLOCK_N>(p, tmem_base, tfull_bar, tempty_bar, warp, lane);
+    conv_epilogue_loop<BLOCK_N>(p, tmem_base, tfull_bar, tempty_bar, warp, lane, &map_y_hi, &map_y_lo,
+                                (Cfg::kStagingBytes > 0 && p.y_hi != nullptr) ? staging : nullptr);
   }
 
   tc_fence_before();
@@ -233,6 +237,11 @@ static int launch_halo(const osvos_conv3x3_args* a, cudaStream_t stream, int use
   }
   int rc = encode_weight_maps(&mw_hi, &mw_lo, a, BLOCK_N);
   if (rc) return rc;
+  CUtensorMap my_hi = mw_hi, my_lo = mw_lo;  // placeholders when there is no act output
+  if (a->y_hi != nullptr && BLOCK_N >= 64) {
+    rc = encode_output_maps(&my_hi, &my_lo, a);
+    if (rc) return rc;
+  }
   auto kern = conv3x3_halo_kernel<BLOCK_N, PLANES, PITCH>;
   static bool attr_done = false;
   if (!attr_done) {
@@ -241,7 +250,7 @@ static int launch_halo(const osvos_conv3x3_args* a, cudaStream_t stream, int use
   }
   const int sms = device_sm_count();
   const int grid = p.total_tiles < sms ? p.total_tiles : sms;
-  kern<<<grid, kConvThreads, Cfg::kSmemBytes, stream>>>(mx_hi, mx_lo, mw_hi, mw_lo, p, use_bo);
+  kern<<<grid, kConvThreads, Cfg::kSmemBytes, stream>>>(mx_hi, mx_lo, mw_hi, mw_lo, my_hi, my_lo, p, use_bo);
   OSVOS_CHECK_CUDA(cudaGetLastError());
   return OSVOS_OK;
 }
@@ -255,8 +264,9 @@ static int dispatch_halo(const osvos_conv3x3_args* a, cudaStream_t stream, int u
 }
 
 int conv3x3_halo_dispatch(const osvos_conv3x3_args* a, cudaStream_t stream, int pitch, int use_bo) {
-  if (pitch == 10) return dispatch_halo<10>(a, stream, use_bo);
-  return dispatch_halo<16>(a, stream, use_bo);
+  (void)pitch;  // pitch 16 (padded rows) was validated equivalent on hardware and dropped: it no longer fits with
+                // the TMA-store staging buffer; packed rows (pitch 10) are the only instantiation.
+  return dispatch_halo<10>(a, stream, use_bo);
 }
 
 }  // namespace osvos

@@ -41,9 +41,20 @@ __device__ __forceinline__ void decode_tile(const ConvParams& p, int tile, int& 
 }
 
 // Epilogue of one warp (TMEM lane quarter q = warp & 3) over all tiles of this CTA.
+__device__ __forceinline__ uint32_t sw128_offset(int row, int chunk) { return row * 128 + ((chunk ^ (row & 7)) << 4); }
+__device__ __forceinline__ void epilogue_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// `staging` (2 x 16 KiB, 1 KiB aligned) + the output tensor maps enable the TMA-store path for the act
+// output: each 64-channel slab of the tile is written to shared memory in the SWIZZLE_128B layout and
+// stored with one bulk tensor copy per plane (full 128-byte rows, image edges clipped by the TMA unit)
+// instead of 16-byte scattered global stores.  staging == nullptr keeps the direct stores.
 template <int BLOCK_N>
 __device__ __forceinline__ void conv_epilogue_loop(const ConvParams& p, uint32_t tmem_base, uint64_t* tfull_bar,
-                                                   uint64_t* tempty_bar, int warp, int lane) {
+                                                   uint64_t* tempty_bar, int warp, int lane,
+                                                   const CUtensorMap* map_y_hi = nullptr,
+                                                   const CUtensorMap* map_y_lo = nullptr, uint8_t* staging = nullptr) {
+    const bool use_tma = (staging != nullptr) && (p.y_hi != nullptr);
+    const bool epi_leader = (warp == 2) && (lane == 0);
     const int q = warp & 3;  // TMEM lane quarter this warp may read
     const int row = q * 32 + lane;
     const int ly = row / kTileW, lx = row % kTileW;
@@ -138,7 +149,7 @@ __device__ __forceinline__ void conv_epilogue_loop(const ConvParams& p, uint32_t
 #pragma unroll
               for (int j = 0; j < 8; ++j) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
             }
-            if (p.y_hi) {
+            if (p.y_hi && !use_tma) {
               uint32_t hi[16], lo[16];
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
@@ -156,6 +167,40 @@ __device__ __forceinline__ void conv_epilogue_loop(const ConvParams& p, uint32_t
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
                   dl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+              }
+            }
+          }
+          if (use_tma) {
+            const int half = (c0 >> 5) & 1;
+            if (half == 0) {  // the previous slab's bulk store must have finished READING the staging buffer
+              if (epi_leader) tma_store_wait_read<0>();
+              epilogue_bar_sync();
+            }
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              __nv_bfloat16 h0, l0, h1, l1;
+              split_bf16(f[2 * j], h0, l0);
+              split_bf16(f[2 * j + 1], h1, l1);
+              hi[j] = pack_bf16x2(h0, h1);
+              lo[j] = pack_bf16x2(l0, l1);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t off = sw128_offset(row, half * 4 + j);
+              *reinterpret_cast<uint4*>(staging + off) = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+              if (p.y_lo)
+                *reinterpret_cast<uint4*>(staging + kABytes + off) =
+                    make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+            }
+            if (half == 1) {
+              fence_proxy_async_smem();
+              epilogue_bar_sync();
+              if (epi_leader) {
+                const int c64 = nb * BLOCK_N + (c0 & ~63);
+                tma_store_4d(map_y_hi, staging, c64, tx * kTileW, ty * kTileH, img);
+                if (p.y_lo) tma_store_4d(map_y_lo, staging + kABytes, c64, tx * kTileW, ty * kTileH, img);
+                tma_store_commit();
               }
             }
           }
@@ -208,6 +253,19 @@ __device__ __forceinline__ void conv_epilogue_loop(const ConvParams& p, uint32_t
       tc_fence_before();
       mbar_arrive(&tempty_bar[as]);
     }
+    if (use_tma && epi_leader) tma_store_wait_all<0>();
+}
+
+// Output act [n,h,w,cout] -> 4-D store maps with box {64, kTileW, kTileH, 1} (SWIZZLE_128B).
+static inline int encode_output_maps(CUtensorMap* hi, CUtensorMap* lo, const osvos_conv3x3_args* a) {
+  const uint64_t dims[4] = {(uint64_t)a->cout, (uint64_t)a->w, (uint64_t)a->h, (uint64_t)a->n};
+  const uint64_t strides[3] = {(uint64_t)a->cout * 2, (uint64_t)a->w * a->cout * 2, (uint64_t)a->h * a->w * a->cout * 2};
+  const uint32_t box[4] = {64, kTileW, kTileH, 1};
+  int rc = encode_tensor_map(hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 4, a->y_hi, dims, strides, box,
+                             CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+  return encode_tensor_map(lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 4, a->y_lo ? a->y_lo : a->y_hi, dims, strides, box,
+                           CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
 // ---- host helpers shared by the launchers ------------------------------------------------

@@ -20,17 +20,19 @@ constexpr int kFirstTcThreads = 320;  // warp 0 idle, warp 1 MMA, warps 2-5 epil
 constexpr int kFirstStages = 3;
 constexpr int kFirstStageBytes = 2 * kABytes;           // hi + lo planes of the A tile (128 rows x 128 B each)
 constexpr int kFirstBBytes = 2 * 64 * 128;              // hi + lo planes of the weights (64 rows x 128 B)
-constexpr int kFirstSmem = kFirstStages * kFirstStageBytes + kFirstBBytes + 1024 + 256;
-
-__device__ __forceinline__ uint32_t sw128_offset(int row, int chunk) { return row * 128 + ((chunk ^ (row & 7)) << 4); }
+constexpr int kFirstStagingBytes = 2 * kABytes;         // TMA-store staging (hi + lo slab of the output tile)
+constexpr int kFirstSmem = kFirstStages * kFirstStageBytes + kFirstBBytes + kFirstStagingBytes + 1024 + 256;
 
 template <int PLANES>
 __global__ void __launch_bounds__(kFirstTcThreads, 1)
-conv_first_tc_kernel(const float* __restrict__ x, const float* __restrict__ wgt, const ConvParams p) {
+conv_first_tc_kernel(const float* __restrict__ x, const float* __restrict__ wgt,
+                     const __grid_constant__ CUtensorMap map_y_hi, const __grid_constant__ CUtensorMap map_y_lo,
+                     const ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_b = smem + kFirstStages * kFirstStageBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + kFirstBBytes);
+  uint8_t* staging = smem_b + kFirstBBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + kFirstStagingBytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kFirstStages;
   uint64_t* tfull_bar = bars + 2 * kFirstStages;
@@ -117,7 +119,7 @@ conv_first_tc_kernel(const float* __restrict__ x, const float* __restrict__ wgt,
       }
     }
   } else if (warp >= 2 && warp < 6) {
-    conv_epilogue_loop<64>(p, tmem_base, tfull_bar, tempty_bar, warp, lane);
+    conv_epilogue_loop<64>(p, tmem_base, tfull_bar, tempty_bar, warp, lane, &map_y_hi, &map_y_lo, staging);
   } else if (warp >= 6) {
     // ------------------------------------------------------------- A builders
     const int row = (warp - 6) * 32 + lane;  // GEMM row = pixel of the tile
@@ -195,6 +197,11 @@ int conv_first_tc_launch(const float* x, const float* w_oihw, const float* bias,
   a.flags = flags;
   ConvParams p;
   fill_conv_params(p, &a, 64);
+  CUtensorMap my_hi, my_lo;
+  {
+    int rc = encode_output_maps(&my_hi, &my_lo, &a);
+    if (rc) return rc;
+  }
   const bool fast = (flags & OSVOS_FLAG_FAST) != 0;
   auto kern = fast ? conv_first_tc_kernel<1> : conv_first_tc_kernel<2>;
   static bool attr_done[2] = {false, false};
@@ -204,7 +211,7 @@ int conv_first_tc_launch(const float* x, const float* w_oihw, const float* bias,
   }
   const int sms = device_sm_count();
   const int grid = p.total_tiles < sms ? p.total_tiles : sms;
-  kern<<<grid, kFirstTcThreads, kFirstSmem, stream>>>(x, w_oihw, p);
+  kern<<<grid, kFirstTcThreads, kFirstSmem, stream>>>(x, w_oihw, my_hi, my_lo, p);
   OSVOS_CHECK_CUDA(cudaGetLastError());
   return OSVOS_OK;
 }

@@ -33,3 +33,13 @@ print(f"{'param':28s} {'(a) full':>10s} {'(b) oracle dL/dx':>16s}")
 for n in og:
     if n in ga:
         print(f"{n:28s} {rel(ga[n], og[n]):10.2e} {rel(gb[n], og[n]):16.2e}")
+
+# ReLU-mask agreement between the native forward activations and the oracle's (explains step-wise jumps above)
+from osvos_pytorch_b200 import ops
+with torch.no_grad():
+    stages = oc.trunk_forward(params, x)
+    _, inter = net._engine.forward_inference(x.cuda(), return_intermediates=True)
+for i in range(5):
+    got = ops.act_to_nchw(inter[f"stage{i}"]).cpu()
+    flips = int(((got > 0) != (stages[i] > 0)).sum())
+    print(f"stage {i} output: {flips} ReLU-mask flips of {got.numel()} (active {int((stages[i] > 0).sum())})")

@@ -54,5 +54,5 @@ def test_dp_allreduce_matches_reference_accumulation(tmp_path):
     for k, v in acc.items():
         err = float((got[k].double() - v.double()).norm() / v.double().norm())
         worst = max(worst, err)
-        assert err < (1e-3 if k.startswith(("fuse", "score_dsn", "side_prep")) else 1e-2), (k, err)
+        assert err < (1e-3 if k.startswith(("fuse", "score_dsn", "side_prep")) else 4e-2), (k, err)   # tiny-map flip bound, see test_gpu_backward.py
     print(f"DP x{world}: worst per-parameter gradient error vs single-process nAveGrad={world} oracle: {worst:.2e}")

@@ -28,7 +28,10 @@ struct HaloCfg {
   static constexpr int kAStages = 2;
   static constexpr int kBPlaneBytes = BLOCK_N * 128;
   static constexpr int kBStageBytes = PLANES * kBPlaneBytes;
-  static constexpr int kStagingBytes = BLOCK_N >= 64 ? 2 * kABytes : 0;   // TMA-store staging (hi + lo slab)
+  // TMA-store staging (hi + lo slab).  Measured on B200: the bulk-store epilogue is NOT faster than direct 16-byte
+  // stores here (the kernels are bound by the ~85-cycle tcgen05.mma instruction floor, not by the epilogue) and its
+  // 32 KiB cost one weight-ring stage, so it is compiled out (set to 2 * kABytes to re-enable).
+  static constexpr int kStagingBytes = 0;
   static constexpr int kBudget = 214 * 1024 - kAStages * kAStageBytes - kStagingBytes;
   static constexpr int kBStagesRaw = kBudget / kBStageBytes;
   static constexpr int kBStages = kBStagesRaw > 9 ? 9 : kBStagesRaw;
@@ -39,7 +42,7 @@ struct HaloCfg {
 };
 
 template <int BLOCK_N, int PLANES, int PITCH>
-__global__ void __launch_bounds__(kConvThreads, 1)
+__global__ void __launch_bounds__(64 + EpiCfg<BLOCK_N>::kThreads, 1)
 conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo,
                     const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
                     const __grid_constant__ CUtensorMap map_y_hi, const __grid_constant__ CUtensorMap map_y_lo,
@@ -81,7 +84,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_c
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 128);
+      mbar_init(&tempty_bar[i], EpiCfg<BLOCK_N>::kThreads);
     }
     fence_barrier_init();
   }
@@ -250,7 +253,7 @@ static int launch_halo(const osvos_conv3x3_args* a, cudaStream_t stream, int use
   }
   const int sms = device_sm_count();
   const int grid = p.total_tiles < sms ? p.total_tiles : sms;
-  kern<<<grid, kConvThreads, Cfg::kSmemBytes, stream>>>(mx_hi, mx_lo, mw_hi, mw_lo, my_hi, my_lo, p, use_bo);
+  kern<<<grid, 64 + EpiCfg<BLOCK_N>::kThreads, Cfg::kSmemBytes, stream>>>(mx_hi, mx_lo, mw_hi, mw_lo, my_hi, my_lo, p, use_bo);
   OSVOS_CHECK_CUDA(cudaGetLastError());
   return OSVOS_OK;
 }

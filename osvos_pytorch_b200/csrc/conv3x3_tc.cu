@@ -44,7 +44,7 @@ struct ConvCfg {
 };
 
 template <int BLOCK_N, int PLANES>
-__global__ void __launch_bounds__(kConvThreads, 1)
+__global__ void __launch_bounds__(64 + EpiCfg<BLOCK_N>::kThreads, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo,
                   const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
                   const ConvParams p) {
@@ -76,7 +76,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_con
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 128);
+      mbar_init(&tempty_bar[i], EpiCfg<BLOCK_N>::kThreads);
     }
     fence_barrier_init();
   }
@@ -213,7 +213,7 @@ static int launch_conv(const osvos_conv3x3_args* a, cudaStream_t stream) {
   }
   const int sms = device_sm_count();
   const int grid = p.total_tiles < sms ? p.total_tiles : sms;
-  kern<<<grid, kConvThreads, Cfg::kSmemBytes, stream>>>(mx_hi, mx_lo, mw_hi, mw_lo, p);
+  kern<<<grid, 64 + EpiCfg<BLOCK_N>::kThreads, Cfg::kSmemBytes, stream>>>(mx_hi, mx_lo, mw_hi, mw_lo, p);
   OSVOS_CHECK_CUDA(cudaGetLastError());
   return OSVOS_OK;
 }
@@ -231,6 +231,7 @@ static int check_conv_args(const osvos_conv3x3_args* a) {
   OSVOS_CHECK_ARG((a->pool_hi == nullptr && a->colsum == nullptr) || a->cout >= 64);
   OSVOS_CHECK_ARG((reinterpret_cast<uintptr_t>(a->x_hi) & 15) == 0);
   OSVOS_CHECK_ARG((reinterpret_cast<uintptr_t>(a->w_packed) & 15) == 0);
+  OSVOS_CHECK_ARG((reinterpret_cast<uintptr_t>(a->bias) & 15) == 0);
   return OSVOS_OK;
 }
 

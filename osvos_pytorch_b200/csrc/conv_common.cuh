@@ -42,8 +42,29 @@ __device__ __forceinline__ void decode_tile(const ConvParams& p, int tile, int& 
 
 // Epilogue of one warp (TMEM lane quarter q = warp & 3) over all tiles of this CTA.
 __device__ __forceinline__ uint32_t sw128_offset(int row, int chunk) { return row * 128 + ((chunk ^ (row & 7)) << 4); }
-__device__ __forceinline__ void epilogue_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epilogue_bar_sync(int nthreads) {
+  asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
+}
 
+// Two floats -> packed bf16x2 "hi" word (one F2FP) and the packed residual "lo" word: v ~= hi + lo.
+__device__ __forceinline__ void split_pack2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));            // upper half <- b, lower half <- a
+  const float ra = a - __uint_as_float(hi << 16);
+  const float rb = b - __uint_as_float(hi & 0xFFFF0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(rb), "f"(ra));
+}
+
+// Number of epilogue warps: 8 (two per TMEM lane quarter, each taking every other 32-column chunk) for
+// BLOCK_N >= 64, 4 for the N = 16 side-branch kernel.  The epilogue is instruction-bound (~125 cycles per
+// output column per tile with 4 warps), which made it the bottleneck of every small-K layer.
+template <int BLOCK_N>
+struct EpiCfg {
+  static constexpr int kGroups = BLOCK_N >= 64 ? 2 : 1;
+  static constexpr int kThreads = 128 * kGroups;
+};
+
+// Epilogue of one warp over all tiles of this CTA.  Epilogue warps are warps 2 .. 2 + 4*kGroups - 1; warp w
+// reads TMEM lane quarter (w & 3) and the 32-column chunks with index parity (w - 2) >> 2.
 // `staging` (2 x 16 KiB, 1 KiB aligned) + the output tensor maps enable the TMA-store path for the act
 // output: each 64-channel slab of the tile is written to shared memory in the SWIZZLE_128B layout and
 // stored with one bulk tensor copy per plane (full 128-byte rows, image edges clipped by the TMA unit)
@@ -53,207 +74,193 @@ __device__ __forceinline__ void conv_epilogue_loop(const ConvParams& p, uint32_t
                                                    uint64_t* tempty_bar, int warp, int lane,
                                                    const CUtensorMap* map_y_hi = nullptr,
                                                    const CUtensorMap* map_y_lo = nullptr, uint8_t* staging = nullptr) {
-    const bool use_tma = (staging != nullptr) && (p.y_hi != nullptr);
-    const bool epi_leader = (warp == 2) && (lane == 0);
-    const int q = warp & 3;  // TMEM lane quarter this warp may read
-    const int row = q * 32 + lane;
-    const int ly = row / kTileW, lx = row % kTileW;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-      int nb, tx, ty, img;
-      decode_tile(p, tile, nb, tx, ty, img);
-      const int as = it & 1;
-      const uint32_t aph = (it >> 1) & 1;
-      const int y = ty * kTileH + ly, x = tx * kTileW + lx;
-      const bool valid = (y < p.h) && (x < p.w);
-      const size_t pix = (static_cast<size_t>(img) * p.h + y) * p.w + x;
+  constexpr int kEpiThreads = EpiCfg<BLOCK_N>::kThreads;
+  const bool use_tma = (staging != nullptr) && (p.y_hi != nullptr);
+  const bool epi_leader = (warp == 2) && (lane == 0);
+  const int group = (warp - 2) >> 2;
+  const int q = warp & 3;  // TMEM lane quarter this warp may read
+  const int row = q * 32 + lane;
+  const int ly = row / kTileW, lx = row % kTileW;
+  const bool relu = (p.flags & OSVOS_FLAG_RELU) != 0;
+  const bool masked = (p.flags & OSVOS_FLAG_RELU_MASK) != 0;
+  int it = 0;
+  for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+    int nb, tx, ty, img;
+    decode_tile(p, tile, nb, tx, ty, img);
+    const int as = it & 1;
+    const uint32_t aph = (it >> 1) & 1;
+    const int y = ty * kTileH + ly, x = tx * kTileW + lx;
+    const bool valid = (y < p.h) && (x < p.w);
+    const size_t pix = (static_cast<size_t>(img) * p.h + y) * p.w + x;
 
-      mbar_wait(&tfull_bar[as], aph);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + as * BLOCK_N + (static_cast<uint32_t>(q * 32) << 16);
+    mbar_wait(&tfull_bar[as], aph);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + as * BLOCK_N + (static_cast<uint32_t>(q * 32) << 16);
 
-      if constexpr (BLOCK_N == 16) {
-        uint32_t v[16];
-        tmem_ld16(taddr, v);
-        tmem_ld_wait();
-        if (valid) {
-          float f[16];
+    if constexpr (BLOCK_N == 16) {
+      uint32_t v[16];
+      tmem_ld16(taddr, v);
+      tmem_ld_wait();
+      if (valid) {
+        float f[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            f[j] = __uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + j) : 0.f);
-            if (p.flags & OSVOS_FLAG_RELU) f[j] = fmaxf(f[j], 0.f);
-          }
-          if (p.y_f32) {
-            float4* dst = reinterpret_cast<float4*>(p.y_f32 + pix * 16);
+        for (int j = 0; j < 16; ++j) {
+          f[j] = __uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + j) : 0.f);
+          if (relu) f[j] = fmaxf(f[j], 0.f);
+        }
+        if (p.y_f32) {
+          float4* dst = reinterpret_cast<float4*>(p.y_f32 + pix * 16);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-          }
-          if (p.y_hi) {
-            uint32_t hi[8], lo[8];
+          for (int j = 0; j < 4; ++j) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+        }
+        if (p.y_hi) {
+          uint32_t hi[8], lo[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              __nv_bfloat16 h0, l0, h1, l1;
-              split_bf16(f[2 * j], h0, l0);
-              split_bf16(f[2 * j + 1], h1, l1);
-              hi[j] = pack_bf16x2(h0, h1);
-              lo[j] = pack_bf16x2(l0, l1);
-            }
-            uint4* dh = reinterpret_cast<uint4*>(p.y_hi + pix * 16);
-            dh[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            dh[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-            if (p.y_lo) {
-              uint4* dl = reinterpret_cast<uint4*>(p.y_lo + pix * 16);
-              dl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-              dl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
-            }
-          }
-          if (p.pq) {
-            float sp = p.proj_b ? __ldg(p.proj_b) : 0.f, sq = 0.f;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              sp = fmaf(f[j], __ldg(p.proj_w + j), sp);
-              sq = fmaf(f[j], __ldg(p.proj_w + 16 + j), sq);
-            }
-            *reinterpret_cast<float2*>(p.pq + pix * 2) = make_float2(sp, sq);
+          for (int j = 0; j < 8; ++j) split_pack2(f[2 * j], f[2 * j + 1], hi[j], lo[j]);
+          uint4* dh = reinterpret_cast<uint4*>(p.y_hi + pix * 16);
+          dh[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          dh[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+          if (p.y_lo) {
+            uint4* dl = reinterpret_cast<uint4*>(p.y_lo + pix * 16);
+            dl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            dl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
           }
         }
-      } else {
-#pragma unroll 1
-        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld32(taddr + c0, v);
-          tmem_ld_wait();
-          const int ch = nb * BLOCK_N + c0;
-          float f[32];
+        if (p.pq) {
+          float sp = p.proj_b ? __ldg(p.proj_b) : 0.f, sq = 0.f;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            f[j] = __uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + ch + j) : 0.f);
-            if (p.flags & OSVOS_FLAG_RELU) f[j] = fmaxf(f[j], 0.f);
+          for (int j = 0; j < 16; ++j) {
+            sp = fmaf(f[j], __ldg(p.proj_w + j), sp);
+            sq = fmaf(f[j], __ldg(p.proj_w + 16 + j), sq);
           }
-          if (valid) {
-            if (p.flags & OSVOS_FLAG_RELU_MASK) {
-              const uint4* mk = reinterpret_cast<const uint4*>(p.mask_hi + pix * p.cout + ch);
+          *reinterpret_cast<float2*>(p.pq + pix * 2) = make_float2(sp, sq);
+        }
+      }
+    } else {
+#pragma unroll 1
+      for (int slab = 0; slab < BLOCK_N / 64; ++slab) {
+        const int c0 = slab * 64 + group * 32;     // this warp's 32-column chunk of the 64-column slab
+        const int ch = nb * BLOCK_N + c0;
+        uint32_t v[32];
+        tmem_ld32(taddr + c0, v);
+        float f[32];
+        if (p.bias) {
+          const float4* bp = reinterpret_cast<const float4*>(p.bias + ch);
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const uint4 m = __ldg(mk + j);
-                const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+          for (int j = 0; j < 8; ++j) {
+            const float4 b4 = __ldg(bp + j);
+            f[4 * j] = b4.x, f[4 * j + 1] = b4.y, f[4 * j + 2] = b4.z, f[4 * j + 3] = b4.w;
+          }
+        } else {
 #pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                  if (!(bf16_lo_to_float(mw[t]) > 0.f)) f[8 * j + 2 * t] = 0.f;
-                  if (!(bf16_hi_to_float(mw[t]) > 0.f)) f[8 * j + 2 * t + 1] = 0.f;
-                }
-              }
+          for (int j = 0; j < 32; ++j) f[j] = 0.f;
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          f[j] += __uint_as_float(v[j]);
+          f[j] = relu ? fmaxf(f[j], 0.f) : f[j];
+        }
+        if (masked && valid) {
+          const uint4* mk = reinterpret_cast<const uint4*>(p.mask_hi + pix * p.cout + ch);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 m = __ldg(mk + j);
+            const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              if (!(bf16_lo_to_float(mw[t]) > 0.f)) f[8 * j + 2 * t] = 0.f;
+              if (!(bf16_hi_to_float(mw[t]) > 0.f)) f[8 * j + 2 * t + 1] = 0.f;
             }
-            if (p.y_f32) {
-              float4* dst = reinterpret_cast<float4*>(p.y_f32 + pix * p.cout + ch);
+          }
+        }
+        if (p.y_f32 && valid) {
+          float4* dst = reinterpret_cast<float4*>(p.y_f32 + pix * p.cout + ch);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-            }
-            if (p.y_hi && !use_tma) {
-              uint32_t hi[16], lo[16];
+          for (int j = 0; j < 8; ++j) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+        }
+        if (p.y_hi) {
+          uint32_t hi[16], lo[16];
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                __nv_bfloat16 h0, l0, h1, l1;
-                split_bf16(f[2 * j], h0, l0);
-                split_bf16(f[2 * j + 1], h1, l1);
-                hi[j] = pack_bf16x2(h0, h1);
-                lo[j] = pack_bf16x2(l0, l1);
-              }
+          for (int j = 0; j < 16; ++j) split_pack2(f[2 * j], f[2 * j + 1], hi[j], lo[j]);
+          if (!use_tma) {
+            if (valid) {
               uint4* dh = reinterpret_cast<uint4*>(p.y_hi + pix * p.cout + ch);
 #pragma unroll
               for (int j = 0; j < 4; ++j) dh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
               if (p.y_lo) {
                 uint4* dl = reinterpret_cast<uint4*>(p.y_lo + pix * p.cout + ch);
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                  dl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+                for (int j = 0; j < 4; ++j) dl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
               }
             }
-          }
-          if (use_tma) {
-            const int half = (c0 >> 5) & 1;
-            if (half == 0) {  // the previous slab's bulk store must have finished READING the staging buffer
-              if (epi_leader) tma_store_wait_read<0>();
-              epilogue_bar_sync();
-            }
-            uint32_t hi[16], lo[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              __nv_bfloat16 h0, l0, h1, l1;
-              split_bf16(f[2 * j], h0, l0);
-              split_bf16(f[2 * j + 1], h1, l1);
-              hi[j] = pack_bf16x2(h0, h1);
-              lo[j] = pack_bf16x2(l0, l1);
-            }
+          } else {
+            // the previous slab's bulk store must have finished READING the staging buffer
+            if (epi_leader) tma_store_wait_read<0>();
+            epilogue_bar_sync(kEpiThreads);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const uint32_t off = sw128_offset(row, half * 4 + j);
+              const uint32_t off = sw128_offset(row, group * 4 + j);
               *reinterpret_cast<uint4*>(staging + off) = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
               if (p.y_lo)
                 *reinterpret_cast<uint4*>(staging + kABytes + off) =
                     make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
             }
-            if (half == 1) {
-              fence_proxy_async_smem();
-              epilogue_bar_sync();
-              if (epi_leader) {
-                const int c64 = nb * BLOCK_N + (c0 & ~63);
-                tma_store_4d(map_y_hi, staging, c64, tx * kTileW, ty * kTileH, img);
-                if (p.y_lo) tma_store_4d(map_y_lo, staging + kABytes, c64, tx * kTileW, ty * kTileH, img);
-                tma_store_commit();
-              }
+            fence_proxy_async_smem();
+            epilogue_bar_sync(kEpiThreads);
+            if (epi_leader) {
+              const int c64 = nb * BLOCK_N + slab * 64;
+              tma_store_4d(map_y_hi, staging, c64, tx * kTileW, ty * kTileH, img);
+              if (p.y_lo) tma_store_4d(map_y_lo, staging + kABytes, c64, tx * kTileW, ty * kTileH, img);
+              tma_store_commit();
             }
           }
-          if (p.colsum) {
-            // fused bias gradient: per-channel sum of this warp's 32 pixels (butterfly), one atomic per lane
-            float mine = 0.f;
+        }
+        if (p.colsum) {
+          // fused bias gradient: per-channel sum of this warp's 32 pixels (butterfly), one atomic per lane
+          float mine = 0.f;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float sj = valid ? f[j] : 0.f;
+          for (int j = 0; j < 32; ++j) {
+            float sj = valid ? f[j] : 0.f;
 #pragma unroll
-              for (int off = 16; off > 0; off >>= 1) sj += __shfl_xor_sync(0xffffffffu, sj, off);
-              if (lane == j) mine = sj;
-            }
-            atomicAdd(p.colsum + ch + lane, mine);
+            for (int off = 16; off > 0; off >>= 1) sj += __shfl_xor_sync(0xffffffffu, sj, off);
+            if (lane == j) mine = sj;
           }
-          if (p.pool_hi) {
-            // fused MaxPool2d(2, 2, ceil_mode=True): the 2x2 partners are lanes ^1 (x) and ^8 (y) of this warp;
-            // out-of-image partners are excluded (ceil mode clips the window).
-            const int oh = (p.h + 1) >> 1, ow = (p.w + 1) >> 1;
-            const bool writer = valid && !(lx & 1) && !(ly & 1);
-            const size_t opix = (static_cast<size_t>(img) * oh + (y >> 1)) * ow + (x >> 1);
-            uint32_t hi[16], lo[16];
+          atomicAdd(p.colsum + ch + lane, mine);
+        }
+        if (p.pool_hi) {
+          // fused MaxPool2d(2, 2, ceil_mode=True): the 2x2 partners are lanes ^1 (x) and ^8 (y) of this warp;
+          // out-of-image partners are excluded (ceil mode clips the window).
+          const int oh = (p.h + 1) >> 1, ow = (p.w + 1) >> 1;
+          const bool writer = valid && !(lx & 1) && !(ly & 1);
+          const size_t opix = (static_cast<size_t>(img) * oh + (y >> 1)) * ow + (x >> 1);
+          uint32_t hi[16], lo[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              float m0 = valid ? f[2 * j] : -INFINITY, m1 = valid ? f[2 * j + 1] : -INFINITY;
-              m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
-              m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
-              m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 8));
-              m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 8));
-              __nv_bfloat16 h0, l0, h1, l1;
-              split_bf16(m0, h0, l0);
-              split_bf16(m1, h1, l1);
-              hi[j] = pack_bf16x2(h0, h1);
-              lo[j] = pack_bf16x2(l0, l1);
-            }
-            if (writer) {
-              uint4* dh = reinterpret_cast<uint4*>(p.pool_hi + opix * p.cout + ch);
+          for (int j = 0; j < 16; ++j) {
+            float m0 = valid ? f[2 * j] : -INFINITY, m1 = valid ? f[2 * j + 1] : -INFINITY;
+            m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
+            m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+            m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 8));
+            m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 8));
+            split_pack2(m0, m1, hi[j], lo[j]);
+          }
+          if (writer) {
+            uint4* dh = reinterpret_cast<uint4*>(p.pool_hi + opix * p.cout + ch);
 #pragma unroll
-              for (int j = 0; j < 4; ++j) dh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-              if (p.pool_lo) {
-                uint4* dl = reinterpret_cast<uint4*>(p.pool_lo + opix * p.cout + ch);
+            for (int j = 0; j < 4; ++j) dh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+            if (p.pool_lo) {
+              uint4* dl = reinterpret_cast<uint4*>(p.pool_lo + opix * p.cout + ch);
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                  dl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
-              }
+              for (int j = 0; j < 4; ++j) dl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
             }
           }
         }
       }
-      tc_fence_before();
-      mbar_arrive(&tempty_bar[as]);
     }
-    if (use_tma && epi_leader) tma_store_wait_all<0>();
+    tc_fence_before();
+    mbar_arrive(&tempty_bar[as]);
+  }
+  if (use_tma && epi_leader) tma_store_wait_all<0>();
 }
 
 // Output act [n,h,w,cout] -> 4-D store maps with box {64, kTileW, kTileH, 1} (SWIZZLE_128B).

@@ -16,7 +16,7 @@
 
 namespace osvos {
 
-constexpr int kFirstTcThreads = 320;  // warp 0 idle, warp 1 MMA, warps 2-5 epilogue, warps 6-9 A builders
+constexpr int kFirstTcThreads = 448;  // warp 0 idle, warp 1 MMA, warps 2-9 epilogue, warps 10-13 A builders
 constexpr int kFirstStages = 3;
 constexpr int kFirstStageBytes = 2 * kABytes;           // hi + lo planes of the A tile (128 rows x 128 B each)
 constexpr int kFirstBBytes = 2 * 64 * 128;              // hi + lo planes of the weights (64 rows x 128 B)
@@ -49,7 +49,7 @@ conv_first_tc_kernel(const float* __restrict__ x, const float* __restrict__ wgt,
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 128);
+      mbar_init(&tempty_bar[i], EpiCfg<64>::kThreads);
     }
     fence_barrier_init();
   }
@@ -118,11 +118,11 @@ conv_first_tc_kernel(const float* __restrict__ x, const float* __restrict__ wgt,
         phase ^= 1;
       }
     }
-  } else if (warp >= 2 && warp < 6) {
+  } else if (warp >= 2 && warp < 10) {
     conv_epilogue_loop<64>(p, tmem_base, tfull_bar, tempty_bar, warp, lane, &map_y_hi, &map_y_lo, staging);
-  } else if (warp >= 6) {
+  } else if (warp >= 10) {
     // ------------------------------------------------------------- A builders
-    const int row = (warp - 6) * 32 + lane;  // GEMM row = pixel of the tile
+    const int row = (warp - 10) * 32 + lane;  // GEMM row = pixel of the tile
     const int ly = row / kTileW, lx = row % kTileW;
     int stage = 0;
     uint32_t phase = 0;

@@ -6,6 +6,8 @@ stream handling; all arithmetic is in csrc/.
 Call graph replaced: reference networks/vgg_osvos.py:59-74 (forward) and, in
 training, the autograd graph PyTorch builds for it.
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -19,6 +21,11 @@ class OSVOSEngine:
         object.__setattr__(self, "m", module)
         self._pack_cache = {}
         self._deconv_checked = {}
+        # CUDA-graph cache for the inference path: (shape, device, precision, parameter versions) -> captured step.
+        # One frame is ~22 kernel launches; replaying a graph removes the Python / launch overhead (OSVOS_CUDA_GRAPH=0
+        # disables it).
+        self._graphs = {}
+        self.use_cuda_graph = os.environ.get("OSVOS_CUDA_GRAPH", "1") != "0"
 
     # ------------------------------------------------------------ weight caches
     def _cached(self, key, params, make):
@@ -77,7 +84,37 @@ class OSVOSEngine:
         if needs_grad:
             from .autograd import osvos_apply
             return osvos_apply(self, x)
+        if self.use_cuda_graph and not torch.cuda.is_current_stream_capturing():
+            return self._forward_graphed(x)
         return self.forward_inference(x)
+
+    def _forward_graphed(self, x):
+        """Inference through a captured CUDA graph: copy the frame into the static input, replay, hand back fresh
+        output tensors (one device copy of the five maps).  Re-captured when shapes or parameters change."""
+        m = self.m
+        key = (tuple(x.shape), x.device.index, m.precision,
+               tuple((p.data_ptr(), p._version) for p in m.parameters()))
+        entry = self._graphs.get(key)
+        if entry is None:
+            if len(self._graphs) >= 4:                       # bounded: each entry pins its activation pool
+                self._graphs.pop(next(iter(self._graphs)))
+            self.forward_inference(x)                        # eager warm-up: packs weights, sets kernel attributes
+            static_x = x.detach().contiguous().float().clone()
+            torch.cuda.synchronize(x.device)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                outs = self.forward_inference(static_x)
+            base = outs[0]._base if outs[0]._base is not None else None
+            entry = (graph, static_x, outs, base)
+            self._graphs[key] = entry
+        graph, static_x, outs, base = entry
+        static_x.copy_(x, non_blocking=True)
+        graph.replay()
+        if base is not None:
+            fresh = base.clone()
+            n, _, h, w = (int(v) for v in x.shape)
+            return [fresh[k, :n * h * w].view(n, 1, h, w) for k in range(5)]
+        return [o.clone() for o in outs]
 
     @torch.no_grad()
     def forward_inference(self, x, simt=False, return_intermediates=False):

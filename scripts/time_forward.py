@@ -26,6 +26,17 @@ torch.cuda.synchronize()
 ms = ev[0].elapsed_time(ev[1]) / reps
 print(f"forward {h}x{w} {prec}: {ms:.3f} ms/frame = {1000/ms:.1f} fps; conv TFLOP/s (algorithmic) {oc.conv_flops(h, w)/ms/1e9:.1f}")
 
+net._engine.use_cuda_graph = False
+for _ in range(3):
+    net(x)
+torch.cuda.synchronize()
+ev[0].record()
+for _ in range(reps):
+    net(x)
+ev[1].record()
+torch.cuda.synchronize()
+ms_e = ev[0].elapsed_time(ev[1]) / reps
+print(f"  (eager, no CUDA graph: {ms_e:.3f} ms/frame = {1000/ms_e:.1f} fps)")
 # per-op timing by wrapping ops
 import osvos_pytorch_b200.ops as O
 rec = []

@@ -86,9 +86,21 @@ def cpu_reference_fps(steps, warmup, workload):
     import torch
     from oracle import osvos_oracle as oc
     cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     params = oc.he_params(seed=0)
     x, gt = oc.synthetic_frame(1, H, W, 1234)
+
+    def probe(threads):
+        torch.set_num_threads(threads)
+        with torch.no_grad():
+            oc.osvos_forward(params, x)          # warm-up (thread pool, MKLDNN primitives)
+            t0 = time.perf_counter()
+            oc.osvos_forward(params, x)
+        return time.perf_counter() - t0
+    # "all the host threads it can use": torch's CPU conv slows down when oversubscribed on many-core hosts,
+    # so the thread count is the fastest of {all cores, 64, 32, 16} on a one-frame probe.
+    cands = sorted({c for c in (cores, 64, 32, 16) if c <= cores}, reverse=True)
+    best = min(cands, key=probe)
+    torch.set_num_threads(best)
 
     def one():
         if workload == "train480":
@@ -188,10 +200,6 @@ def run_parent(args, rank, world, local, dev):
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
-
-
-def conv_calls_per_step(rec):
-    return 16          # 12 trunk convs (conv1_1 is a separate kernel) + 4 side_prep convs per forward
 
 
 def main():
@@ -316,14 +324,16 @@ def main():
         eng.ops.conv3x3 = wrapped
         net._engine.use_cuda_graph = False          # per-launch events need the eager path
         reps = min(steps, 20)
+        for i in range(3):                          # eager warm-up passes, not counted
+            step(i)
+        torch.cuda.synchronize()
+        rec.clear()
         for i in range(reps):
             step(i)
         torch.cuda.synchronize()
         ops.conv3x3 = orig
         eng.ops.conv3x3 = orig
         net._engine.use_cuda_graph = graphs_on
-        rec = rec[-(len(rec) // reps) * (reps - 3):] if reps > 5 else rec     # drop the first passes (warm-up)
-        reps = max(1, len(rec) // max(1, conv_calls_per_step(rec)))
         conv_ms = sum(s.elapsed_time(e) for s, e, _ in rec) / reps
         conv_flops = sum(f for _, _, f in rec) / reps
         conv_calls = len(rec) // reps

@@ -28,6 +28,7 @@ struct ConvParams {
   float* colsum;           // optional fused per-channel sum of the output (bias gradient), atomically accumulated
   int n, h, w, cin, cout;
   int tiles_x, tiles_y, n_blocks, total_tiles, k_chunks;
+  int m_tiles, total_pairs;  // CTA-pair kernels: m_tiles pixel tiles, total_pairs = ceil(m_tiles / 2) * n_blocks work items
   int flags;
 };
 
@@ -63,17 +64,40 @@ struct EpiCfg {
   static constexpr int kThreads = 128 * kGroups;
 };
 
+// CTA-pair work item w -> this CTA's pixel tile (rank 0 / 1 take the even / odd tile of the pair).  A pair whose
+// second tile does not exist gets a dummy tile placed below the image: TMA zero-fills it and nothing is stored.
+__device__ __forceinline__ void decode_pair(const ConvParams& p, int w, int rank, int& nb, int& tx, int& ty, int& img) {
+  nb = w % p.n_blocks;
+  int m = 2 * (w / p.n_blocks) + rank;
+  if (m >= p.m_tiles) {
+    tx = 0;
+    ty = p.tiles_y;
+    img = p.n - 1;
+    return;
+  }
+  tx = m % p.tiles_x;
+  m /= p.tiles_x;
+  ty = m % p.tiles_y;
+  img = m / p.tiles_y;
+}
+
 // Epilogue of one warp over all tiles of this CTA.  Epilogue warps are warps 2 .. 2 + 4*kGroups - 1; warp w
 // reads TMEM lane quarter (w & 3) and the 32-column chunks with index parity (w - 2) >> 2.
 // `staging` (2 x 16 KiB, 1 KiB aligned) + the output tensor maps enable the TMA-store path for the act
 // output: each 64-channel slab of the tile is written to shared memory in the SWIZZLE_128B layout and
 // stored with one bulk tensor copy per plane (full 128-byte rows, image edges clipped by the TMA unit)
 // instead of 16-byte scattered global stores.  staging == nullptr keeps the direct stores.
-template <int BLOCK_N>
+template <int BLOCK_N, bool PAIR = false>
 __device__ __forceinline__ void conv_epilogue_loop(const ConvParams& p, uint32_t tmem_base, uint64_t* tfull_bar,
                                                    uint64_t* tempty_bar, int warp, int lane,
                                                    const CUtensorMap* map_y_hi = nullptr,
                                                    const CUtensorMap* map_y_lo = nullptr, uint8_t* staging = nullptr) {
+  // PAIR: this CTA is one half of a cta_group::2 pair; the TMEM-empty barrier lives in the leader (rank 0)
+  const int rank = PAIR ? static_cast<int>(cluster_ctarank()) : 0;
+  const int w_first = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int w_stride = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const int w_total = PAIR ? p.total_pairs : p.total_tiles;
+  const uint32_t tempty_remote = PAIR ? mapa_shared(smem_u32(tempty_bar), 0) : 0u;
   constexpr int kEpiThreads = EpiCfg<BLOCK_N>::kThreads;
   const bool use_tma = (staging != nullptr) && (p.y_hi != nullptr);
   const bool epi_leader = (warp == 2) && (lane == 0);
@@ -84,9 +108,10 @@ __device__ __forceinline__ void conv_epilogue_loop(const ConvParams& p, uint32_t
   const bool relu = (p.flags & OSVOS_FLAG_RELU) != 0;
   const bool masked = (p.flags & OSVOS_FLAG_RELU_MASK) != 0;
   int it = 0;
-  for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+  for (int tile = w_first; tile < w_total; tile += w_stride, ++it) {
     int nb, tx, ty, img;
-    decode_tile(p, tile, nb, tx, ty, img);
+    if (PAIR) decode_pair(p, tile, rank, nb, tx, ty, img);
+    else decode_tile(p, tile, nb, tx, ty, img);
     const int as = it & 1;
     const uint32_t aph = (it >> 1) & 1;
     const int y = ty * kTileH + ly, x = tx * kTileW + lx;
@@ -258,7 +283,8 @@ __device__ __forceinline__ void conv_epilogue_loop(const ConvParams& p, uint32_t
       }
     }
     tc_fence_before();
-    mbar_arrive(&tempty_bar[as]);
+    if (PAIR) mbar_arrive_cluster(tempty_remote + as * 8);
+    else mbar_arrive(&tempty_bar[as]);
   }
   if (use_tma && epi_leader) tma_store_wait_all<0>();
 }
@@ -297,6 +323,8 @@ static inline void fill_conv_params(ConvParams& p, const osvos_conv3x3_args* a, 
   p.tiles_y = (a->h + kTileH - 1) / kTileH;
   p.n_blocks = a->cout / block_n;
   p.total_tiles = p.tiles_x * p.tiles_y * a->n * p.n_blocks;
+  p.m_tiles = p.tiles_x * p.tiles_y * a->n;
+  p.total_pairs = ((p.m_tiles + 1) / 2) * p.n_blocks;
   p.k_chunks = a->cin / kBlockK;
   p.flags = a->flags;
 }
@@ -317,6 +345,7 @@ static inline int encode_weight_maps(CUtensorMap* hi, CUtensorMap* lo, const osv
 
 int conv_first_tc_launch(const float* x, const float* w_oihw, const float* bias, void* y_hi, void* y_lo, int n, int h,
                          int w, int flags, cudaStream_t stream);
+int conv3x3_halo2_dispatch(const osvos_conv3x3_args* a, cudaStream_t stream);
 int conv3x3_halo_dispatch(const osvos_conv3x3_args* a, cudaStream_t stream, int pitch, int use_bo);
 
 }  // namespace osvos

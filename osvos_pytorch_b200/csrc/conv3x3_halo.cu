@@ -32,10 +32,16 @@ struct HaloCfg {
   // stores here (the kernels are bound by the ~85-cycle tcgen05.mma instruction floor, not by the epilogue) and its
   // 32 KiB cost one weight-ring stage, so it is compiled out (set to 2 * kABytes to re-enable).
   static constexpr int kStagingBytes = 0;
-  static constexpr int kBudget = 214 * 1024 - kAStages * kAStageBytes - kStagingBytes;
+  static constexpr int kBudget = 225 * 1024 - kAStages * kAStageBytes - kStagingBytes;   // 227 KiB per CTA minus align/barriers
   static constexpr int kBStagesRaw = kBudget / kBStageBytes;
   static constexpr int kBStages = kBStagesRaw > 9 ? 9 : kBStagesRaw;
-  static constexpr int kTmemCols = (2 * BLOCK_N) < 32 ? 32 : 2 * BLOCK_N;
+  // Exact mode with BLOCK_N <= 128: N-concatenated split-B.  The hi and lo weight planes are contiguous in the B
+  // stage, so ONE tcgen05.mma of N = 2 * BLOCK_N computes [A_hi.B_hi | A_hi.B_lo] into two column halves of the
+  // accumulator; with the N = BLOCK_N pass A_lo.B_hi that is 2 instructions per K step instead of 3 (the per-
+  // instruction floor of ~85 cycles makes instruction count, not flops, the cost).  The epilogue adds the halves.
+  static constexpr bool kSplitAcc = (PLANES == 2) && (BLOCK_N <= 128);
+  static constexpr int kAccCols = kSplitAcc ? 2 * BLOCK_N : BLOCK_N;
+  static constexpr int kTmemCols = (2 * kAccCols) < 32 ? 32 : 2 * kAccCols;
   static constexpr int kSmemBytes = kAStages * kAStageBytes + kBStages * kBStageBytes + kStagingBytes + 1024 + 512;
   static_assert(kBStages >= 2, "weight ring too shallow");
   static_assert(kBStageBytes % 1024 == 0, "B stage must keep 1024-byte alignment");
@@ -148,6 +154,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_c
     // -------------------------------------------------------------- MMA issuer (warp-uniform, elected lane issues)
     {
       constexpr uint32_t idesc = make_idesc_f16(kBlockM, BLOCK_N, /*bf16=*/true);
+      constexpr uint32_t idesc2 = make_idesc_f16(kBlockM, Cfg::kSplitAcc ? 2 * BLOCK_N : BLOCK_N, /*bf16=*/true);
       int a_stage = 0, b_stage = 0;
       uint32_t a_phase = 0, b_phase = 0;
       int it = 0;
@@ -156,7 +163,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_c
         const uint32_t aph = (it >> 1) & 1;
         mbar_wait(&tempty_bar[as], aph ^ 1);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + as * BLOCK_N;
+        const uint32_t tmem_d = tmem_base + as * Cfg::kAccCols;
         for (int kc = 0; kc < p.k_chunks; ++kc) {
           mbar_wait(&a_full[a_stage], a_phase);
           tc_fence_after();
@@ -180,7 +187,10 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_c
             for (int k = 0; k < kBlockK / 16; ++k) {
               const uint64_t adv = static_cast<uint64_t>(k * 2);
               const uint32_t first = (kc | tap | k) != 0;
-              if (PLANES == 2) {
+              if (Cfg::kSplitAcc) {
+                umma_f16(tmem_d, da_hi + adv, db_hi + adv, idesc2, first);   // [A_hi.B_hi | A_hi.B_lo], N = 2 * BLOCK_N
+                umma_f16(tmem_d, da_lo + adv, db_hi + adv, idesc, 1);        // + A_lo.B_hi into the first half
+              } else if (PLANES == 2) {
                 umma_f16(tmem_d, da_lo + adv, db_hi + adv, idesc, first);
                 umma_f16(tmem_d, da_hi + adv, db_lo + adv, idesc, 1);
                 umma_f16(tmem_d, da_hi + adv, db_hi + adv, idesc, 1);
@@ -208,8 +218,9 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_c
       }
     }
   } else {
-    conv_epilogue_loop<BLOCK_N>(p, tmem_base, tfull_bar, tempty_bar, warp, lane, &map_y_hi, &map_y_lo,
-                                (Cfg::kStagingBytes > 0 && p.y_hi != nullptr) ? staging : nullptr);
+    conv_epilogue_loop<BLOCK_N, false, Cfg::kSplitAcc>(p, tmem_base, tfull_bar, tempty_bar, warp, lane, &map_y_hi,
+                                                       &map_y_lo,
+                                                       (Cfg::kStagingBytes > 0 && p.y_hi != nullptr) ? staging : nullptr);
   }
 
   tc_fence_before();
@@ -263,6 +274,17 @@ static int dispatch_halo(const osvos_conv3x3_args* a, cudaStream_t stream, int u
   const bool fast = (a->flags & OSVOS_FLAG_FAST) != 0;
   if (a->cout == 16) return fast ? launch_halo<16, 1, PITCH>(a, stream, use_bo) : launch_halo<16, 2, PITCH>(a, stream, use_bo);
   if (a->cout == 64) return fast ? launch_halo<64, 1, PITCH>(a, stream, use_bo) : launch_halo<64, 2, PITCH>(a, stream, use_bo);
+  // N = 256 tiles (one tcgen05.mma of 128 cycles instead of two of ~85-100) whenever there are enough pixel tiles
+  // to fill the chip; OSVOS_CONV_N256=0 disables.
+  const char* n256 = getenv("OSVOS_CONV_N256");
+  const int m_tiles = ((a->w + kTileW - 1) / kTileW) * ((a->h + kTileH - 1) / kTileH) * a->n;
+  const int sms = device_sm_count();
+  const long waves128 = (static_cast<long>(m_tiles) * (a->cout / 128) + sms - 1) / sms;
+  const long waves256 = (static_cast<long>(m_tiles) * (a->cout / 256) + sms - 1) / sms;
+  // measured cycles per (tap, 64-channel) step: N = 128 ~ 1000 (2 + 1 instructions), N = 256 ~ 2200 exact
+  const bool prefer256 = fast ? waves256 * 1100 < waves128 * 700 : waves256 * 2200 < waves128 * 1000;
+  if (a->cout % 256 == 0 && prefer256 && !(n256 && atoi(n256) == 0))
+    return fast ? launch_halo<256, 1, PITCH>(a, stream, use_bo) : launch_halo<256, 2, PITCH>(a, stream, use_bo);
   return fast ? launch_halo<128, 1, PITCH>(a, stream, use_bo) : launch_halo<128, 2, PITCH>(a, stream, use_bo);
 }
 

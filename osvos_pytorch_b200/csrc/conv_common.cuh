@@ -87,7 +87,9 @@ __device__ __forceinline__ void decode_pair(const ConvParams& p, int w, int rank
 // output: each 64-channel slab of the tile is written to shared memory in the SWIZZLE_128B layout and
 // stored with one bulk tensor copy per plane (full 128-byte rows, image edges clipped by the TMA unit)
 // instead of 16-byte scattered global stores.  staging == nullptr keeps the direct stores.
-template <int BLOCK_N, bool PAIR = false>
+// SPLIT_ACC: the accumulator stage holds 2 * BLOCK_N columns - [A.B_hi | A.B_lo] produced by one N-concatenated
+// tcgen05.mma - and the result is the sum of the two halves.
+template <int BLOCK_N, bool PAIR = false, bool SPLIT_ACC = false>
 __device__ __forceinline__ void conv_epilogue_loop(const ConvParams& p, uint32_t tmem_base, uint64_t* tfull_bar,
                                                    uint64_t* tempty_bar, int warp, int lane,
                                                    const CUtensorMap* map_y_hi = nullptr,
@@ -120,17 +122,20 @@ __device__ __forceinline__ void conv_epilogue_loop(const ConvParams& p, uint32_t
 
     mbar_wait(&tfull_bar[as], aph);
     tc_fence_after();
-    const uint32_t taddr = tmem_base + as * BLOCK_N + (static_cast<uint32_t>(q * 32) << 16);
+    constexpr int kAccCols = SPLIT_ACC ? 2 * BLOCK_N : BLOCK_N;
+    const uint32_t taddr = tmem_base + as * kAccCols + (static_cast<uint32_t>(q * 32) << 16);
 
     if constexpr (BLOCK_N == 16) {
       uint32_t v[16];
       tmem_ld16(taddr, v);
+      uint32_t v2[16];
+      if (SPLIT_ACC) tmem_ld16(taddr + 16, v2);
       tmem_ld_wait();
       if (valid) {
         float f[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          f[j] = __uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + j) : 0.f);
+          f[j] = __uint_as_float(v[j]) + (SPLIT_ACC ? __uint_as_float(v2[j]) : 0.f) + (p.bias ? __ldg(p.bias + j) : 0.f);
           if (relu) f[j] = fmaxf(f[j], 0.f);
         }
         if (p.y_f32) {
@@ -168,6 +173,8 @@ __device__ __forceinline__ void conv_epilogue_loop(const ConvParams& p, uint32_t
         const int ch = nb * BLOCK_N + c0;
         uint32_t v[32];
         tmem_ld32(taddr + c0, v);
+        uint32_t v2[32];
+        if (SPLIT_ACC) tmem_ld32(taddr + BLOCK_N + c0, v2);
         float f[32];
         if (p.bias) {
           const float4* bp = reinterpret_cast<const float4*>(p.bias + ch);
@@ -184,6 +191,7 @@ __device__ __forceinline__ void conv_epilogue_loop(const ConvParams& p, uint32_t
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           f[j] += __uint_as_float(v[j]);
+          if (SPLIT_ACC) f[j] += __uint_as_float(v2[j]);
           f[j] = relu ? fmaxf(f[j], 0.f) : f[j];
         }
         if (masked && valid) {

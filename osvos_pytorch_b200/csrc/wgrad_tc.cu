@@ -49,7 +49,12 @@ struct WgCfg {
   static constexpr int kStageBytes = PLANES * (kPBytes + kQBytes);
   static constexpr int kStagesRaw = (212 * 1024) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
-  static constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
+  // Exact mode: N-concatenated split-Q.  The hi and lo planes of the Q tile are contiguous (uniform LBO between
+  // the 64-wide MN atoms), so one tcgen05.mma of N = 2 * BLOCK_N yields [P_hi.Q_hi | P_hi.Q_lo]; with P_lo.Q_hi
+  // that is 2 instructions per K step instead of 3 (see conv3x3_halo.cu).  The epilogue adds the two halves.
+  static constexpr bool kSplitAcc = (PLANES == 2) && (BLOCK_N <= 128);
+  static constexpr int kAccCols = kSplitAcc ? 2 * BLOCK_N : BLOCK_N;
+  static constexpr int kTmemCols = 2 * kAccCols < 32 ? 32 : 2 * kAccCols;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
 };
 
@@ -148,6 +153,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_p_hi, const __grid_const
   } else if (warp == 1) {
     {
       constexpr uint32_t idesc = make_idesc_f16(128, BLOCK_N, true, /*a_mn=*/true, /*b_mn=*/true);
+      constexpr uint32_t idesc2 = make_idesc_f16(128, Cfg::kAccCols, true, /*a_mn=*/true, /*b_mn=*/true);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -161,7 +167,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_p_hi, const __grid_const
         const uint32_t aph = (it >> 1) & 1;
         mbar_wait(&tempty_bar[as], aph ^ 1);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + as * BLOCK_N;
+        const uint32_t tmem_d = tmem_base + as * Cfg::kAccCols;
         for (int patch = pb; patch < pe; ++patch) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -177,7 +183,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_p_hi, const __grid_const
           for (int k = 0; k < kWgBlockK / 16; ++k) {
             const uint64_t adv = static_cast<uint64_t>(k * (2048 >> 4));  // 16 pixel rows x 128 B
             const uint32_t acc = (patch != pb || k != 0) ? 1u : 0u;
-            if (PLANES == 2) {
+            if (Cfg::kSplitAcc) {
+              umma_f16(tmem_d, dp_hi + adv, dq_hi + adv, idesc2, acc);   // [P_hi.Q_hi | P_hi.Q_lo]
+              umma_f16(tmem_d, dp_lo + adv, dq_hi + adv, idesc, 1);      // + P_lo.Q_hi into the first half
+            } else if (PLANES == 2) {
               umma_f16(tmem_d, dp_lo + adv, dq_hi + adv, idesc, acc);
               umma_f16(tmem_d, dp_hi + adv, dq_lo + adv, idesc, 1);
               umma_f16(tmem_d, dp_hi + adv, dq_hi + adv, idesc, 1);
@@ -208,18 +217,25 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_p_hi, const __grid_const
       const int m = mb * 128 + row;
       mbar_wait(&tfull_bar[as], aph);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + as * BLOCK_N + (static_cast<uint32_t>(q * 32) << 16);
+      const uint32_t taddr = tmem_base + as * Cfg::kAccCols + (static_cast<uint32_t>(q * 32) << 16);
       float* dst = p.ws + (static_cast<size_t>(tap) * p.m_total + m) * p.n_total + nb * BLOCK_N;
 #pragma unroll 1
       for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-        uint32_t v[32];
+        uint32_t v[32], v2[32];
         tmem_ld32(taddr + c0, v);
+        if (Cfg::kSplitAcc) tmem_ld32(taddr + BLOCK_N + c0, v2);
         tmem_ld_wait();
         if (m < p.m_valid) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             float4 val = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
                                      __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+            if (Cfg::kSplitAcc) {
+              val.x += __uint_as_float(v2[4 * j]);
+              val.y += __uint_as_float(v2[4 * j + 1]);
+              val.z += __uint_as_float(v2[4 * j + 2]);
+              val.w += __uint_as_float(v2[4 * j + 3]);
+            }
             atomicAdd(reinterpret_cast<float4*>(dst + c0 + 4 * j), val);
           }
         }

@@ -366,7 +366,7 @@ def main():
     }
     if conv_ms > 0:
         ach = conv_flops / (conv_ms * 1e-3) / 1e12
-        line["roofline"] = {"bound": "tensor", "kernel": "conv3x3_tc_kernel (tcgen05 implicit GEMM)",
+        line["roofline"] = {"bound": "tensor", "kernel": "conv3x3_halo_kernel (tcgen05 implicit GEMM, halo reuse; 16 launches per step)",
                             "achieved": ach, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
                             "frac": ach / peaks["tflops_sustained"],
                             "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernel timed inside the step)",

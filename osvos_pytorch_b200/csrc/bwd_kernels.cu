@@ -297,56 +297,90 @@ channel_sum_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __
 }
 
 // -------------------------------------------------------------- conv1_1 bwd
-// dW[co][ci][r][s] = sum_px dz[px][co] * x[ci][px + (r-1, s-1)]   (1728 outputs)
-// block: 256 threads = 64 co x 4 groups of <= 7 taps-by-channel indices; pixels staged 32 at a time.
+// dW[co][ci][r][s] = sum_px dz[px][co] * x[ci][px + (r-1, s-1)]   (64 x 27 outputs, reduction over all pixels)
+// Register-tiled: a thread owns a 4 (co) x 7 (k) tile of dW; 64 threads cover the 64 x 28 tile, the block's four
+// 64-thread units take every fourth pixel of a staged 64-pixel chunk.  Per pixel a thread does one float4 + 7 scalar
+// shared-memory loads for 28 FMAs.
+constexpr int kFwPix = 64;
 __global__ void __launch_bounds__(256)
 conv_first_wgrad_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dz_hi,
                         const __nv_bfloat16* __restrict__ dz_lo, float* __restrict__ dw, int n, int h, int w) {
-  __shared__ float dzs[32][65];
-  __shared__ float xs[32][28];
-  const int co = threadIdx.x & 63, kg = threadIdx.x >> 6;
-  const int k0 = kg * 7;
-  float acc[7] = {0, 0, 0, 0, 0, 0, 0};
+  __shared__ __align__(16) float dzs[kFwPix][68];
+  __shared__ float xs[kFwPix][28];
+  __shared__ float red[64 * 28];
+  const int unit = threadIdx.x >> 6;         // 0..3: which pixels of the chunk
+  const int t = threadIdx.x & 63;
+  const int cg = t & 15, kg = t >> 4;        // co = 4*cg .. 4*cg+3 ; k = 7*kg .. 7*kg+6
+  float acc[4][7];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 7; ++j) acc[i][j] = 0.f;
   const size_t npix = static_cast<size_t>(n) * h * w;
-  for (size_t base = static_cast<size_t>(blockIdx.x) * 32; base < npix; base += static_cast<size_t>(gridDim.x) * 32) {
-    // stage dz (32 px x 64 co) and the 27 shifted inputs of each pixel
-    for (int i = threadIdx.x; i < 32 * 64; i += 256) {
-      const int pp = i >> 6, cc = i & 63;
+  for (size_t base = static_cast<size_t>(blockIdx.x) * kFwPix; base < npix; base += static_cast<size_t>(gridDim.x) * kFwPix) {
+    // stage dz: 64 px x 64 co, 8 channels (16 B per plane) per thread-iteration
+    for (int i = threadIdx.x; i < kFwPix * 8; i += 256) {
+      const int pp = i >> 3, g = i & 7;
       const size_t px = base + pp;
-      float v = 0.f;
+      float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
       if (px < npix) {
-        v = __bfloat162float(dz_hi[px * 64 + cc]);
-        if (dz_lo) v += __bfloat162float(dz_lo[px * 64 + cc]);
+        const uint4 vh = __ldg(reinterpret_cast<const uint4*>(dz_hi + px * 64 + g * 8));
+        uint4 vl = make_uint4(0, 0, 0, 0);
+        if (dz_lo) vl = __ldg(reinterpret_cast<const uint4*>(dz_lo + px * 64 + g * 8));
+        const uint32_t hw[4] = {vh.x, vh.y, vh.z, vh.w};
+        const uint32_t lw[4] = {vl.x, vl.y, vl.z, vl.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          v[2 * q] = bf16_lo_to_float(hw[q]) + bf16_lo_to_float(lw[q]);
+          v[2 * q + 1] = bf16_hi_to_float(hw[q]) + bf16_hi_to_float(lw[q]);
+        }
       }
-      dzs[pp][cc] = v;
+      *reinterpret_cast<float4*>(&dzs[pp][g * 8]) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(&dzs[pp][g * 8 + 4]) = make_float4(v[4], v[5], v[6], v[7]);
     }
-    for (int i = threadIdx.x; i < 32 * 27; i += 256) {
-      const int pp = i / 27, k = i - pp * 27;
+    for (int i = threadIdx.x; i < kFwPix * 28; i += 256) {
+      const int pp = i / 28, k = i - pp * 28;
       const size_t px = base + pp;
       float v = 0.f;
-      if (px < npix) {
+      if (px < npix && k < 27) {
         const int xx = static_cast<int>(px % w);
         const int yy = static_cast<int>((px / w) % h);
         const int nn = static_cast<int>(px / (static_cast<size_t>(w) * h));
-        const int ci = k / 9, r = (k % 9) / 3, s = k % 3;
-        const int iy = yy + r - 1, ix = xx + s - 1;
+        const int ci = k / 9, r = (k % 9) / 3, sft = k % 3;
+        const int iy = yy + r - 1, ix = xx + sft - 1;
         if (iy >= 0 && iy < h && ix >= 0 && ix < w) v = __ldg(x + ((static_cast<size_t>(nn) * 3 + ci) * h + iy) * w + ix);
       }
       xs[pp][k] = v;
     }
     __syncthreads();
 #pragma unroll 4
-    for (int pp = 0; pp < 32; ++pp) {
-      const float d = dzs[pp][co];
+    for (int pp = unit; pp < kFwPix; pp += 4) {
+      const float4 d = *reinterpret_cast<const float4*>(&dzs[pp][cg * 4]);
+      float xv[7];
 #pragma unroll
-      for (int j = 0; j < 7; ++j)
-        if (k0 + j < 27) acc[j] = fmaf(d, xs[pp][k0 + j], acc[j]);
+      for (int j = 0; j < 7; ++j) xv[j] = xs[pp][kg * 7 + j];
+#pragma unroll
+      for (int j = 0; j < 7; ++j) {
+        acc[0][j] = fmaf(d.x, xv[j], acc[0][j]);
+        acc[1][j] = fmaf(d.y, xv[j], acc[1][j]);
+        acc[2][j] = fmaf(d.z, xv[j], acc[2][j]);
+        acc[3][j] = fmaf(d.w, xv[j], acc[3][j]);
+      }
     }
     __syncthreads();
   }
+  // reduce the four units in shared memory, then one global atomic per output and block
+  for (int i = threadIdx.x; i < 64 * 28; i += 256) red[i] = 0.f;
+  __syncthreads();
 #pragma unroll
-  for (int j = 0; j < 7; ++j)
-    if (k0 + j < 27) atomicAdd(dw + co * 27 + k0 + j, acc[j]);
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 7; ++j) atomicAdd(&red[(cg * 4 + i) * 28 + kg * 7 + j], acc[i][j]);
+  __syncthreads();
+  for (int i = threadIdx.x; i < 64 * 27; i += 256) {
+    const int co = i / 27, k = i - co * 27;
+    atomicAdd(dw + i, red[co * 28 + k]);
+  }
 }
 
 // dx[ci][y][x] = sum_{r,s,co} dz[y - (r-1)][x - (s-1)][co] * w[co][ci][r][s]
@@ -494,7 +528,7 @@ extern "C" int osvos_conv_first_bwd(const float* x_nchw, const void* dz_hi, cons
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   OSVOS_CHECK_CUDA(cudaMemsetAsync(dw, 0, 64 * 27 * sizeof(float), stream));
   const size_t npix = static_cast<size_t>(n) * h * w;
-  conv_first_wgrad_kernel<<<grid_cap((npix + 31) / 32, 4), 256, 0, stream>>>(
+  conv_first_wgrad_kernel<<<grid_cap((npix + kFwPix - 1) / kFwPix, 4), 256, 0, stream>>>(
       x_nchw, static_cast<const __nv_bfloat16*>(dz_hi), static_cast<const __nv_bfloat16*>(dz_lo), dw, n, h, w);
   if (dx_nchw) {
     dim3 grid((w + 127) / 128, h, n);

@@ -27,7 +27,7 @@
 
 namespace osvos {
 
-constexpr int kWgThreads = 192;
+constexpr int kWgThreads = 224;   // warp 0: P producer, 1: MMA, 2-5: epilogue, 6: Q producer
 constexpr int kWgPatchW = 8, kWgPatchH = 8;
 constexpr int kWgBlockK = 64;                  // pixels per K block
 constexpr int kWgBoxBytes = kWgBlockK * 128;   // 8 KiB: 64 pixels x 64 channels of bf16
@@ -90,7 +90,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_p_hi, const __grid_const
     tma_prefetch_desc(&map_p_hi);
     tma_prefetch_desc(&map_q_hi);
     for (int i = 0; i < kStages; ++i) {
-      mbar_init(&full_bar[i], 1);
+      mbar_init(&full_bar[i], 2);   // one arrive.expect_tx from each of the two producer warps
       mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -105,8 +105,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_p_hi, const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
-    {  // warp-uniform control flow, one elected lane issues (see conv3x3_tc.cu)
+  if (warp == 0 || warp == 6) {
+    {  // two producer warps (P operand: warp 0, Q operand: warp 6) halve the per-K-block TMA issue time; warp-uniform
+       // control flow, one elected lane issues (see conv3x3_tc.cu)
+      const bool load_p = (warp == 0);
       int stage = 0;
       uint32_t phase = 0;
       for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
@@ -126,21 +128,28 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_p_hi, const __grid_const
           const int x0 = px * kWgPatchW, y0 = py * kWgPatchH;
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (elect_one()) {
-          uint8_t* st = smem + stage * Cfg::kStageBytes;
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            uint8_t* st = smem + stage * Cfg::kStageBytes;
+            if (load_p) {
+              mbar_arrive_expect_tx(&full_bar[stage], PLANES * Cfg::kPBytes);
 #pragma unroll
-          for (int pl = 0; pl < PLANES; ++pl) {
-            const CUtensorMap* mp = pl == 0 ? &map_p_hi : &map_p_lo;
-            const CUtensorMap* mq = pl == 0 ? &map_q_hi : &map_q_lo;
-            uint8_t* sp = st + pl * Cfg::kPBytes;
-            uint8_t* sq = st + PLANES * Cfg::kPBytes + pl * Cfg::kQBytes;
+              for (int pl = 0; pl < PLANES; ++pl) {
+                const CUtensorMap* mp = pl == 0 ? &map_p_hi : &map_p_lo;
+                uint8_t* sp = st + pl * Cfg::kPBytes;
 #pragma unroll
-            for (int j = 0; j < 2; ++j)
-              tma_load_4d(mp, &full_bar[stage], sp + j * kWgBoxBytes, mb * 128 + j * 64, x0 + pdx, y0 + pdy, img);
+                for (int j = 0; j < 2; ++j)
+                  tma_load_4d(mp, &full_bar[stage], sp + j * kWgBoxBytes, mb * 128 + j * 64, x0 + pdx, y0 + pdy, img);
+              }
+            } else {
+              mbar_arrive_expect_tx(&full_bar[stage], PLANES * Cfg::kQBytes);
 #pragma unroll
-            for (int j = 0; j < BLOCK_N / 64; ++j)
-              tma_load_4d(mq, &full_bar[stage], sq + j * kWgBoxBytes, nb * BLOCK_N + j * 64, x0 + qdx, y0 + qdy, img);
-          }
+              for (int pl = 0; pl < PLANES; ++pl) {
+                const CUtensorMap* mq = pl == 0 ? &map_q_hi : &map_q_lo;
+                uint8_t* sq = st + PLANES * Cfg::kPBytes + pl * Cfg::kQBytes;
+#pragma unroll
+                for (int j = 0; j < BLOCK_N / 64; ++j)
+                  tma_load_4d(mq, &full_bar[stage], sq + j * kWgBoxBytes, nb * BLOCK_N + j * 64, x0 + qdx, y0 + qdy, img);
+              }
+            }
           }
           __syncwarp();
           if (++stage == kStages) {
@@ -205,7 +214,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_p_hi, const __grid_const
         }
       }
     }
-  } else {
+  } else if (warp >= 2 && warp < 6) {
     const int q = warp & 3;
     const int row = q * 32 + lane;
     int it = 0;

@@ -243,3 +243,45 @@ def test_backward_480p_vs_oracle(net):
                 worst = (name, err)
     print(f"480p online fwd+bwd: loss {float(loss):.4f}; worst per-parameter gradient error {worst[1]:.2e} ({worst[0]})")
     assert worst[1] < GRAD_TOL
+
+
+def test_online_finetune_trajectory_vs_oracle():
+    """BASELINE.json configs[2] in miniature: the online fine-tuning loop (fuse loss, nAveGrad accumulation, SGD with the
+    reference's per-group learning rates / momentum / weight decay, train_online.py:77-88,112-149) run through the
+    product's training.online_finetune and, step for step, on the CPU oracle with torch.optim.SGD."""
+    from osvos_pytorch_b200 import training
+    from osvos_pytorch_b200.networks.vgg_osvos import OSVOS
+    h, w, iters, nave, lr = 64, 96, 8, 2, 2e-9
+    params = oc.he_params(seed=0)
+    net = OSVOS(pretrained=0, verbose=False)
+    net.load_state_dict(params, strict=False)
+    net = net.cuda()
+    x, gt = oc.synthetic_frame(1, h, w, 77)
+    sample = {"image": x.cuda(), "gt": gt.cuda()}
+    hist = training.online_finetune(net, lambda it: sample, iters, nave, lr=lr, log_every=1, log=lambda s: None)
+    # the same loop on the oracle
+    ref = OSVOS(pretrained=0, verbose=False)
+    ref.load_state_dict(params, strict=False)
+    opt = training.make_optimizer(ref, "online", lr=lr)
+    leaves = {k: v for k, v in ref.named_parameters()}
+    ref_hist = []
+    opt.zero_grad()
+    for it in range(iters):
+        outs = oc.osvos_forward({k: v for k, v in leaves.items() if not k.startswith("upscale")}, x)
+        loss = oc.class_balanced_cross_entropy_loss(outs[-1], gt, size_average=False)
+        ref_hist.append(float(loss))
+        (loss / nave).backward()
+        if (it + 1) % nave == 0:
+            opt.step()
+            opt.zero_grad()
+    print("online loss trajectory (native):", [f"{v:.3f}" for v in hist])
+    print("online loss trajectory (oracle):", [f"{v:.3f}" for v in ref_hist])
+    assert abs(ref_hist[-1] - ref_hist[0]) > 1e-4 * abs(ref_hist[0])           # the steps actually move the loss
+    for a, b in zip(hist, ref_hist):
+        assert abs(a - b) < 2e-4 * abs(b)
+    for name, p in net.named_parameters():
+        if not name.startswith("upscale"):
+            q = dict(ref.named_parameters())[name]
+            step = (q.detach() - params[name]).double().norm()
+            if float(step) > 0:
+                assert float((p.detach().cpu().double() - q.detach().double()).norm()) < 5e-2 * float(step) + 1e-12, name

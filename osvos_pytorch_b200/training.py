@@ -61,7 +61,8 @@ def online_finetune(net, sample_fn, iters, n_ave_grad=5, lr=1e-8, wd=0.0002, log
         inputs, gts = sample["image"], sample["gt"]
         outputs = net.forward(inputs)
         loss = class_balanced_cross_entropy_loss(outputs[-1], gts, size_average=False)
-        running = loss.detach() if running is None else running + loss.detach()
+        # clone: `loss /= n_ave_grad` below is in place (as in the reference) and must not scale the logged value
+        running = loss.detach().clone() if running is None else running + loss.detach()
         loss /= n_ave_grad
         loss.backward()
         if (it + 1) % n_ave_grad == 0:

@@ -26,7 +26,8 @@ def parse():
     ap.add_argument("--iters", type=int, default=None, help="forward/backward passes (default 2000 * nAveGrad)")
     ap.add_argument("--parent-epoch", type=int, default=240)
     ap.add_argument("--parent-name", default="parent")
-    ap.add_argument("--lr", type=float, default=1e-8)
+    ap.add_argument("--lr", type=float, default=None, help="default 1e-8 (reference); 1e-10 with --synthetic, whose "
+                    "He-initialised network produces O(10)-scale logits and therefore much larger summed-loss gradients")
     ap.add_argument("--wd", type=float, default=0.0002)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--gpu-id", type=int, default=0)
@@ -42,6 +43,8 @@ def parse():
 def main():
     a = parse()
     iters = a.iters if a.iters is not None else 2000 * a.n_ave_grad
+    if a.lr is None:
+        a.lr = 1e-10 if a.synthetic else 1e-8
     log_every = a.log_every if a.log_every is not None else max(1, iters // 20)
     save_dir = Path.save_root_dir()
     os.makedirs(save_dir, exist_ok=True)
@@ -51,6 +54,9 @@ def main():
     net = vo.OSVOS(pretrained=0, precision=a.precision)
     if a.synthetic:
         vo.he_init_(net, seed=a.seed)
+        with torch.no_grad():               # keep the synthetic logits O(10): scale the side branch down
+            for mod in list(net.side_prep) + [net.fuse]:
+                mod.weight.mul_(0.1)
     else:
         ckpt = os.path.join(save_dir, f"{a.parent_name}_epoch-{a.parent_epoch - 1}.pth")
         net.load_state_dict(torch.load(ckpt, map_location="cpu"))
@@ -90,6 +96,8 @@ def main():
     torch.cuda.synchronize()
     dt = timeit.default_timer() - t0
     print(f"Online training time: {dt:.2f} s ({iters / dt:.1f} fwd+bwd/s, {iters / a.n_ave_grad / dt:.1f} SGD steps/s)")
+    if history and not all(v == v and abs(v) != float("inf") for v in history):
+        print("WARNING: non-finite loss - lower --lr for this initialisation")
     if not a.no_save:
         torch.save(net.state_dict(), os.path.join(save_dir, f"{a.seq_name}_epoch-{iters - 1}.pth"))
 

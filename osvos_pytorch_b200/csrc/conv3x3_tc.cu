@@ -248,6 +248,11 @@ extern "C" int osvos_conv3x3(const osvos_conv3x3_args* a, osvos_stream_t stream_
   // swizzle is a function of the absolute smem address, so shifted descriptor starts need no base offset.
   // OSVOS_CONV_IMPL=tap selects the one-box-per-tap kernel below (kept as a cross-check).
   const char* impl = getenv("OSVOS_CONV_IMPL");
+  // side_prep shape (16 outputs, fp32 features / projections only): nine-taps-along-N kernel (side_conv.cu)
+  if (a->cout == 16 && a->y_hi == nullptr && !(a->flags & OSVOS_FLAG_RELU_MASK) && a->colsum == nullptr && impl == nullptr) {
+    const char* side = getenv("OSVOS_SIDE_IMPL");
+    if (side == nullptr || strcmp(side, "generic") != 0) return side_conv_dispatch(a, stream);
+  }
   if (impl != nullptr && strcmp(impl, "halo2") == 0) return conv3x3_halo2_dispatch(a, stream);
   if (impl == nullptr || strcmp(impl, "tap") != 0) {
     const char* ps = getenv("OSVOS_HALO_PITCH");

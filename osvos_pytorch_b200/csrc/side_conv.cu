@@ -1,0 +1,313 @@
+// side_prep: 3x3 convolution C -> 16 (no ReLU) + the fused 1x1 projections, with the NINE TAPS CONCATENATED ALONG N.
+//
+// With N = 16 a tcgen05.mma still costs its ~85-cycle floor, and the generic kernel issues one per (tap, K step, pass):
+// the four side convolutions took 137 us of a 866 us frame at 9-14 % tensor activity.  Here the GEMM is turned around:
+//   Y[p][tap*16 + co] = sum_ci X[p][ci] * W[tap][co][ci]        p = pixel of the UNSHIFTED halo patch
+// i.e. ONE MMA of N = 144 per K step and pass (A = the 12 x 10-pixel halo patch of a 10 x 8 output tile, 120 of the 128
+// GEMM rows; B = all nine 16 x 64 weight slabs of the chunk, one TMA box {64, 16, 9}), 9x fewer instructions.  The
+// spatial shift moves to the epilogue: out[y][x][co] = sum_{r,s} Y[(y + r) * 10 + (x + s)][(3r + s) * 16 + co], done
+// through a shared-memory exchange in three deterministic rounds (one tap row each).
+//
+// Replaces side_prep[i] (+ score_dsn[i] and this scale's slice of fuse as projections), reference
+// networks/vgg_osvos.py:41,44,54 run at :67,69,72.  Same argument contract as osvos_conv3x3 with cout == 16.
+#include "conv_common.cuh"
+
+namespace osvos {
+
+constexpr int kSideTileW = 8, kSideTileH = 10;              // output tile
+constexpr int kSideHaloW = 10, kSideHaloH = 12;             // 120 halo pixels = GEMM rows
+constexpr int kSideN = 144;                                 // 9 taps x 16 channels
+constexpr int kSideThreads = 192;                           // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+constexpr int kSideABox = kSideHaloW * kSideHaloH * 128;    // 15360 B
+constexpr int kSideAPlane = 128 * 128;                      // the MMA reads 128 rows
+constexpr int kSideBPlane = kSideN * 128;                   // 18432 B
+constexpr int kSideAStages = 2, kSideBStages = 3;
+constexpr int kSideYBuf = 3 * 16 * 128 * 4;                 // one tap row: [s][co][halo px (128)] floats = 24 KiB
+
+struct SideParams {
+  const float* bias;
+  float* y_f32;
+  const float* proj_w;
+  const float* proj_b;
+  float* pq;
+  int n, h, w, cin;
+  int tiles_x, tiles_y, total_tiles, k_chunks;
+  int relu;
+};
+
+template <int PLANES>
+struct SideCfg {
+  static constexpr int kAStage = PLANES * kSideAPlane;
+  static constexpr int kBStage = PLANES * kSideBPlane;
+  static constexpr int kSmem = kSideAStages * kAStage + kSideBStages * kBStage + kSideYBuf + 1024 + 256;
+};
+
+__device__ __forceinline__ void side_decode(const SideParams& p, int tile, int& tx, int& ty, int& img) {
+  tx = tile % p.tiles_x;
+  const int t = tile / p.tiles_x;
+  ty = t % p.tiles_y;
+  img = t / p.tiles_y;
+}
+
+template <int PLANES>
+__global__ void __launch_bounds__(kSideThreads, 1)
+side_conv_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo,
+                 const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
+                 const SideParams p) {
+  using Cfg = SideCfg<PLANES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem_a + kSideAStages * Cfg::kAStage;
+  float* ybuf = reinterpret_cast<float*>(smem_b + kSideBStages * Cfg::kBStage);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(ybuf) + kSideYBuf);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = bars + kSideAStages;
+  uint64_t* b_full = a_empty + kSideAStages;
+  uint64_t* b_empty = b_full + kSideBStages;
+  uint64_t* tfull_bar = b_empty + kSideBStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map_x_hi);
+    tma_prefetch_desc(&map_w_hi);
+    for (int i = 0; i < kSideAStages; ++i) {
+      mbar_init(&a_full[i], 1);
+      mbar_init(&a_empty[i], 1);
+    }
+    for (int i = 0; i < kSideBStages; ++i) {
+      mbar_init(&b_full[i], 1);
+      mbar_init(&b_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);  // 2 accumulator stages x 144 columns (256-column stride)
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    int a_stage = 0, b_stage = 0;
+    uint32_t a_phase = 0, b_phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      int tx, ty, img;
+      side_decode(p, tile, tx, ty, img);
+      for (int kc = 0; kc < p.k_chunks; ++kc) {
+        mbar_wait(&a_empty[a_stage], a_phase ^ 1);
+        mbar_wait(&b_empty[b_stage], b_phase ^ 1);
+        if (elect_one()) {
+          uint8_t* sa = smem_a + a_stage * Cfg::kAStage;
+          uint8_t* sb = smem_b + b_stage * Cfg::kBStage;
+          mbar_arrive_expect_tx(&a_full[a_stage], PLANES * kSideABox);
+          tma_load_4d(&map_x_hi, &a_full[a_stage], sa, kc * 64, tx * kSideTileW - 1, ty * kSideTileH - 1, img);
+          if (PLANES == 2)
+            tma_load_4d(&map_x_lo, &a_full[a_stage], sa + kSideAPlane, kc * 64, tx * kSideTileW - 1,
+                        ty * kSideTileH - 1, img);
+          mbar_arrive_expect_tx(&b_full[b_stage], PLANES * kSideBPlane);
+          tma_load_3d(&map_w_hi, &b_full[b_stage], sb, kc * 64, 0, 0);
+          if (PLANES == 2) tma_load_3d(&map_w_lo, &b_full[b_stage], sb + kSideBPlane, kc * 64, 0, 0);
+        }
+        __syncwarp();
+        if (++a_stage == kSideAStages) {
+          a_stage = 0;
+          a_phase ^= 1;
+        }
+        if (++b_stage == kSideBStages) {
+          b_stage = 0;
+          b_phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = make_idesc_f16(128, kSideN, /*bf16=*/true);
+    int a_stage = 0, b_stage = 0;
+    uint32_t a_phase = 0, b_phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aph = (it >> 1) & 1;
+      mbar_wait(&tempty_bar[as], aph ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + as * 256;
+      for (int kc = 0; kc < p.k_chunks; ++kc) {
+        mbar_wait(&a_full[a_stage], a_phase);
+        mbar_wait(&b_full[b_stage], b_phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a_hi = smem_u32(smem_a + a_stage * Cfg::kAStage);
+          const uint32_t b_hi = smem_u32(smem_b + b_stage * Cfg::kBStage);
+          const uint64_t da_hi = make_smem_desc(a_hi, 16, 1024, kLayoutSW128);
+          const uint64_t da_lo = make_smem_desc(a_hi + kSideAPlane, 16, 1024, kLayoutSW128);
+          const uint64_t db_hi = make_smem_desc(b_hi, 16, 1024, kLayoutSW128);
+          const uint64_t db_lo = make_smem_desc(b_hi + kSideBPlane, 16, 1024, kLayoutSW128);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t adv = static_cast<uint64_t>(k * 2);
+            if (PLANES == 2) {
+              umma_f16(tmem_d, da_lo + adv, db_hi + adv, idesc, (kc | k) != 0);
+              umma_f16(tmem_d, da_hi + adv, db_lo + adv, idesc, 1);
+              umma_f16(tmem_d, da_hi + adv, db_hi + adv, idesc, 1);
+            } else {
+              umma_f16(tmem_d, da_hi + adv, db_hi + adv, idesc, (kc | k) != 0);
+            }
+          }
+          umma_commit(&a_empty[a_stage]);
+          umma_commit(&b_empty[b_stage]);
+          if (kc == p.k_chunks - 1) umma_commit(&tfull_bar[as]);
+        }
+        __syncwarp();
+        if (++a_stage == kSideAStages) {
+          a_stage = 0;
+          a_phase ^= 1;
+        }
+        if (++b_stage == kSideBStages) {
+          b_stage = 0;
+          b_phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue: shift-add through shared memory
+    const int q = warp & 3;
+    const int row = q * 32 + lane;                 // halo pixel index (valid < 120) / output thread index (< 80)
+    const int oy = row / kSideTileW, ox = row % kSideTileW;   // as an OUTPUT pixel of the tile (row < 80)
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      int tx, ty, img;
+      side_decode(p, tile, tx, ty, img);
+      const int as = it & 1;
+      const uint32_t aph = (it >> 1) & 1;
+      mbar_wait(&tfull_bar[as], aph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + as * 256 + (static_cast<uint32_t>(q * 32) << 16);
+      float acc[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc[j] = p.bias ? __ldg(p.bias + j) : 0.f;
+#pragma unroll 1
+      for (int r = 0; r < 3; ++r) {
+        // (1) every halo-pixel thread publishes its three taps of row r: ybuf[s][co][pixel]
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+          uint32_t v[16];
+          tmem_ld16(taddr + (r * 3 + s) * 16, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int co = 0; co < 16; ++co) ybuf[(s * 16 + co) * 128 + row] = __uint_as_float(v[co]);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        // (2) output-pixel threads gather: halo pixel (oy + r, ox + s)
+        if (row < kSideTileW * kSideTileH) {
+#pragma unroll
+          for (int s = 0; s < 3; ++s) {
+            const int src = (oy + r) * kSideHaloW + ox + s;
+#pragma unroll
+            for (int co = 0; co < 16; ++co) acc[co] += ybuf[(s * 16 + co) * 128 + src];
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[as]);
+      const int y = ty * kSideTileH + oy, x = tx * kSideTileW + ox;
+      if (row < kSideTileW * kSideTileH && y < p.h && x < p.w) {
+        const size_t pix = (static_cast<size_t>(img) * p.h + y) * p.w + x;
+        if (p.relu) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[j] = fmaxf(acc[j], 0.f);
+        }
+        if (p.y_f32) {
+          float4* dst = reinterpret_cast<float4*>(p.y_f32 + pix * 16);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dst[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+        }
+        if (p.pq) {
+          float sp = p.proj_b ? __ldg(p.proj_b) : 0.f, sq = 0.f;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            sp = fmaf(acc[j], __ldg(p.proj_w + j), sp);
+            sq = fmaf(acc[j], __ldg(p.proj_w + 16 + j), sq);
+          }
+          *reinterpret_cast<float2*>(p.pq + pix * 2) = make_float2(sp, sq);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int PLANES>
+static int launch_side(const osvos_conv3x3_args* a, cudaStream_t stream) {
+  using Cfg = SideCfg<PLANES>;
+  SideParams p;
+  p.bias = a->bias;
+  p.y_f32 = a->y_f32;
+  p.proj_w = a->proj_w;
+  p.proj_b = a->proj_b;
+  p.pq = a->pq;
+  p.n = a->n;
+  p.h = a->h;
+  p.w = a->w;
+  p.cin = a->cin;
+  p.tiles_x = (a->w + kSideTileW - 1) / kSideTileW;
+  p.tiles_y = (a->h + kSideTileH - 1) / kSideTileH;
+  p.total_tiles = p.tiles_x * p.tiles_y * a->n;
+  p.k_chunks = a->cin / 64;
+  p.relu = (a->flags & OSVOS_FLAG_RELU) ? 1 : 0;
+  CUtensorMap mx_hi, mx_lo, mw_hi, mw_lo;
+  {
+    const uint64_t dims[4] = {(uint64_t)a->cin, (uint64_t)a->w, (uint64_t)a->h, (uint64_t)a->n};
+    const uint64_t strides[3] = {(uint64_t)a->cin * 2, (uint64_t)a->w * a->cin * 2, (uint64_t)a->h * a->w * a->cin * 2};
+    const uint32_t box[4] = {64, kSideHaloW, kSideHaloH, 1};
+    int rc = encode_tensor_map(&mx_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 4, a->x_hi, dims, strides, box,
+                               CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    rc = encode_tensor_map(&mx_lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 4, PLANES == 2 ? a->x_lo : a->x_hi, dims, strides,
+                           box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  {
+    const size_t plane = static_cast<size_t>(9) * 16 * a->cin;
+    const uint64_t dims[3] = {(uint64_t)a->cin, 16, 9};
+    const uint64_t strides[2] = {(uint64_t)a->cin * 2, (uint64_t)16 * a->cin * 2};
+    const uint32_t box[3] = {64, 16, 9};
+    const __nv_bfloat16* wp = static_cast<const __nv_bfloat16*>(a->w_packed);
+    int rc = encode_tensor_map(&mw_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 3, wp, dims, strides, box,
+                               CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    rc = encode_tensor_map(&mw_lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 3, wp + plane, dims, strides, box,
+                           CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  auto kern = side_conv_kernel<PLANES>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    OSVOS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
+    attr_done = true;
+  }
+  const int sms = device_sm_count();
+  const int grid = p.total_tiles < sms ? p.total_tiles : sms;
+  kern<<<grid, kSideThreads, Cfg::kSmem, stream>>>(mx_hi, mx_lo, mw_hi, mw_lo, p);
+  OSVOS_CHECK_CUDA(cudaGetLastError());
+  return OSVOS_OK;
+}
+
+int side_conv_dispatch(const osvos_conv3x3_args* a, cudaStream_t stream) {
+  return (a->flags & OSVOS_FLAG_FAST) ? launch_side<1>(a, stream) : launch_side<2>(a, stream);
+}
+
+}  // namespace osvos

@@ -285,3 +285,24 @@ def test_online_finetune_trajectory_vs_oracle():
             step = (q.detach() - params[name]).double().norm()
             if float(step) > 0:
                 assert float((p.detach().cpu().double() - q.detach().double()).norm()) < 5e-2 * float(step) + 1e-12, name
+
+
+def test_backward_batch2_parent_objective_vs_oracle(net):
+    """Batch > 1: the loss's class-balance counts span the whole batch tensor (layers/osvos_layers.py:30-32) and every
+    kernel iterates over images."""
+    from osvos_pytorch_b200.layers.osvos_layers import class_balanced_cross_entropy_loss as cbce
+    x, gt = oc.synthetic_frame(2, 96, 128, 314)
+    params = {k: v.detach().cpu() for k, v in net.state_dict().items() if not k.startswith("upscale")}
+    net.zero_grad()
+    outs = net(x.cuda())
+    ls = [cbce(o, gt.cuda(), size_average=False) for o in outs]
+    loss = 0.3 * sum(ls[:-1]) + ls[-1]
+    loss.backward()
+    ref_loss, _, ograds = oc.forward_backward(params, x, gt, objective="parent", side_weight=0.3)
+    assert abs(float(loss) - float(ref_loss)) < 1e-4 * abs(float(ref_loss))
+    worst = 0.0
+    for name, p in net.named_parameters():
+        if name in ograds:
+            worst = max(worst, relnorm(p.grad, ograds[name]))
+    print(f"batch-2 parent objective 96x128: worst per-parameter gradient error {worst:.2e}")
+    assert worst < GRAD_TOL_TINY

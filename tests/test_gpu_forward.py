@@ -112,3 +112,34 @@ def test_fast_mode_reports_its_error(net):
     flips, _, iou = mask_report(outs[4], ref[4].numpy(), LOGIT_TOL)
     print(f"fast mode 240x427 fused: maxrel {err:.2e} flips {flips} IoU {iou:.5f}")
     assert err < 5e-2 and iou > 0.97
+
+
+@pytest.mark.parametrize("n,h,w", [(1, 720, 1280), (3, 97, 131), (1, 17, 9)])
+def test_forward_other_resolutions_vs_oracle(net, n, h, w):
+    """BASELINE.json configs[4] shapes (720p; 1080p is covered by the timing sweep), a ragged batch, and a frame
+    smaller than one tile at every stage."""
+    x, _ = oc.synthetic_frame(n, h, w, 99)
+    params = oc.he_params(seed=0)
+    with torch.no_grad():
+        ref = oc.osvos_forward(params, x)
+        outs = net(x.cuda())
+    for i, (o, r) in enumerate(zip(outs, ref)):
+        err = maxrel(o, r)
+        flips, hard_flips, iou = mask_report(o, r.numpy(), LOGIT_TOL)
+        print(f"{n}x{h}x{w} out{i}: maxrel {err:.2e} flips {flips} (outside band {hard_flips}) IoU {iou:.6f}")
+        assert err <= LOGIT_TOL and hard_flips == 0
+
+
+def test_forward_is_deterministic_and_graph_equals_eager(net):
+    x, _ = oc.synthetic_frame(1, 96, 160, 5)
+    xc = x.cuda()
+    with torch.no_grad():
+        a = net(xc)
+        b = net(xc)
+        net._engine.use_cuda_graph = False
+        try:
+            c = net(xc)
+        finally:
+            net._engine.use_cuda_graph = True
+    for u, v, z in zip(a, b, c):
+        assert torch.equal(u, v) and torch.equal(u, z)

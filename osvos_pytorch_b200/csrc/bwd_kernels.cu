@@ -17,36 +17,44 @@ struct TailBwdParams {
   int n, h, w, hk, wk, s, top, left;
 };
 
+// LANES threads cooperate on one low-res pixel (2 / 8 / 32 / 32 for s = 2 / 4 / 8 / 16): 8 .. 32 taps per lane,
+// sub-warp shuffle reduction.
+template <int LANES>
 __global__ void __launch_bounds__(256) tail_bwd_kernel(const TailBwdParams p) {
-  const int lane = threadIdx.x & 31;
-  const size_t warp_global = (blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x) >> 5;
-  const size_t nwarps = (static_cast<size_t>(gridDim.x) * blockDim.x) >> 5;
+  const int sub = threadIdx.x % LANES;
+  const size_t grp_global = (blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x) / LANES;
+  const size_t ngroups = (static_cast<size_t>(gridDim.x) * blockDim.x) / LANES;
   const size_t total = static_cast<size_t>(p.n) * p.hk * p.wk;
   const int fs = 2 * p.s;
   const float inv = 1.f / static_cast<float>(p.s);
-  for (size_t i = warp_global; i < total; i += nwarps) {
-    const int ix = static_cast<int>(i % p.wk);
-    const int iy = static_cast<int>((i / p.wk) % p.hk);
-    const int img = static_cast<int>(i / (static_cast<size_t>(p.wk) * p.hk));
-    const size_t base = static_cast<size_t>(img) * p.h * p.w;
+  const size_t rounds = (total + ngroups - 1) / ngroups;   // uniform trip count: every lane takes part in the shuffles
+  for (size_t rd = 0; rd < rounds; ++rd) {
+    const size_t i = grp_global + rd * ngroups;
+    const bool live = i < total;
     float dp = 0.f, dq = 0.f;
-    for (int t = lane; t < fs * fs; t += 32) {
-      const int ty = t / fs, tx = t - ty * fs;
-      const int y = iy * p.s + ty - p.top, x = ix * p.s + tx - p.left;
-      if (y < 0 || y >= p.h || x < 0 || x >= p.w) continue;
-      const float fy = 1.f - fabsf(static_cast<float>(ty) - (static_cast<float>(p.s) - 0.5f)) * inv;
-      const float fx = 1.f - fabsf(static_cast<float>(tx) - (static_cast<float>(p.s) - 0.5f)) * inv;
-      const float wgt = fy * fx;
-      const size_t o = base + static_cast<size_t>(y) * p.w + x;
-      if (p.gk) dp = fmaf(wgt, __ldg(p.gk + o), dp);
-      if (p.g4) dq = fmaf(wgt, __ldg(p.g4 + o), dq);
+    if (live) {
+      const int ix = static_cast<int>(i % p.wk);
+      const int iy = static_cast<int>((i / p.wk) % p.hk);
+      const int img = static_cast<int>(i / (static_cast<size_t>(p.wk) * p.hk));
+      const size_t base = static_cast<size_t>(img) * p.h * p.w;
+      for (int t = sub; t < fs * fs; t += LANES) {
+        const int ty = t / fs, tx = t - ty * fs;
+        const int y = iy * p.s + ty - p.top, x = ix * p.s + tx - p.left;
+        if (y < 0 || y >= p.h || x < 0 || x >= p.w) continue;
+        const float fy = 1.f - fabsf(static_cast<float>(ty) - (static_cast<float>(p.s) - 0.5f)) * inv;
+        const float fx = 1.f - fabsf(static_cast<float>(tx) - (static_cast<float>(p.s) - 0.5f)) * inv;
+        const float wgt = fy * fx;
+        const size_t o = base + static_cast<size_t>(y) * p.w + x;
+        if (p.gk) dp = fmaf(wgt, __ldg(p.gk + o), dp);
+        if (p.g4) dq = fmaf(wgt, __ldg(p.g4 + o), dq);
+      }
     }
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
+    for (int off = LANES / 2; off > 0; off >>= 1) {
       dp += __shfl_xor_sync(0xffffffffu, dp, off);
       dq += __shfl_xor_sync(0xffffffffu, dq, off);
     }
-    if (lane == 0) *reinterpret_cast<float2*>(p.dpq + i * 2) = make_float2(dp, dq);
+    if (live && sub == 0) *reinterpret_cast<float2*>(p.dpq + i * 2) = make_float2(dp, dq);
   }
 }
 
@@ -154,11 +162,27 @@ side_bwd_kernel(const float* __restrict__ feat, const float* __restrict__ dpq, c
 
 // ------------------------------------------------- max-unpool + add + ReLU mask
 // dz[n,h,w,c] = (x > 0) * (dside + (pixel is the argmax of its 2x2 window ? dpool : 0))
-__global__ void unpool_add_mask_kernel(const __nv_bfloat16* __restrict__ dp_hi, const __nv_bfloat16* __restrict__ dp_lo,
-                                       const __nv_bfloat16* __restrict__ x_hi, const __nv_bfloat16* __restrict__ x_lo,
-                                       const float* __restrict__ dside, __nv_bfloat16* __restrict__ dz_hi,
-                                       __nv_bfloat16* __restrict__ dz_lo, float* __restrict__ colsum, int n, int h,
-                                       int w, int c, int oh, int ow) {
+// One thread per (pooled pixel, 8 channels).  Pass 1 reads the four activations and keeps only the argmax index and
+// the sign bits (a few registers, so that many threads / loads are in flight); pass 2 streams dside / dpool and writes.
+__device__ __forceinline__ void load_pair8(const __nv_bfloat16* hi, const __nv_bfloat16* lo, size_t off, float (&v)[8]) {
+  const uint4 vh = __ldg(reinterpret_cast<const uint4*>(hi + off));
+  uint4 vl = make_uint4(0, 0, 0, 0);
+  if (lo) vl = __ldg(reinterpret_cast<const uint4*>(lo + off));
+  const uint32_t hw[4] = {vh.x, vh.y, vh.z, vh.w};
+  const uint32_t lw[4] = {vl.x, vl.y, vl.z, vl.w};
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    v[2 * t] = bf16_lo_to_float(hw[t]) + bf16_lo_to_float(lw[t]);
+    v[2 * t + 1] = bf16_hi_to_float(hw[t]) + bf16_hi_to_float(lw[t]);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+unpool_add_mask_kernel(const __nv_bfloat16* __restrict__ dp_hi, const __nv_bfloat16* __restrict__ dp_lo,
+                       const __nv_bfloat16* __restrict__ x_hi, const __nv_bfloat16* __restrict__ x_lo,
+                       const float* __restrict__ dside, __nv_bfloat16* __restrict__ dz_hi,
+                       __nv_bfloat16* __restrict__ dz_lo, float* __restrict__ colsum, int n, int h, int w, int c,
+                       int oh, int ow) {
   extern __shared__ float cs[];  // [c] block-local channel sums (fused bias gradient)
   if (colsum) {
     for (int i = threadIdx.x; i < c; i += blockDim.x) cs[i] = 0.f;
@@ -176,57 +200,31 @@ __global__ void unpool_add_mask_kernel(const __nv_bfloat16* __restrict__ dp_hi, 
     r /= ow;
     const int oy = static_cast<int>(r % oh);
     const int nn = static_cast<int>(r / oh);
-    float xv[4][8];
-    bool inb[4];
+    // pass 1: argmax (first maximum in (dy, dx) scan order) and positivity of the four window elements
+    float best[8];
+    uint32_t arg = 0, pos = 0;  // arg: 2 bits per channel; pos: bit (q * 8 + j) = x[q][j] > 0
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int iy = 2 * oy + (q >> 1), ix = 2 * ox + (q & 1);
-      inb[q] = iy < h && ix < w;
-      if (!inb[q]) continue;
-      const size_t src = ((static_cast<size_t>(nn) * h + iy) * w + ix) * c + g * 8;
-      const uint4 vh = __ldg(reinterpret_cast<const uint4*>(x_hi + src));
-      uint4 vl = make_uint4(0, 0, 0, 0);
-      if (x_lo) vl = __ldg(reinterpret_cast<const uint4*>(x_lo + src));
-      const uint32_t hw[4] = {vh.x, vh.y, vh.z, vh.w};
-      const uint32_t lw[4] = {vl.x, vl.y, vl.z, vl.w};
+      if (iy >= h || ix >= w) continue;
+      float v[8];
+      load_pair8(x_hi, x_lo, ((static_cast<size_t>(nn) * h + iy) * w + ix) * c + g * 8, v);
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        xv[q][2 * t] = bf16_lo_to_float(hw[t]) + bf16_lo_to_float(lw[t]);
-        xv[q][2 * t + 1] = bf16_hi_to_float(hw[t]) + bf16_hi_to_float(lw[t]);
-      }
-    }
-    // gradient of the pooled value
-    float dpv[8];
-    {
-      const size_t src = ((static_cast<size_t>(nn) * oh + oy) * ow + ox) * c + g * 8;
-      const uint4 vh = __ldg(reinterpret_cast<const uint4*>(dp_hi + src));
-      uint4 vl = make_uint4(0, 0, 0, 0);
-      if (dp_lo) vl = __ldg(reinterpret_cast<const uint4*>(dp_lo + src));
-      const uint32_t hw[4] = {vh.x, vh.y, vh.z, vh.w};
-      const uint32_t lw[4] = {vl.x, vl.y, vl.z, vl.w};
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        dpv[2 * t] = bf16_lo_to_float(hw[t]) + bf16_lo_to_float(lw[t]);
-        dpv[2 * t + 1] = bf16_hi_to_float(hw[t]) + bf16_hi_to_float(lw[t]);
-      }
-    }
-    int arg[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      int best = 0;
-      float bv = xv[0][j];
-#pragma unroll
-      for (int q = 1; q < 4; ++q)
-        if (inb[q] && xv[q][j] > bv) {
-          bv = xv[q][j];
-          best = q;
+      for (int j = 0; j < 8; ++j) {
+        if (q == 0 || v[j] > best[j]) {
+          best[j] = v[j];
+          arg = (arg & ~(3u << (2 * j))) | (static_cast<uint32_t>(q) << (2 * j));
         }
-      arg[j] = best;
+        if (v[j] > 0.f) pos |= 1u << (q * 8 + j);
+      }
     }
+    float dpv[8];
+    load_pair8(dp_hi, dp_lo, ((static_cast<size_t>(nn) * oh + oy) * ow + ox) * c + g * 8, dpv);
+    // pass 2: gradients of the four positions
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      if (!inb[q]) continue;
       const int iy = 2 * oy + (q >> 1), ix = 2 * ox + (q & 1);
+      if (iy >= h || ix >= w) continue;
       const size_t dst = ((static_cast<size_t>(nn) * h + iy) * w + ix) * c + g * 8;
       float ds[8] = {0, 0, 0, 0, 0, 0, 0, 0};
       if (dside) {
@@ -237,10 +235,10 @@ __global__ void unpool_add_mask_kernel(const __nv_bfloat16* __restrict__ dp_hi, 
       uint32_t hi[4], lo[4];
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
-        float v0 = ds[2 * t] + (arg[2 * t] == q ? dpv[2 * t] : 0.f);
-        float v1 = ds[2 * t + 1] + (arg[2 * t + 1] == q ? dpv[2 * t + 1] : 0.f);
-        if (!(xv[q][2 * t] > 0.f)) v0 = 0.f;
-        if (!(xv[q][2 * t + 1] > 0.f)) v1 = 0.f;
+        float v0 = ds[2 * t] + (((arg >> (4 * t)) & 3u) == static_cast<uint32_t>(q) ? dpv[2 * t] : 0.f);
+        float v1 = ds[2 * t + 1] + (((arg >> (4 * t + 2)) & 3u) == static_cast<uint32_t>(q) ? dpv[2 * t + 1] : 0.f);
+        if (!((pos >> (q * 8 + 2 * t)) & 1u)) v0 = 0.f;
+        if (!((pos >> (q * 8 + 2 * t + 1)) & 1u)) v1 = 0.f;
         csum[2 * t] += v0;
         csum[2 * t + 1] += v1;
         __nv_bfloat16 h0, l0, h1, l1;
@@ -462,8 +460,10 @@ extern "C" int osvos_tail_bwd(const osvos_tail_bwd_args* a, osvos_stream_t strea
     p.s = 2 << k;
     p.top = ((hk + 1) * p.s - a->h) / 2;
     p.left = ((wk + 1) * p.s - a->w) / 2;
-    const size_t warps = static_cast<size_t>(a->n) * hk * wk;
-    tail_bwd_kernel<<<grid_cap((warps + 7) / 8, 16), 256, 0, stream>>>(p);
+    const size_t pixels = static_cast<size_t>(a->n) * hk * wk;
+    if (k == 0) tail_bwd_kernel<2><<<grid_cap((pixels * 2 + 255) / 256, 16), 256, 0, stream>>>(p);
+    else if (k == 1) tail_bwd_kernel<8><<<grid_cap((pixels * 8 + 255) / 256, 16), 256, 0, stream>>>(p);
+    else tail_bwd_kernel<32><<<grid_cap((pixels * 32 + 255) / 256, 16), 256, 0, stream>>>(p);
   }
   OSVOS_CHECK_CUDA(cudaGetLastError());
   return OSVOS_OK;

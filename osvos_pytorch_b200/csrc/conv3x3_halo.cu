@@ -283,6 +283,9 @@ static int dispatch_halo(const osvos_conv3x3_args* a, cudaStream_t stream, int u
   const long waves256 = (static_cast<long>(m_tiles) * (a->cout / 256) + sms - 1) / sms;
   // measured cycles per (tap, 64-channel) step: N = 128 ~ 1000 (2 + 1 instructions), N = 256 ~ 2200 exact
   const bool prefer256 = fast ? waves256 * 1100 < waves128 * 700 : waves256 * 2200 < waves128 * 1000;
+  // few pixel tiles (stage 5 at 480p: 14): N = 64 tiles double the CTA count at ~0.8x the time per tile
+  if (waves128 == 1 && static_cast<long>(m_tiles) * (a->cout / 128) * 5 <= static_cast<long>(sms) * 3)
+    return fast ? launch_halo<64, 1, PITCH>(a, stream, use_bo) : launch_halo<64, 2, PITCH>(a, stream, use_bo);
   if (a->cout % 256 == 0 && prefer256 && !(n256 && atoi(n256) == 0))
     return fast ? launch_halo<256, 1, PITCH>(a, stream, use_bo) : launch_halo<256, 2, PITCH>(a, stream, use_bo);
   return fast ? launch_halo<128, 1, PITCH>(a, stream, use_bo) : launch_halo<128, 2, PITCH>(a, stream, use_bo);

@@ -212,6 +212,7 @@ def main():
     ap.add_argument("--batch", type=int, default=12, help="parent480: frames per GPU per optimizer step")
     ap.add_argument("--precision", default="exact", choices=["exact", "fast"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--eager-train", action="store_true", help="train480: eager launches instead of the step graph")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -246,14 +247,24 @@ def main():
     out_host = torch.empty((1, 1, H, W), dtype=torch.float32).pin_memory()
     loss_host = torch.empty((), dtype=torch.float32).pin_memory()
 
+    graphed = {"step": None}
+
     def step(i, x=None):
         x = xs[i % n_in] if x is None else x
         if train:
-            net.zero_grad(set_to_none=False)
-            outs = net(x)
-            loss = class_balanced_cross_entropy_loss(outs[-1], gts[i % n_in], size_average=False)
-            loss.backward()
-            return loss
+            if args.eager_train:
+                net.zero_grad(set_to_none=False)
+                outs = net(x)
+                loss = class_balanced_cross_entropy_loss(outs[-1], gts[i % n_in], size_average=False)
+                loss.backward()
+                return loss
+            # fwd + online loss + bwd of the micro-batch as one replayed CUDA graph (osvos_pytorch_b200.training)
+            sample = {"image": x, "gt": gts[i % n_in]}
+            if graphed["step"] is None:
+                from osvos_pytorch_b200.training import GraphedTrainStep
+                graphed["step"] = GraphedTrainStep(
+                    net, lambda outs, gt: class_balanced_cross_entropy_loss(outs[-1], gt, size_average=False), sample)
+            return graphed["step"](sample)          # gradients accumulate, as between the reference's optimizer steps
         with torch.no_grad():
             return net(x)[-1]
 
@@ -279,10 +290,13 @@ def main():
     # exactly these launches; the training step is always eager)
     graphs_on = net._engine.use_cuda_graph
     net._engine.use_cuda_graph = False
+    eager_flag = args.eager_train
+    args.eager_train = True                          # count launches on an eager pass
     step(0)
     l0 = ops.KERNEL_LAUNCHES[0]
     step(1)
     launches = ops.KERNEL_LAUNCHES[0] - l0
+    args.eager_train = eager_flag
     net._engine.use_cuda_graph = graphs_on
     for i in range(warmup):
         step(i)
@@ -356,8 +370,8 @@ def main():
                    "parallelism": f"replicas x{world} (no collective on this path)",
                    "l2": "per-step activation traffic (~0.9 GB exact) exceeds the 126 MB L2; inputs rotate over 4 frames; no explicit flush",
                    "timing": "CUDA events on the launching stream, max over ranks",
-                   "launch": ("captured CUDA graph of the step's kernels, replayed per step" if (graphs_on and not train)
-                              else "eager launches")},
+                   "launch": ("captured CUDA graph of the step's kernels, replayed per step"
+                              if ((graphs_on and not train) or (train and not args.eager_train)) else "eager launches")},
         "e2e": {"value": world * 1000.0 / ms_e2e, "unit": "frames/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": 3 * H * W * 4, "d2h_bytes_per_step": (4 if train else H * W * 4),
                 "path": "pinned host frame -> .to(cuda) -> OSVOS.forward (nn.Module API) -> D2H of the fused logit map"},

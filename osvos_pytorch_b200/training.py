@@ -48,26 +48,92 @@ def synthetic_batch(n, h, w, seed, device):
     return {"image": img.to(device), "gt": gt.to(device)}
 
 
-def online_finetune(net, sample_fn, iters, n_ave_grad=5, lr=1e-8, wd=0.0002, log_every=0, log=print):
+class GraphedTrainStep:
+    """Forward + objective + backward of one fixed-shape micro-batch captured in a CUDA graph (SURVEY.md 8f item 1:
+    at > 250 fwd+bwd/s the ~120 kernel launches and the Python around them cost as much as the kernels).
+
+    Gradients ACCUMULATE into the static ``p.grad`` buffers exactly like repeated ``loss.backward()`` calls
+    (train_online.py:140-149): call ``zero_grads()`` after ``optimizer.step()`` (``optimizer.zero_grad()`` with
+    set_to_none would detach the graph from its buffers).  The weight-packing kernels are part of the graph, so
+    parameter updates between replays are picked up.  ``objective(outputs, gts) -> scalar tensor``.
+    """
+
+    def __init__(self, net, objective, sample, grad_scale=1.0):
+        self.net, self.objective, self.grad_scale = net, objective, float(grad_scale)
+        self.x = sample["image"].detach().clone()
+        self.gt = sample["gt"].detach().clone()
+        self.params = [p for n, p in net.named_parameters() if not n.startswith("upscale")]
+        for p in self.params:
+            if p.grad is None:
+                p.grad = torch.zeros_like(p)
+        keep = [p.grad.clone() for p in self.params]
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(2):                              # warm-up: lazy kernel attributes, allocator, autograd
+                self._body()
+        cur.wait_stream(side)
+        for p, g in zip(self.params, keep):                 # undo the warm-up accumulation
+            p.grad.copy_(g)
+        net._engine._pack_cache.clear()                     # so that packing is recorded inside the graph
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = self._body()
+        net._engine._pack_cache.clear()                     # graph-private buffers must not serve eager calls
+
+    def _body(self):
+        outputs = self.net(self.x)
+        loss = self.objective(outputs, self.gt)
+        (loss * self.grad_scale).backward()
+        return loss.detach()
+
+    def __call__(self, sample=None):
+        if sample is not None:
+            self.x.copy_(sample["image"], non_blocking=True)
+            self.gt.copy_(sample["gt"], non_blocking=True)
+        self.graph.replay()
+        return self.loss
+
+    def zero_grads(self):
+        for p in self.params:
+            p.grad.zero_()
+
+
+def online_finetune(net, sample_fn, iters, n_ave_grad=5, lr=1e-8, wd=0.0002, log_every=0, log=print, use_graph=True):
     """`iters` forward/backward passes on the annotated frame, SGD step every `n_ave_grad` (reference
     train_online.py:112-149).  Losses are kept on the device; one host read per `log_every` iterations
-    instead of the reference's per-iteration .item() sync.  Returns the list of logged losses."""
+    instead of the reference's per-iteration .item() sync.  With `use_graph` the fwd+loss+bwd of a micro-batch
+    is a replayed CUDA graph (shapes must not change between iterations).  Returns the list of logged losses."""
     net.train()
     opt = make_optimizer(net, "online", lr, wd)
     opt.zero_grad()
     history, running = [], None
+    step = None
     for it in range(iters):
         sample = sample_fn(it)
         inputs, gts = sample["image"], sample["gt"]
-        outputs = net.forward(inputs)
-        loss = class_balanced_cross_entropy_loss(outputs[-1], gts, size_average=False)
-        # clone: `loss /= n_ave_grad` below is in place (as in the reference) and must not scale the logged value
-        running = loss.detach().clone() if running is None else running + loss.detach()
-        loss /= n_ave_grad
-        loss.backward()
-        if (it + 1) % n_ave_grad == 0:
-            opt.step()
-            opt.zero_grad()
+        if use_graph:
+            if step is None:
+                step = GraphedTrainStep(
+                    net, lambda outs, gt: class_balanced_cross_entropy_loss(outs[-1], gt, size_average=False), sample,
+                    grad_scale=1.0 / n_ave_grad)
+            loss_val = step(sample)
+            running = loss_val.clone() if running is None else running + loss_val
+            if (it + 1) % n_ave_grad == 0:
+                opt.step()
+                step.zero_grads()
+        else:
+            outputs = net.forward(inputs)
+            loss = class_balanced_cross_entropy_loss(outputs[-1], gts, size_average=False)
+            # clone: `loss /= n_ave_grad` below is in place (as in the reference) and must not scale the logged value
+            running = loss.detach().clone() if running is None else running + loss.detach()
+            loss /= n_ave_grad
+            loss.backward()
+            if (it + 1) % n_ave_grad == 0:
+                opt.step()
+                opt.zero_grad()
         if log_every and (it + 1) % log_every == 0:
             val = float(running) / log_every
             history.append(val)

@@ -259,6 +259,13 @@ def test_online_finetune_trajectory_vs_oracle():
     x, gt = oc.synthetic_frame(1, h, w, 77)
     sample = {"image": x.cuda(), "gt": gt.cuda()}
     hist = training.online_finetune(net, lambda it: sample, iters, nave, lr=lr, log_every=1, log=lambda s: None)
+    # the eager (no CUDA graph) loop must produce the same trajectory
+    net_e = OSVOS(pretrained=0, verbose=False)
+    net_e.load_state_dict(params, strict=False)
+    hist_e = training.online_finetune(net_e.cuda(), lambda it: sample, iters, nave, lr=lr, log_every=1,
+                                      log=lambda s: None, use_graph=False)
+    for a, b in zip(hist, hist_e):
+        assert abs(a - b) <= 1e-5 * abs(b), (hist, hist_e)
     # the same loop on the oracle
     ref = OSVOS(pretrained=0, verbose=False)
     ref.load_state_dict(params, strict=False)

@@ -108,9 +108,11 @@ class _OSVOSFunction(torch.autograd.Function):
             cst = s_out.shape[3]
             last_bias = bias_slices[convs[i][-1]]
             if dpool is None:        # deepest stage: the side branch is the only consumer
-                dz, _, _ = ops.conv3x3(dfeats[i - 1], wt_side, None, cst, fast=fast, mask=s_out.hi, colsum=last_bias)
+                dz, _, _ = ops.conv3x3(dfeats[i - 1], wt_side, None, cst, fast=fast, mask=s_out.hi, colsum=last_bias,
+                                       k_valid=16)
             else:
-                _, dside, _ = ops.conv3x3(dfeats[i - 1], wt_side, None, cst, fast=fast, out_act=False, out_f32=True)
+                _, dside, _ = ops.conv3x3(dfeats[i - 1], wt_side, None, cst, fast=fast, out_act=False, out_f32=True,
+                                          k_valid=16)
                 dz = ops.unpool_add_mask(dpool, s_out, dside, colsum=last_bias)
             for j in range(len(convs[i]) - 1, -1, -1):
                 conv = convs[i][j]

@@ -185,6 +185,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_c
             const uint64_t db_lo = make_smem_desc(b_hi + Cfg::kBPlaneBytes, 16, 1024, kLayoutSW128);
 #pragma unroll
             for (int k = 0; k < kBlockK / 16; ++k) {
+              if (k >= p.k_steps) break;                      // padded input channels (k_valid) are skipped
               const uint64_t adv = static_cast<uint64_t>(k * 2);
               const uint32_t first = (kc | tap | k) != 0;
               if (Cfg::kSplitAcc) {

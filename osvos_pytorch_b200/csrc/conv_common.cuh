@@ -28,6 +28,7 @@ struct ConvParams {
   float* colsum;           // optional fused per-channel sum of the output (bias gradient), atomically accumulated
   int n, h, w, cin, cout;
   int tiles_x, tiles_y, n_blocks, total_tiles, k_chunks;
+  int k_steps;               // tcgen05.mma K steps (of 16 channels) issued per 64-channel chunk: 4, or fewer (k_valid)
   int m_tiles, total_pairs;  // CTA-pair kernels: m_tiles pixel tiles, total_pairs = ceil(m_tiles / 2) * n_blocks work items
   int flags;
 };
@@ -334,6 +335,7 @@ static inline void fill_conv_params(ConvParams& p, const osvos_conv3x3_args* a, 
   p.m_tiles = p.tiles_x * p.tiles_y * a->n;
   p.total_pairs = ((p.m_tiles + 1) / 2) * p.n_blocks;
   p.k_chunks = a->cin / kBlockK;
+  p.k_steps = (a->k_valid > 0 && a->k_valid < kBlockK) ? (a->k_valid + 15) / 16 : kBlockK / 16;
   p.flags = a->flags;
 }
 

@@ -40,6 +40,8 @@ struct WgradParams {
   int patches_x, patches_y, patches_total, patches_per_split;
   int total_items;
   int p_shifted;  // 1: P is the shifted operand, 0: Q is
+  int tap_pairs;  // 1: Q has 64 channels and the two 64-wide N atoms of a 128-wide item are TWO TAPS (2g, 2g+1)
+  int tap_items;  // 9, or 5 tap groups in tap_pairs mode
 };
 
 template <int BLOCK_N, int PLANES>
@@ -63,8 +65,8 @@ __device__ __forceinline__ void wg_decode_item(const WgradParams& p, int item, i
   int t = item / p.n_blocks;
   mb = t % p.m_blocks;
   t /= p.m_blocks;
-  tap = t % 9;
-  split = t / 9;
+  tap = t % p.tap_items;   // tap index, or tap-group index in tap_pairs mode
+  split = t / p.tap_items;
 }
 
 template <int BLOCK_N, int PLANES>
@@ -114,7 +116,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_p_hi, const __grid_const
       for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
         int mb, nb, tap, split;
         wg_decode_item(p, item, mb, nb, tap, split);
-        const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+        const int tap0 = p.tap_pairs ? 2 * tap : tap;
+        const int tap1 = (p.tap_pairs && tap0 + 1 < 9) ? tap0 + 1 : tap0;   // second N atom (tap 8 is alone: repeated, unused)
+        const int dy = tap0 / 3 - 1, dx = tap0 % 3 - 1;
+        const int dy1 = tap1 / 3 - 1, dx1 = tap1 % 3 - 1;
         const int pdy = p.p_shifted ? dy : 0, pdx = p.p_shifted ? dx : 0;
         const int qdy = p.p_shifted ? 0 : dy, qdx = p.p_shifted ? 0 : dx;
         const int pb = split * p.patches_per_split;
@@ -146,8 +151,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_p_hi, const __grid_const
                 const CUtensorMap* mq = pl == 0 ? &map_q_hi : &map_q_lo;
                 uint8_t* sq = st + PLANES * Cfg::kPBytes + pl * Cfg::kQBytes;
 #pragma unroll
-                for (int j = 0; j < BLOCK_N / 64; ++j)
-                  tma_load_4d(mq, &full_bar[stage], sq + j * kWgBoxBytes, nb * BLOCK_N + j * 64, x0 + qdx, y0 + qdy, img);
+                for (int j = 0; j < BLOCK_N / 64; ++j) {
+                  if (p.tap_pairs)   // atom j = tap (2g + j) of the single 64-channel block
+                    tma_load_4d(mq, &full_bar[stage], sq + j * kWgBoxBytes, 0, x0 + (j ? dx1 : dx), y0 + (j ? dy1 : dy), img);
+                  else
+                    tma_load_4d(mq, &full_bar[stage], sq + j * kWgBoxBytes, nb * BLOCK_N + j * 64, x0 + qdx, y0 + qdy, img);
+                }
               }
             }
           }
@@ -227,14 +236,18 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_p_hi, const __grid_const
       mbar_wait(&tfull_bar[as], aph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + as * Cfg::kAccCols + (static_cast<uint32_t>(q * 32) << 16);
-      float* dst = p.ws + (static_cast<size_t>(tap) * p.m_total + m) * p.n_total + nb * BLOCK_N;
 #pragma unroll 1
       for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        // destination of this 32-column chunk: channel block nb, or (tap_pairs) tap 2g + c0/64 of the 64 channels
+        const int tap_c = p.tap_pairs ? 2 * tap + (c0 >> 6) : tap;
+        const bool chunk_ok = tap_c < 9;
+        float* dst = p.ws + (static_cast<size_t>(chunk_ok ? tap_c : 0) * p.m_total + m) * p.n_total +
+                     (p.tap_pairs ? -(c0 & ~63) : nb * BLOCK_N);
         uint32_t v[32], v2[32];
         tmem_ld32(taddr + c0, v);
         if (Cfg::kSplitAcc) tmem_ld32(taddr + BLOCK_N + c0, v2);
         tmem_ld_wait();
-        if (m < p.m_valid) {
+        if (m < p.m_valid && chunk_ok) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             float4 val = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
@@ -300,11 +313,15 @@ static int launch_wgrad(const osvos_wgrad_args* a, cudaStream_t stream) {
   p.m_valid = cp;
   p.n_total = cq;
   p.m_blocks = (cp + 127) / 128;
-  p.n_blocks = cq / BLOCK_N;
+  // Cin = 64 trunk layers (conv1_2, conv2_1): the 128-wide item holds two TAPS of the single 64-channel block, which
+  // halves the number of tcgen05.mma (the ~85-cycle instruction floor makes N = 64 items twice as expensive per flop)
+  p.tap_pairs = (!swapped && cq == 64 && BLOCK_N == 128) ? 1 : 0;
+  p.tap_items = p.tap_pairs ? 5 : 9;
+  p.n_blocks = p.tap_pairs ? 1 : cq / BLOCK_N;
   p.patches_x = (a->w + kWgPatchW - 1) / kWgPatchW;
   p.patches_y = (a->h + kWgPatchH - 1) / kWgPatchH;
   p.patches_total = p.patches_x * p.patches_y * a->n;
-  const int tiles = p.m_blocks * p.n_blocks * 9;
+  const int tiles = p.m_blocks * p.n_blocks * p.tap_items;
   const int sms = device_sm_count();
   int splits = (2 * sms + tiles - 1) / tiles;
   const int max_splits = (p.patches_total + 3) / 4;
@@ -366,6 +383,7 @@ extern "C" int osvos_conv3x3_wgrad(const osvos_wgrad_args* a, osvos_stream_t str
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const bool fast = (a->flags & OSVOS_FLAG_FAST) != 0;
   const int cq = a->swapped ? a->dz_channels : a->cin;
-  if (cq % 128 == 0) return fast ? launch_wgrad<128, 1>(a, stream) : launch_wgrad<128, 2>(a, stream);
+  if (cq % 128 == 0 || (!a->swapped && cq == 64))   // Cin = 64: tap-pair mode of the 128-wide kernel
+    return fast ? launch_wgrad<128, 1>(a, stream) : launch_wgrad<128, 2>(a, stream);
   return fast ? launch_wgrad<64, 1>(a, stream) : launch_wgrad<64, 2>(a, stream);
 }

@@ -9,6 +9,9 @@
 // Generic-proxy smem writes are made visible to the tensor core with fence.proxy.async before the
 // mbarrier arrive.
 //
+// Measured alternatives (round 1): staging the 3 x 18 x 10 input patch in shared memory and gathering the taps from
+// it was slower (110 vs 74 us); direct 16-byte global stores instead of the TMA-store epilogue were slower (93 us).
+//
 // Replaces stages[0][0..1] of the reference (networks/vgg_osvos.py:61,142-143).
 #include <string.h>
 

@@ -221,6 +221,50 @@ OSVOS_API int osvos_conv_first_bwd(const float* x_nchw, const void* dz_hi, const
                                    float* dw, float* dx_nchw /* or NULL */, int n, int h, int w,
                                    osvos_stream_t stream);
 
+/* ===================== SURVEY.md 8(f) "next" rows: callers either side ===================== */
+
+/* ---- test-time output path (train_online.py:181-187) --------------------------------
+ * The reference copies the fused logits to the host, applies 1/(1+exp(-x)) in numpy and hands
+ * the float map to scipy.misc.imsave, which rescales [min,max] of the frame to [0,255]
+ * ("bytescale").  Here the 8-bit map is produced on the device so only H*W bytes cross PCIe.
+ *   OSVOS_U8_PROB      out = floor(255*sigmoid(x) + 0.5)
+ *   OSVOS_U8_BYTESCALE out = floor(clip((p - pmin) * 255/(pmax - pmin), 0, 255) + 0.5), p = sigmoid(x),
+ *                      pmin/pmax over each frame (pmax == pmin -> divisor 1): the PNG the reference writes
+ *   OSVOS_U8_MASK      out = x > 0 ? 255 : 0   (the thresholded mask, sigmoid(x) > 0.5)
+ * logits [frames][per_frame] fp32, out [frames][per_frame] u8, minmax_ws: 2 uint32 per frame
+ * (only used by BYTESCALE; zeroed by the call).                                                   */
+enum { OSVOS_U8_PROB = 0, OSVOS_U8_BYTESCALE = 1, OSVOS_U8_MASK = 2 };
+OSVOS_API int osvos_logits_to_u8(const float* logits, uint8_t* out, uint32_t* minmax_ws, int frames, size_t per_frame,
+                                 int mode, osvos_stream_t stream);
+
+/* ---- optimizer step (train_online.py:79-88,147; train_parent.py:87-103,170) -------------
+ * torch.optim.SGD(momentum, weight_decay, dampening 0, no nesterov) over every trainable tensor in ONE launch:
+ *     g' = g + wd*p ;  m = mu*m + g' ;  p = p - lr*m        (m starts at 0, so the first step gives m = g')
+ * with per-tensor lr / wd / mu (the reference's parameter groups), optionally zeroing g in the same pass
+ * (optimizer.zero_grad(), train_online.py:148), and - for 3x3 conv weights whose `packed_*` pointers are set -
+ * re-emitting the tensor-core operand layouts of osvos_pack_conv3x3_weights (forward, col_pad = colp_fwd multiple;
+ * transposed+flipped for dgrad) from the updated values, so no separate repack pass runs after the step.
+ * `segments` is a DEVICE array of `count` descriptors (<= OSVOS_SGD_MAX_SEGMENTS); `work_items` of each
+ * descriptor = osvos_sgd_work_items(numel, cout, cin) (host helper).  Pad columns of the packed layouts are not
+ * touched (they stay zero from the initial osvos_pack_conv3x3_weights call).                           */
+#define OSVOS_SGD_MAX_SEGMENTS 64
+typedef struct osvos_sgd_segment {
+  float* param;         /* [numel] fp32, updated in place                                         */
+  float* grad;          /* [numel] fp32 (zeroed when zero_grad != 0)                              */
+  float* momentum;      /* [numel] fp32 momentum buffer, updated in place                         */
+  uint64_t numel;
+  float lr, weight_decay, momentum_coef;
+  int32_t cout, cin;    /* 3x3 conv weight [cout][cin][3][3] when packed_fwd/packed_flip are set  */
+  int32_t colp_fwd;     /* padded column count of the forward layout  (multiple of its col_pad)   */
+  int32_t colp_flip;    /* padded column count of the flipped layout                              */
+  uint32_t work_items;  /* osvos_sgd_work_items(numel, cout, cin) when packing, (numel, 0, 0) else */
+  void* packed_fwd;     /* or NULL */
+  void* packed_flip;    /* or NULL */
+} osvos_sgd_segment;
+OSVOS_API uint32_t osvos_sgd_work_items(uint64_t numel, int cout, int cin);
+OSVOS_API int osvos_sgd_step(const osvos_sgd_segment* segments /* device */, int count, uint32_t total_work_items,
+                             int zero_grad, osvos_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -363,3 +363,35 @@ def conv_flops(h: int, w: int, n: int = 1) -> float:
         if i > 0:
             total += 2.0 * n * hh * ww * SIDE_CHANNELS * 9 * cin
     return total
+
+
+# --------------------------------------------------------------------------
+# 8(f) rows: test-time output and the optimizer step
+# --------------------------------------------------------------------------
+def png_payload(fused_logits: np.ndarray) -> np.ndarray:
+    """The 8-bit image the reference writes for one frame (train_online.py:182-187): ``pred = 1/(1+exp(-pred))``
+    in numpy fp32, then ``scipy.misc.imsave`` -> ``toimage`` -> ``bytescale(data, high=255, low=0)`` with
+    cmin/cmax = data.min()/data.max().  scipy.misc was removed from SciPy (absent in this image's scipy 1.18; the
+    reference pins no version): this restates the published algorithm of scipy 1.0's ``scipy/misc/pilutil.py``
+    ``bytescale``: ``cscale = cmax - cmin (1 if 0); scale = 255/cscale; bytedata = (data - cmin)*scale;
+    (bytedata.clip(0, 255) + 0.5).astype(uint8)``.  PARITY UNPINNED for this function (the reference's own
+    dependency cannot be run here); the anchor is the call site above.  fused_logits: [H, W] fp32."""
+    x = np.asarray(fused_logits, dtype=np.float32)
+    pred = (1.0 / (1.0 + np.exp(-x))).astype(np.float32)
+    cmin, cmax = pred.min(), pred.max()
+    cscale = np.float32(cmax - cmin)
+    if cscale == 0:
+        cscale = np.float32(1.0)
+    scale = np.float32(255.0) / cscale
+    bytedata = (pred - cmin) * scale
+    return (bytedata.clip(0, 255) + 0.5).astype(np.uint8)
+
+
+def sgd_momentum_step(p: torch.Tensor, g: torch.Tensor, buf, lr: float, wd: float, momentum: float):
+    """torch.optim.SGD as the reference configures it (train_online.py:79-88: momentum 0.9, per-group weight_decay,
+    dampening 0, no nesterov): g' = g + wd*p; buf = g' on the first step, momentum*buf + g' afterwards;
+    p <- p - lr*buf.  Returns (p_new, buf_new).  fp64 inside so it can arbitrate between fp32 implementations."""
+    p64, g64 = p.double(), g.double()
+    gp = g64 + wd * p64
+    b = gp if buf is None else momentum * buf.double() + gp
+    return (p64 - lr * b).float(), b.float()

@@ -6,7 +6,8 @@ library cannot be loaded, or a call fails, an exception is raised.
 """
 import ctypes
 import os
-from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_size_t, c_void_p
+from ctypes import (POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_size_t, c_uint32, c_uint64,
+                    c_void_p)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libosvos_b200.so")
@@ -45,6 +46,17 @@ class TailBwdArgs(Structure):
     _fields_ = [("grad_out", c_void_p * 5), ("dpq", c_void_p * 4), ("n", c_int), ("h", c_int), ("w", c_int)]
 
 
+class SgdSegment(Structure):
+    """osvos_sgd_segment (include/osvos_b200.h); 80 bytes, uploaded as a device table."""
+    _fields_ = [("param", c_void_p), ("grad", c_void_p), ("momentum", c_void_p), ("numel", c_uint64),
+                ("lr", c_float), ("weight_decay", c_float), ("momentum_coef", c_float),
+                ("cout", c_int32), ("cin", c_int32), ("colp_fwd", c_int32), ("colp_flip", c_int32),
+                ("work_items", c_uint32), ("packed_fwd", c_void_p), ("packed_flip", c_void_p)]
+
+
+U8_PROB, U8_BYTESCALE, U8_MASK = 0, 1, 2
+SGD_MAX_SEGMENTS = 64
+
 # name -> (restype, argtypes); mirrors include/osvos_b200.h one to one (tests/test_abi.py checks it)
 SIGNATURES = {
     "osvos_version": (c_int, []),
@@ -73,6 +85,9 @@ SIGNATURES = {
     "osvos_conv_first_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                      c_void_p]),
     "osvos_side_project": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "osvos_logits_to_u8": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_size_t, c_int, c_void_p]),
+    "osvos_sgd_work_items": (c_uint32, [c_uint64, c_int, c_int]),
+    "osvos_sgd_step": (c_int, [c_void_p, c_int, c_uint32, c_int, c_void_p]),
 }
 
 _lib = None

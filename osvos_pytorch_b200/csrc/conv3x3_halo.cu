@@ -152,6 +152,10 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_c
     }
   } else if (warp == 1) {
     // -------------------------------------------------------------- MMA issuer (warp-uniform, elected lane issues)
+    // Negative result kept for the record: flattening the (tile, chunk, tap) nest into one step stream and waiting /
+    // probing (mbarrier.test_wait) the NEXT step's barriers between the first and second K step of the current one
+    // — to hide the ~180-cycle try_wait behind queued MMAs — measured 8 % slower end to end (0.85 vs 0.78 ms at
+    // 480x854): the extra index math on the issuing thread costs more than the overlap gains.
     {
       constexpr uint32_t idesc = make_idesc_f16(kBlockM, BLOCK_N, /*bf16=*/true);
       constexpr uint32_t idesc2 = make_idesc_f16(kBlockM, Cfg::kSplitAcc ? 2 * BLOCK_N : BLOCK_N, /*bf16=*/true);

@@ -41,6 +41,46 @@ class OSVOSEngine:
         return self._cached((key, transpose_flip, col_pad), [conv.weight],
                             lambda: ops.pack_conv3x3_weights(conv.weight, transpose_flip, col_pad))
 
+    def _tensor_core_convs(self):
+        """(conv module, cache key) of every 3x3 conv that runs on the packed tensor-core path (conv1_1 takes its
+        OIHW weights directly)."""
+        m = self.m
+        out = []
+        for i in range(5):
+            convs = [c for c in m.stages[i] if isinstance(c, nn.Conv2d)]
+            for j, conv in enumerate(convs):
+                if i == 0 and j == 0:
+                    continue
+                out.append((conv, f"s{i}c{j}"))
+        out += [(m.side_prep[i - 1], f"sp{i}") for i in range(1, 5)]
+        return out
+
+    def packed_weight_table(self):
+        """[(weight Parameter, forward layout, transposed+flipped layout)] of the tensor-core convs, packed now if
+        stale.  optim.FusedSGD rewrites these buffers in place from the updated weights."""
+        return [(conv.weight, self._packed(conv, key), self._packed(conv, key, transpose_flip=True))
+                for conv, key in self._tensor_core_convs()]
+
+    def restamp_packed(self):
+        """Declare the cached layouts current for the present parameter versions (called by optim.FusedSGD after it
+        has updated the weights AND their packed layouts in one kernel)."""
+        for conv, key in self._tensor_core_convs():
+            ver = ((conv.weight.data_ptr(), conv.weight._version),)
+            for flip in (False, True):
+                hit = self._pack_cache.get((key, flip, 64))
+                if hit is not None:
+                    self._pack_cache[(key, flip, 64)] = (ver, hit[1])
+
+    def drop_derived_caches(self, keep_packed=False):
+        """Forget cached derived tensors; with keep_packed the packed conv layouts (static buffers a captured graph
+        may point at) are kept."""
+        if not keep_packed:
+            self._pack_cache.clear()
+            return
+        for k in [k for k in self._pack_cache if not (isinstance(k, tuple) and len(k) == 3 and k[2] == 64
+                                                      and isinstance(k[1], bool))]:
+            del self._pack_cache[k]
+
     def _param_list(self):
         """Parameters the native path differentiates (everything except the fixed deconvolution taps)."""
         m = self.m
@@ -81,6 +121,9 @@ class OSVOSEngine:
             raise RuntimeError("osvos_pytorch_b200.OSVOS runs on CUDA (sm_100a) only: move the module and the input "
                                "to the GPU.  There is no CPU fallback for the hot path.")
         needs_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.m.parameters()))
+        if x.device != torch.device("cuda", torch.cuda.current_device()):
+            with torch.cuda.device(x.device):       # kernels are enqueued on the current stream of x's device
+                return self.forward(x)
         if needs_grad:
             from .autograd import osvos_apply
             return osvos_apply(self, x)

@@ -276,3 +276,24 @@ def conv_first_bwd(x, dz, weight, need_dx):
     nat.check(lib.osvos_conv_first_bwd(x.data_ptr(), dz.hi.data_ptr(), nat.ptr(dz.lo), weight.data_ptr(),
                                        dw.data_ptr(), nat.ptr(dx), n, h, w, _stream()), "osvos_conv_first_bwd")
     return dw, dx
+
+
+_U8_MODES = {"prob": nat.U8_PROB, "bytescale": nat.U8_BYTESCALE, "mask": nat.U8_MASK}
+
+
+def logits_to_u8(logits, mode="bytescale", out=None):
+    """Test-time output path on the device (reference train_online.py:181-187): fused logits [N,1,H,W] fp32 ->
+    uint8 [N,1,H,W].  mode 'bytescale' is the PNG payload the reference's sigmoid + scipy.misc.imsave writes,
+    'prob' is round(255*sigmoid), 'mask' is 255*(logit > 0)."""
+    lib = nat.load()
+    _require_cuda(logits, "logits")
+    x = logits.detach().contiguous().float()
+    frames = int(x.shape[0])
+    per = x.numel() // frames
+    if out is None:
+        out = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
+    ws = torch.empty(2 * frames, dtype=torch.int32, device=x.device) if mode == "bytescale" else None
+    _count(3 if mode == "bytescale" else 1)
+    nat.check(lib.osvos_logits_to_u8(x.data_ptr(), out.data_ptr(), nat.ptr(ws), frames, per, _U8_MODES[mode], _stream()),
+              "osvos_logits_to_u8")
+    return out

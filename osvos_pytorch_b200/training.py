@@ -16,8 +16,9 @@ def _named(module, key):
     return [p for n, p in module.named_parameters() if key in n]
 
 
-def make_optimizer(net, mode, lr=1e-8, wd=0.0002, momentum=0.9):
-    """SGD with the reference's parameter groups.
+def make_optimizer(net, mode, lr=1e-8, wd=0.0002, momentum=0.9, fused=False):
+    """SGD with the reference's parameter groups (``fused``: optim.FusedSGD - one launch per step, packed conv
+    layouts re-emitted in the same pass - instead of torch.optim.SGD).
     online (train_online.py:77-88): stages / side_prep weights (wd) and biases (2 lr), deconvs lr 0,
     fuse at lr/100; score_dsn is NOT optimised.  parent (train_parent.py:85-103): additionally score_dsn at lr/10."""
     groups = [
@@ -37,6 +38,9 @@ def make_optimizer(net, mode, lr=1e-8, wd=0.0002, momentum=0.9):
         {"params": [net.fuse.weight], "lr": lr / 100, "initial_lr": lr / 100, "weight_decay": wd},
         {"params": [net.fuse.bias], "lr": 2 * lr / 100, "initial_lr": 2 * lr / 100},
     ]
+    if fused:
+        from .optim import FusedSGD
+        return FusedSGD(groups, lr=lr, momentum=momentum, engine=net._engine)
     return torch.optim.SGD(groups, lr=lr, momentum=momentum)
 
 
@@ -55,10 +59,12 @@ class GraphedTrainStep:
     Gradients ACCUMULATE into the static ``p.grad`` buffers exactly like repeated ``loss.backward()`` calls
     (train_online.py:140-149): call ``zero_grads()`` after ``optimizer.step()`` (``optimizer.zero_grad()`` with
     set_to_none would detach the graph from its buffers).  The weight-packing kernels are part of the graph, so
-    parameter updates between replays are picked up.  ``objective(outputs, gts) -> scalar tensor``.
+    parameter updates between replays are picked up - unless ``external_pack`` is set: then the packed conv
+    layouts are static buffers outside the graph that ``optim.FusedSGD`` rewrites in its update kernel (no
+    packing work per micro-batch; only valid with that optimizer).  ``objective(outputs, gts) -> scalar tensor``.
     """
 
-    def __init__(self, net, objective, sample, grad_scale=1.0):
+    def __init__(self, net, objective, sample, grad_scale=1.0, external_pack=False):
         self.net, self.objective, self.grad_scale = net, objective, float(grad_scale)
         self.x = sample["image"].detach().clone()
         self.gt = sample["gt"].detach().clone()
@@ -76,12 +82,15 @@ class GraphedTrainStep:
         cur.wait_stream(side)
         for p, g in zip(self.params, keep):                 # undo the warm-up accumulation
             p.grad.copy_(g)
-        net._engine._pack_cache.clear()                     # so that packing is recorded inside the graph
+        if external_pack:
+            net._engine.packed_weight_table()               # packed now, outside the graph
+        # everything else derived from parameters is recomputed inside the graph
+        net._engine.drop_derived_caches(keep_packed=external_pack)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.loss = self._body()
-        net._engine._pack_cache.clear()                     # graph-private buffers must not serve eager calls
+        net._engine.drop_derived_caches(keep_packed=external_pack)   # graph-private buffers must not serve eager calls
 
     def _body(self):
         outputs = self.net(self.x)
@@ -96,19 +105,26 @@ class GraphedTrainStep:
         self.graph.replay()
         return self.loss
 
-    def zero_grads(self):
+    def zero_grads(self, skip=()):
+        """Zero the accumulated gradients (``skip``: parameters already cleared, e.g. by FusedSGD.step(zero_grad=True))."""
+        skip = {id(p) for p in skip}
         for p in self.params:
-            p.grad.zero_()
+            if id(p) not in skip:
+                p.grad.zero_()
 
 
-def online_finetune(net, sample_fn, iters, n_ave_grad=5, lr=1e-8, wd=0.0002, log_every=0, log=print, use_graph=True):
+def online_finetune(net, sample_fn, iters, n_ave_grad=5, lr=1e-8, wd=0.0002, log_every=0, log=print, use_graph=True,
+                    fused_optimizer=True):
     """`iters` forward/backward passes on the annotated frame, SGD step every `n_ave_grad` (reference
     train_online.py:112-149).  Losses are kept on the device; one host read per `log_every` iterations
     instead of the reference's per-iteration .item() sync.  With `use_graph` the fwd+loss+bwd of a micro-batch
-    is a replayed CUDA graph (shapes must not change between iterations).  Returns the list of logged losses."""
+    is a replayed CUDA graph (shapes must not change between iterations); with `fused_optimizer` the SGD step,
+    the gradient zeroing and the repack of the conv weights are one kernel (optim.FusedSGD).  Returns the list of
+    logged losses."""
     net.train()
-    opt = make_optimizer(net, "online", lr, wd)
+    opt = make_optimizer(net, "online", lr, wd, fused=fused_optimizer)
     opt.zero_grad()
+    opt_params = [p for g in opt.param_groups for p in g["params"]]
     history, running = [], None
     step = None
     for it in range(iters):
@@ -118,12 +134,16 @@ def online_finetune(net, sample_fn, iters, n_ave_grad=5, lr=1e-8, wd=0.0002, log
             if step is None:
                 step = GraphedTrainStep(
                     net, lambda outs, gt: class_balanced_cross_entropy_loss(outs[-1], gt, size_average=False), sample,
-                    grad_scale=1.0 / n_ave_grad)
+                    grad_scale=1.0 / n_ave_grad, external_pack=fused_optimizer)
             loss_val = step(sample)
             running = loss_val.clone() if running is None else running + loss_val
             if (it + 1) % n_ave_grad == 0:
-                opt.step()
-                step.zero_grads()
+                if fused_optimizer:
+                    opt.step(zero_grad=True)
+                    step.zero_grads(skip=opt_params)
+                else:
+                    opt.step()
+                    step.zero_grads()
         else:
             outputs = net.forward(inputs)
             loss = class_balanced_cross_entropy_loss(outputs[-1], gts, size_average=False)
@@ -132,8 +152,11 @@ def online_finetune(net, sample_fn, iters, n_ave_grad=5, lr=1e-8, wd=0.0002, log
             loss /= n_ave_grad
             loss.backward()
             if (it + 1) % n_ave_grad == 0:
-                opt.step()
-                opt.zero_grad()
+                if fused_optimizer:
+                    opt.step(zero_grad=True)
+                else:
+                    opt.step()
+                    opt.zero_grad()
         if log_every and (it + 1) % log_every == 0:
             val = float(running) / log_every
             history.append(val)
@@ -160,8 +183,11 @@ def parent_epoch(net, opt, bucket, batches, epoch, n_epochs, n_ave_grad=1, group
         loss.backward()
         if (it + 1) % n_ave_grad == 0:
             bucket.allreduce_mean(group)
-            opt.step()
-            bucket.zero_()
+            if hasattr(opt, "_engine"):                     # optim.FusedSGD: update + zeroing + repack in one kernel
+                opt.step(zero_grad=True)
+            else:
+                opt.step()
+                bucket.zero_()
     return (totals / max(count, 1)).tolist()
 
 

@@ -210,3 +210,30 @@ def test_param_inventory():
     assert frozen == 349520 and total - frozen == 14917637
     assert abs(oc.conv_flops(480, 854) / 1e9 - 258.23) < 0.01
     assert abs(oc.conv_flops(240, 427) / 1e9 - 64.77) < 0.01
+
+
+# ---- 8(f) rows ------------------------------------------------------------------------------------------
+def test_png_payload_known_answers():
+    """bytescale of the sigmoid map (train_online.py:183-187 + scipy 1.0 pilutil.bytescale): extrema map to 0 / 255,
+    a constant map to 0, and the mid value rounds half up."""
+    x = np.array([[-50.0, 50.0], [0.0, 0.0]], dtype=np.float32)
+    out = oc.png_payload(x)
+    assert out.dtype == np.uint8 and out[0, 0] == 0 and out[0, 1] == 255
+    assert out[1, 0] == 128                                     # (0.5 - ~0) * 255 = 127.5 -> +0.5 -> 128
+    assert int(oc.png_payload(np.full((3, 4), 2.0, np.float32)).max()) == 0
+    y = np.linspace(-4, 4, 97, dtype=np.float32).reshape(1, -1)
+    o = oc.png_payload(y)
+    assert o[0, 0] == 0 and o[0, -1] == 255 and np.all(np.diff(o[0].astype(int)) >= 0)
+
+
+def test_sgd_oracle_matches_torch_optim_sgd():
+    """The reference's optimizer IS torch.optim.SGD (train_online.py:79-88): pin the fp64 restatement to it."""
+    g = torch.Generator().manual_seed(0)
+    p = torch.nn.Parameter(torch.randn(257, generator=g))
+    opt = torch.optim.SGD([{"params": [p], "weight_decay": 0.02}], lr=0.03, momentum=0.9)
+    rp, rb = p.detach().clone(), None
+    for _ in range(4):
+        p.grad = torch.randn(257, generator=g)
+        rp, rb = oc.sgd_momentum_step(rp, p.grad, rb, 0.03, 0.02, 0.9)
+        opt.step()
+        assert float((p.detach() - rp).abs().max()) < 1e-6

@@ -49,7 +49,9 @@ enum {
   OSVOS_FLAG_RELU = 1,       /* fwd: y = max(y, 0)            (networks/vgg_osvos.py:143) */
   OSVOS_FLAG_FAST = 2,       /* single-pass bf16 operands (hi planes only)               */
   OSVOS_FLAG_RELU_MASK = 4,  /* dgrad: dx *= (mask_hi > 0)    (autograd of :143)          */
-  OSVOS_FLAG_ACCUMULATE = 8  /* add into the existing output instead of overwriting it    */
+  OSVOS_FLAG_ACCUMULATE = 8, /* add into the existing output instead of overwriting it    */
+  OSVOS_FLAG_DEFER_FINISH = 16 /* osvos_conv3x3_wgrad: accumulate into a caller-zeroed workspace only; the
+                                  workspace -> OIHW step is done later by osvos_wgrad_finish for many layers */
 };
 
 typedef void* osvos_stream_t; /* cudaStream_t */
@@ -178,10 +180,23 @@ typedef struct {
   float* workspace;
   int n, h, w, cin, cout, dz_channels;
   int swapped;
-  int flags;          /* OSVOS_FLAG_FAST */
+  int flags;          /* OSVOS_FLAG_FAST | OSVOS_FLAG_DEFER_FINISH (then dw may be NULL) */
 } osvos_wgrad_args;
 OSVOS_API size_t osvos_wgrad_workspace_bytes(int dz_channels, int cin);
 OSVOS_API int osvos_conv3x3_wgrad(const osvos_wgrad_args* args /* host */, osvos_stream_t stream);
+
+/* Deferred finish of up to OSVOS_WGRAD_FINISH_MAX weight gradients in ONE launch: workspace [9][a][b] -> OIHW,
+ * dw = (accumulate ? dw : 0) + scale * ws.  With accumulate the destination can be the parameter's .grad itself
+ * (what autograd's AccumulateGrad would do with a separate add kernel, train_online.py:141).                    */
+#define OSVOS_WGRAD_FINISH_MAX 24
+typedef struct {
+  const float* workspace;  /* as passed to osvos_conv3x3_wgrad with OSVOS_FLAG_DEFER_FINISH */
+  float* dw;               /* [cout][cin][3][3] */
+  int cout, cin, dz_channels, swapped;
+  int accumulate;
+  float scale;
+} osvos_wgrad_finish_item;
+OSVOS_API int osvos_wgrad_finish(const osvos_wgrad_finish_item* items /* host */, int count, osvos_stream_t stream);
 
 /* ---- adjoint of the tail: gradients of the five maps -> low-res dp/dq ------------
  * Backward of osvos_tail_fwd (autograd of networks/vgg_osvos.py:68-72): strided bilinear

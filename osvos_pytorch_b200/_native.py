@@ -16,6 +16,8 @@ FLAG_RELU = 1
 FLAG_FAST = 2
 FLAG_RELU_MASK = 4
 FLAG_ACCUMULATE = 8
+FLAG_DEFER_FINISH = 16
+WGRAD_FINISH_MAX = 24
 
 
 class NativeLibraryError(RuntimeError):
@@ -40,6 +42,11 @@ class WgradArgs(Structure):
     _fields_ = [("x_hi", c_void_p), ("x_lo", c_void_p), ("dz_hi", c_void_p), ("dz_lo", c_void_p), ("dw", c_void_p),
                 ("workspace", c_void_p), ("n", c_int), ("h", c_int), ("w", c_int), ("cin", c_int), ("cout", c_int),
                 ("dz_channels", c_int), ("swapped", c_int), ("flags", c_int)]
+
+
+class WgradFinishItem(Structure):
+    _fields_ = [("workspace", c_void_p), ("dw", c_void_p), ("cout", c_int), ("cin", c_int), ("dz_channels", c_int),
+                ("swapped", c_int), ("accumulate", c_int), ("scale", c_float)]
 
 
 class TailBwdArgs(Structure):
@@ -75,6 +82,7 @@ SIGNATURES = {
     "osvos_cbce_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_size_t, c_void_p, c_void_p]),
     "osvos_wgrad_workspace_bytes": (c_size_t, [c_int, c_int]),
     "osvos_conv3x3_wgrad": (c_int, [POINTER(WgradArgs), c_void_p]),
+    "osvos_wgrad_finish": (c_int, [POINTER(WgradFinishItem), c_int, c_void_p]),
     "osvos_tail_bwd": (c_int, [POINTER(TailBwdArgs), c_void_p]),
     "osvos_sum_f32": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
     "osvos_side_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,

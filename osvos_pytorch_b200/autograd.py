@@ -74,6 +74,44 @@ class _OSVOSFunction(torch.autograd.Function):
         pg = {}                                   # parameter -> gradient tensor
         if all(g is None for g in grads):
             return (None, None) + tuple(None for _ in engine._param_list())
+        # ---- weight-gradient plumbing: ONE zeroed arena for all tensor-core wgrad workspaces, ONE finish launch at
+        # the end.  In direct mode (engine.accumulate_param_grads_in_place, set by the package's training loops) the
+        # finish adds straight into an existing p.grad and the bias column sums are accumulated into p.grad by the
+        # dgrad epilogues - what autograd's AccumulateGrad would otherwise do with one add kernel per parameter.
+        direct = bool(getattr(engine, "accumulate_param_grads_in_place", False))
+
+        def grad_target(p):
+            g = p.grad
+            if direct and p.requires_grad and g is not None and g.is_cuda and g.dtype == torch.float32 \
+                    and g.is_contiguous() and g.device == xin.device:
+                return g
+            return None
+        wconvs = [c for stage in convs for c in stage][1:] + list(m.side_prep)
+        ws_sizes = [ops.wgrad_workspace_floats(64 if c.out_channels == 16 else c.out_channels, c.in_channels)
+                    for c in wconvs]
+        arena = torch.zeros(sum(ws_sizes), dtype=torch.float32, device=xin.device)
+        ws_of, off = {}, 0
+        for c, sz in zip(wconvs, ws_sizes):
+            ws_of[c] = arena[off:off + sz]
+            off += sz
+        fresh = [c for c in wconvs if grad_target(c.weight) is None]
+        fresh_buf = torch.empty(sum(c.weight.numel() for c in fresh), dtype=torch.float32, device=xin.device)
+        finish_items, off = [], 0
+
+        def wgrad(conv, inp, dz_act, swapped=False):
+            nonlocal off
+            it = ops.conv3x3_wgrad(inp, dz_act, conv.out_channels, swapped=swapped, fast=fast, deferred_ws=ws_of[conv])
+            tgt = grad_target(conv.weight)
+            if tgt is not None:
+                it["dw"], it["accumulate"] = tgt, True
+                pg[conv.weight] = None
+            else:
+                nel = conv.weight.numel()
+                it["dw"], it["accumulate"] = fresh_buf[off:off + nel].view(conv.weight.shape), False
+                off += nel
+                pg[conv.weight] = it["dw"]
+            finish_items.append(it)
+
         dpq = ops.tail_bwd(list(grads), n, h, w)
         if grads[4] is not None:
             pg[m.fuse.bias] = ops.sum_f32(grads[4]).reshape(m.fuse.bias.shape)
@@ -81,10 +119,16 @@ class _OSVOSFunction(torch.autograd.Function):
         # one zeroed buffer for all 13 trunk bias gradients; the dgrad / unpool epilogues accumulate into its slices
         flat_convs = [c for stage in convs for c in stage]
         bias_buf = torch.zeros(sum(c.out_channels for c in flat_convs), dtype=torch.float32, device=xin.device)
-        bias_slices, off = {}, 0
+        bias_slices, bias_direct, boff = {}, set(), 0
         for c in flat_convs:
-            bias_slices[c] = bias_buf[off:off + c.out_channels]
-            off += c.out_channels
+            tgt = grad_target(c.bias)
+            if tgt is not None:
+                bias_direct.add(c)
+            bias_slices[c] = tgt if tgt is not None else bias_buf[boff:boff + c.out_channels]
+            boff += c.out_channels
+
+        def bias_grad(c):                              # None: already accumulated into c.bias.grad
+            return None if c in bias_direct else bias_slices[c]
         dfeats = []
         for i in range(4):
             d, g50 = ops.side_bwd(feats[i], dpq[i], engine._proj(i), fast)
@@ -95,7 +139,7 @@ class _OSVOSFunction(torch.autograd.Function):
             if fuse_w_grad is not None:
                 fuse_w_grad[16 * i:16 * i + 16] = g50[17:33]           # slice copy (plumbing)
             sp = m.side_prep[i]
-            pg[sp.weight] = ops.conv3x3_wgrad(acts[i + 1][-1], d, 16, swapped=True, fast=fast)
+            wgrad(sp, acts[i + 1][-1], d, swapped=True)
             pg[sp.bias] = g50[34:50]
         if fuse_w_grad is not None:
             pg[m.fuse.weight] = fuse_w_grad.reshape(m.fuse.weight.shape)
@@ -117,8 +161,8 @@ class _OSVOSFunction(torch.autograd.Function):
             for j in range(len(convs[i]) - 1, -1, -1):
                 conv = convs[i][j]
                 inp = acts[i][j - 1] if j > 0 else pooled[i]
-                pg[conv.weight] = ops.conv3x3_wgrad(inp, dz, conv.out_channels, fast=fast)
-                pg[conv.bias] = bias_slices[conv]
+                wgrad(conv, inp, dz)
+                pg[conv.bias] = bias_grad(conv)
                 wt = engine._packed(conv, f"s{i}c{j}", transpose_flip=True)
                 if j > 0:
                     dz, _, _ = ops.conv3x3(dz, wt, None, conv.in_channels, fast=fast, mask=inp.hi,
@@ -128,13 +172,14 @@ class _OSVOSFunction(torch.autograd.Function):
         # stage 1 (no side branch)
         c12, c11 = convs[0][1], convs[0][0]
         dz = ops.unpool_add_mask(dpool, acts[0][1], None, colsum=bias_slices[c12])
-        pg[c12.weight] = ops.conv3x3_wgrad(acts[0][0], dz, 64, fast=fast)
-        pg[c12.bias] = bias_slices[c12]
+        wgrad(c12, acts[0][0], dz)
+        pg[c12.bias] = bias_grad(c12)
         dz, _, _ = ops.conv3x3(dz, engine._packed(c12, "s0c1", transpose_flip=True), None, 64, fast=fast,
                                mask=acts[0][0].hi, colsum=bias_slices[c11])
         dw0, dx = ops.conv_first_bwd(xin, dz, c11.weight.detach(), ctx.needs_input_grad[1])
         pg[c11.weight] = dw0
-        pg[c11.bias] = bias_slices[c11]
+        pg[c11.bias] = bias_grad(c11)
+        ops.wgrad_finish(finish_items)
         ctx.saved = None
         return (None, dx) + tuple(pg.get(p) for p in engine._param_list())
 

@@ -290,6 +290,58 @@ __global__ void wgrad_finish_kernel(const float* __restrict__ ws, float* __restr
   }
 }
 
+// Deferred finish of many layers in one launch.  A work item is one output row (co) x 64 input channels x 9 taps
+// = 576 contiguous OIHW floats: the nine workspace rows are read coalesced (256 B each), transposed through shared
+// memory and written coalesced.  The thin side_prep gradients (swapped roles, 16 x C x 9) take the element-wise path.
+struct FinishLayer {
+  const float* ws;
+  float* dw;
+  int cout, cin, ld_a, ld_b, swapped, accumulate;
+  float scale;
+  int items;
+};
+struct FinishTable {
+  FinishLayer layer[OSVOS_WGRAD_FINISH_MAX];
+  int count;
+};
+constexpr int kFinishThreads = 192;
+constexpr int kFinishChunk = 576;
+
+__global__ void __launch_bounds__(kFinishThreads)
+wgrad_finish_multi_kernel(const __grid_constant__ FinishTable t) {
+  __shared__ float tile[9][65];
+  int item = blockIdx.x, li = 0;
+  while (li < t.count && item >= t.layer[li].items) {
+    item -= t.layer[li].items;
+    ++li;
+  }
+  if (li >= t.count) return;
+  const FinishLayer& L = t.layer[li];
+  if (L.swapped) {
+    const int total = L.cout * L.cin * 9;
+    for (int i = item * kFinishChunk + threadIdx.x; i < min(total, (item + 1) * kFinishChunk); i += kFinishThreads) {
+      const int tap = i % 9;
+      const int ci = (i / 9) % L.cin;
+      const int co = i / (9 * L.cin);
+      const float v = L.ws[(static_cast<size_t>(tap) * L.ld_a + ci) * L.ld_b + co] * L.scale;
+      L.dw[i] = L.accumulate ? L.dw[i] + v : v;
+    }
+    return;
+  }
+  const int chunks = L.cin / 64;
+  const int co = item / chunks, ci0 = (item % chunks) * 64;
+  for (int i = threadIdx.x; i < kFinishChunk; i += kFinishThreads) {
+    const int tap = i / 64, c = i % 64;
+    tile[tap][c] = L.ws[(static_cast<size_t>(tap) * L.ld_a + co) * L.ld_b + ci0 + c];
+  }
+  __syncthreads();
+  float* out = L.dw + (static_cast<size_t>(co) * L.cin + ci0) * 9;
+  for (int i = threadIdx.x; i < kFinishChunk; i += kFinishThreads) {
+    const float v = tile[i % 9][i / 9] * L.scale;
+    out[i] = L.accumulate ? out[i] + v : v;
+  }
+}
+
 template <int BLOCK_N, int PLANES>
 static int launch_wgrad(const osvos_wgrad_args* a, cudaStream_t stream) {
   using Cfg = WgCfg<BLOCK_N, PLANES>;
@@ -346,8 +398,9 @@ static int launch_wgrad(const osvos_wgrad_args* a, cudaStream_t stream) {
   if ((rc = enc(&mq_hi, q_hi, cq))) return rc;
   if ((rc = enc(&mq_lo, PLANES == 2 ? q_lo : q_hi, cq))) return rc;
 
+  const bool deferred = (a->flags & OSVOS_FLAG_DEFER_FINISH) != 0;
   const size_t ws_bytes = static_cast<size_t>(9) * p.m_total * p.n_total * sizeof(float);
-  OSVOS_CHECK_CUDA(cudaMemsetAsync(a->workspace, 0, ws_bytes, stream));
+  if (!deferred) OSVOS_CHECK_CUDA(cudaMemsetAsync(a->workspace, 0, ws_bytes, stream));
   auto kern = wgrad_tc_kernel<BLOCK_N, PLANES>;
   static bool attr_done = false;
   if (!attr_done) {
@@ -357,6 +410,7 @@ static int launch_wgrad(const osvos_wgrad_args* a, cudaStream_t stream) {
   const int grid = p.total_items < sms ? p.total_items : sms;
   kern<<<grid, kWgThreads, Cfg::kSmemBytes, stream>>>(mp_hi, mp_lo, mq_hi, mq_lo, p);
   OSVOS_CHECK_CUDA(cudaGetLastError());
+  if (deferred) return OSVOS_OK;
   const int total = a->cout * a->cin * 9;
   wgrad_finish_kernel<<<(total + 255) / 256, 256, 0, stream>>>(a->workspace, a->dw, a->cout, a->cin, p.m_total,
                                                                 p.n_total, swapped ? 1 : 0, 1.0f, 0);
@@ -372,9 +426,36 @@ extern "C" size_t osvos_wgrad_workspace_bytes(int cout_or_padded, int cin) {
   return static_cast<size_t>(9) * cout_or_padded * cin * sizeof(float);
 }
 
+extern "C" int osvos_wgrad_finish(const osvos_wgrad_finish_item* items, int count, osvos_stream_t stream_) {
+  OSVOS_CHECK_ARG(items != nullptr && count > 0 && count <= OSVOS_WGRAD_FINISH_MAX);
+  FinishTable t;
+  t.count = count;
+  long long total_items = 0;
+  for (int i = 0; i < count; ++i) {
+    const osvos_wgrad_finish_item& it = items[i];
+    OSVOS_CHECK_ARG(it.workspace != nullptr && it.dw != nullptr && it.cout > 0 && it.cin > 0 && it.cin % 64 == 0);
+    OSVOS_CHECK_ARG(it.dz_channels % 64 == 0 && it.cout <= it.dz_channels);
+    FinishLayer& L = t.layer[i];
+    L.ws = it.workspace;
+    L.dw = it.dw;
+    L.cout = it.cout;
+    L.cin = it.cin;
+    L.swapped = it.swapped ? 1 : 0;
+    L.ld_a = it.swapped ? it.cin : it.dz_channels;
+    L.ld_b = it.swapped ? it.dz_channels : it.cin;
+    L.accumulate = it.accumulate ? 1 : 0;
+    L.scale = it.scale;
+    L.items = it.swapped ? (it.cout * it.cin * 9 + kFinishChunk - 1) / kFinishChunk : it.cout * (it.cin / 64);
+    total_items += L.items;
+  }
+  wgrad_finish_multi_kernel<<<static_cast<unsigned>(total_items), kFinishThreads, 0, static_cast<cudaStream_t>(stream_)>>>(t);
+  OSVOS_CHECK_CUDA(cudaGetLastError());
+  return OSVOS_OK;
+}
+
 extern "C" int osvos_conv3x3_wgrad(const osvos_wgrad_args* a, osvos_stream_t stream_) {
-  OSVOS_CHECK_ARG(a != nullptr && a->x_hi != nullptr && a->dz_hi != nullptr && a->dw != nullptr &&
-                  a->workspace != nullptr);
+  OSVOS_CHECK_ARG(a != nullptr && a->x_hi != nullptr && a->dz_hi != nullptr && a->workspace != nullptr);
+  OSVOS_CHECK_ARG(a->dw != nullptr || (a->flags & OSVOS_FLAG_DEFER_FINISH));
   OSVOS_CHECK_ARG(a->n > 0 && a->h > 0 && a->w > 0 && a->cin % 64 == 0 && a->dz_channels % 64 == 0);
   OSVOS_CHECK_ARG(a->cout <= a->dz_channels);
   OSVOS_CHECK_ARG((a->flags & OSVOS_FLAG_FAST) || (a->x_lo != nullptr && a->dz_lo != nullptr));

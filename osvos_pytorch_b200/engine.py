@@ -26,6 +26,23 @@ class OSVOSEngine:
         # disables it).
         self._graphs = {}
         self.use_cuda_graph = os.environ.get("OSVOS_CUDA_GRAPH", "1") != "0"
+        # training loops of this package set this: backward adds weight / trunk-bias gradients straight into an
+        # existing p.grad (and hands autograd None for them) instead of returning tensors for AccumulateGrad
+        self.accumulate_param_grads_in_place = False
+
+    def direct_grad_accumulation(self):
+        """Context manager enabling in-place gradient accumulation for the backward passes run inside it."""
+        eng = self
+
+        class _Ctx:
+            def __enter__(self):
+                self.prev = eng.accumulate_param_grads_in_place
+                eng.accumulate_param_grads_in_place = True
+
+            def __exit__(self, *exc):
+                eng.accumulate_param_grads_in_place = self.prev
+                return False
+        return _Ctx()
 
     # ------------------------------------------------------------ weight caches
     def _cached(self, key, params, make):

@@ -177,23 +177,50 @@ def tail_fwd(pqs, fuse_bias, n, h, w, label=None, out=None):
 
 
 # ------------------------------------------------------------------ backward ops
-def conv3x3_wgrad(x, dz, cout, swapped=False, fast=False):
-    """dW [cout, cin, 3, 3] of a 3x3 conv from its input act `x` and output-gradient act `dz`."""
+def wgrad_workspace_floats(dz_channels, cin):
+    return nat.load().osvos_wgrad_workspace_bytes(dz_channels, cin) // 4
+
+
+def conv3x3_wgrad(x, dz, cout, swapped=False, fast=False, deferred_ws=None):
+    """dW [cout, cin, 3, 3] of a 3x3 conv from its input act `x` and output-gradient act `dz`.
+    With `deferred_ws` (a ZEROED fp32 workspace of wgrad_workspace_floats(dz.channels, cin)) only the tensor-core
+    accumulation is enqueued and a finish item for ops.wgrad_finish is returned instead of dW."""
     lib = nat.load()
     n, h, w, cin = x.shape
     dzc = dz.shape[3]
     dev = x.hi.device
-    dw = torch.empty((cout, cin, 3, 3), dtype=torch.float32, device=dev)
-    ws = torch.empty(lib.osvos_wgrad_workspace_bytes(dzc, cin) // 4, dtype=torch.float32, device=dev)
     a = nat.WgradArgs()
     a.x_hi, a.x_lo, a.dz_hi, a.dz_lo = x.hi.data_ptr(), nat.ptr(x.lo), dz.hi.data_ptr(), nat.ptr(dz.lo)
-    a.dw, a.workspace = dw.data_ptr(), ws.data_ptr()
     a.n, a.h, a.w, a.cin, a.cout, a.dz_channels = n, h, w, cin, cout, dzc
     a.swapped = int(swapped)
     a.flags = nat.FLAG_FAST if fast else 0
+    if deferred_ws is not None:
+        a.dw, a.workspace = None, deferred_ws.data_ptr()
+        a.flags |= nat.FLAG_DEFER_FINISH
+        _count(1)
+        nat.check(lib.osvos_conv3x3_wgrad(byref(a), _stream()), "osvos_conv3x3_wgrad")
+        return {"ws": deferred_ws, "cout": cout, "cin": cin, "dz_channels": dzc, "swapped": int(swapped)}
+    dw = torch.empty((cout, cin, 3, 3), dtype=torch.float32, device=dev)
+    ws = torch.empty(lib.osvos_wgrad_workspace_bytes(dzc, cin) // 4, dtype=torch.float32, device=dev)
+    a.dw, a.workspace = dw.data_ptr(), ws.data_ptr()
     _count(3)
     nat.check(lib.osvos_conv3x3_wgrad(byref(a), _stream()), "osvos_conv3x3_wgrad")
     return dw
+
+
+def wgrad_finish(items):
+    """One launch for the workspace -> OIHW step of many layers.  items: dicts from conv3x3_wgrad(deferred_ws=...)
+    extended with 'dw' (destination tensor) and 'accumulate' (add into it, e.g. the parameter's .grad)."""
+    lib = nat.load()
+    for lo in range(0, len(items), nat.WGRAD_FINISH_MAX):
+        part = items[lo:lo + nat.WGRAD_FINISH_MAX]
+        arr = (nat.WgradFinishItem * len(part))()
+        for f, it in zip(arr, part):
+            f.workspace, f.dw = it["ws"].data_ptr(), it["dw"].data_ptr()
+            f.cout, f.cin, f.dz_channels, f.swapped = it["cout"], it["cin"], it["dz_channels"], it["swapped"]
+            f.accumulate, f.scale = int(bool(it.get("accumulate"))), 1.0
+        _count(1)
+        nat.check(lib.osvos_wgrad_finish(arr, len(part), _stream()), "osvos_wgrad_finish")
 
 
 def tail_bwd(grads, n, h, w):

@@ -95,7 +95,8 @@ class GraphedTrainStep:
     def _body(self):
         outputs = self.net(self.x)
         loss = self.objective(outputs, self.gt)
-        (loss * self.grad_scale).backward()
+        with self.net._engine.direct_grad_accumulation():   # p.grad buffers are static: add into them in the kernels
+            (loss * self.grad_scale).backward()
         return loss.detach()
 
     def __call__(self, sample=None):
@@ -150,7 +151,8 @@ def online_finetune(net, sample_fn, iters, n_ave_grad=5, lr=1e-8, wd=0.0002, log
             # clone: `loss /= n_ave_grad` below is in place (as in the reference) and must not scale the logged value
             running = loss.detach().clone() if running is None else running + loss.detach()
             loss /= n_ave_grad
-            loss.backward()
+            with net._engine.direct_grad_accumulation():
+                loss.backward()
             if (it + 1) % n_ave_grad == 0:
                 if fused_optimizer:
                     opt.step(zero_grad=True)
@@ -180,7 +182,8 @@ def parent_epoch(net, opt, bucket, batches, epoch, n_epochs, n_ave_grad=1, group
         count += 1
         loss = side_w * sum(losses[:-1]) + losses[-1]
         loss /= n_ave_grad
-        loss.backward()
+        with net._engine.direct_grad_accumulation():
+            loss.backward()
         if (it + 1) % n_ave_grad == 0:
             bucket.allreduce_mean(group)
             if hasattr(opt, "_engine"):                     # optim.FusedSGD: update + zeroing + repack in one kernel

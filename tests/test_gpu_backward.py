@@ -315,3 +315,37 @@ def test_backward_batch2_parent_objective_vs_oracle(net):
             worst = max(worst, relnorm(p.grad, ograds[name]))
     print(f"batch-2 parent objective 96x128: worst per-parameter gradient error {worst:.2e}")
     assert worst < GRAD_TOL_TINY
+
+
+def test_direct_grad_accumulation_equals_autograd_accumulation():
+    """engine.direct_grad_accumulation(): weight / trunk-bias gradients are added into an existing p.grad by the
+    kernels; the result must equal autograd's AccumulateGrad path (two backward passes accumulate in both)."""
+    from osvos_pytorch_b200.layers.osvos_layers import class_balanced_cross_entropy_loss as cbce
+    from osvos_pytorch_b200.networks.vgg_osvos import OSVOS, he_init_
+    x, gt = oc.synthetic_frame(2, 40, 56, 21)
+    x, gt = x.cuda(), gt.cuda()
+    grads = {}
+    for direct in (False, True):
+        net = he_init_(OSVOS(pretrained=0, verbose=False), seed=0).cuda().train()
+        for name, p in net.named_parameters():
+            if not name.startswith("upscale"):
+                p.grad = torch.full_like(p, 0.5)                      # pre-existing gradient to accumulate onto
+        for rep in range(2):
+            outs = net(x)
+            loss = sum(cbce(o, gt, size_average=False) for o in outs)
+            if direct:
+                with net._engine.direct_grad_accumulation():
+                    loss.backward()
+            else:
+                loss.backward()
+        grads[direct] = {n: p.grad.clone() for n, p in net.named_parameters() if p.grad is not None}
+    assert grads[False].keys() == grads[True].keys()
+    for n in grads[False]:
+        a, b = grads[False][n], grads[True][n]
+        # same kernels and operands; only the summation order of (old grad + new) differs
+        assert float((a - b).abs().max()) <= 2e-5 * float(a.abs().max()) + 1e-6, n
+    # without an existing .grad the direct mode falls back to returning tensors
+    net = he_init_(OSVOS(pretrained=0, verbose=False), seed=0).cuda().train()
+    with net._engine.direct_grad_accumulation():
+        cbce(net(x)[-1], gt, size_average=False).backward()
+    assert net.stages[2][1].weight.grad is not None and net.score_dsn[0].weight.grad is None

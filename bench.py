@@ -202,6 +202,9 @@ def run_parent(args, rank, world, local, dev):
         dist.destroy_process_group()
 
 
+NCU_CONV_DRAM_BYTES_PER_STEP = 476.16e6
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -421,7 +424,13 @@ def main():
                             "algorithmic_flops_per_step": conv_flops, "launches_per_step": conv_calls,
                             "kernel_ms_per_step": conv_ms, "share_of_step": conv_ms / ms,
                             "tensor_pipe_passes": 3 if args.precision == "exact" else 1,
-                            "traffic": None}
+                            # dram__bytes_read.sum + dram__bytes_write.sum of the 16 conv launches of one 480x854 exact
+                            # frame, from the committed `ncu --set full` capture (profiles/r01d_ncu_full_forward_kernels.csv):
+                            # 476.2 MB per step = 29.8 MB per launch (activations in + out; weights stay in L2)
+                            "traffic": (NCU_CONV_DRAM_BYTES_PER_STEP / conv_calls
+                                        if args.precision == "exact" and conv_calls == 16 else None),
+                            "traffic_unit": "bytes per launch (average over the step's conv launches)",
+                            "traffic_source": "profiles/r01d_ncu_full_forward_kernels.csv"}
     if not args.no_cpu_baseline:
         cfps, cms, cores, threads = cpu_reference_fps(3, 1, args.workload)
         line["cpu_baseline"] = {"value": cfps, "unit": "frames/s", "cores": threads, "kind": "port",

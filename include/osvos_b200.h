@@ -152,7 +152,7 @@ OSVOS_API int osvos_side_project(const float* feat /* [n,h,w,16] */, const float
                        int n, int h, int w, osvos_stream_t stream);
 
 /* ---- class_balanced_cross_entropy_loss (layers/osvos_layers.py:19-48) -----------
- * forward: sums[0..3] = {S_pos, S_neg, P, N} (fp64, zeroed by the call), loss[0] =
+ * forward: sums[0..3] = {S_pos, S_neg, P, N} (5 doubles, zeroed by the call; sums[4] is an arrival counter), loss[0] =
  * (Nn/N*S_pos + P/N*S_neg)/divisor with divisor = numel (size_average), batch
  * (batch_average) or 1.  backward: grad_in = grad_out[0] * w * (sigmoid(x) - y) / divisor
  * (grad_out == NULL means 1).                                                        */
@@ -209,14 +209,14 @@ typedef struct {
 } osvos_tail_bwd_args;
 OSVOS_API int osvos_tail_bwd(const osvos_tail_bwd_args* args /* host */, osvos_stream_t stream);
 
-/* out[0] = sum(x[0:n]) (fuse.bias gradient); scratch: 1 double.                          */
+/* out[0] = sum(x[0:n]) (fuse.bias gradient); scratch: 2 doubles (total, arrival counter).  */
 OSVOS_API int osvos_sum_f32(const float* x, size_t n, double* scratch, float* out, osvos_stream_t stream);
 
 /* ---- backward of score_dsn / the fuse slice (1x1 convs, networks/vgg_osvos.py:44,54) --
  * dfeat = dp*w_score + dq*w_fuse_slice as an act with 64 channels (16..63 zero);
  * param_grads[0:16] = d score_dsn.weight, [16] = d score_dsn.bias,
  * [17:33] = d fuse.weight slice, [33] = sum dq, [34:50] = d side_prep.bias (= w_score*sum dp +
- * w_fuse*sum dq).  param_grads: 50 floats; scratch: 34 doubles.  feat may be NULL (then only
+ * w_fuse*sum dq).  param_grads: 50 floats; scratch: 35 doubles.  feat may be NULL (then only
  * dfeat, the plain sums and the bias gradient are produced).                              */
 OSVOS_API int osvos_side_bwd(const float* feat, const float* dpq, const float* proj_w, void* dfeat_hi, void* dfeat_lo,
                              double* scratch, float* param_grads, int n, int h, int w, osvos_stream_t stream);
@@ -231,9 +231,12 @@ OSVOS_API int osvos_unpool_add_mask(const void* dpool_hi, const void* dpool_lo, 
 OSVOS_API int osvos_channel_sum(const void* act_hi, const void* act_lo, float* out, size_t npix, int c,
                                 osvos_stream_t stream);
 
-/* ---- conv1_1 backward: dw [64][3][3][3] and (optionally) dx [n,3,h,w] --------------- */
+/* ---- conv1_1 backward: dw [64][3][3][3] and (optionally) dx [n,3,h,w] ---------------
+ * workspace: osvos_conv_first_bwd_workspace_bytes() bytes (replicated partial sums + arrival counter; zeroed by
+ * the call).                                                                                  */
+OSVOS_API size_t osvos_conv_first_bwd_workspace_bytes(void);
 OSVOS_API int osvos_conv_first_bwd(const float* x_nchw, const void* dz_hi, const void* dz_lo, const float* w_oihw,
-                                   float* dw, float* dx_nchw /* or NULL */, int n, int h, int w,
+                                   float* dw, float* dx_nchw /* or NULL */, void* workspace, int n, int h, int w,
                                    osvos_stream_t stream);
 
 /* ===================== SURVEY.md 8(f) "next" rows: callers either side ===================== */
@@ -279,6 +282,20 @@ typedef struct osvos_sgd_segment {
 OSVOS_API uint32_t osvos_sgd_work_items(uint64_t numel, int cout, int cin);
 OSVOS_API int osvos_sgd_step(const osvos_sgd_segment* segments /* device */, int count, uint32_t total_work_items,
                              int zero_grad, osvos_stream_t stream);
+
+/* ---- data augmentation on the device (dataloaders/custom_transforms.py:7-54 ScaleNRotate, :87-100
+ * RandomHorizontalFlip, composed flip-then-warp at train_online.py:92-94 / train_parent.py:108-110) -----
+ * The reference warps every sample on the host with cv2.warpAffine(tmp, getRotationMatrix2D(center, rot, sc),
+ * (w, h), flags) - INTER_CUBIC for the image, INTER_NEAREST for the 0/1 mask, BORDER_CONSTANT 0.  This entry point
+ * restates OpenCV's published algorithm (cv2 is not vendored by the reference and absent from this image):
+ * fixed-point source coordinates X = (rint((m1*y+m2)*1024) + delta + rint(m0*x*1024)) >> s with 1/32-pixel
+ * sub-positions for cubic (delta 16, s 5) and whole pixels for nearest (delta 512, s 10); bicubic taps with
+ * A = -0.75 evaluated in fp32 at the 1/32 position; taps outside the image contribute 0.
+ * src/dst [n][c][h][w] fp32; inv_matrices_host: n x 6 doubles, the INVERTED 2x3 matrix (dst -> src) as
+ * cv::warpAffine computes it; flips_host[n]: 1 = the source is mirrored horizontally first (cv2.flip(.., 1)).   */
+enum { OSVOS_WARP_CUBIC = 0, OSVOS_WARP_NEAREST = 1 };
+OSVOS_API int osvos_affine_warp(const float* src, float* dst, const double* inv_matrices_host, const int* flips_host,
+                                int n, int c, int h, int w, int mode, osvos_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -395,3 +395,80 @@ def sgd_momentum_step(p: torch.Tensor, g: torch.Tensor, buf, lr: float, wd: floa
     gp = g64 + wd * p64
     b = gp if buf is None else momentum * buf.double() + gp
     return (p64 - lr * b).float(), b.float()
+
+
+def _cv_rotation_matrix(center, angle_deg: float, scale: float) -> np.ndarray:
+    """cv2.getRotationMatrix2D (OpenCV imgproc/imgwarp.cpp): alpha = s*cos, beta = s*sin (degrees, positive =
+    counter-clockwise for a top-left origin)."""
+    a = scale * math.cos(angle_deg * math.pi / 180.0)
+    b = scale * math.sin(angle_deg * math.pi / 180.0)
+    return np.array([[a, b, (1 - a) * center[0] - b * center[1]],
+                     [-b, a, b * center[0] + (1 - a) * center[1]]], dtype=np.float64)
+
+
+def scale_n_rotate(img: np.ndarray, rot: float, sc: float, flip: bool, nearest: bool) -> np.ndarray:
+    """RandomHorizontalFlip then ScaleNRotate on one [C, H, W] fp32 array (reference
+    dataloaders/custom_transforms.py:87-100 then :7-54; the reference holds HWC arrays at that point and ToTensor
+    transposes afterwards - per-channel arithmetic is identical).  ``cv2.flip(tmp, 1)``; ``M =
+    cv2.getRotationMatrix2D((w/2, h/2), rot, sc)``; ``cv2.warpAffine(tmp, M, (w, h), flags)`` with INTER_NEAREST for
+    0/1 masks, INTER_CUBIC otherwise, BORDER_CONSTANT 0.
+    cv2 is a third-party dependency the reference does not vendor or pin and that is absent from this image:
+    PARITY UNPINNED for this function.  It restates OpenCV's published algorithm (imgwarp.cpp WarpAffineInvoker +
+    remap): the inverse matrix in fp64; source coordinates in fixed point with AB_BITS = 10,
+    ``X = (cvRound((m1*y + m2)*1024) + round_delta + cvRound(m0*x*1024)) >> shift`` with round_delta 16 / shift 5
+    (1/32-pixel positions) for cubic and 512 / 10 for nearest; cubic weights ``interpolateCubic`` with A = -0.75
+    in fp32 at the 1/32 position, the 4x4 window anchored one pixel up-left; out-of-image taps read 0."""
+    x = np.asarray(img, dtype=np.float32)
+    c, h, w = x.shape
+    if flip:
+        x = x[:, :, ::-1]
+    m = _cv_rotation_matrix((w / 2, h / 2), rot, sc)
+    full = np.vstack([m, [0.0, 0.0, 1.0]])
+    inv = np.linalg.inv(full)[:2]                      # == OpenCV's explicit 2x3 inversion up to fp64 rounding
+    # OpenCV's own inversion, restated (keeps the same rounding as the library)
+    d = m[0, 0] * m[1, 1] - m[0, 1] * m[1, 0]
+    d = 1.0 / d if d != 0 else 0.0
+    i00, i11 = m[1, 1] * d, m[0, 0] * d
+    i01, i10 = -m[0, 1] * d, -m[1, 0] * d
+    i02 = -i00 * m[0, 2] - i01 * m[1, 2]
+    i12 = -i10 * m[0, 2] - i11 * m[1, 2]
+    assert np.allclose(inv, [[i00, i01, i02], [i10, i11, i12]], rtol=1e-9, atol=1e-9)
+    xs = np.arange(w, dtype=np.float64)
+    ys = np.arange(h, dtype=np.float64)
+    rd = 512 if nearest else 16
+    X0 = np.rint((i01 * ys + i02) * 1024.0).astype(np.int64) + rd
+    Y0 = np.rint((i11 * ys + i12) * 1024.0).astype(np.int64) + rd
+    ad = np.rint(i00 * xs * 1024.0).astype(np.int64)
+    bd = np.rint(i10 * xs * 1024.0).astype(np.int64)
+    Xf = X0[:, None] + ad[None, :]
+    Yf = Y0[:, None] + bd[None, :]
+    out = np.zeros((c, h, w), dtype=np.float32)
+    if nearest:
+        sx, sy = Xf >> 10, Yf >> 10
+        ok = (sx >= 0) & (sx < w) & (sy >= 0) & (sy < h)
+        out[:, ok] = x[:, sy[ok], sx[ok]]
+        return out
+    X, Y = Xf >> 5, Yf >> 5
+    sx, sy = (X >> 5) - 1, (Y >> 5) - 1
+    fx = ((X & 31).astype(np.float32) * np.float32(1.0 / 32.0))
+    fy = ((Y & 31).astype(np.float32) * np.float32(1.0 / 32.0))
+
+    def coeffs(t):
+        a = np.float32(-0.75)
+        one = np.float32(1.0)
+        c0 = ((a * (t + one) - np.float32(5) * a) * (t + one) + np.float32(8) * a) * (t + one) - np.float32(4) * a
+        c1 = ((a + np.float32(2)) * t - (a + np.float32(3))) * t * t + one
+        u = one - t
+        c2 = ((a + np.float32(2)) * u - (a + np.float32(3))) * u * u + one
+        return [c0, c1, c2, one - c0 - c1 - c2]
+    cx, cy = coeffs(fx), coeffs(fy)
+    acc = np.zeros((c, h, w), dtype=np.float32)
+    for ky in range(4):
+        yy = sy + ky
+        for kx in range(4):
+            xx = sx + kx
+            ok = (xx >= 0) & (xx < w) & (yy >= 0) & (yy < h)
+            wgt = (cy[ky] * cx[kx]).astype(np.float32)
+            vals = x[:, np.clip(yy, 0, h - 1), np.clip(xx, 0, w - 1)]
+            acc += np.where(ok[None], vals * wgt[None], np.float32(0)).astype(np.float32)
+    return acc

@@ -90,12 +90,15 @@ SIGNATURES = {
     "osvos_unpool_add_mask": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                       c_int, c_int, c_int, c_int, c_void_p]),
     "osvos_channel_sum": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
-    "osvos_conv_first_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+    "osvos_conv_first_bwd_workspace_bytes": (c_size_t, []),
+    "osvos_conv_first_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                      c_void_p]),
     "osvos_side_project": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "osvos_logits_to_u8": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_size_t, c_int, c_void_p]),
     "osvos_sgd_work_items": (c_uint32, [c_uint64, c_int, c_int]),
     "osvos_sgd_step": (c_int, [c_void_p, c_int, c_uint32, c_int, c_void_p]),
+    "osvos_affine_warp": (c_int, [c_void_p, c_void_p, POINTER(c_double), POINTER(c_int), c_int, c_int, c_int, c_int,
+                                  c_int, c_void_p]),
 }
 
 _lib = None

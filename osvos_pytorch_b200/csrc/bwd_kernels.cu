@@ -19,11 +19,17 @@ struct TailBwdParams {
 
 // LANES threads cooperate on one low-res pixel (2 / 8 / 32 / 32 for s = 2 / 4 / 8 / 16): 8 .. 32 taps per lane,
 // sub-warp shuffle reduction.
+// All four scales run in ONE launch: blockIdx.y selects the scale, each with its own share of blockIdx.x.
+struct TailBwdAll {
+  TailBwdParams k[4];
+  int blocks[4];
+};
+
 template <int LANES>
-__global__ void __launch_bounds__(256) tail_bwd_kernel(const TailBwdParams p) {
+__device__ __forceinline__ void tail_bwd_body(const TailBwdParams& p, int nblocks) {
   const int sub = threadIdx.x % LANES;
   const size_t grp_global = (blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x) / LANES;
-  const size_t ngroups = (static_cast<size_t>(gridDim.x) * blockDim.x) / LANES;
+  const size_t ngroups = (static_cast<size_t>(nblocks) * blockDim.x) / LANES;
   const size_t total = static_cast<size_t>(p.n) * p.hk * p.wk;
   const int fs = 2 * p.s;
   const float inv = 1.f / static_cast<float>(p.s);
@@ -58,8 +64,17 @@ __global__ void __launch_bounds__(256) tail_bwd_kernel(const TailBwdParams p) {
   }
 }
 
+__global__ void __launch_bounds__(256) tail_bwd_kernel(const __grid_constant__ TailBwdAll a) {
+  const int k = blockIdx.y;
+  if (static_cast<int>(blockIdx.x) >= a.blocks[k]) return;
+  if (k == 0) tail_bwd_body<2>(a.k[0], a.blocks[0]);
+  else if (k == 1) tail_bwd_body<8>(a.k[1], a.blocks[1]);
+  else tail_bwd_body<32>(a.k[k], a.blocks[k]);
+}
+
 // ---------------------------------------------------------------- generic sum
-__global__ void __launch_bounds__(256) sum_f32_kernel(const float* __restrict__ x, size_t n, double* __restrict__ out) {
+__global__ void __launch_bounds__(256) sum_f32_kernel(const float* __restrict__ x, size_t n, double* __restrict__ out,
+                                                      float* __restrict__ result) {
   float acc = 0.f;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<size_t>(gridDim.x) * blockDim.x)
@@ -74,18 +89,10 @@ __global__ void __launch_bounds__(256) sum_f32_kernel(const float* __restrict__ 
     for (int i = 0; i < 8; ++i) t += static_cast<double>(red[i]);
     atomicAdd(out, t);
   }
+  // the last block to finish converts the fp64 total (out[1] holds the arrival counter)
+  if (last_block_arrives(reinterpret_cast<unsigned int*>(out + 1)) && threadIdx.x == 0)
+    result[0] = static_cast<float>(__ldcg(out));
 }
-__global__ void f64_to_f32_kernel(const double* __restrict__ in, float* __restrict__ out, int n) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = static_cast<float>(in[i]);
-}
-// side_bwd finalize: out[0:34] = sums; out[34+c] = d side_prep.bias[c] = w_score[c]*sum(dp) + w_fuse[c]*sum(dq)
-__global__ void side_finalize_kernel(const double* __restrict__ in, const float* __restrict__ pw, float* __restrict__ out) {
-  const int i = threadIdx.x;
-  if (i < 34) out[i] = static_cast<float>(in[i]);
-  else if (i < 50) out[i] = static_cast<float>(static_cast<double>(pw[i - 34]) * in[16] + static_cast<double>(pw[i - 18]) * in[33]);
-}
-
 // ------------------------------------------------------------------ side bwd
 // feat [npix][16] fp32, dpq [npix][2], pw[32] = {score_dsn w, fuse slice}:
 //   dfeat[px][c] = dp*pw[c] + dq*pw[16+c]  -> act with 64 channels (16..63 zero)
@@ -93,7 +100,7 @@ __global__ void side_finalize_kernel(const double* __restrict__ in, const float*
 __global__ void __launch_bounds__(256)
 side_bwd_kernel(const float* __restrict__ feat, const float* __restrict__ dpq, const float* __restrict__ pw,
                 __nv_bfloat16* __restrict__ d_hi, __nv_bfloat16* __restrict__ d_lo, double* __restrict__ acc,
-                size_t npix) {
+                float* __restrict__ out, size_t npix) {
   float a[34];
 #pragma unroll
   for (int j = 0; j < 34; ++j) a[j] = 0.f;
@@ -158,6 +165,14 @@ side_bwd_kernel(const float* __restrict__ feat, const float* __restrict__ dpq, c
     for (int i = 0; i < 8; ++i) t += static_cast<double>(red[i][threadIdx.x]);
     atomicAdd(acc + threadIdx.x, t);
   }
+  // finalize in the last block to arrive (acc[34] holds the arrival counter):
+  // out[0:34] = sums; out[34+c] = d side_prep.bias[c] = w_score[c]*sum(dp) + w_fuse[c]*sum(dq)
+  if (last_block_arrives(reinterpret_cast<unsigned int*>(acc + 34))) {
+    const int i = threadIdx.x;
+    if (i < 34) out[i] = static_cast<float>(__ldcg(acc + i));
+    else if (i < 50) out[i] = static_cast<float>(static_cast<double>(pw[i - 34]) * __ldcg(acc + 16) +
+                                                 static_cast<double>(pw[i - 18]) * __ldcg(acc + 33));
+  }
 }
 
 // ------------------------------------------------- max-unpool + add + ReLU mask
@@ -177,7 +192,7 @@ __device__ __forceinline__ void load_pair8(const __nv_bfloat16* hi, const __nv_b
   }
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 unpool_add_mask_kernel(const __nv_bfloat16* __restrict__ dp_hi, const __nv_bfloat16* __restrict__ dp_lo,
                        const __nv_bfloat16* __restrict__ x_hi, const __nv_bfloat16* __restrict__ x_lo,
                        const float* __restrict__ dside, __nv_bfloat16* __restrict__ dz_hi,
@@ -189,17 +204,19 @@ unpool_add_mask_kernel(const __nv_bfloat16* __restrict__ dp_hi, const __nv_bfloa
     __syncthreads();
   }
   const int groups = c / 8;
-  const size_t total = static_cast<size_t>(n) * oh * ow * groups;
-  // blockDim (256) is a multiple of `groups`, so a thread keeps the same channel group over the whole loop
+  // blockDim (256) is a multiple of `groups`: a thread keeps the same channel group over the whole loop, and a block
+  // iteration covers 256 / groups consecutive pooled pixels of one pooled row (32-bit index math only)
   const int g = static_cast<int>(threadIdx.x % groups);
+  const int pl = static_cast<int>(threadIdx.x / groups);
+  const int ppb = 256 / groups;
+  const int tiles_x = (ow + ppb - 1) / ppb;
+  const int total_tiles = n * oh * tiles_x;
   float csum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    size_t r = i / groups;
-    const int ox = static_cast<int>(r % ow);
-    r /= ow;
-    const int oy = static_cast<int>(r % oh);
-    const int nn = static_cast<int>(r / oh);
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const int tx = tile % tiles_x, row = tile / tiles_x;
+    const int oy = row % oh, nn = row / oh;
+    const int ox = tx * ppb + pl;
+    if (ox >= ow) continue;
     // pass 1: argmax (first maximum in (dy, dx) scan order) and positivity of the four window elements
     float best[8];
     uint32_t arg = 0, pos = 0;  // arg: 2 bits per channel; pos: bit (q * 8 + j) = x[q][j] > 0
@@ -295,89 +312,163 @@ channel_sum_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __
 }
 
 // -------------------------------------------------------------- conv1_1 bwd
-// dW[co][ci][r][s] = sum_px dz[px][co] * x[ci][px + (r-1, s-1)]   (64 x 27 outputs, reduction over all pixels)
-// Register-tiled: a thread owns a 4 (co) x 7 (k) tile of dW; 64 threads cover the 64 x 28 tile, the block's four
-// 64-thread units take every fourth pixel of a staged 64-pixel chunk.  Per pixel a thread does one float4 + 7 scalar
-// shared-memory loads for 28 FMAs.
+// dW[co][ci][r][s] = sum_px dz[px][co] * x[ci][px + (r-1, s-1)]: a [32 (27 used) x 64] output with the whole image
+// as reduction axis - 1.4 GFLOP at 480x854 against 105 MB of dz, i.e. HBM-bound once the arithmetic is cheap.  The
+// tile is too thin for tcgen05 (N = 27), so the products run on warp-level mma.sync.m16n8k16 (bf16 in, fp32 acc):
+//   C[k][co] += A[k][px] * B[px][co],  A = im2col rows of x (split into bf16 hi/lo here), B = dz (already hi/lo),
+// three passes hi*hi + hi*lo + lo*hi like every other product of the path.  A chunk is 64 consecutive pixels of one
+// image row: dz is copied 16 B at a time into padded rows (ldmatrix.trans reads them conflict-free), the 27 shifted
+// row segments of x are coalesced loads with no index division.  Each of the 8 warps owns 8 output channels.
+// (History: flat-pixel chunks + fp32 register tiles 146 us -> row chunks 103 us -> this kernel, see profiles/.)
 constexpr int kFwPix = 64;
+constexpr int kFwDzStride = 72;   // bf16 elements per smem row of a dz plane (64 + 8 pad -> 144 B, odd multiple of 16 B)
+constexpr int kFwXStride = 72;    // bf16 elements per smem row of an im2col plane
+constexpr int kFwCopies = 16;     // replicas of the partial result (atomic contention)
+constexpr int kFwRawStride = 68;  // fp32 elements per staged source row (66 used)
+// offset of im2col row k = ci*9 + r*3 + s inside the staged source rows: (ci*3 + r) * kFwRawStride + s
+__constant__ int c_fw_koff[27] = {
+    0 * 68 + 0, 0 * 68 + 1, 0 * 68 + 2, 1 * 68 + 0, 1 * 68 + 1, 1 * 68 + 2, 2 * 68 + 0, 2 * 68 + 1, 2 * 68 + 2,
+    3 * 68 + 0, 3 * 68 + 1, 3 * 68 + 2, 4 * 68 + 0, 4 * 68 + 1, 4 * 68 + 2, 5 * 68 + 0, 5 * 68 + 1, 5 * 68 + 2,
+    6 * 68 + 0, 6 * 68 + 1, 6 * 68 + 2, 7 * 68 + 0, 7 * 68 + 1, 7 * 68 + 2, 8 * 68 + 0, 8 * 68 + 1, 8 * 68 + 2};
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(static_cast<uint32_t>(__cvta_generic_to_shared(p))));
+}
+__device__ __forceinline__ void ldmatrix_x2_trans(uint32_t (&r)[2], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];\n"
+               : "=r"(r[0]), "=r"(r[1])
+               : "r"(static_cast<uint32_t>(__cvta_generic_to_shared(p))));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
 __global__ void __launch_bounds__(256)
 conv_first_wgrad_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dz_hi,
-                        const __nv_bfloat16* __restrict__ dz_lo, float* __restrict__ dw, int n, int h, int w) {
-  __shared__ __align__(16) float dzs[kFwPix][68];
-  __shared__ float xs[kFwPix][28];
-  __shared__ float red[64 * 28];
-  const int unit = threadIdx.x >> 6;         // 0..3: which pixels of the chunk
-  const int t = threadIdx.x & 63;
-  const int cg = t & 15, kg = t >> 4;        // co = 4*cg .. 4*cg+3 ; k = 7*kg .. 7*kg+6
-  float acc[4][7];
+                        const __nv_bfloat16* __restrict__ dz_lo, float* __restrict__ dw, float* __restrict__ partial,
+                        int n, int h, int w) {
+  __shared__ __align__(16) __nv_bfloat16 dzs[2][kFwPix][kFwDzStride];   // [plane][px][co]
+  __shared__ __align__(16) __nv_bfloat16 xs[2][32][kFwXStride];          // [plane][k][px]
+  __shared__ float raw[9 * kFwRawStride];                                // [ci*3 + r][x0 - 1 + cc]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float acc[2][4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 2; ++i)
 #pragma unroll
-    for (int j = 0; j < 7; ++j) acc[i][j] = 0.f;
-  const size_t npix = static_cast<size_t>(n) * h * w;
-  for (size_t base = static_cast<size_t>(blockIdx.x) * kFwPix; base < npix; base += static_cast<size_t>(gridDim.x) * kFwPix) {
-    // stage dz: 64 px x 64 co, 8 channels (16 B per plane) per thread-iteration
-    for (int i = threadIdx.x; i < kFwPix * 8; i += 256) {
-      const int pp = i >> 3, g = i & 7;
-      const size_t px = base + pp;
-      float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      if (px < npix) {
-        const uint4 vh = __ldg(reinterpret_cast<const uint4*>(dz_hi + px * 64 + g * 8));
-        uint4 vl = make_uint4(0, 0, 0, 0);
-        if (dz_lo) vl = __ldg(reinterpret_cast<const uint4*>(dz_lo + px * 64 + g * 8));
-        const uint32_t hw[4] = {vh.x, vh.y, vh.z, vh.w};
-        const uint32_t lw[4] = {vl.x, vl.y, vl.z, vl.w};
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int i = threadIdx.x; i < 2 * 5 * kFwXStride; i += 256)             // k = 27..31 are padding rows
+    xs[i / (5 * kFwXStride)][27 + (i / kFwXStride) % 5][i % kFwXStride] = __float2bfloat16_rn(0.f);
+  const int chunks_x = (w + kFwPix - 1) / kFwPix;
+  const int total = n * h * chunks_x;
+  const int planes = dz_lo ? 2 : 1;
+  // Register double buffering: the global loads of tile i+1 (4 x 16 B of dz and up to 3 source pixels per thread) are
+  // issued before the shared-memory work of tile i, so their latency overlaps the im2col expansion and the MMAs
+  // (a single-buffered version spent half of its stall samples on the smem stores waiting for these loads).
+  uint4 rdz[4];
+  float rx[3];
+  int valid = 0;
+  auto fetch = [&](int tile) {
+    const int cx = tile % chunks_x;
+    const int row = tile / chunks_x;           // nn * h + yy
+    const int yy = row % h, nn = row / h;
+    const int x0 = cx * kFwPix;
+    const int vld = min(kFwPix, w - x0);
+    const size_t pbase = static_cast<size_t>(row) * w + x0;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          v[2 * q] = bf16_lo_to_float(hw[q]) + bf16_lo_to_float(lw[q]);
-          v[2 * q + 1] = bf16_hi_to_float(hw[q]) + bf16_hi_to_float(lw[q]);
-        }
-      }
-      *reinterpret_cast<float4*>(&dzs[pp][g * 8]) = make_float4(v[0], v[1], v[2], v[3]);
-      *reinterpret_cast<float4*>(&dzs[pp][g * 8 + 4]) = make_float4(v[4], v[5], v[6], v[7]);
+    for (int u = 0; u < 4; ++u) {              // dz: 2 planes x 64 px x 8 groups of 16 B
+      const int i = threadIdx.x + 256 * u;
+      const int pl = i >> 9, pp = (i >> 3) & 63, g = i & 7;
+      rdz[u] = make_uint4(0, 0, 0, 0);
+      if (pp < vld && pl < planes)
+        rdz[u] = __ldg(reinterpret_cast<const uint4*>((pl ? dz_lo : dz_hi) + (pbase + pp) * 64 + g * 8));
     }
-    for (int i = threadIdx.x; i < kFwPix * 28; i += 256) {
-      const int pp = i / 28, k = i - pp * 28;
-      const size_t px = base + pp;
-      float v = 0.f;
-      if (px < npix && k < 27) {
-        const int xx = static_cast<int>(px % w);
-        const int yy = static_cast<int>((px / w) % h);
-        const int nn = static_cast<int>(px / (static_cast<size_t>(w) * h));
-        const int ci = k / 9, r = (k % 9) / 3, sft = k % 3;
-        const int iy = yy + r - 1, ix = xx + sft - 1;
-        if (iy >= 0 && iy < h && ix >= 0 && ix < w) v = __ldg(x + ((static_cast<size_t>(nn) * 3 + ci) * h + iy) * w + ix);
-      }
-      xs[pp][k] = v;
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {              // the 9 source rows (3 channels x 3 dy), 66 pixels each
+      const int e = threadIdx.x + 256 * u;
+      const int rr = e / kFwRawStride, cc = e - rr * kFwRawStride;      // rr = ci * 3 + r
+      const int ci = rr / 3, r = rr - ci * 3;
+      const int iy = yy + r - 1, ix = x0 + cc - 1;
+      rx[u] = 0.f;
+      if (rr < 9 && cc < kFwPix + 2 && cc <= vld + 1 && iy >= 0 && iy < h && ix >= 0 && ix < w)
+        rx[u] = __ldg(x + ((static_cast<size_t>(nn) * 3 + ci) * h + iy) * w + ix);
     }
+    return vld;
+  };
+  int next_valid = blockIdx.x < total ? fetch(blockIdx.x) : 0;
+  for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    valid = next_valid;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = threadIdx.x + 256 * u;
+      *reinterpret_cast<uint4*>(&dzs[i >> 9][(i >> 3) & 63][(i & 7) * 8]) = rdz[u];
+    }
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+      const int e = threadIdx.x + 256 * u;
+      if (e < 9 * kFwRawStride) raw[e] = rx[u];
+    }
+    if (tile + static_cast<int>(gridDim.x) < total) next_valid = fetch(tile + gridDim.x);
     __syncthreads();
-#pragma unroll 4
-    for (int pp = unit; pp < kFwPix; pp += 4) {
-      const float4 d = *reinterpret_cast<const float4*>(&dzs[pp][cg * 4]);
-      float xv[7];
-#pragma unroll
-      for (int j = 0; j < 7; ++j) xv[j] = xs[pp][kg * 7 + j];
+    // ... expanded into the 27 im2col rows, split into bf16 hi / lo (a warp works on one k: uniform table index)
+    {
+      const int pp = threadIdx.x & 63, q = threadIdx.x >> 6;
 #pragma unroll
       for (int j = 0; j < 7; ++j) {
-        acc[0][j] = fmaf(d.x, xv[j], acc[0][j]);
-        acc[1][j] = fmaf(d.y, xv[j], acc[1][j]);
-        acc[2][j] = fmaf(d.z, xv[j], acc[2][j]);
-        acc[3][j] = fmaf(d.w, xv[j], acc[3][j]);
+        const int k = q * 7 + j;
+        if (k < 27) {
+          const float v = pp < valid ? raw[c_fw_koff[k] + pp] : 0.f;
+          __nv_bfloat16 hi, lo;
+          split_bf16(v, hi, lo);
+          xs[0][k][pp] = hi;
+          xs[1][k][pp] = lo;
+        }
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int ks = 0; ks < kFwPix / 16; ++ks) {
+      uint32_t bh[2], bl[2];
+      ldmatrix_x2_trans(bh, &dzs[0][16 * ks + (lane & 15)][8 * warp]);
+      ldmatrix_x2_trans(bl, &dzs[1][16 * ks + (lane & 15)][8 * warp]);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        uint32_t ah[4], al[4];
+        const int ar = mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, ac = 16 * ks + (lane >> 4) * 8;
+        ldmatrix_x4(ah, &xs[0][ar][ac]);
+        ldmatrix_x4(al, &xs[1][ar][ac]);
+        mma_bf16_16816(acc[mt], ah, bh);
+        if (planes == 2) {
+          mma_bf16_16816(acc[mt], ah, bl);
+          mma_bf16_16816(acc[mt], al, bh);
+        } else {
+          mma_bf16_16816(acc[mt], al, bh);       // x keeps both halves even when dz is single-plane (fast mode)
+        }
       }
     }
     __syncthreads();
   }
-  // reduce the four units in shared memory, then one global atomic per output and block
-  for (int i = threadIdx.x; i < 64 * 28; i += 256) red[i] = 0.f;
-  __syncthreads();
+  // C fragment: rows g / g+8 (k), columns 2t, 2t+1 (co within the warp's 8 channels)
+  const int g = lane >> 2, t = lane & 3;
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-    for (int j = 0; j < 7; ++j) atomicAdd(&red[(cg * 4 + i) * 28 + kg * 7 + j], acc[i][j]);
-  __syncthreads();
-  for (int i = threadIdx.x; i < 64 * 27; i += 256) {
-    const int co = i / 27, k = i - co * 27;
-    atomicAdd(dw + i, red[co * 28 + k]);
+    for (int j = 0; j < 4; ++j) {
+      const int k = mt * 16 + g + (j >> 1) * 8;
+      const int co = 8 * warp + 2 * t + (j & 1);
+      // kFwCopies replicas of the 64 x 27 result spread the same-address atomic traffic of the blocks
+      if (k < 27) atomicAdd(partial + (blockIdx.x % kFwCopies) * (64 * 27) + co * 27 + k, acc[mt][j]);
+    }
+  if (last_block_arrives(reinterpret_cast<unsigned int*>(partial + kFwCopies * 64 * 27))) {
+    for (int i = threadIdx.x; i < 64 * 27; i += 256) {
+      float t = 0.f;
+#pragma unroll
+      for (int c = 0; c < kFwCopies; ++c) t += __ldcg(partial + c * (64 * 27) + i);
+      dw[i] = t;
+    }
   }
 }
 
@@ -444,11 +535,13 @@ extern "C" int osvos_tail_bwd(const osvos_tail_bwd_args* a, osvos_stream_t strea
   OSVOS_CHECK_ARG(a != nullptr && a->n > 0 && a->h > 0 && a->w > 0);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   int hk = a->h, wk = a->w;
+  TailBwdAll all;
+  int max_blocks = 1;
   for (int k = 0; k < 4; ++k) {
     hk = (hk + 1) / 2;
     wk = (wk + 1) / 2;
     OSVOS_CHECK_ARG(a->dpq[k] != nullptr);
-    TailBwdParams p;
+    TailBwdParams& p = all.k[k];
     p.gk = a->grad_out[k];
     p.g4 = a->grad_out[4];
     p.dpq = a->dpq[k];
@@ -461,10 +554,11 @@ extern "C" int osvos_tail_bwd(const osvos_tail_bwd_args* a, osvos_stream_t strea
     p.top = ((hk + 1) * p.s - a->h) / 2;
     p.left = ((wk + 1) * p.s - a->w) / 2;
     const size_t pixels = static_cast<size_t>(a->n) * hk * wk;
-    if (k == 0) tail_bwd_kernel<2><<<grid_cap((pixels * 2 + 255) / 256, 16), 256, 0, stream>>>(p);
-    else if (k == 1) tail_bwd_kernel<8><<<grid_cap((pixels * 8 + 255) / 256, 16), 256, 0, stream>>>(p);
-    else tail_bwd_kernel<32><<<grid_cap((pixels * 32 + 255) / 256, 16), 256, 0, stream>>>(p);
+    const int lanes = k == 0 ? 2 : (k == 1 ? 8 : 32);
+    all.blocks[k] = grid_cap((pixels * lanes + 255) / 256, 4);
+    if (all.blocks[k] > max_blocks) max_blocks = all.blocks[k];
   }
+  tail_bwd_kernel<<<dim3(max_blocks, 4), 256, 0, stream>>>(all);
   OSVOS_CHECK_CUDA(cudaGetLastError());
   return OSVOS_OK;
 }
@@ -472,9 +566,8 @@ extern "C" int osvos_tail_bwd(const osvos_tail_bwd_args* a, osvos_stream_t strea
 extern "C" int osvos_sum_f32(const float* x, size_t n, double* scratch, float* out, osvos_stream_t stream_) {
   OSVOS_CHECK_ARG(x != nullptr && scratch != nullptr && out != nullptr && n > 0);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  OSVOS_CHECK_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double), stream));
-  sum_f32_kernel<<<grid_cap((n + 255) / 256, 4), 256, 0, stream>>>(x, n, scratch);
-  f64_to_f32_kernel<<<1, 32, 0, stream>>>(scratch, out, 1);
+  OSVOS_CHECK_CUDA(cudaMemsetAsync(scratch, 0, 2 * sizeof(double), stream));
+  sum_f32_kernel<<<grid_cap((n + 255) / 256, 4), 256, 0, stream>>>(x, n, scratch, out);
   OSVOS_CHECK_CUDA(cudaGetLastError());
   return OSVOS_OK;
 }
@@ -485,10 +578,10 @@ extern "C" int osvos_side_bwd(const float* feat, const float* dpq, const float* 
                   param_grads != nullptr && n > 0 && h > 0 && w > 0);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const size_t npix = static_cast<size_t>(n) * h * w;
-  OSVOS_CHECK_CUDA(cudaMemsetAsync(scratch, 0, 34 * sizeof(double), stream));
+  OSVOS_CHECK_CUDA(cudaMemsetAsync(scratch, 0, 35 * sizeof(double), stream));
   side_bwd_kernel<<<grid_cap((npix + 255) / 256, 4), 256, 0, stream>>>(
-      feat, dpq, proj_w, static_cast<__nv_bfloat16*>(dfeat_hi), static_cast<__nv_bfloat16*>(dfeat_lo), scratch, npix);
-  side_finalize_kernel<<<1, 64, 0, stream>>>(scratch, proj_w, param_grads);
+      feat, dpq, proj_w, static_cast<__nv_bfloat16*>(dfeat_hi), static_cast<__nv_bfloat16*>(dfeat_lo), scratch,
+      param_grads, npix);
   OSVOS_CHECK_CUDA(cudaGetLastError());
   return OSVOS_OK;
 }
@@ -498,8 +591,11 @@ extern "C" int osvos_unpool_add_mask(const void* dpool_hi, const void* dpool_lo,
                                      int c, osvos_stream_t stream_) {
   OSVOS_CHECK_ARG(dpool_hi != nullptr && x_hi != nullptr && dz_hi != nullptr && n > 0 && h > 0 && w > 0 && c % 8 == 0);
   const int oh = (h + 1) / 2, ow = (w + 1) / 2;
-  const size_t total = static_cast<size_t>(n) * oh * ow * (c / 8);
-  unpool_add_mask_kernel<<<grid_cap((total + 255) / 256, 8), 256, c * sizeof(float), static_cast<cudaStream_t>(stream_)>>>(
+  OSVOS_CHECK_ARG(c <= 2048 && 256 % (c / 8) == 0);
+  const int ppb = 256 / (c / 8);
+  const size_t tiles = static_cast<size_t>(n) * oh * ((ow + ppb - 1) / ppb);
+  OSVOS_CHECK_ARG(tiles < (static_cast<size_t>(1) << 31));
+  unpool_add_mask_kernel<<<grid_cap(tiles, 4), 256, c * sizeof(float), static_cast<cudaStream_t>(stream_)>>>(
       static_cast<const __nv_bfloat16*>(dpool_hi), static_cast<const __nv_bfloat16*>(dpool_lo),
       static_cast<const __nv_bfloat16*>(x_hi), static_cast<const __nv_bfloat16*>(x_lo), dside,
       static_cast<__nv_bfloat16*>(dz_hi), static_cast<__nv_bfloat16*>(dz_lo), colsum, n, h, w, c, oh, ow);
@@ -521,15 +617,20 @@ extern "C" int osvos_channel_sum(const void* act_hi, const void* act_lo, float* 
   return OSVOS_OK;
 }
 
+extern "C" size_t osvos_conv_first_bwd_workspace_bytes(void) { return (kFwCopies * 64 * 27 + 4) * sizeof(float); }
+
 extern "C" int osvos_conv_first_bwd(const float* x_nchw, const void* dz_hi, const void* dz_lo, const float* w_oihw,
-                                    float* dw, float* dx_nchw, int n, int h, int w, osvos_stream_t stream_) {
-  OSVOS_CHECK_ARG(x_nchw != nullptr && dz_hi != nullptr && dw != nullptr && n > 0 && h > 0 && w > 0);
+                                    float* dw, float* dx_nchw, void* workspace, int n, int h, int w,
+                                    osvos_stream_t stream_) {
+  OSVOS_CHECK_ARG(x_nchw != nullptr && dz_hi != nullptr && dw != nullptr && workspace != nullptr && n > 0 && h > 0 &&
+                  w > 0);
   OSVOS_CHECK_ARG(dx_nchw == nullptr || w_oihw != nullptr);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  OSVOS_CHECK_CUDA(cudaMemsetAsync(dw, 0, 64 * 27 * sizeof(float), stream));
-  const size_t npix = static_cast<size_t>(n) * h * w;
-  conv_first_wgrad_kernel<<<grid_cap((npix + kFwPix - 1) / kFwPix, 4), 256, 0, stream>>>(
-      x_nchw, static_cast<const __nv_bfloat16*>(dz_hi), static_cast<const __nv_bfloat16*>(dz_lo), dw, n, h, w);
+  OSVOS_CHECK_CUDA(cudaMemsetAsync(workspace, 0, osvos_conv_first_bwd_workspace_bytes(), stream));
+  const size_t tiles = static_cast<size_t>(n) * h * ((w + kFwPix - 1) / kFwPix);
+  conv_first_wgrad_kernel<<<grid_cap(tiles, 4), 256, 0, stream>>>(
+      x_nchw, static_cast<const __nv_bfloat16*>(dz_hi), static_cast<const __nv_bfloat16*>(dz_lo), dw,
+      static_cast<float*>(workspace), n, h, w);
   if (dx_nchw) {
     dim3 grid((w + 127) / 128, h, n);
     conv_first_dgrad_kernel<<<grid, 128, 0, stream>>>(static_cast<const __nv_bfloat16*>(dz_hi),

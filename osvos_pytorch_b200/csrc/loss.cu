@@ -13,7 +13,8 @@ constexpr int kLossThreads = 256;
 __device__ __forceinline__ float softplus_l(float x) { return fmaxf(x, 0.f) + log1pf(__expf(-fabsf(x))); }
 
 __global__ void __launch_bounds__(kLossThreads)
-cbce_fwd_kernel(const float* __restrict__ x, const float* __restrict__ label, size_t total, double* __restrict__ sums) {
+cbce_fwd_kernel(const float* __restrict__ x, const float* __restrict__ label, size_t total, double* __restrict__ sums,
+                double divisor, float* __restrict__ loss) {
   float s_pos = 0.f, s_neg = 0.f, cnt = 0.f;
   const size_t nvec = total / 4;
   for (size_t v = blockIdx.x * static_cast<size_t>(kLossThreads) + threadIdx.x; v < nvec;
@@ -62,13 +63,13 @@ cbce_fwd_kernel(const float* __restrict__ x, const float* __restrict__ label, si
     for (int w = 0; w < kLossThreads / 32; ++w) acc += static_cast<double>(red[w][threadIdx.x]);
     atomicAdd(sums + threadIdx.x, acc);
   }
-}
-
-// loss[0] = (Nn/N * S_pos + P/N * S_neg) / divisor ; sums[3] = N
-__global__ void cbce_finalize_kernel(double* sums, double total, double divisor, float* loss) {
-  const double p = sums[2], nn = total - p;
-  sums[3] = total;
-  loss[0] = static_cast<float>((nn / total * sums[0] + p / total * sums[1]) / divisor);
+  // last block to arrive (counter in sums[4]): loss[0] = (Nn/N * S_pos + P/N * S_neg) / divisor ; sums[3] = N
+  if (last_block_arrives(reinterpret_cast<unsigned int*>(sums + 4)) && threadIdx.x == 0) {
+    const double tot = static_cast<double>(total);
+    const double p = __ldcg(sums + 2), nn = tot - p;
+    sums[3] = tot;
+    loss[0] = static_cast<float>((nn / tot * __ldcg(sums + 0) + p / tot * __ldcg(sums + 1)) / divisor);
+  }
 }
 
 __global__ void __launch_bounds__(kLossThreads)
@@ -118,9 +119,8 @@ extern "C" int osvos_cbce_fwd(const float* output, const float* label, size_t nu
   OSVOS_CHECK_ARG(((reinterpret_cast<uintptr_t>(output) | reinterpret_cast<uintptr_t>(label)) & 15) == 0);
   OSVOS_CHECK_ARG(divisor > 0);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  OSVOS_CHECK_CUDA(cudaMemsetAsync(sums, 0, 4 * sizeof(double), stream));
-  cbce_fwd_kernel<<<loss_grid(numel), kLossThreads, 0, stream>>>(output, label, numel, sums);
-  cbce_finalize_kernel<<<1, 1, 0, stream>>>(sums, static_cast<double>(numel), divisor, loss);
+  OSVOS_CHECK_CUDA(cudaMemsetAsync(sums, 0, 5 * sizeof(double), stream));
+  cbce_fwd_kernel<<<loss_grid(numel), kLossThreads, 0, stream>>>(output, label, numel, sums, divisor, loss);
   OSVOS_CHECK_CUDA(cudaGetLastError());
   return OSVOS_OK;
 }

@@ -303,42 +303,67 @@ struct FinishLayer {
 struct FinishTable {
   FinishLayer layer[OSVOS_WGRAD_FINISH_MAX];
   int count;
+  int total_items;
 };
 constexpr int kFinishThreads = 192;
 constexpr int kFinishChunk = 576;
 
 __global__ void __launch_bounds__(kFinishThreads)
 wgrad_finish_multi_kernel(const __grid_constant__ FinishTable t) {
-  __shared__ float tile[9][65];
-  int item = blockIdx.x, li = 0;
-  while (li < t.count && item >= t.layer[li].items) {
-    item -= t.layer[li].items;
-    ++li;
-  }
-  if (li >= t.count) return;
-  const FinishLayer& L = t.layer[li];
-  if (L.swapped) {
-    const int total = L.cout * L.cin * 9;
-    for (int i = item * kFinishChunk + threadIdx.x; i < min(total, (item + 1) * kFinishChunk); i += kFinishThreads) {
-      const int tap = i % 9;
-      const int ci = (i / 9) % L.cin;
-      const int co = i / (9 * L.cin);
-      const float v = L.ws[(static_cast<size_t>(tap) * L.ld_a + ci) * L.ld_b + co] * L.scale;
-      L.dw[i] = L.accumulate ? L.dw[i] + v : v;
+  __shared__ __align__(16) float tile[9][68];
+  // each block takes a contiguous range of items, so the layer index only moves forward
+  const int per = (t.total_items + gridDim.x - 1) / gridDim.x;
+  const int begin = blockIdx.x * per, end = min(begin + per, t.total_items);
+  int li = 0, base = 0;
+  for (int work = begin; work < end; ++work) {
+    while (work - base >= t.layer[li].items) {
+      base += t.layer[li].items;
+      ++li;
     }
-    return;
-  }
-  const int chunks = L.cin / 64;
-  const int co = item / chunks, ci0 = (item % chunks) * 64;
-  for (int i = threadIdx.x; i < kFinishChunk; i += kFinishThreads) {
-    const int tap = i / 64, c = i % 64;
-    tile[tap][c] = L.ws[(static_cast<size_t>(tap) * L.ld_a + co) * L.ld_b + ci0 + c];
-  }
-  __syncthreads();
-  float* out = L.dw + (static_cast<size_t>(co) * L.cin + ci0) * 9;
-  for (int i = threadIdx.x; i < kFinishChunk; i += kFinishThreads) {
-    const float v = tile[i % 9][i / 9] * L.scale;
-    out[i] = L.accumulate ? out[i] + v : v;
+    const FinishLayer& L = t.layer[li];
+    const int item = work - base;
+    if (L.swapped) {
+      const int total = L.cout * L.cin * 9;
+      for (int i = item * kFinishChunk + threadIdx.x; i < min(total, (item + 1) * kFinishChunk); i += kFinishThreads) {
+        const int tap = i % 9;
+        const int ci = (i / 9) % L.cin;
+        const int co = i / (9 * L.cin);
+        const float v = L.ws[(static_cast<size_t>(tap) * L.ld_a + ci) * L.ld_b + co] * L.scale;
+        L.dw[i] = L.accumulate ? L.dw[i] + v : v;
+      }
+      continue;
+    }
+    const int chunks = L.cin / 64;
+    const int co = item / chunks, ci0 = (item - co * chunks) * 64;
+    __syncthreads();   // previous item's readers of `tile` are done
+    if (threadIdx.x < 144) {   // 9 taps x 16 float4
+      const int tap = threadIdx.x >> 4, c4 = threadIdx.x & 15;
+      const float4 v = __ldg(reinterpret_cast<const float4*>(L.ws + (static_cast<size_t>(tap) * L.ld_a + co) * L.ld_b + ci0) + c4);
+      *reinterpret_cast<float4*>(&tile[tap][c4 * 4]) = v;
+    }
+    __syncthreads();
+    float* out = L.dw + (static_cast<size_t>(co) * L.cin + ci0) * 9;
+    if ((reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+      if (threadIdx.x < 144) {   // 576 contiguous floats = 144 float4
+        const int e = threadIdx.x * 4;
+        float4 v;
+        v.x = tile[e % 9][e / 9] * L.scale;
+        v.y = tile[(e + 1) % 9][(e + 1) / 9] * L.scale;
+        v.z = tile[(e + 2) % 9][(e + 2) / 9] * L.scale;
+        v.w = tile[(e + 3) % 9][(e + 3) / 9] * L.scale;
+        float4* o = reinterpret_cast<float4*>(out) + threadIdx.x;
+        if (L.accumulate) {
+          const float4 g = *o;
+          v.x += g.x, v.y += g.y, v.z += g.z, v.w += g.w;
+        }
+        *o = v;
+      }
+    } else {
+      for (int i = threadIdx.x; i < kFinishChunk; i += kFinishThreads) {
+        const float v = tile[i % 9][i / 9] * L.scale;
+        out[i] = L.accumulate ? out[i] + v : v;
+      }
+    }
   }
 }
 
@@ -448,7 +473,11 @@ extern "C" int osvos_wgrad_finish(const osvos_wgrad_finish_item* items, int coun
     L.items = it.swapped ? (it.cout * it.cin * 9 + kFinishChunk - 1) / kFinishChunk : it.cout * (it.cin / 64);
     total_items += L.items;
   }
-  wgrad_finish_multi_kernel<<<static_cast<unsigned>(total_items), kFinishThreads, 0, static_cast<cudaStream_t>(stream_)>>>(t);
+  OSVOS_CHECK_ARG(total_items < (1ll << 31));
+  t.total_items = static_cast<int>(total_items);
+  const long long cap = static_cast<long long>(device_sm_count()) * 10;   // 10 x 192 threads resident per SM
+  const unsigned grid = static_cast<unsigned>(total_items < cap ? total_items : cap);
+  wgrad_finish_multi_kernel<<<grid, kFinishThreads, 0, static_cast<cudaStream_t>(stream_)>>>(t);
   OSVOS_CHECK_CUDA(cudaGetLastError());
   return OSVOS_OK;
 }

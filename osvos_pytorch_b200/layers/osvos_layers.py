@@ -70,7 +70,7 @@ class _ClassBalancedBCE(torch.autograd.Function):
         x = output.detach().contiguous().float()
         y = label.detach().to(x.device).contiguous().float()
         assert x.numel() == y.numel()
-        sums = torch.empty(4, dtype=torch.float64, device=x.device)
+        sums = torch.empty(5, dtype=torch.float64, device=x.device)
         loss = torch.empty((), dtype=torch.float32, device=x.device)   # 0-dim, not a view: `loss /= k` must work
         stream = torch.cuda.current_stream().cuda_stream
         nat.check(lib.osvos_cbce_fwd(x.data_ptr(), y.data_ptr(), x.numel(), float(divisor), sums.data_ptr(),

@@ -242,7 +242,7 @@ def tail_bwd(grads, n, h, w):
         dpq.append(t)
         a.dpq[k] = t.data_ptr()
     a.n, a.h, a.w = n, h, w
-    _count(4)
+    _count(1)
     nat.check(lib.osvos_tail_bwd(byref(a), _stream()), "osvos_tail_bwd")
     return dpq
 
@@ -250,9 +250,9 @@ def tail_bwd(grads, n, h, w):
 def sum_f32(x):
     lib = nat.load()
     x = x.contiguous().float()
-    scratch = torch.empty(1, dtype=torch.float64, device=x.device)
+    scratch = torch.empty(2, dtype=torch.float64, device=x.device)
     out = torch.empty(1, dtype=torch.float32, device=x.device)
-    _count(2)
+    _count(1)
     nat.check(lib.osvos_sum_f32(x.data_ptr(), x.numel(), scratch.data_ptr(), out.data_ptr(), _stream()),
               "osvos_sum_f32")
     return out
@@ -264,9 +264,9 @@ def side_bwd(feat, dpq, proj_w, fast=False):
     n, h, w, _ = (int(v) for v in dpq.shape)
     dev = dpq.device
     d = Act.empty(n, h, w, 64, dev, fast)
-    scratch = torch.empty(34, dtype=torch.float64, device=dev)
+    scratch = torch.empty(35, dtype=torch.float64, device=dev)
     pg = torch.empty(50, dtype=torch.float32, device=dev)
-    _count(2)
+    _count(1)
     nat.check(lib.osvos_side_bwd(nat.ptr(feat), dpq.data_ptr(), proj_w.data_ptr(), d.hi.data_ptr(), nat.ptr(d.lo),
                                  scratch.data_ptr(), pg.data_ptr(), n, h, w, _stream()), "osvos_side_bwd")
     return d, pg
@@ -299,9 +299,11 @@ def conv_first_bwd(x, dz, weight, need_dx):
     n, _, h, w = (int(v) for v in x.shape)
     dw = torch.empty((64, 3, 3, 3), dtype=torch.float32, device=x.device)
     dx = torch.empty_like(x) if need_dx else None
+    ws = torch.empty(lib.osvos_conv_first_bwd_workspace_bytes(), dtype=torch.uint8, device=x.device)
     _count(2 if need_dx else 1)
     nat.check(lib.osvos_conv_first_bwd(x.data_ptr(), dz.hi.data_ptr(), nat.ptr(dz.lo), weight.data_ptr(),
-                                       dw.data_ptr(), nat.ptr(dx), n, h, w, _stream()), "osvos_conv_first_bwd")
+                                       dw.data_ptr(), nat.ptr(dx), ws.data_ptr(), n, h, w, _stream()),
+              "osvos_conv_first_bwd")
     return dw, dx
 
 

@@ -237,3 +237,28 @@ def test_sgd_oracle_matches_torch_optim_sgd():
         rp, rb = oc.sgd_momentum_step(rp, p.grad, rb, 0.03, 0.02, 0.9)
         opt.step()
         assert float((p.detach() - rp).abs().max()) < 1e-6
+
+
+def test_scale_n_rotate_known_answers():
+    """Analytic cases of the warp restatement (custom_transforms.py:7-54): identity, pure flip, 180 degrees about
+    (w/2, h/2), and a 2x zoom sampling the half-pixel grid with the A = -0.75 cubic."""
+    g = np.random.default_rng(0)
+    img = g.standard_normal((3, 12, 17)).astype(np.float32)
+    assert np.array_equal(oc.scale_n_rotate(img, 0.0, 1.0, False, False), img)           # X & 31 == 0 -> weights 0,1,0,0
+    assert np.array_equal(oc.scale_n_rotate(img, 0.0, 1.0, True, False), img[:, :, ::-1])
+    m = (g.random((1, 12, 17)) > 0.5).astype(np.float32)
+    assert np.array_equal(oc.scale_n_rotate(m, 0.0, 1.0, False, True), m)
+    r = oc.scale_n_rotate(img, 180.0, 1.0, False, True)                                    # dst(x,y) = src(w-x, h-y)
+    assert np.array_equal(r[:, 1:, 1:], img[:, :0:-1, :0:-1]) and not r[:, 0].any() and not r[:, :, 0].any()
+    ramp = np.tile(np.arange(17, dtype=np.float32), (1, 12, 1))                            # linear ramp along x
+    z = oc.scale_n_rotate(ramp, 0.0, 2.0, False, False)                                    # src_x = 8.5 + (x - 8.5)/2
+    xs = np.arange(4, 14)
+    # OpenCV's A = -0.75 cubic does not reproduce linear ramps off the half-pixel: at fraction 1/4 the weights are
+    # (-0.10546875, 0.87890625, 0.26171875, -0.03515625) -> first moment 0.296875 instead of 0.25 (and 0.703125 at 3/4)
+    src = 8.5 + (xs - 8.5) / 2
+    want = np.floor(src) + np.where(src - np.floor(src) < 0.5, 0.296875, 0.703125)
+    assert np.allclose(z[0, 6, xs], want, atol=1e-5)
+    const = np.full((1, 12, 17), 3.0, dtype=np.float32)
+    assert np.allclose(oc.scale_n_rotate(const, 10.0, 1.2, False, False)[0, 3:9, 4:13], 3.0, atol=1e-5)   # weights sum to 1
+    q = oc.scale_n_rotate(img, 17.0, 0.9, True, False)
+    assert q.shape == img.shape and np.isfinite(q).all() and abs(q).max() <= abs(img).max() * 1.6

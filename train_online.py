@@ -37,6 +37,9 @@ def parse():
     ap.add_argument("--width", type=int, default=854)
     ap.add_argument("--log-every", type=int, default=None)
     ap.add_argument("--no-save", action="store_true")
+    ap.add_argument("--gpu-augment", action="store_true",
+                    help="RandomHorizontalFlip + ScaleNRotate on the device (osvos_pytorch_b200.augment) on the "
+                         "GPU-resident annotated frame instead of cv2 in a DataLoader worker")
     return ap.parse_args()
 
 
@@ -65,8 +68,16 @@ def main():
     if a.synthetic:
         fixed = training.synthetic_batch(1, a.height, a.width, 1234 + a.seed, device)
 
-        def sample_fn(it):
-            return fixed
+        if a.gpu_augment:
+            import random
+            from osvos_pytorch_b200 import augment
+            rng = random.Random(a.seed)
+
+            def sample_fn(it):
+                return augment.augment_batch(fixed, rng=rng)
+        else:
+            def sample_fn(it):
+                return fixed
         test_frames = [fixed]
     else:
         from dataloaders import davis_2016 as db
@@ -79,8 +90,18 @@ def main():
         db_test = db.DAVIS2016(train=False, db_root_dir=Path.db_root_dir(), transform=tr.ToTensor(), seq_name=a.seq_name)
         loader = DataLoader(db_train, batch_size=1, shuffle=True, num_workers=1, persistent_workers=True)
         state = {"it": iter(loader)}
+        if a.gpu_augment:
+            # the online set is the single annotated frame (train=True with seq_name): keep it on the GPU and draw a
+            # fresh flip / rotation / scale per iteration there
+            import random
+            from osvos_pytorch_b200 import augment
+            raw = db.DAVIS2016(train=True, db_root_dir=Path.db_root_dir(), transform=tr.ToTensor(), seq_name=a.seq_name)[0]
+            base = {"image": raw["image"][None].to(device), "gt": raw["gt"][None].to(device)}
+            rng = random.Random(a.seed)
 
         def sample_fn(it):
+            if a.gpu_augment:
+                return augment.augment_batch(base, rng=rng)
             np.random.seed(a.seed + it)
             try:
                 s = next(state["it"])

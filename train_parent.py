@@ -59,7 +59,7 @@ def main():
         ckpt = os.path.join(save_dir, f"{a.model_name}_epoch-{a.resume_epoch - 1}.pth")
         net.load_state_dict(torch.load(ckpt, map_location="cpu"))
     net.to(device)
-    opt = training.make_optimizer(net, "parent", a.lr, a.wd)
+    opt = training.make_optimizer(net, "parent", a.lr, a.wd, fused=True)
     bucket = parallel.GradientBucket(parallel.trainable_parameters(net), device)
 
     if a.synthetic:

@@ -117,8 +117,14 @@ typedef struct {
    * chunk can be non-zero (the 16-channel side-branch gradient is stored padded to 64): the remaining K steps
    * are skipped - fewer tcgen05.mma, identical result. */
   int k_valid;
+  /* optional split-K workspace (osvos_conv3x3_splitk_workspace_bytes bytes, or NULL): layers with fewer output
+   * tiles than half the SMs (stage 5 at 480p: 56 tiles of 128 px x 128 channels) then run 2 or 4 CTAs per tile,
+   * each reducing a share of the input channels; the helpers' fp32 partial accumulators go through this buffer. */
+  void* splitk_ws;
 } osvos_conv3x3_args;
 OSVOS_API int osvos_conv3x3(const osvos_conv3x3_args* args /* host */, osvos_stream_t stream);
+/* 0 when the layer would not be split (then splitk_ws may be NULL). */
+OSVOS_API size_t osvos_conv3x3_splitk_workspace_bytes(int n, int h, int w, int cin, int cout);
 /* Same contract on CUDA cores (fp32 FMA over hi+lo); debugging cross-check only. */
 OSVOS_API int osvos_conv3x3_simt(const osvos_conv3x3_args* args /* host */, osvos_stream_t stream);
 

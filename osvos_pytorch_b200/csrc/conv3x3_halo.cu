@@ -99,6 +99,10 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // split-K: ksplit consecutive CTAs share a tile, each reducing its own range of channel chunks (conv_common.cuh)
+  const int w_first = static_cast<int>(blockIdx.x) / p.ksplit, w_stride = static_cast<int>(gridDim.x) / p.ksplit;
+  const int kc_per = p.k_chunks / p.ksplit;
+  const int kc_begin = (static_cast<int>(blockIdx.x) % p.ksplit) * kc_per, kc_end = kc_begin + kc_per;
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (warp-uniform, elected lane issues)
@@ -123,15 +127,15 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_c
           a_phase ^= 1;
         }
       };
-      if (static_cast<int>(blockIdx.x) < p.total_tiles) issue_a(blockIdx.x, 0);
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      if (w_first < p.total_tiles) issue_a(w_first, kc_begin);
+      for (int tile = w_first; tile < p.total_tiles; tile += w_stride) {
         int nb, tx, ty, img;
         decode_tile(p, tile, nb, tx, ty, img);
-        for (int kc = 0; kc < p.k_chunks; ++kc) {
+        for (int kc = kc_begin; kc < kc_end; ++kc) {
           for (int tap = 0; tap < 9; ++tap) {
             if (tap == 3) {  // prefetch the next chunk's halo while this one is being consumed
-              if (kc + 1 < p.k_chunks) issue_a(tile, kc + 1);
-              else if (tile + static_cast<int>(gridDim.x) < p.total_tiles) issue_a(tile + gridDim.x, 0);
+              if (kc + 1 < kc_end) issue_a(tile, kc + 1);
+              else if (tile + w_stride < p.total_tiles) issue_a(tile + w_stride, kc_begin);
             }
             mbar_wait(&b_empty[b_stage], b_phase ^ 1);
             if (elect_one()) {
@@ -162,13 +166,13 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_c
       int a_stage = 0, b_stage = 0;
       uint32_t a_phase = 0, b_phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      for (int tile = w_first; tile < p.total_tiles; tile += w_stride, ++it) {
         const int as = it & 1;
         const uint32_t aph = (it >> 1) & 1;
         mbar_wait(&tempty_bar[as], aph ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * Cfg::kAccCols;
-        for (int kc = 0; kc < p.k_chunks; ++kc) {
+        for (int kc = kc_begin; kc < kc_end; ++kc) {
           mbar_wait(&a_full[a_stage], a_phase);
           tc_fence_after();
           const uint32_t a_base = smem_u32(smem_a + a_stage * Cfg::kAStageBytes);
@@ -191,7 +195,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_c
             for (int k = 0; k < kBlockK / 16; ++k) {
               if (k >= p.k_steps) break;                      // padded input channels (k_valid) are skipped
               const uint64_t adv = static_cast<uint64_t>(k * 2);
-              const uint32_t first = (kc | tap | k) != 0;
+              const uint32_t first = ((kc - kc_begin) | tap | k) != 0;
               if (Cfg::kSplitAcc) {
                 umma_f16(tmem_d, da_hi + adv, db_hi + adv, idesc2, first);   // [A_hi.B_hi | A_hi.B_lo], N = 2 * BLOCK_N
                 umma_f16(tmem_d, da_lo + adv, db_hi + adv, idesc, 1);        // + A_lo.B_hi into the first half
@@ -206,7 +210,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_c
             umma_commit(&b_empty[b_stage]);
             if (tap == 8) {
               umma_commit(&a_empty[a_stage]);
-              if (kc == p.k_chunks - 1) umma_commit(&tfull_bar[as]);
+              if (kc == kc_end - 1) umma_commit(&tfull_bar[as]);
             }
             }
             __syncwarp();
@@ -236,11 +240,40 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_c
   }
 }
 
+// split-K factor for a layer run with 128-wide tiles: the largest of {4, 2} that still fits one CTA per SM and leaves
+// every part at least two channel chunks; 1 = no split.  (All ksplit * tiles CTAs are co-resident - one per SM - so
+// the owner's wait on its helpers cannot deadlock.)
+// OPT-IN (OSVOS_SPLITK=1): measured on B200 it is SLOWER than the N = 64 tiles it was meant to replace - stage 5 at
+// 480x854 (56 tiles -> 112 CTAs, 4 chunks each): 41 us vs 37 us per layer, 240x427 whole frame 0.463 vs 0.417 ms -
+// the helper's partial write, the owner's wait and the extra memset outweigh the halved MMA chain at this size.
+static int splitk_factor(int n, int h, int w, int cin, int cout) {
+  const char* on = getenv("OSVOS_SPLITK");
+  if (cout % 128 != 0 || cin % 64 != 0 || on == nullptr || atoi(on) == 0) return 1;
+  const int m_tiles = ((w + kTileW - 1) / kTileW) * ((h + kTileH - 1) / kTileH) * n;
+  const long tiles = static_cast<long>(m_tiles) * (cout / 128);
+  const int k_chunks = cin / kBlockK;
+  const int sms = device_sm_count();
+  for (int ks = 4; ks >= 2; ks >>= 1)
+    if (tiles * ks <= sms && k_chunks % ks == 0 && k_chunks / ks >= 2) return ks;
+  return 1;
+}
+static size_t splitk_partial_bytes(int n, int h, int w, int cout, int ks) {
+  const int m_tiles = ((w + kTileW - 1) / kTileW) * ((h + kTileH - 1) / kTileH) * n;
+  return static_cast<size_t>(m_tiles) * (cout / 128) * (ks - 1) * kBlockM * 128 * sizeof(float);
+}
+
 template <int BLOCK_N, int PLANES, int PITCH>
-static int launch_halo(const osvos_conv3x3_args* a, cudaStream_t stream, int use_bo) {
+static int launch_halo(const osvos_conv3x3_args* a, cudaStream_t stream, int use_bo, int ksplit = 1) {
   using Cfg = HaloCfg<BLOCK_N, PLANES, PITCH>;
   ConvParams p;
   fill_conv_params(p, a, BLOCK_N);
+  if (ksplit > 1) {
+    p.ksplit = ksplit;
+    p.sk_partial = static_cast<float*>(a->splitk_ws);
+    p.sk_flags = reinterpret_cast<unsigned int*>(static_cast<uint8_t*>(a->splitk_ws) +
+                                                 splitk_partial_bytes(a->n, a->h, a->w, a->cout, ksplit));
+    OSVOS_CHECK_CUDA(cudaMemsetAsync(p.sk_flags, 0, sizeof(unsigned int) * p.total_tiles, stream));
+  }
   CUtensorMap mx_hi, mx_lo, mw_hi, mw_lo;
   {
     const uint64_t dims[4] = {(uint64_t)a->cin, (uint64_t)a->w, (uint64_t)a->h, (uint64_t)a->n};
@@ -268,7 +301,7 @@ static int launch_halo(const osvos_conv3x3_args* a, cudaStream_t stream, int use
     attr_done = true;
   }
   const int sms = device_sm_count();
-  const int grid = p.total_tiles < sms ? p.total_tiles : sms;
+  const int grid = ksplit > 1 ? p.total_tiles * ksplit : (p.total_tiles < sms ? p.total_tiles : sms);
   kern<<<grid, 64 + EpiCfg<BLOCK_N>::kThreads, Cfg::kSmemBytes, stream>>>(mx_hi, mx_lo, mw_hi, mw_lo, my_hi, my_lo, p, use_bo);
   OSVOS_CHECK_CUDA(cudaGetLastError());
   return OSVOS_OK;
@@ -288,12 +321,23 @@ static int dispatch_halo(const osvos_conv3x3_args* a, cudaStream_t stream, int u
   const long waves256 = (static_cast<long>(m_tiles) * (a->cout / 256) + sms - 1) / sms;
   // measured cycles per (tap, 64-channel) step: N = 128 ~ 1000 (2 + 1 instructions), N = 256 ~ 2200 exact
   const bool prefer256 = fast ? waves256 * 1100 < waves128 * 700 : waves256 * 2200 < waves128 * 1000;
-  // few pixel tiles (stage 5 at 480p: 14): N = 64 tiles double the CTA count at ~0.8x the time per tile
+  // few tiles (stage 5 at 480p: 56 of 128 px x 128 ch): split the reduction over 2 or 4 CTAs per tile
+  const int ks = a->splitk_ws != nullptr ? splitk_factor(a->n, a->h, a->w, a->cin, a->cout) : 1;
+  if (ks > 1)
+    return fast ? launch_halo<128, 1, PITCH>(a, stream, use_bo, ks) : launch_halo<128, 2, PITCH>(a, stream, use_bo, ks);
+  // without a workspace: N = 64 tiles double the CTA count at ~0.8x the time per tile
   if (waves128 == 1 && static_cast<long>(m_tiles) * (a->cout / 128) * 5 <= static_cast<long>(sms) * 3)
     return fast ? launch_halo<64, 1, PITCH>(a, stream, use_bo) : launch_halo<64, 2, PITCH>(a, stream, use_bo);
   if (a->cout % 256 == 0 && prefer256 && !(n256 && atoi(n256) == 0))
     return fast ? launch_halo<256, 1, PITCH>(a, stream, use_bo) : launch_halo<256, 2, PITCH>(a, stream, use_bo);
   return fast ? launch_halo<128, 1, PITCH>(a, stream, use_bo) : launch_halo<128, 2, PITCH>(a, stream, use_bo);
+}
+
+size_t conv3x3_splitk_workspace_bytes(int n, int h, int w, int cin, int cout) {
+  const int ks = splitk_factor(n, h, w, cin, cout);
+  if (ks <= 1) return 0;
+  const int m_tiles = ((w + kTileW - 1) / kTileW) * ((h + kTileH - 1) / kTileH) * n;
+  return splitk_partial_bytes(n, h, w, cout, ks) + sizeof(unsigned int) * m_tiles * (cout / 128) + 256;
 }
 
 int conv3x3_halo_dispatch(const osvos_conv3x3_args* a, cudaStream_t stream, int pitch, int use_bo) {

@@ -240,6 +240,13 @@ static int check_conv_args(const osvos_conv3x3_args* a) {
 
 using namespace osvos;
 
+extern "C" size_t osvos_conv3x3_splitk_workspace_bytes(int n, int h, int w, int cin, int cout) {
+  if (n <= 0 || h <= 0 || w <= 0 || cin <= 0 || cout <= 0) return 0;
+  const char* impl = getenv("OSVOS_CONV_IMPL");
+  if (impl != nullptr && (strcmp(impl, "tap") == 0 || strcmp(impl, "halo2") == 0)) return 0;
+  return conv3x3_splitk_workspace_bytes(n, h, w, cin, cout);
+}
+
 extern "C" int osvos_conv3x3(const osvos_conv3x3_args* a, osvos_stream_t stream_) {
   int rc = check_conv_args(a);
   if (rc) return rc;

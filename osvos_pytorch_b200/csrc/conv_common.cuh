@@ -31,6 +31,12 @@ struct ConvParams {
   int k_steps;               // tcgen05.mma K steps (of 16 channels) issued per 64-channel chunk: 4, or fewer (k_valid)
   int m_tiles, total_pairs;  // CTA-pair kernels: m_tiles pixel tiles, total_pairs = ceil(m_tiles / 2) * n_blocks work items
   int flags;
+  // split-K (halo kernel, layers with fewer tiles than half the SMs): ksplit CTAs share one output tile, each
+  // reducing k_chunks / ksplit channel chunks; CTA (tile, part > 0) writes its fp32 partial accumulator to
+  // sk_partial[tile][part - 1][128][BLOCK_N] and bumps sk_flags[tile]; part 0 adds them in its epilogue.
+  int ksplit;                // 1 = off
+  float* sk_partial;
+  unsigned int* sk_flags;    // zeroed by the launcher
 };
 
 __device__ __forceinline__ void decode_tile(const ConvParams& p, int tile, int& nb, int& tx, int& ty, int& img) {
@@ -97,8 +103,10 @@ __device__ __forceinline__ void conv_epilogue_loop(const ConvParams& p, uint32_t
                                                    const CUtensorMap* map_y_lo = nullptr, uint8_t* staging = nullptr) {
   // PAIR: this CTA is one half of a cta_group::2 pair; the TMEM-empty barrier lives in the leader (rank 0)
   const int rank = PAIR ? static_cast<int>(cluster_ctarank()) : 0;
-  const int w_first = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
-  const int w_stride = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const int ks = PAIR ? 1 : p.ksplit;                                   // split-K parts per tile (1 = off)
+  const int part = static_cast<int>(blockIdx.x) % ks;
+  const int w_first = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x) / ks;
+  const int w_stride = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x) / ks;
   const int w_total = PAIR ? p.total_pairs : p.total_tiles;
   const uint32_t tempty_remote = PAIR ? mapa_shared(smem_u32(tempty_bar), 0) : 0u;
   constexpr int kEpiThreads = EpiCfg<BLOCK_N>::kThreads;
@@ -125,6 +133,18 @@ __device__ __forceinline__ void conv_epilogue_loop(const ConvParams& p, uint32_t
     tc_fence_after();
     constexpr int kAccCols = SPLIT_ACC ? 2 * BLOCK_N : BLOCK_N;
     const uint32_t taddr = tmem_base + as * kAccCols + (static_cast<uint32_t>(q * 32) << 16);
+    if (ks > 1 && part == 0) {
+      // split-K owner: the other parts' partial accumulators must be in memory before they are added below
+      if (lane == 0) {
+        const int need = (ks - 1) * (kEpiThreads / 32);
+        unsigned int spins = 0;
+        while (static_cast<int>(ld_acquire_gpu_u32(p.sk_flags + tile)) < need) {
+          __nanosleep(64);
+          if (++spins > (1u << 24)) __trap();
+        }
+      }
+      __syncwarp();
+    }
 
     if constexpr (BLOCK_N == 16) {
       uint32_t v[16];
@@ -189,6 +209,30 @@ __device__ __forceinline__ void conv_epilogue_loop(const ConvParams& p, uint32_t
           for (int j = 0; j < 32; ++j) f[j] = 0.f;
         }
         tmem_ld_wait();
+        if (ks > 1) {
+          float* part_base = p.sk_partial + ((static_cast<size_t>(tile) * (ks - 1)) * kBlockM + row) * BLOCK_N + c0;
+          if (part > 0) {   // helper: raw partial accumulator (no bias) -> workspace, nothing else
+            float4* dst = reinterpret_cast<float4*>(part_base + static_cast<size_t>(part - 1) * kBlockM * BLOCK_N);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 o;
+              o.x = __uint_as_float(v[4 * j]) + (SPLIT_ACC ? __uint_as_float(v2[4 * j]) : 0.f);
+              o.y = __uint_as_float(v[4 * j + 1]) + (SPLIT_ACC ? __uint_as_float(v2[4 * j + 1]) : 0.f);
+              o.z = __uint_as_float(v[4 * j + 2]) + (SPLIT_ACC ? __uint_as_float(v2[4 * j + 2]) : 0.f);
+              o.w = __uint_as_float(v[4 * j + 3]) + (SPLIT_ACC ? __uint_as_float(v2[4 * j + 3]) : 0.f);
+              __stcg(dst + j, o);
+            }
+            continue;
+          }
+          for (int hp = 0; hp < ks - 1; ++hp) {   // owner: add the helpers' partials
+            const float4* src = reinterpret_cast<const float4*>(part_base + static_cast<size_t>(hp) * kBlockM * BLOCK_N);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 o = __ldcg(src + j);
+              f[4 * j] += o.x, f[4 * j + 1] += o.y, f[4 * j + 2] += o.z, f[4 * j + 3] += o.w;
+            }
+          }
+        }
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           f[j] += __uint_as_float(v[j]);
@@ -291,6 +335,11 @@ __device__ __forceinline__ void conv_epilogue_loop(const ConvParams& p, uint32_t
         }
       }
     }
+    if (ks > 1 && part > 0) {   // helper: publish the partial (one count per epilogue warp)
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) red_release_gpu_add_u32(p.sk_flags + tile, 1u);
+    }
     tc_fence_before();
     if (PAIR) mbar_arrive_cluster(tempty_remote + as * 8);
     else mbar_arrive(&tempty_bar[as]);
@@ -337,6 +386,9 @@ static inline void fill_conv_params(ConvParams& p, const osvos_conv3x3_args* a, 
   p.k_chunks = a->cin / kBlockK;
   p.k_steps = (a->k_valid > 0 && a->k_valid < kBlockK) ? (a->k_valid + 15) / 16 : kBlockK / 16;
   p.flags = a->flags;
+  p.ksplit = 1;
+  p.sk_partial = nullptr;
+  p.sk_flags = nullptr;
 }
 
 // Packed weights [plane][tap][cout][cin] -> two 3-D maps with box {64, block_n, 1}.
@@ -358,5 +410,6 @@ int conv_first_tc_launch(const float* x, const float* w_oihw, const float* bias,
 int side_conv_dispatch(const osvos_conv3x3_args* a, cudaStream_t stream);
 int conv3x3_halo2_dispatch(const osvos_conv3x3_args* a, cudaStream_t stream);
 int conv3x3_halo_dispatch(const osvos_conv3x3_args* a, cudaStream_t stream, int pitch, int use_bo);
+size_t conv3x3_splitk_workspace_bytes(int n, int h, int w, int cin, int cout);
 
 }  // namespace osvos

@@ -122,6 +122,9 @@ def conv3x3(x, w_packed, bias, cout, relu=False, fast=False, out_act=True, out_f
     a.colsum = nat.ptr(colsum)
     a.k_valid = k_valid
     a.n, a.h, a.w, a.cin, a.cout = n, h, w, cin, cout
+    skb = 0 if simt else lib.osvos_conv3x3_splitk_workspace_bytes(n, h, w, cin, cout)
+    sk_ws = torch.empty(skb, dtype=torch.uint8, device=dev) if skb else None   # small layers: split-K partials
+    a.splitk_ws = nat.ptr(sk_ws)
     a.flags = (nat.FLAG_RELU if relu else 0) | (nat.FLAG_FAST if fast else 0) | \
               (nat.FLAG_RELU_MASK if mask is not None else 0)
     fn = lib.osvos_conv3x3_simt if simt else lib.osvos_conv3x3

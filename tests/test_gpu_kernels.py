@@ -88,6 +88,30 @@ def test_conv3x3_tensor_core(dev, n, h, w, cin, cout, relu, fast):
     assert maxrel(got_f32, ys.permute(0, 3, 1, 2).cpu()) < 2e-5
 
 
+@pytest.mark.parametrize("n,h,w,cin,cout,expect_ks", [(1, 30, 54, 512, 512, 2), (1, 15, 27, 512, 512, 4),
+                                                        (2, 9, 11, 256, 128, 2), (1, 33, 45, 128, 256, 0)])
+def test_conv3x3_split_k_opt_in(dev, monkeypatch, n, h, w, cin, cout, expect_ks):
+    """OSVOS_SPLITK=1: 2 / 4 CTAs per output tile, partial accumulators exchanged through the workspace
+    (kept opt-in: measured slower than the N = 64 tiles at these sizes).  Same result as the default path."""
+    from osvos_pytorch_b200 import _native as nat, ops
+    g = torch.Generator().manual_seed(7 + h + cin)
+    x = torch.randn(n, cin, h, w, generator=g) * 3.0
+    wt = torch.randn(cout, cin, 3, 3, generator=g) * math.sqrt(2.0 / (9 * cin))
+    b = torch.randn(cout, generator=g) * 0.1
+    a = ops.nchw_to_act(x.to(dev))
+    wp = ops.pack_conv3x3_weights(wt.to(dev))
+    _, base, _ = ops.conv3x3(a, wp, b.to(dev), cout, relu=True, out_act=False, out_f32=True)
+    monkeypatch.setenv("OSVOS_SPLITK", "1")
+    nbytes = nat.load().osvos_conv3x3_splitk_workspace_bytes(n, h, w, cin, cout)
+    assert (nbytes > 0) == (expect_ks > 0)
+    y, split, _ = ops.conv3x3(a, wp, b.to(dev), cout, relu=True, out_act=True, out_f32=True)
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.double(), wt.double(), b.double(), padding=1).relu()
+    assert maxrel(split.permute(0, 3, 1, 2).cpu(), ref) < EXACT_TOL
+    assert maxrel(split, base) < 1e-5                       # only the fp32 summation order differs
+    assert torch.equal(ops.act_to_nchw(y).cpu(), split_round(split.permute(0, 3, 1, 2).cpu()))
+
+
 def test_conv3x3_relu_mask_and_projection(dev):
     from osvos_pytorch_b200 import ops
     g = torch.Generator().manual_seed(7)

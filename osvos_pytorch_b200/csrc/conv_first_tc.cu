@@ -130,11 +130,13 @@ conv_first_tc_kernel(const float* __restrict__ x, const float* __restrict__ wgt,
     int stage = 0;
     uint32_t phase = 0;
     const size_t plane_sz = static_cast<size_t>(p.h) * p.w;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    // Register double buffering: the 27 taps of the NEXT tile are requested before the current tile is converted and
+    // written, so the global-load latency (the builders handle one tile at a time) overlaps the shared-memory work
+    // and the wait for a free stage instead of being paid once per tile.
+    auto load_tile = [&](int tile, float (&v)[27]) {
       int nb, tx, ty, img;
       decode_tile(p, tile, nb, tx, ty, img);
       const int y = ty * kTileH + ly, xx = tx * kTileW + lx;
-      float v[32];
 #pragma unroll
       for (int ci = 0; ci < 3; ++ci) {
         const float* pl = x + (static_cast<size_t>(img) * 3 + ci) * plane_sz;
@@ -149,8 +151,16 @@ conv_first_tc_kernel(const float* __restrict__ x, const float* __restrict__ wgt,
           }
         }
       }
+    };
+    float vn[27];
+    if (static_cast<int>(blockIdx.x) < p.total_tiles) load_tile(blockIdx.x, vn);
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      float v[32];
+#pragma unroll
+      for (int k = 0; k < 27; ++k) v[k] = vn[k];
 #pragma unroll
       for (int k = 27; k < 32; ++k) v[k] = 0.f;
+      if (tile + static_cast<int>(gridDim.x) < p.total_tiles) load_tile(tile + gridDim.x, vn);
       mbar_wait(&empty_bar[stage], phase ^ 1);
       uint8_t* st = smem + stage * kFirstStageBytes;
 #pragma unroll

@@ -4,6 +4,7 @@
 // They replace the autograd graph PyTorch builds for reference
 // networks/vgg_osvos.py:59-74 (triggered at train_online.py:141, train_parent.py:164).
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace osvos {
 
@@ -203,6 +204,8 @@ unpool_add_mask_kernel(const __nv_bfloat16* __restrict__ dp_hi, const __nv_bfloa
     for (int i = threadIdx.x; i < c; i += blockDim.x) cs[i] = 0.f;
     __syncthreads();
   }
+  pdl_wait();               // dpool / dside are the previous kernels' outputs (ptx.cuh)
+  pdl_launch_dependents();
   const int groups = c / 8;
   // blockDim (256) is a multiple of `groups`: a thread keeps the same channel group over the whole loop, and a block
   // iteration covers 256 / groups consecutive pooled pixels of one pooled row (32-bit index math only)
@@ -595,11 +598,11 @@ extern "C" int osvos_unpool_add_mask(const void* dpool_hi, const void* dpool_lo,
   const int ppb = 256 / (c / 8);
   const size_t tiles = static_cast<size_t>(n) * oh * ((ow + ppb - 1) / ppb);
   OSVOS_CHECK_ARG(tiles < (static_cast<size_t>(1) << 31));
-  unpool_add_mask_kernel<<<grid_cap(tiles, 4), 256, c * sizeof(float), static_cast<cudaStream_t>(stream_)>>>(
-      static_cast<const __nv_bfloat16*>(dpool_hi), static_cast<const __nv_bfloat16*>(dpool_lo),
-      static_cast<const __nv_bfloat16*>(x_hi), static_cast<const __nv_bfloat16*>(x_lo), dside,
-      static_cast<__nv_bfloat16*>(dz_hi), static_cast<__nv_bfloat16*>(dz_lo), colsum, n, h, w, c, oh, ow);
-  OSVOS_CHECK_CUDA(cudaGetLastError());
+  OSVOS_CHECK_CUDA(launch_pdl(unpool_add_mask_kernel, dim3(grid_cap(tiles, 4)), dim3(256), c * sizeof(float),
+                              static_cast<cudaStream_t>(stream_), static_cast<const __nv_bfloat16*>(dpool_hi),
+                              static_cast<const __nv_bfloat16*>(dpool_lo), static_cast<const __nv_bfloat16*>(x_hi),
+                              static_cast<const __nv_bfloat16*>(x_lo), dside, static_cast<__nv_bfloat16*>(dz_hi),
+                              static_cast<__nv_bfloat16*>(dz_lo), colsum, n, h, w, c, oh, ow));
   return OSVOS_OK;
 }
 

@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 
 #include "../../include/osvos_b200.h"
 
@@ -38,6 +39,30 @@ int encode_tensor_map(CUtensorMap* map, CUtensorMapDataType dtype, int elem_byte
                       CUtensorMapSwizzle swizzle);
 
 int device_sm_count();
+
+// Programmatic dependent launch: opt-in with OSVOS_PDL=1 (read once per process); otherwise plain stream-ordered
+// launches.
+bool pdl_enabled();
+
+// Launches `kern` on `stream`; with PDL enabled the launch carries the programmatic-stream-serialization attribute,
+// so the kernel's prologue (barrier init, TMEM allocation, descriptor prefetch) overlaps the previous kernel's tail.
+// ONLY for kernels that execute pdl_wait() (ptx.cuh) before their first dependent global access.
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                     Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 
 // ---- split-bf16 ("bf16x2") representation of an fp32 value: v ~= hi + lo ------
 __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {

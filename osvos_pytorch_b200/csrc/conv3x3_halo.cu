@@ -99,6 +99,10 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // PDL: everything above touched only shared memory, TMEM and the kernel parameters; the previous kernel's
+  // outputs (activations, masks, pooled planes, workspaces) are first accessed below.
+  pdl_wait();
+  pdl_launch_dependents();
   // split-K: ksplit consecutive CTAs share a tile, each reducing its own range of channel chunks (conv_common.cuh)
   const int w_first = static_cast<int>(blockIdx.x) / p.ksplit, w_stride = static_cast<int>(gridDim.x) / p.ksplit;
   const int kc_per = p.k_chunks / p.ksplit;
@@ -302,8 +306,8 @@ static int launch_halo(const osvos_conv3x3_args* a, cudaStream_t stream, int use
   }
   const int sms = device_sm_count();
   const int grid = ksplit > 1 ? p.total_tiles * ksplit : (p.total_tiles < sms ? p.total_tiles : sms);
-  kern<<<grid, 64 + EpiCfg<BLOCK_N>::kThreads, Cfg::kSmemBytes, stream>>>(mx_hi, mx_lo, mw_hi, mw_lo, my_hi, my_lo, p, use_bo);
-  OSVOS_CHECK_CUDA(cudaGetLastError());
+  OSVOS_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(64 + EpiCfg<BLOCK_N>::kThreads), Cfg::kSmemBytes, stream, mx_hi, mx_lo,
+                              mw_hi, mw_lo, my_hi, my_lo, p, use_bo));
   return OSVOS_OK;
 }
 

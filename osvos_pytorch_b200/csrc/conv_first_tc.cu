@@ -56,6 +56,11 @@ conv_first_tc_kernel(const float* __restrict__ x, const float* __restrict__ wgt,
     }
     fence_barrier_init();
   }
+  if (warp == 1) tmem_alloc(tmem_slot, 128);
+  // PDL: the weights may have been rewritten by the previous kernel of the stream (the optimizer step), so even
+  // the resident B operand is built after the wait; only barrier init and the TMEM allocation overlap its tail.
+  pdl_wait();
+  pdl_launch_dependents();
   // resident B operand: rows = co, k = ci*9 + 3r + s (the OIHW flattening), chunks 0..3 (k < 32)
   for (int i = threadIdx.x; i < 64 * 4; i += kFirstTcThreads) {
     const int co = i >> 2, chunk = i & 3;
@@ -75,7 +80,6 @@ conv_first_tc_kernel(const float* __restrict__ x, const float* __restrict__ wgt,
     *reinterpret_cast<uint4*>(smem_b + 64 * 128 + sw128_offset(co, chunk)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
   }
   fence_proxy_async_smem();
-  if (warp == 1) tmem_alloc(tmem_slot, 128);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -224,8 +228,7 @@ int conv_first_tc_launch(const float* x, const float* w_oihw, const float* bias,
   }
   const int sms = device_sm_count();
   const int grid = p.total_tiles < sms ? p.total_tiles : sms;
-  kern<<<grid, kFirstTcThreads, kFirstSmem, stream>>>(x, w_oihw, my_hi, my_lo, p);
-  OSVOS_CHECK_CUDA(cudaGetLastError());
+  OSVOS_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(kFirstTcThreads), kFirstSmem, stream, x, w_oihw, my_hi, my_lo, p));
   return OSVOS_OK;
 }
 

@@ -30,6 +30,15 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// ------------------------------------------------- programmatic dependent launch
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while the previous kernel
+// of the stream is still draining.  pdl_wait() blocks until that kernel has COMPLETED and its memory is visible
+// (a no-op for a normal launch): nothing written by an earlier kernel may be read, and nothing it reads may be
+// overwritten, before this point.  pdl_launch_dependents() lets the NEXT kernel's blocks be scheduled as soon as
+// every block of this grid has issued it (they then park in their own pdl_wait()).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ----------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

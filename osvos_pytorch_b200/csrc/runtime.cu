@@ -2,6 +2,7 @@
 // through a run-time resolved driver entry point (no link-time libcuda
 // dependency, so the .so loads on a CPU-only box for the symbol tests).
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -79,6 +80,15 @@ int device_sm_count() {
     sms[dev] = v;
   }
   return sms[dev];
+}
+
+bool pdl_enabled() {
+  static int state = -1;   // read once: the choice must not change between a graph's capture and its replays
+  if (state < 0) {
+    const char* e = getenv("OSVOS_PDL");
+    state = (e != nullptr && atoi(e) != 0) ? 1 : 0;
+  }
+  return state == 1;
 }
 
 }  // namespace osvos

@@ -94,6 +94,8 @@ side_conv_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();               // the previous kernel's activations are first read below (ptx.cuh)
+  pdl_launch_dependents();
 
   if (warp == 0) {
     int a_stage = 0, b_stage = 0;
@@ -301,8 +303,7 @@ static int launch_side(const osvos_conv3x3_args* a, cudaStream_t stream) {
   }
   const int sms = device_sm_count();
   const int grid = p.total_tiles < sms ? p.total_tiles : sms;
-  kern<<<grid, kSideThreads, Cfg::kSmem, stream>>>(mx_hi, mx_lo, mw_hi, mw_lo, p);
-  OSVOS_CHECK_CUDA(cudaGetLastError());
+  OSVOS_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(kSideThreads), Cfg::kSmem, stream, mx_hi, mx_lo, mw_hi, mw_lo, p));
   return OSVOS_OK;
 }
 

@@ -15,6 +15,7 @@
 // a (weight (r + .5)/s, if a < h_k) and a - 1 (weight 1 - (r + .5)/s, if a >= 1);
 // rows outside the source contribute zero (zero padding => attenuated border).
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace osvos {
 
@@ -37,6 +38,8 @@ constexpr int kTailThreads = 256;
 __device__ __forceinline__ float softplus_f(float x) { return fmaxf(x, 0.f) + log1pf(__expf(-fabsf(x))); }
 
 __global__ void __launch_bounds__(kTailThreads) tail_fwd_kernel(const TailParams p) {
+  pdl_wait();               // side maps, biases and the accumulators all come from earlier kernels (ptx.cuh)
+  pdl_launch_dependents();
   const size_t hw = static_cast<size_t>(p.h) * p.w;
   const size_t total = static_cast<size_t>(p.n) * hw;
   const size_t nvec = (total + 3) / 4;
@@ -196,7 +199,9 @@ extern "C" int osvos_tail_fwd(const osvos_tail_fwd_args* a, osvos_stream_t strea
   size_t blocks = (nvec + kTailThreads - 1) / kTailThreads;
   const size_t cap = static_cast<size_t>(device_sm_count()) * 8;
   if (blocks > cap) blocks = cap;
-  tail_fwd_kernel<<<static_cast<int>(blocks), kTailThreads, 0, stream>>>(p);
+  // (with a loss, the memset above is this kernel's stream predecessor: plain launch)
+  if (a->sums) tail_fwd_kernel<<<static_cast<int>(blocks), kTailThreads, 0, stream>>>(p);
+  else OSVOS_CHECK_CUDA(launch_pdl(tail_fwd_kernel, dim3(static_cast<unsigned>(blocks)), dim3(kTailThreads), 0, stream, p));
   OSVOS_CHECK_CUDA(cudaGetLastError());
   return OSVOS_OK;
 }

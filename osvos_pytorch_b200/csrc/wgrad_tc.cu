@@ -106,6 +106,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_p_hi, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();               // dz / x come from the previous kernels of the stream (ptx.cuh)
+  pdl_launch_dependents();
 
   if (warp == 0 || warp == 6) {
     {  // two producer warps (P operand: warp 0, Q operand: warp 6) halve the per-K-block TMA issue time; warp-uniform
@@ -433,9 +435,12 @@ static int launch_wgrad(const osvos_wgrad_args* a, cudaStream_t stream) {
     attr_done = true;
   }
   const int grid = p.total_items < sms ? p.total_items : sms;
+  if (deferred) {   // (otherwise the memset above is this kernel's stream predecessor: plain launch)
+    OSVOS_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(kWgThreads), Cfg::kSmemBytes, stream, mp_hi, mp_lo, mq_hi, mq_lo, p));
+    return OSVOS_OK;
+  }
   kern<<<grid, kWgThreads, Cfg::kSmemBytes, stream>>>(mp_hi, mp_lo, mq_hi, mq_lo, p);
   OSVOS_CHECK_CUDA(cudaGetLastError());
-  if (deferred) return OSVOS_OK;
   const int total = a->cout * a->cin * 9;
   wgrad_finish_kernel<<<(total + 255) / 256, 256, 0, stream>>>(a->workspace, a->dw, a->cout, a->cin, p.m_total,
                                                                 p.n_total, swapped ? 1 : 0, 1.0f, 0);

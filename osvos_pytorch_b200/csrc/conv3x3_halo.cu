@@ -14,6 +14,8 @@
 // (start >> 7) & 7.  (Both knobs exist to validate the descriptor semantics on hardware.)
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "conv_common.cuh"
 
 namespace osvos {
@@ -109,126 +111,158 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_c
   const int kc_begin = (static_cast<int>(blockIdx.x) % p.ksplit) * kc_per, kc_end = kc_begin + kc_per;
 
   if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer (warp-uniform, elected lane issues)
-    {
+    // ------------------------------------------------------------ TMA producer (one elected thread)
+    // Same economy as the MMA issuer below: ONE elected thread runs the whole loop (no per-step ELECT / warp
+    // reconvergence), taps unrolled (the tap coordinate is an immediate), tile coordinates decoded once per tile
+    // (three integer divisions) instead of once per halo load.
+    if (elect_one()) {
       int a_stage = 0, b_stage = 0;
       uint32_t a_phase = 0, b_phase = 0;
-      auto issue_a = [&](int tile, int kc) {
-        int nb, tx, ty, img;
-        decode_tile(p, tile, nb, tx, ty, img);
+      const bool skip_a = (p.ablate & 2) != 0, skip_b = (p.ablate & 1) != 0;
+      auto issue_a = [&](int x0, int y0, int img, int kc) {
         mbar_wait(&a_empty[a_stage], a_phase ^ 1);
-        if (elect_one()) {
+        if (skip_a) {
+          mbar_arrive(&a_full[a_stage]);
+        } else {
           uint8_t* st = smem_a + a_stage * Cfg::kAStageBytes;
           mbar_arrive_expect_tx(&a_full[a_stage], PLANES * Cfg::kABoxBytes);
-          tma_load_4d(&map_x_hi, &a_full[a_stage], st, kc * kBlockK, tx * kTileW - 1, ty * kTileH - 1, img);
-          if (PLANES == 2)
-            tma_load_4d(&map_x_lo, &a_full[a_stage], st + Cfg::kAPlaneBytes, kc * kBlockK, tx * kTileW - 1,
-                        ty * kTileH - 1, img);
+          tma_load_4d(&map_x_hi, &a_full[a_stage], st, kc * kBlockK, x0, y0, img);
+          if (PLANES == 2) tma_load_4d(&map_x_lo, &a_full[a_stage], st + Cfg::kAPlaneBytes, kc * kBlockK, x0, y0, img);
         }
-        __syncwarp();
         if (++a_stage == SA) {
           a_stage = 0;
           a_phase ^= 1;
         }
       };
-      if (w_first < p.total_tiles) issue_a(w_first, kc_begin);
+      int nb = 0, tx = 0, ty = 0, img = 0;
+      if (w_first < p.total_tiles) {
+        decode_tile(p, w_first, nb, tx, ty, img);
+        issue_a(tx * kTileW - 1, ty * kTileH - 1, img, kc_begin);
+      }
       for (int tile = w_first; tile < p.total_tiles; tile += w_stride) {
-        int nb, tx, ty, img;
-        decode_tile(p, tile, nb, tx, ty, img);
+        const bool has_next = tile + w_stride < p.total_tiles;
+        int nnb = 0, ntx = 0, nty = 0, nimg = 0;
+        if (has_next) decode_tile(p, tile + w_stride, nnb, ntx, nty, nimg);
+        const int n0 = nb * BLOCK_N;
         for (int kc = kc_begin; kc < kc_end; ++kc) {
+          const int c0 = kc * kBlockK;
+#pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
             if (tap == 3) {  // prefetch the next chunk's halo while this one is being consumed
-              if (kc + 1 < kc_end) issue_a(tile, kc + 1);
-              else if (tile + w_stride < p.total_tiles) issue_a(tile + w_stride, kc_begin);
+              if (kc + 1 < kc_end) issue_a(tx * kTileW - 1, ty * kTileH - 1, img, kc + 1);
+              else if (has_next) issue_a(ntx * kTileW - 1, nty * kTileH - 1, nimg, kc_begin);
             }
             mbar_wait(&b_empty[b_stage], b_phase ^ 1);
-            if (elect_one()) {
+            if (skip_b) {
+              mbar_arrive(&b_full[b_stage]);
+            } else {
               uint8_t* st = smem_b + b_stage * Cfg::kBStageBytes;
               mbar_arrive_expect_tx(&b_full[b_stage], Cfg::kBStageBytes);
-              tma_load_3d(&map_w_hi, &b_full[b_stage], st, kc * kBlockK, nb * BLOCK_N, tap);
-              if (PLANES == 2)
-                tma_load_3d(&map_w_lo, &b_full[b_stage], st + Cfg::kBPlaneBytes, kc * kBlockK, nb * BLOCK_N, tap);
+              tma_load_3d(&map_w_hi, &b_full[b_stage], st, c0, n0, tap);
+              if (PLANES == 2) tma_load_3d(&map_w_lo, &b_full[b_stage], st + Cfg::kBPlaneBytes, c0, n0, tap);
             }
-            __syncwarp();
             if (++b_stage == SB) {
               b_stage = 0;
               b_phase ^= 1;
             }
           }
         }
+        nb = nnb, tx = ntx, ty = nty, img = nimg;
       }
     }
+    __syncwarp();
   } else if (warp == 1) {
-    // -------------------------------------------------------------- MMA issuer (warp-uniform, elected lane issues)
-    // Negative result kept for the record: flattening the (tile, chunk, tap) nest into one step stream and waiting /
-    // probing (mbarrier.test_wait) the NEXT step's barriers between the first and second K step of the current one
-    // — to hide the ~180-cycle try_wait behind queued MMAs — measured 8 % slower end to end (0.85 vs 0.78 ms at
-    // 480x854): the extra index math on the issuing thread costs more than the overlap gains.
+    // -------------------------------------------------------------- MMA issuer (one elected thread)
+    // The per-tap scalar work of this warp is what bounds the kernel, not the tensor pipe: timing ablations
+    // (scripts/ablate.py, profiles/r01f_ablation_480p.txt) showed that with every load, MMA and store removed the
+    // barrier skeleton alone still took 50-100 % of the full time, i.e. 600-900 cycles per (tap, 64-channel) step
+    // against 448 (N = 64) / 768 (N = 128) cycles of MMA time, while a bare issue loop sustains 48 / 64 cycles per
+    // MMA (scripts/microbench/operand_reuse_bench.cu).  So: the nine taps are unrolled (tap offsets are immediates),
+    // descriptors are formed by ADDING to one per-chunk base instead of being rebuilt, and nothing is recomputed
+    // per K step.  (A negative result from before, for the record: flattening the (tile, chunk, tap) nest to probe
+    // the next step's barrier between MMAs was 8 % slower - more index math on this warp.)
     {
       constexpr uint32_t idesc = make_idesc_f16(kBlockM, BLOCK_N, /*bf16=*/true);
       constexpr uint32_t idesc2 = make_idesc_f16(kBlockM, Cfg::kSplitAcc ? 2 * BLOCK_N : BLOCK_N, /*bf16=*/true);
-      int a_stage = 0, b_stage = 0;
-      uint32_t a_phase = 0, b_phase = 0;
-      int it = 0;
-      for (int tile = w_first; tile < p.total_tiles; tile += w_stride, ++it) {
-        const int as = it & 1;
-        const uint32_t aph = (it >> 1) & 1;
-        mbar_wait(&tempty_bar[as], aph ^ 1);
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + as * Cfg::kAccCols;
-        for (int kc = kc_begin; kc < kc_end; ++kc) {
-          mbar_wait(&a_full[a_stage], a_phase);
+      // descriptor templates without the start-address field (bits [0,14) = address >> 4): adding (bytes >> 4) to a
+      // descriptor moves its start address (shared-memory addresses stay below 2^18, no carry out of the field)
+      constexpr uint64_t kDescA = (static_cast<uint64_t>(16 >> 4) << 16) | (static_cast<uint64_t>((PITCH * 128) >> 4) << 32) |
+                                  (1ull << 46) | (static_cast<uint64_t>(kLayoutSW128) << 61);
+      constexpr uint64_t kDescB = (static_cast<uint64_t>(16 >> 4) << 16) | (static_cast<uint64_t>(1024 >> 4) << 32) |
+                                  (1ull << 46) | (static_cast<uint64_t>(kLayoutSW128) << 61);
+      constexpr uint32_t kLoPlaneA = Cfg::kAPlaneBytes >> 4, kLoPlaneB = Cfg::kBPlaneBytes >> 4;
+      const uint32_t smem_a_u32 = smem_u32(smem_a), smem_b_u32 = smem_u32(smem_b);
+      const int k_steps = (p.ablate & 4) ? 0 : p.k_steps;   // < 4 only for zero-padded input channels (k_valid)
+      // One tap = wait for its weight slab, FULLK ? 8 : up to 8 MMAs, release the slab.  FULLK (all four K steps of
+      // the 64-channel chunk) is the common case and has no per-K-step branches.
+      auto run = [&](auto fullk_tag) {
+        constexpr bool FULLK = decltype(fullk_tag)::value;
+        int a_stage = 0, b_stage = 0;
+        uint32_t a_phase = 0, b_phase = 0;
+        int it = 0;
+        for (int tile = w_first; tile < p.total_tiles; tile += w_stride, ++it) {
+          const int as = it & 1;
+          const uint32_t aph = (it >> 1) & 1;
+          mbar_wait(&tempty_bar[as], aph ^ 1);
           tc_fence_after();
-          const uint32_t a_base = smem_u32(smem_a + a_stage * Cfg::kAStageBytes);
-#pragma unroll 1
-          for (int tap = 0; tap < 9; ++tap) {
-            const int r = tap / 3, s = tap - 3 * r;
-            mbar_wait(&b_full[b_stage], b_phase);
+          const uint32_t tmem_d = tmem_base + as * Cfg::kAccCols;
+          for (int kc = kc_begin; kc < kc_end; ++kc) {
+            mbar_wait(&a_full[a_stage], a_phase);
             tc_fence_after();
-            if (elect_one()) {
-            const uint32_t a_hi = a_base + (r * PITCH + s) * 128;
-            const uint32_t a_lo = a_hi + Cfg::kAPlaneBytes;
-            const uint32_t b_hi = smem_u32(smem_b + b_stage * Cfg::kBStageBytes);
-            const uint32_t bo_hi = use_base_offset ? ((a_hi >> 7) & 7) : 0;
-            const uint32_t bo_lo = use_base_offset ? ((a_lo >> 7) & 7) : 0;
-            const uint64_t da_hi = make_smem_desc(a_hi, 16, PITCH * 128, kLayoutSW128, bo_hi);
-            const uint64_t da_lo = make_smem_desc(a_lo, 16, PITCH * 128, kLayoutSW128, bo_lo);
-            const uint64_t db_hi = make_smem_desc(b_hi, 16, 1024, kLayoutSW128);
-            const uint64_t db_lo = make_smem_desc(b_hi + Cfg::kBPlaneBytes, 16, 1024, kLayoutSW128);
+            const uint64_t da0 = kDescA | static_cast<uint64_t>((smem_a_u32 + a_stage * Cfg::kAStageBytes) >> 4);
+            const uint32_t not_first_chunk = kc != kc_begin;
+            const bool last_chunk = kc == kc_end - 1;
 #pragma unroll
-            for (int k = 0; k < kBlockK / 16; ++k) {
-              if (k >= p.k_steps) break;                      // padded input channels (k_valid) are skipped
-              const uint64_t adv = static_cast<uint64_t>(k * 2);
-              const uint32_t first = ((kc - kc_begin) | tap | k) != 0;
-              if (Cfg::kSplitAcc) {
-                umma_f16(tmem_d, da_hi + adv, db_hi + adv, idesc2, first);   // [A_hi.B_hi | A_hi.B_lo], N = 2 * BLOCK_N
-                umma_f16(tmem_d, da_lo + adv, db_hi + adv, idesc, 1);        // + A_lo.B_hi into the first half
-              } else if (PLANES == 2) {
-                umma_f16(tmem_d, da_lo + adv, db_hi + adv, idesc, first);
-                umma_f16(tmem_d, da_hi + adv, db_lo + adv, idesc, 1);
-                umma_f16(tmem_d, da_hi + adv, db_hi + adv, idesc, 1);
-              } else {
-                umma_f16(tmem_d, da_hi + adv, db_hi + adv, idesc, first);
+            for (int tap = 0; tap < 9; ++tap) {
+              constexpr int kRowBytes16 = 128 >> 4;
+              const uint32_t tap_off = static_cast<uint32_t>(((tap / 3) * PITCH + (tap % 3)) * kRowBytes16);
+              mbar_wait(&b_full[b_stage], b_phase);
+              tc_fence_after();
+              const uint64_t db_hi = kDescB | static_cast<uint64_t>((smem_b_u32 + b_stage * Cfg::kBStageBytes) >> 4);
+              {
+                const uint64_t da_hi = da0 + tap_off;
+                const uint64_t da_lo = da_hi + kLoPlaneA;
+#pragma unroll
+                for (int k = 0; k < kBlockK / 16; ++k) {
+                  if (FULLK || k < k_steps) {
+                    const uint32_t acc = (tap == 0 && k == 0) ? not_first_chunk : 1u;
+                    if (Cfg::kSplitAcc) {
+                      umma_f16(tmem_d, da_hi + 2 * k, db_hi + 2 * k, idesc2, acc);   // [A_hi.B_hi | A_hi.B_lo], N = 2 * BLOCK_N
+                      umma_f16(tmem_d, da_lo + 2 * k, db_hi + 2 * k, idesc, 1);      // + A_lo.B_hi into the first half
+                    } else if (PLANES == 2) {
+                      umma_f16(tmem_d, da_lo + 2 * k, db_hi + 2 * k, idesc, acc);
+                      umma_f16(tmem_d, da_hi + 2 * k, db_hi + kLoPlaneB + 2 * k, idesc, 1);
+                      umma_f16(tmem_d, da_hi + 2 * k, db_hi + 2 * k, idesc, 1);
+                    } else {
+                      umma_f16(tmem_d, da_hi + 2 * k, db_hi + 2 * k, idesc, acc);
+                    }
+                  }
+                }
+                umma_commit(&b_empty[b_stage]);
+                if (tap == 8) {
+                  umma_commit(&a_empty[a_stage]);
+                  if (last_chunk) umma_commit(&tfull_bar[as]);
+                }
+              }
+              if (++b_stage == SB) {
+                b_stage = 0;
+                b_phase ^= 1;
               }
             }
-            umma_commit(&b_empty[b_stage]);
-            if (tap == 8) {
-              umma_commit(&a_empty[a_stage]);
-              if (kc == kc_end - 1) umma_commit(&tfull_bar[as]);
+            if (++a_stage == SA) {
+              a_stage = 0;
+              a_phase ^= 1;
             }
-            }
-            __syncwarp();
-            if (++b_stage == SB) {
-              b_stage = 0;
-              b_phase ^= 1;
-            }
-          }
-          if (++a_stage == SA) {
-            a_stage = 0;
-            a_phase ^= 1;
           }
         }
+      };
+      // ONE elected thread runs the whole issue loop (waits included): no per-tap ELECT / BSSY / BSYNC / warp
+      // reconvergence; the other 31 lanes go straight to the closing __syncthreads.
+      if (elect_one()) {
+        if (k_steps == kBlockK / 16) run(std::true_type{});
+        else run(std::false_type{});
       }
+      __syncwarp();
     }
   } else {
     conv_epilogue_loop<BLOCK_N, false, Cfg::kSplitAcc>(p, tmem_base, tfull_bar, tempty_bar, warp, lane, &map_y_hi,

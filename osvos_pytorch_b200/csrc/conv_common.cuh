@@ -2,6 +2,8 @@
 // conv3x3_halo.cu: halo patch loaded once per channel chunk): tile geometry, parameters, tile decode and
 // the epilogue (TMEM -> registers -> bias / ReLU / mask / split-bf16 / projections -> global).
 #pragma once
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -35,6 +37,9 @@ struct ConvParams {
   // reducing k_chunks / ksplit channel chunks; CTA (tile, part > 0) writes its fp32 partial accumulator to
   // sk_partial[tile][part - 1][128][BLOCK_N] and bumps sk_flags[tile]; part 0 adds them in its epilogue.
   int ksplit;                // 1 = off
+  // Timing ablations (OSVOS_ABLATE bit mask, diagnosis only - results are garbage): 1 = no weight TMA loads,
+  // 2 = no activation TMA loads, 4 = no tcgen05.mma, 8 = no global stores in the epilogue.  0 in production.
+  int ablate;
   float* sk_partial;
   unsigned int* sk_flags;    // zeroed by the launcher
 };
@@ -118,6 +123,7 @@ __device__ __forceinline__ void conv_epilogue_loop(const ConvParams& p, uint32_t
   const int ly = row / kTileW, lx = row % kTileW;
   const bool relu = (p.flags & OSVOS_FLAG_RELU) != 0;
   const bool masked = (p.flags & OSVOS_FLAG_RELU_MASK) != 0;
+  const bool store_ok = !(p.ablate & 8);
   int it = 0;
   for (int tile = w_first; tile < w_total; tile += w_stride, ++it) {
     int nb, tx, ty, img;
@@ -126,7 +132,7 @@ __device__ __forceinline__ void conv_epilogue_loop(const ConvParams& p, uint32_t
     const int as = it & 1;
     const uint32_t aph = (it >> 1) & 1;
     const int y = ty * kTileH + ly, x = tx * kTileW + lx;
-    const bool valid = (y < p.h) && (x < p.w);
+    const bool valid = (y < p.h) && (x < p.w) && store_ok;
     const size_t pix = (static_cast<size_t>(img) * p.h + y) * p.w + x;
 
     mbar_wait(&tfull_bar[as], aph);
@@ -387,6 +393,14 @@ static inline void fill_conv_params(ConvParams& p, const osvos_conv3x3_args* a, 
   p.k_steps = (a->k_valid > 0 && a->k_valid < kBlockK) ? (a->k_valid + 15) / 16 : kBlockK / 16;
   p.flags = a->flags;
   p.ksplit = 1;
+  {
+    static int ablate = -1;
+    if (ablate < 0) {
+      const char* e = getenv("OSVOS_ABLATE");
+      ablate = e ? atoi(e) : 0;
+    }
+    p.ablate = ablate;
+  }
   p.sk_partial = nullptr;
   p.sk_flags = nullptr;
 }

@@ -86,7 +86,8 @@ conv_first_tc_kernel(const float* __restrict__ x, const float* __restrict__ wgt,
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 1) {
-    // -------------------------------------------------------------- MMA issuer
+    // -------------------------------------------------------------- MMA issuer (one elected thread, see conv3x3_halo.cu)
+    if (elect_one()) {
     constexpr uint32_t idesc = make_idesc_f16(kBlockM, 64, /*bf16=*/true);
     int stage = 0;
     uint32_t phase = 0;
@@ -97,7 +98,7 @@ conv_first_tc_kernel(const float* __restrict__ x, const float* __restrict__ wgt,
       mbar_wait(&tempty_bar[as], aph ^ 1);
       mbar_wait(&full_bar[stage], phase);
       tc_fence_after();
-      if (elect_one()) {
+      {
         const uint32_t tmem_d = tmem_base + as * 64;
         const uint32_t a_hi = smem_u32(smem + stage * kFirstStageBytes);
         const uint32_t b_hi = smem_u32(smem_b);
@@ -119,12 +120,13 @@ conv_first_tc_kernel(const float* __restrict__ x, const float* __restrict__ wgt,
         umma_commit(&empty_bar[stage]);
         umma_commit(&tfull_bar[as]);
       }
-      __syncwarp();
       if (++stage == kFirstStages) {
         stage = 0;
         phase ^= 1;
       }
     }
+    }
+    __syncwarp();
   } else if (warp >= 2 && warp < 10) {
     conv_epilogue_loop<64>(p, tmem_base, tfull_bar, tempty_bar, warp, lane, &map_y_hi, &map_y_lo, staging);
   } else if (warp >= 10) {

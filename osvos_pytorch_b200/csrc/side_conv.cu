@@ -98,6 +98,8 @@ side_conv_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
   pdl_launch_dependents();
 
   if (warp == 0) {
+    // ONE elected thread runs the whole producer loop (see conv3x3_halo.cu)
+    if (elect_one()) {
     int a_stage = 0, b_stage = 0;
     uint32_t a_phase = 0, b_phase = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -106,7 +108,7 @@ side_conv_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
       for (int kc = 0; kc < p.k_chunks; ++kc) {
         mbar_wait(&a_empty[a_stage], a_phase ^ 1);
         mbar_wait(&b_empty[b_stage], b_phase ^ 1);
-        if (elect_one()) {
+        {
           uint8_t* sa = smem_a + a_stage * Cfg::kAStage;
           uint8_t* sb = smem_b + b_stage * Cfg::kBStage;
           mbar_arrive_expect_tx(&a_full[a_stage], PLANES * kSideABox);
@@ -118,7 +120,6 @@ side_conv_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
           tma_load_3d(&map_w_hi, &b_full[b_stage], sb, kc * 64, 0, 0);
           if (PLANES == 2) tma_load_3d(&map_w_lo, &b_full[b_stage], sb + kSideBPlane, kc * 64, 0, 0);
         }
-        __syncwarp();
         if (++a_stage == kSideAStages) {
           a_stage = 0;
           a_phase ^= 1;
@@ -129,7 +130,11 @@ side_conv_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
         }
       }
     }
+    }
+    __syncwarp();
   } else if (warp == 1) {
+    // MMA issuer: one elected thread for the whole loop
+    if (elect_one()) {
     constexpr uint32_t idesc = make_idesc_f16(128, kSideN, /*bf16=*/true);
     int a_stage = 0, b_stage = 0;
     uint32_t a_phase = 0, b_phase = 0;
@@ -144,7 +149,7 @@ side_conv_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
         mbar_wait(&a_full[a_stage], a_phase);
         mbar_wait(&b_full[b_stage], b_phase);
         tc_fence_after();
-        if (elect_one()) {
+        {
           const uint32_t a_hi = smem_u32(smem_a + a_stage * Cfg::kAStage);
           const uint32_t b_hi = smem_u32(smem_b + b_stage * Cfg::kBStage);
           const uint64_t da_hi = make_smem_desc(a_hi, 16, 1024, kLayoutSW128);
@@ -166,7 +171,6 @@ side_conv_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
           umma_commit(&b_empty[b_stage]);
           if (kc == p.k_chunks - 1) umma_commit(&tfull_bar[as]);
         }
-        __syncwarp();
         if (++a_stage == kSideAStages) {
           a_stage = 0;
           a_phase ^= 1;
@@ -177,6 +181,8 @@ side_conv_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
         }
       }
     }
+    }
+    __syncwarp();
   } else {
     // ---------------------------------------------------------------- epilogue: shift-add through shared memory
     const int q = warp & 3;

@@ -110,8 +110,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_p_hi, const __grid_const
   pdl_launch_dependents();
 
   if (warp == 0 || warp == 6) {
-    {  // two producer warps (P operand: warp 0, Q operand: warp 6) halve the per-K-block TMA issue time; warp-uniform
-       // control flow, one elected lane issues (see conv3x3_tc.cu)
+    // two producer warps (P operand: warp 0, Q operand: warp 6) halve the per-K-block TMA issue time.  ONE elected
+    // thread per warp runs the whole loop (no per-step ELECT / reconvergence - see conv3x3_halo.cu); the patch
+    // coordinates advance incrementally instead of by two integer divisions per K block.
+    if (elect_one()) {
       const bool load_p = (warp == 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -127,42 +129,46 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_p_hi, const __grid_const
         const int pb = split * p.patches_per_split;
         int pe = pb + p.patches_per_split;
         if (pe > p.patches_total) pe = p.patches_total;
+        int px = pb % p.patches_x;
+        int py = (pb / p.patches_x) % p.patches_y;
+        int img = pb / (p.patches_x * p.patches_y);
+        const int c_p = mb * 128, c_q = nb * BLOCK_N;
         for (int patch = pb; patch < pe; ++patch) {
-          const int px = patch % p.patches_x;
-          const int t = patch / p.patches_x;
-          const int py = t % p.patches_y;
-          const int img = t / p.patches_y;
           const int x0 = px * kWgPatchW, y0 = py * kWgPatchH;
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          if (elect_one()) {
-            uint8_t* st = smem + stage * Cfg::kStageBytes;
-            if (load_p) {
-              mbar_arrive_expect_tx(&full_bar[stage], PLANES * Cfg::kPBytes);
+          uint8_t* st = smem + stage * Cfg::kStageBytes;
+          if (load_p) {
+            mbar_arrive_expect_tx(&full_bar[stage], PLANES * Cfg::kPBytes);
 #pragma unroll
-              for (int pl = 0; pl < PLANES; ++pl) {
-                const CUtensorMap* mp = pl == 0 ? &map_p_hi : &map_p_lo;
-                uint8_t* sp = st + pl * Cfg::kPBytes;
+            for (int pl = 0; pl < PLANES; ++pl) {
+              const CUtensorMap* mp = pl == 0 ? &map_p_hi : &map_p_lo;
+              uint8_t* sp = st + pl * Cfg::kPBytes;
 #pragma unroll
-                for (int j = 0; j < 2; ++j)
-                  tma_load_4d(mp, &full_bar[stage], sp + j * kWgBoxBytes, mb * 128 + j * 64, x0 + pdx, y0 + pdy, img);
-              }
-            } else {
-              mbar_arrive_expect_tx(&full_bar[stage], PLANES * Cfg::kQBytes);
+              for (int j = 0; j < 2; ++j)
+                tma_load_4d(mp, &full_bar[stage], sp + j * kWgBoxBytes, c_p + j * 64, x0 + pdx, y0 + pdy, img);
+            }
+          } else {
+            mbar_arrive_expect_tx(&full_bar[stage], PLANES * Cfg::kQBytes);
 #pragma unroll
-              for (int pl = 0; pl < PLANES; ++pl) {
-                const CUtensorMap* mq = pl == 0 ? &map_q_hi : &map_q_lo;
-                uint8_t* sq = st + PLANES * Cfg::kPBytes + pl * Cfg::kQBytes;
+            for (int pl = 0; pl < PLANES; ++pl) {
+              const CUtensorMap* mq = pl == 0 ? &map_q_hi : &map_q_lo;
+              uint8_t* sq = st + PLANES * Cfg::kPBytes + pl * Cfg::kQBytes;
 #pragma unroll
-                for (int j = 0; j < BLOCK_N / 64; ++j) {
-                  if (p.tap_pairs)   // atom j = tap (2g + j) of the single 64-channel block
-                    tma_load_4d(mq, &full_bar[stage], sq + j * kWgBoxBytes, 0, x0 + (j ? dx1 : dx), y0 + (j ? dy1 : dy), img);
-                  else
-                    tma_load_4d(mq, &full_bar[stage], sq + j * kWgBoxBytes, nb * BLOCK_N + j * 64, x0 + qdx, y0 + qdy, img);
-                }
+              for (int j = 0; j < BLOCK_N / 64; ++j) {
+                if (p.tap_pairs)   // atom j = tap (2g + j) of the single 64-channel block
+                  tma_load_4d(mq, &full_bar[stage], sq + j * kWgBoxBytes, 0, x0 + (j ? dx1 : dx), y0 + (j ? dy1 : dy), img);
+                else
+                  tma_load_4d(mq, &full_bar[stage], sq + j * kWgBoxBytes, c_q + j * 64, x0 + qdx, y0 + qdy, img);
               }
             }
           }
-          __syncwarp();
+          if (++px == p.patches_x) {
+            px = 0;
+            if (++py == p.patches_y) {
+              py = 0;
+              ++img;
+            }
+          }
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
@@ -170,10 +176,17 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_p_hi, const __grid_const
         }
       }
     }
+    __syncwarp();
   } else if (warp == 1) {
-    {
+    // MMA issuer: one elected thread, descriptors formed by adding the stage offset to a constant template
+    if (elect_one()) {
       constexpr uint32_t idesc = make_idesc_f16(128, BLOCK_N, true, /*a_mn=*/true, /*b_mn=*/true);
       constexpr uint32_t idesc2 = make_idesc_f16(128, Cfg::kAccCols, true, /*a_mn=*/true, /*b_mn=*/true);
+      // MN-major SW128: LBO = bytes between 64-wide MN atoms, SBO = bytes between 8-row K groups
+      constexpr uint64_t kDesc = (static_cast<uint64_t>(kWgBoxBytes >> 4) << 16) | (static_cast<uint64_t>(1024 >> 4) << 32) |
+                                 (1ull << 46) | (static_cast<uint64_t>(kLayoutSW128) << 61);
+      constexpr uint32_t kQOff = (PLANES * Cfg::kPBytes) >> 4, kPLo = Cfg::kPBytes >> 4, kQLo = Cfg::kQBytes >> 4;
+      const uint32_t smem_base = smem_u32(smem);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -191,18 +204,14 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_p_hi, const __grid_const
         for (int patch = pb; patch < pe; ++patch) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          if (elect_one()) {
-          const uint32_t sp = smem_u32(smem + stage * Cfg::kStageBytes);
-          const uint32_t sq = sp + PLANES * Cfg::kPBytes;
-          // MN-major SW128: LBO = bytes between 64-wide MN atoms, SBO = bytes between 8-row K groups
-          const uint64_t dp_hi = make_smem_desc(sp, kWgBoxBytes, 1024, kLayoutSW128);
-          const uint64_t dq_hi = make_smem_desc(sq, kWgBoxBytes, 1024, kLayoutSW128);
-          const uint64_t dp_lo = make_smem_desc(sp + Cfg::kPBytes, kWgBoxBytes, 1024, kLayoutSW128);
-          const uint64_t dq_lo = make_smem_desc(sq + Cfg::kQBytes, kWgBoxBytes, 1024, kLayoutSW128);
+          const uint64_t dp_hi = kDesc | static_cast<uint64_t>((smem_base + stage * Cfg::kStageBytes) >> 4);
+          const uint64_t dq_hi = dp_hi + kQOff;
+          const uint64_t dp_lo = dp_hi + kPLo;
+          const uint64_t dq_lo = dq_hi + kQLo;
 #pragma unroll
           for (int k = 0; k < kWgBlockK / 16; ++k) {
-            const uint64_t adv = static_cast<uint64_t>(k * (2048 >> 4));  // 16 pixel rows x 128 B
-            const uint32_t acc = (patch != pb || k != 0) ? 1u : 0u;
+            const uint32_t adv = static_cast<uint32_t>(k * (2048 >> 4));  // 16 pixel rows x 128 B
+            const uint32_t acc = (k != 0) ? 1u : (patch != pb ? 1u : 0u);
             if (Cfg::kSplitAcc) {
               umma_f16(tmem_d, dp_hi + adv, dq_hi + adv, idesc2, acc);   // [P_hi.Q_hi | P_hi.Q_lo]
               umma_f16(tmem_d, dp_lo + adv, dq_hi + adv, idesc, 1);      // + P_lo.Q_hi into the first half
@@ -216,8 +225,6 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_p_hi, const __grid_const
           }
           umma_commit(&empty_bar[stage]);
           if (patch == pe - 1) umma_commit(&tfull_bar[as]);
-          }
-          __syncwarp();
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
@@ -225,6 +232,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_p_hi, const __grid_const
         }
       }
     }
+    __syncwarp();
   } else if (warp >= 2 && warp < 6) {
     const int q = warp & 3;
     const int row = q * 32 + lane;

@@ -213,7 +213,7 @@ def run_parent(args, rank, world, local, dev):
         dist.destroy_process_group()
 
 
-NCU_CONV_DRAM_BYTES_PER_STEP = 476.16e6
+NCU_CONV_DRAM_BYTES_PER_STEP = 465.34e6
 
 
 def main():
@@ -446,12 +446,13 @@ def main():
                             # tensor pipe EXECUTES passes x the algorithmic flops; this is that figure over the peak
                             "issued_mma_frac": ach * (3 if args.precision == "exact" else 1) / peaks["tflops_sustained"],
                             # dram__bytes_read.sum + dram__bytes_write.sum of the 16 conv launches of one 480x854 exact
-                            # frame, from the committed `ncu --set full` capture (profiles/r01d_ncu_full_forward_kernels.csv):
-                            # 476.2 MB per step = 29.8 MB per launch (activations in + out; weights stay in L2)
+                            # frame, from the committed ncu launch list (profiles/r01f_launches_infer480.csv; the
+                            # `--set full` capture r01d_ncu_full_forward_kernels.csv had 476.2 MB): 465.3 MB per step =
+                            # 29.1 MB per launch (activations in + out; weights stay in L2)
                             "traffic": (NCU_CONV_DRAM_BYTES_PER_STEP / conv_calls
                                         if args.precision == "exact" and conv_calls == 16 else None),
                             "traffic_unit": "bytes per launch (average over the step's conv launches)",
-                            "traffic_source": "profiles/r01d_ncu_full_forward_kernels.csv"}
+                            "traffic_source": "profiles/r01f_launches_infer480.csv"}
     if not args.no_cpu_baseline:
         cfps, cms, cores, threads = cpu_reference_fps(3, 1, args.workload)
         line["cpu_baseline"] = {"value": cfps, "unit": "frames/s", "cores": threads, "kind": "port",

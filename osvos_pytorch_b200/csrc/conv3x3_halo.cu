@@ -22,7 +22,7 @@ namespace osvos {
 
 constexpr int kHaloRows = kTileH + 2;  // 18
 
-template <int BLOCK_N, int PLANES, int PITCH>
+template <int BLOCK_N, int PLANES, int PITCH, bool SPLIT>
 struct HaloCfg {
   static constexpr int kABoxBytes = kHaloRows * PITCH * 128;                // one plane, one chunk
   static constexpr int kAPlaneBytes = (kABoxBytes + 1023) / 1024 * 1024;    // keep 1 KiB alignment
@@ -41,7 +41,8 @@ struct HaloCfg {
   // stage, so ONE tcgen05.mma of N = 2 * BLOCK_N computes [A_hi.B_hi | A_hi.B_lo] into two column halves of the
   // accumulator; with the N = BLOCK_N pass A_lo.B_hi that is 2 instructions per K step instead of 3 (the per-
   // instruction floor of ~85 cycles makes instruction count, not flops, the cost).  The epilogue adds the halves.
-  static constexpr bool kSplitAcc = (PLANES == 2) && (BLOCK_N <= 128);
+  static constexpr bool kSplitAcc = SPLIT;
+  static_assert(!SPLIT || (PLANES == 2 && BLOCK_N <= 128), "split accumulators need two planes and 2 * BLOCK_N <= 256");
   static constexpr int kAccCols = kSplitAcc ? 2 * BLOCK_N : BLOCK_N;
   static constexpr int kTmemCols = (2 * kAccCols) < 32 ? 32 : 2 * kAccCols;
   static constexpr int kSmemBytes = kAStages * kAStageBytes + kBStages * kBStageBytes + kStagingBytes + 1024 + 512;
@@ -49,13 +50,13 @@ struct HaloCfg {
   static_assert(kBStageBytes % 1024 == 0, "B stage must keep 1024-byte alignment");
 };
 
-template <int BLOCK_N, int PLANES, int PITCH>
+template <int BLOCK_N, int PLANES, int PITCH, bool SPLIT>
 __global__ void __launch_bounds__(64 + EpiCfg<BLOCK_N>::kThreads, 1)
 conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo,
                     const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
                     const __grid_constant__ CUtensorMap map_y_hi, const __grid_constant__ CUtensorMap map_y_lo,
                     const ConvParams p, const int use_base_offset) {
-  using Cfg = HaloCfg<BLOCK_N, PLANES, PITCH>;
+  using Cfg = HaloCfg<BLOCK_N, PLANES, PITCH, SPLIT>;
   constexpr int SA = Cfg::kAStages, SB = Cfg::kBStages;
 
   extern __shared__ uint8_t smem_raw[];
@@ -300,9 +301,9 @@ static size_t splitk_partial_bytes(int n, int h, int w, int cout, int ks) {
   return static_cast<size_t>(m_tiles) * (cout / 128) * (ks - 1) * kBlockM * 128 * sizeof(float);
 }
 
-template <int BLOCK_N, int PLANES, int PITCH>
+template <int BLOCK_N, int PLANES, int PITCH, bool SPLIT = (PLANES == 2 && BLOCK_N <= 128)>
 static int launch_halo(const osvos_conv3x3_args* a, cudaStream_t stream, int use_bo, int ksplit = 1) {
-  using Cfg = HaloCfg<BLOCK_N, PLANES, PITCH>;
+  using Cfg = HaloCfg<BLOCK_N, PLANES, PITCH, SPLIT>;
   ConvParams p;
   fill_conv_params(p, a, BLOCK_N);
   if (ksplit > 1) {
@@ -332,7 +333,7 @@ static int launch_halo(const osvos_conv3x3_args* a, cudaStream_t stream, int use
     rc = encode_output_maps(&my_hi, &my_lo, a);
     if (rc) return rc;
   }
-  auto kern = conv3x3_halo_kernel<BLOCK_N, PLANES, PITCH>;
+  auto kern = conv3x3_halo_kernel<BLOCK_N, PLANES, PITCH, SPLIT>;
   static bool attr_done = false;
   if (!attr_done) {
     OSVOS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
@@ -368,7 +369,14 @@ static int dispatch_halo(const osvos_conv3x3_args* a, cudaStream_t stream, int u
     return fast ? launch_halo<64, 1, PITCH>(a, stream, use_bo) : launch_halo<64, 2, PITCH>(a, stream, use_bo);
   if (a->cout % 256 == 0 && prefer256 && !(n256 && atoi(n256) == 0))
     return fast ? launch_halo<256, 1, PITCH>(a, stream, use_bo) : launch_halo<256, 2, PITCH>(a, stream, use_bo);
-  return fast ? launch_halo<128, 1, PITCH>(a, stream, use_bo) : launch_halo<128, 2, PITCH>(a, stream, use_bo);
+  if (fast) return launch_halo<128, 1, PITCH>(a, stream, use_bo);
+  // Exact mode, N = 128: the N-concatenated split accumulator (2 MMAs per K step, 256 accumulator columns, the
+  // epilogue reads and sums two halves) and the plain three-pass form (3 MMAs, 128 columns) cost the SAME tensor
+  // time - 128 + 64 = 3 x 64 cycles per K step (scripts/microbench/operand_reuse_bench.cu) - so the choice is
+  // issuer instructions against epilogue work.  OSVOS_SPLITACC128=0 selects the three-pass form (read per launch).
+  const char* sp = getenv("OSVOS_SPLITACC128");
+  if (sp != nullptr && atoi(sp) == 0) return launch_halo<128, 2, PITCH, false>(a, stream, use_bo);
+  return launch_halo<128, 2, PITCH>(a, stream, use_bo);
 }
 
 size_t conv3x3_splitk_workspace_bytes(int n, int h, int w, int cin, int cout) {

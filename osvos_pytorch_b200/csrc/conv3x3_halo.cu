@@ -8,10 +8,13 @@
 // the per-tap kernel.  The weight slabs stream through their own, deeper ring
 // (one stage per tap), and the next chunk's halo is prefetched while the current one is being consumed.
 //
-// PITCH is the smem row pitch in pixels: 16 keeps every 8-row group 1 KiB-periodic (2 KiB per patch row,
-// 6 pad pixels loaded); 10 packs the rows (1280 B) and relies on the swizzle being a function of the
-// absolute smem address.  OSVOS_HALO_BO=1 additionally sets the descriptor's base-offset field to
-// (start >> 7) & 7.  (Both knobs exist to validate the descriptor semantics on hardware.)
+// PITCH is the smem row pitch in pixels: 10 packs the patch rows (1280 B) and relies on the UMMA swizzle being a
+// function of the absolute shared-memory address, validated on hardware together with the padded 16-pixel pitch and the
+// descriptor's base-offset field (scripts/halo_experiment.py; the base-offset field must stay 0).  The kernel keeps
+// its trailing `use_base_offset` parameter for that experiment's launcher but no longer reads it.
+//
+// Producer and issuer loops: one elected thread each, taps unrolled, descriptors by addition - see the comments at
+// the two loops and DESIGN.md section 4 for the measurements behind that.
 #include <stdlib.h>
 
 #include <type_traits>

@@ -25,7 +25,7 @@ namespace osvos {
 
 constexpr int kHaloRows = kTileH + 2;  // 18
 
-template <int BLOCK_N, int PLANES, int PITCH, bool SPLIT>
+template <int BLOCK_N, int PLANES, int PITCH, bool SPLIT, bool TMAST = false>
 struct HaloCfg {
   static constexpr int kABoxBytes = kHaloRows * PITCH * 128;                // one plane, one chunk
   static constexpr int kAPlaneBytes = (kABoxBytes + 1023) / 1024 * 1024;    // keep 1 KiB alignment
@@ -33,10 +33,11 @@ struct HaloCfg {
   static constexpr int kAStages = 2;
   static constexpr int kBPlaneBytes = BLOCK_N * 128;
   static constexpr int kBStageBytes = PLANES * kBPlaneBytes;
-  // TMA-store staging (hi + lo slab).  Measured on B200: the bulk-store epilogue is NOT faster than direct 16-byte
-  // stores here (the kernels are bound by the ~85-cycle tcgen05.mma instruction floor, not by the epilogue) and its
-  // 32 KiB cost one weight-ring stage, so it is compiled out (set to 2 * kABytes to re-enable).
-  static constexpr int kStagingBytes = 0;
+  // TMA-store staging (hi + lo slab), TMAST only.  Measured in round 1 while the MMA issuer was still the bottleneck: no
+  // faster than direct 16-byte stores, and its 32 KiB cost one weight-ring stage - so it is off by default.  The direct
+  // stores do cost the epilogue-bound layers (32 half-filled sectors per STG.128; ablation: conv2_1 49 -> 37 us without
+  // stores), hence the opt-in instantiations behind OSVOS_HALO_TMA_STORE=1 for the next measurement.
+  static constexpr int kStagingBytes = TMAST ? 2 * kABytes : 0;
   static constexpr int kBudget = 225 * 1024 - kAStages * kAStageBytes - kStagingBytes;   // 227 KiB per CTA minus align/barriers
   static constexpr int kBStagesRaw = kBudget / kBStageBytes;
   static constexpr int kBStages = kBStagesRaw > 9 ? 9 : kBStagesRaw;
@@ -53,13 +54,13 @@ struct HaloCfg {
   static_assert(kBStageBytes % 1024 == 0, "B stage must keep 1024-byte alignment");
 };
 
-template <int BLOCK_N, int PLANES, int PITCH, bool SPLIT>
+template <int BLOCK_N, int PLANES, int PITCH, bool SPLIT, bool TMAST>
 __global__ void __launch_bounds__(64 + EpiCfg<BLOCK_N>::kThreads, 1)
 conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo,
                     const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
                     const __grid_constant__ CUtensorMap map_y_hi, const __grid_constant__ CUtensorMap map_y_lo,
                     const ConvParams p, const int use_base_offset) {
-  using Cfg = HaloCfg<BLOCK_N, PLANES, PITCH, SPLIT>;
+  using Cfg = HaloCfg<BLOCK_N, PLANES, PITCH, SPLIT, TMAST>;
   constexpr int SA = Cfg::kAStages, SB = Cfg::kBStages;
 
   extern __shared__ uint8_t smem_raw[];
@@ -304,9 +305,9 @@ static size_t splitk_partial_bytes(int n, int h, int w, int cout, int ks) {
   return static_cast<size_t>(m_tiles) * (cout / 128) * (ks - 1) * kBlockM * 128 * sizeof(float);
 }
 
-template <int BLOCK_N, int PLANES, int PITCH, bool SPLIT = (PLANES == 2 && BLOCK_N <= 128)>
+template <int BLOCK_N, int PLANES, int PITCH, bool SPLIT = (PLANES == 2 && BLOCK_N <= 128), bool TMAST = false>
 static int launch_halo(const osvos_conv3x3_args* a, cudaStream_t stream, int use_bo, int ksplit = 1) {
-  using Cfg = HaloCfg<BLOCK_N, PLANES, PITCH, SPLIT>;
+  using Cfg = HaloCfg<BLOCK_N, PLANES, PITCH, SPLIT, TMAST>;
   ConvParams p;
   fill_conv_params(p, a, BLOCK_N);
   if (ksplit > 1) {
@@ -336,7 +337,7 @@ static int launch_halo(const osvos_conv3x3_args* a, cudaStream_t stream, int use
     rc = encode_output_maps(&my_hi, &my_lo, a);
     if (rc) return rc;
   }
-  auto kern = conv3x3_halo_kernel<BLOCK_N, PLANES, PITCH, SPLIT>;
+  auto kern = conv3x3_halo_kernel<BLOCK_N, PLANES, PITCH, SPLIT, TMAST>;
   static bool attr_done = false;
   if (!attr_done) {
     OSVOS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
@@ -379,6 +380,9 @@ static int dispatch_halo(const osvos_conv3x3_args* a, cudaStream_t stream, int u
   // issuer instructions against epilogue work.  OSVOS_SPLITACC128=0 selects the three-pass form (read per launch).
   const char* sp = getenv("OSVOS_SPLITACC128");
   if (sp != nullptr && atoi(sp) == 0) return launch_halo<128, 2, PITCH, false>(a, stream, use_bo);
+  // opt-in: act output through a swizzled staging buffer + bulk tensor stores (full 128-byte rows) - see HaloCfg
+  const char* ts = getenv("OSVOS_HALO_TMA_STORE");
+  if (ts != nullptr && atoi(ts) != 0 && a->y_hi != nullptr) return launch_halo<128, 2, PITCH, true, true>(a, stream, use_bo);
   return launch_halo<128, 2, PITCH>(a, stream, use_bo);
 }
 

@@ -354,7 +354,12 @@ template <int PITCH>
 static int dispatch_halo(const osvos_conv3x3_args* a, cudaStream_t stream, int use_bo) {
   const bool fast = (a->flags & OSVOS_FLAG_FAST) != 0;
   if (a->cout == 16) return fast ? launch_halo<16, 1, PITCH>(a, stream, use_bo) : launch_halo<16, 2, PITCH>(a, stream, use_bo);
-  if (a->cout == 64) return fast ? launch_halo<64, 1, PITCH>(a, stream, use_bo) : launch_halo<64, 2, PITCH>(a, stream, use_bo);
+  const char* ts = getenv("OSVOS_HALO_TMA_STORE");   // opt-in bulk-store epilogue, see HaloCfg::kStagingBytes
+  const bool tma_store = ts != nullptr && atoi(ts) != 0 && a->y_hi != nullptr && !fast;
+  if (a->cout == 64) {
+    if (tma_store) return launch_halo<64, 2, PITCH, true, true>(a, stream, use_bo);
+    return fast ? launch_halo<64, 1, PITCH>(a, stream, use_bo) : launch_halo<64, 2, PITCH>(a, stream, use_bo);
+  }
   // N = 256 tiles (one tcgen05.mma of 128 cycles instead of two of ~85-100) whenever there are enough pixel tiles
   // to fill the chip; OSVOS_CONV_N256=0 disables.
   const char* n256 = getenv("OSVOS_CONV_N256");
@@ -381,8 +386,7 @@ static int dispatch_halo(const osvos_conv3x3_args* a, cudaStream_t stream, int u
   const char* sp = getenv("OSVOS_SPLITACC128");
   if (sp != nullptr && atoi(sp) == 0) return launch_halo<128, 2, PITCH, false>(a, stream, use_bo);
   // opt-in: act output through a swizzled staging buffer + bulk tensor stores (full 128-byte rows) - see HaloCfg
-  const char* ts = getenv("OSVOS_HALO_TMA_STORE");
-  if (ts != nullptr && atoi(ts) != 0 && a->y_hi != nullptr) return launch_halo<128, 2, PITCH, true, true>(a, stream, use_bo);
+  if (tma_store) return launch_halo<128, 2, PITCH, true, true>(a, stream, use_bo);
   return launch_halo<128, 2, PITCH>(a, stream, use_bo);
 }
 

@@ -25,7 +25,7 @@ namespace osvos {
 
 constexpr int kHaloRows = kTileH + 2;  // 18
 
-template <int BLOCK_N, int PLANES, int PITCH, bool SPLIT, bool TMAST = false>
+template <int BLOCK_N, int PLANES, int PITCH, bool SPLIT, int STORE = 0>
 struct HaloCfg {
   static constexpr int kABoxBytes = kHaloRows * PITCH * 128;                // one plane, one chunk
   static constexpr int kAPlaneBytes = (kABoxBytes + 1023) / 1024 * 1024;    // keep 1 KiB alignment
@@ -33,11 +33,12 @@ struct HaloCfg {
   static constexpr int kAStages = 2;
   static constexpr int kBPlaneBytes = BLOCK_N * 128;
   static constexpr int kBStageBytes = PLANES * kBPlaneBytes;
-  // TMA-store staging (hi + lo slab), TMAST only.  Measured in round 1 while the MMA issuer was still the bottleneck: no
+  // Output store flavour STORE: 0 = 16-byte direct stores (default), 1 = bulk tensor stores through a staging buffer,
+  // 2 = 32-byte direct stores (st.global.v8.b32).  TMA-store staging (hi + lo slab), STORE == 1 only.  Measured in round 1 while the MMA issuer was still the bottleneck: no
   // faster than direct 16-byte stores, and its 32 KiB cost one weight-ring stage - so it is off by default.  The direct
   // stores do cost the epilogue-bound layers (32 half-filled sectors per STG.128; ablation: conv2_1 49 -> 37 us without
   // stores), hence the opt-in instantiations behind OSVOS_HALO_TMA_STORE=1 for the next measurement.
-  static constexpr int kStagingBytes = TMAST ? 2 * kABytes : 0;
+  static constexpr int kStagingBytes = STORE == 1 ? 2 * kABytes : 0;
   static constexpr int kBudget = 225 * 1024 - kAStages * kAStageBytes - kStagingBytes;   // 227 KiB per CTA minus align/barriers
   static constexpr int kBStagesRaw = kBudget / kBStageBytes;
   static constexpr int kBStages = kBStagesRaw > 9 ? 9 : kBStagesRaw;
@@ -54,13 +55,13 @@ struct HaloCfg {
   static_assert(kBStageBytes % 1024 == 0, "B stage must keep 1024-byte alignment");
 };
 
-template <int BLOCK_N, int PLANES, int PITCH, bool SPLIT, bool TMAST>
+template <int BLOCK_N, int PLANES, int PITCH, bool SPLIT, int STORE>
 __global__ void __launch_bounds__(64 + EpiCfg<BLOCK_N>::kThreads, 1)
 conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo,
                     const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
                     const __grid_constant__ CUtensorMap map_y_hi, const __grid_constant__ CUtensorMap map_y_lo,
                     const ConvParams p, const int use_base_offset) {
-  using Cfg = HaloCfg<BLOCK_N, PLANES, PITCH, SPLIT, TMAST>;
+  using Cfg = HaloCfg<BLOCK_N, PLANES, PITCH, SPLIT, STORE>;
   constexpr int SA = Cfg::kAStages, SB = Cfg::kBStages;
 
   extern __shared__ uint8_t smem_raw[];
@@ -270,7 +271,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_c
       __syncwarp();
     }
   } else {
-    conv_epilogue_loop<BLOCK_N, false, Cfg::kSplitAcc>(p, tmem_base, tfull_bar, tempty_bar, warp, lane, &map_y_hi,
+    conv_epilogue_loop<BLOCK_N, false, Cfg::kSplitAcc, STORE == 2>(p, tmem_base, tfull_bar, tempty_bar, warp, lane, &map_y_hi,
                                                        &map_y_lo,
                                                        (Cfg::kStagingBytes > 0 && p.y_hi != nullptr) ? staging : nullptr);
   }
@@ -305,9 +306,9 @@ static size_t splitk_partial_bytes(int n, int h, int w, int cout, int ks) {
   return static_cast<size_t>(m_tiles) * (cout / 128) * (ks - 1) * kBlockM * 128 * sizeof(float);
 }
 
-template <int BLOCK_N, int PLANES, int PITCH, bool SPLIT = (PLANES == 2 && BLOCK_N <= 128), bool TMAST = false>
+template <int BLOCK_N, int PLANES, int PITCH, bool SPLIT = (PLANES == 2 && BLOCK_N <= 128), int STORE = 0>
 static int launch_halo(const osvos_conv3x3_args* a, cudaStream_t stream, int use_bo, int ksplit = 1) {
-  using Cfg = HaloCfg<BLOCK_N, PLANES, PITCH, SPLIT, TMAST>;
+  using Cfg = HaloCfg<BLOCK_N, PLANES, PITCH, SPLIT, STORE>;
   ConvParams p;
   fill_conv_params(p, a, BLOCK_N);
   if (ksplit > 1) {
@@ -337,7 +338,7 @@ static int launch_halo(const osvos_conv3x3_args* a, cudaStream_t stream, int use
     rc = encode_output_maps(&my_hi, &my_lo, a);
     if (rc) return rc;
   }
-  auto kern = conv3x3_halo_kernel<BLOCK_N, PLANES, PITCH, SPLIT, TMAST>;
+  auto kern = conv3x3_halo_kernel<BLOCK_N, PLANES, PITCH, SPLIT, STORE>;
   static bool attr_done = false;
   if (!attr_done) {
     OSVOS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
@@ -354,10 +355,17 @@ template <int PITCH>
 static int dispatch_halo(const osvos_conv3x3_args* a, cudaStream_t stream, int use_bo) {
   const bool fast = (a->flags & OSVOS_FLAG_FAST) != 0;
   if (a->cout == 16) return fast ? launch_halo<16, 1, PITCH>(a, stream, use_bo) : launch_halo<16, 2, PITCH>(a, stream, use_bo);
-  const char* ts = getenv("OSVOS_HALO_TMA_STORE");   // opt-in bulk-store epilogue, see HaloCfg::kStagingBytes
+  // opt-in store flavours of the exact-mode epilogue (see HaloCfg): OSVOS_HALO_TMA_STORE=1 bulk tensor stores,
+  // OSVOS_HALO_ST256=1 32-byte direct stores (all output planes must be 32-byte aligned)
+  const char* ts = getenv("OSVOS_HALO_TMA_STORE");
   const bool tma_store = ts != nullptr && atoi(ts) != 0 && a->y_hi != nullptr && !fast;
+  const char* s256 = getenv("OSVOS_HALO_ST256");
+  auto aligned32 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 31) == 0; };
+  const bool st256 = s256 != nullptr && atoi(s256) != 0 && !fast && !tma_store && aligned32(a->y_hi) && aligned32(a->y_lo) &&
+                     aligned32(a->y_f32) && aligned32(a->pool_hi) && aligned32(a->pool_lo);
   if (a->cout == 64) {
-    if (tma_store) return launch_halo<64, 2, PITCH, true, true>(a, stream, use_bo);
+    if (tma_store) return launch_halo<64, 2, PITCH, true, 1>(a, stream, use_bo);
+    if (st256) return launch_halo<64, 2, PITCH, true, 2>(a, stream, use_bo);
     return fast ? launch_halo<64, 1, PITCH>(a, stream, use_bo) : launch_halo<64, 2, PITCH>(a, stream, use_bo);
   }
   // N = 256 tiles (one tcgen05.mma of 128 cycles instead of two of ~85-100) whenever there are enough pixel tiles
@@ -386,7 +394,8 @@ static int dispatch_halo(const osvos_conv3x3_args* a, cudaStream_t stream, int u
   const char* sp = getenv("OSVOS_SPLITACC128");
   if (sp != nullptr && atoi(sp) == 0) return launch_halo<128, 2, PITCH, false>(a, stream, use_bo);
   // opt-in: act output through a swizzled staging buffer + bulk tensor stores (full 128-byte rows) - see HaloCfg
-  if (tma_store) return launch_halo<128, 2, PITCH, true, true>(a, stream, use_bo);
+  if (tma_store) return launch_halo<128, 2, PITCH, true, 1>(a, stream, use_bo);
+  if (st256) return launch_halo<128, 2, PITCH, true, 2>(a, stream, use_bo);
   return launch_halo<128, 2, PITCH>(a, stream, use_bo);
 }
 

@@ -101,7 +101,9 @@ __device__ __forceinline__ void decode_pair(const ConvParams& p, int w, int rank
 // instead of 16-byte scattered global stores.  staging == nullptr keeps the direct stores.
 // SPLIT_ACC: the accumulator stage holds 2 * BLOCK_N columns - [A.B_hi | A.B_lo] produced by one N-concatenated
 // tcgen05.mma - and the result is the sum of the two halves.
-template <int BLOCK_N, bool PAIR = false, bool SPLIT_ACC = false>
+// STORE256: the act / pooled / fp32 outputs of the BLOCK_N >= 64 path are written with 256-bit stores (one full sector
+// per lane and instruction, half the store instructions); needs 32-byte aligned output planes.
+template <int BLOCK_N, bool PAIR = false, bool SPLIT_ACC = false, bool STORE256 = false>
 __device__ __forceinline__ void conv_epilogue_loop(const ConvParams& p, uint32_t tmem_base, uint64_t* tfull_bar,
                                                    uint64_t* tempty_bar, int warp, int lane,
                                                    const CUtensorMap* map_y_hi = nullptr,
@@ -259,9 +261,18 @@ __device__ __forceinline__ void conv_epilogue_loop(const ConvParams& p, uint32_t
           }
         }
         if (p.y_f32 && valid) {
-          float4* dst = reinterpret_cast<float4*>(p.y_f32 + pix * p.cout + ch);
+          if constexpr (STORE256) {
+            float* dst = p.y_f32 + pix * p.cout + ch;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+            for (int j = 0; j < 4; ++j)
+              st_global_256(dst + 8 * j, __float_as_uint(f[8 * j]), __float_as_uint(f[8 * j + 1]), __float_as_uint(f[8 * j + 2]),
+                            __float_as_uint(f[8 * j + 3]), __float_as_uint(f[8 * j + 4]), __float_as_uint(f[8 * j + 5]),
+                            __float_as_uint(f[8 * j + 6]), __float_as_uint(f[8 * j + 7]));
+          } else {
+            float4* dst = reinterpret_cast<float4*>(p.y_f32 + pix * p.cout + ch);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+          }
         }
         if (p.y_hi) {
           uint32_t hi[16], lo[16];
@@ -269,13 +280,28 @@ __device__ __forceinline__ void conv_epilogue_loop(const ConvParams& p, uint32_t
           for (int j = 0; j < 16; ++j) split_pack2(f[2 * j], f[2 * j + 1], hi[j], lo[j]);
           if (!use_tma) {
             if (valid) {
-              uint4* dh = reinterpret_cast<uint4*>(p.y_hi + pix * p.cout + ch);
+              if constexpr (STORE256) {
+                __nv_bfloat16* dh = p.y_hi + pix * p.cout + ch;
 #pragma unroll
-              for (int j = 0; j < 4; ++j) dh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-              if (p.y_lo) {
-                uint4* dl = reinterpret_cast<uint4*>(p.y_lo + pix * p.cout + ch);
+                for (int j = 0; j < 2; ++j)
+                  st_global_256(dh + 16 * j, hi[8 * j], hi[8 * j + 1], hi[8 * j + 2], hi[8 * j + 3], hi[8 * j + 4], hi[8 * j + 5],
+                                hi[8 * j + 6], hi[8 * j + 7]);
+                if (p.y_lo) {
+                  __nv_bfloat16* dl = p.y_lo + pix * p.cout + ch;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) dl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+                  for (int j = 0; j < 2; ++j)
+                    st_global_256(dl + 16 * j, lo[8 * j], lo[8 * j + 1], lo[8 * j + 2], lo[8 * j + 3], lo[8 * j + 4], lo[8 * j + 5],
+                                  lo[8 * j + 6], lo[8 * j + 7]);
+                }
+              } else {
+                uint4* dh = reinterpret_cast<uint4*>(p.y_hi + pix * p.cout + ch);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+                if (p.y_lo) {
+                  uint4* dl = reinterpret_cast<uint4*>(p.y_lo + pix * p.cout + ch);
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) dl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+                }
               }
             }
           } else {
@@ -329,13 +355,28 @@ __device__ __forceinline__ void conv_epilogue_loop(const ConvParams& p, uint32_t
             split_pack2(m0, m1, hi[j], lo[j]);
           }
           if (writer) {
-            uint4* dh = reinterpret_cast<uint4*>(p.pool_hi + opix * p.cout + ch);
+            if constexpr (STORE256) {
+              __nv_bfloat16* dh = p.pool_hi + opix * p.cout + ch;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) dh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-            if (p.pool_lo) {
-              uint4* dl = reinterpret_cast<uint4*>(p.pool_lo + opix * p.cout + ch);
+              for (int j = 0; j < 2; ++j)
+                st_global_256(dh + 16 * j, hi[8 * j], hi[8 * j + 1], hi[8 * j + 2], hi[8 * j + 3], hi[8 * j + 4], hi[8 * j + 5],
+                              hi[8 * j + 6], hi[8 * j + 7]);
+              if (p.pool_lo) {
+                __nv_bfloat16* dl = p.pool_lo + opix * p.cout + ch;
 #pragma unroll
-              for (int j = 0; j < 4; ++j) dl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+                for (int j = 0; j < 2; ++j)
+                  st_global_256(dl + 16 * j, lo[8 * j], lo[8 * j + 1], lo[8 * j + 2], lo[8 * j + 3], lo[8 * j + 4], lo[8 * j + 5],
+                                lo[8 * j + 6], lo[8 * j + 7]);
+              }
+            } else {
+              uint4* dh = reinterpret_cast<uint4*>(p.pool_hi + opix * p.cout + ch);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) dh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+              if (p.pool_lo) {
+                uint4* dl = reinterpret_cast<uint4*>(p.pool_lo + opix * p.cout + ch);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+              }
             }
           }
         }

@@ -39,6 +39,15 @@ __device__ __forceinline__ bool elect_one() {
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// 256-bit global store (sm_100: STG.E.ENL2.256): one full 32-byte sector per lane and instruction.  `p` must be
+// 32-byte aligned.
+__device__ __forceinline__ void st_global_256(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e,
+                                              uint32_t f, uint32_t g, uint32_t h) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d),
+               "r"(e), "r"(f), "r"(g), "r"(h)
+               : "memory");
+}
+
 // ----------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

@@ -362,7 +362,7 @@ static int dispatch_halo(const osvos_conv3x3_args* a, cudaStream_t stream, int u
   const char* s256 = getenv("OSVOS_HALO_ST256");
   auto aligned32 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 31) == 0; };
   const bool st256 = s256 != nullptr && atoi(s256) != 0 && !fast && !tma_store && aligned32(a->y_hi) && aligned32(a->y_lo) &&
-                     aligned32(a->y_f32) && aligned32(a->pool_hi) && aligned32(a->pool_lo);
+                     aligned32(a->y_f32) && aligned32(a->pool_hi) && aligned32(a->pool_lo) && aligned32(a->mask_hi);
   if (a->cout == 64) {
     if (tma_store) return launch_halo<64, 2, PITCH, true, 1>(a, stream, use_bo);
     if (st256) return launch_halo<64, 2, PITCH, true, 2>(a, stream, use_bo);

@@ -248,15 +248,28 @@ __device__ __forceinline__ void conv_epilogue_loop(const ConvParams& p, uint32_t
           f[j] = relu ? fmaxf(f[j], 0.f) : f[j];
         }
         if (masked && valid) {
-          const uint4* mk = reinterpret_cast<const uint4*>(p.mask_hi + pix * p.cout + ch);
+          if constexpr (STORE256) {   // same mask, two 32-byte loads instead of four 16-byte ones
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint4 m = __ldg(mk + j);
-            const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+            for (int j = 0; j < 2; ++j) {
+              uint32_t mw[8];
+              ld_global_nc_256(p.mask_hi + pix * p.cout + ch + 16 * j, mw);
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              if (!(bf16_lo_to_float(mw[t]) > 0.f)) f[8 * j + 2 * t] = 0.f;
-              if (!(bf16_hi_to_float(mw[t]) > 0.f)) f[8 * j + 2 * t + 1] = 0.f;
+              for (int t = 0; t < 8; ++t) {
+                if (!(bf16_lo_to_float(mw[t]) > 0.f)) f[16 * j + 2 * t] = 0.f;
+                if (!(bf16_hi_to_float(mw[t]) > 0.f)) f[16 * j + 2 * t + 1] = 0.f;
+              }
+            }
+          } else {
+            const uint4* mk = reinterpret_cast<const uint4*>(p.mask_hi + pix * p.cout + ch);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 m = __ldg(mk + j);
+              const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                if (!(bf16_lo_to_float(mw[t]) > 0.f)) f[8 * j + 2 * t] = 0.f;
+                if (!(bf16_hi_to_float(mw[t]) > 0.f)) f[8 * j + 2 * t + 1] = 0.f;
+              }
             }
           }
         }

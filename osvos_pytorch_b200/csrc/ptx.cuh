@@ -48,6 +48,13 @@ __device__ __forceinline__ void st_global_256(void* p, uint32_t a, uint32_t b, u
                : "memory");
 }
 
+// 256-bit read-only global load (LDG.E.ENL2.256.CONSTANT).  `p` must be 32-byte aligned.
+__device__ __forceinline__ void ld_global_nc_256(const void* p, uint32_t (&v)[8]) {
+  asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "l"(p));
+}
+
 // ----------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

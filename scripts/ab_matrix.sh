@@ -4,7 +4,7 @@
 cd "$(dirname "$0")/.."
 for sw in OSVOS_HALO_ST256 OSVOS_HALO_TMA_STORE OSVOS_SPLITK; do
   echo "== $sw (0 = default)"
-  timeout 120 python scripts/ab_env.py $sw 0 1 || echo "FAILED: $sw"
+  timeout 200 python scripts/ab_env.py $sw 0 1 --train || echo "FAILED: $sw"
 done
 echo "== OSVOS_SPLITACC128 (1 = default)"
 timeout 120 python scripts/ab_env.py OSVOS_SPLITACC128 1 0 || echo "FAILED"

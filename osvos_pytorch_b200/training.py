@@ -2,12 +2,9 @@
 optimizer construction with the reference's per-group learning rates, synthetic DAVIS-shaped data,
 the online fine-tune loop (train_online.py:112-149 of the reference) and the parent loop with the new
 data-parallel exchange step (train_parent.py:129-176 + parallel.py)."""
-import time
-
 import torch
 
 from .layers.osvos_layers import class_balanced_cross_entropy_loss
-from .parallel import GradientBucket, trainable_parameters
 
 MEANVAL = (104.00699, 116.66877, 122.67892)      # dataloaders/davis_2016.py:19 of the reference
 

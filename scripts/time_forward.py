@@ -1,10 +1,9 @@
 """Per-kernel CUDA-event timing of one 480x854 forward (development aid, not the bench)."""
-import sys, os, time
+import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 torch.set_grad_enabled(False)
 from oracle import osvos_oracle as oc
-from osvos_pytorch_b200 import ops
 from osvos_pytorch_b200.networks.vgg_osvos import OSVOS, he_init_
 
 h, w = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (480, 854)

@@ -407,6 +407,125 @@ __device__ __forceinline__ void conv_epilogue_loop(const ConvParams& p, uint32_t
   if (use_tma && epi_leader) tma_store_wait_all<0>();
 }
 
+// LEAN epilogue (opt-in, OSVOS_HALO_LEAN=1; UNMEASURED at the time of writing - see DESIGN.md section 4, round-2 list):
+// the inference / plain-forward feature set only - bias, ReLU, split-bf16 act output and / or fused 2x2 max pool, exact
+// mode with the N-concatenated accumulator - written against what ncu showed of the general epilogue on the Cin <= 128
+// layers (profiles/r01f_ncu_stall_by_role.txt):
+//  * stores are 256-bit (one full sector per lane and instruction; the 16-byte ones left write-after-read waits on
+//    queued STG as the top stall);
+//  * the tcgen05.ld of the NEXT 32-column chunk is issued as soon as the current chunk has been folded into f[], so its
+//    latency overlaps the split / store / pool work (21 % of the busy samples were waits on the first use);
+//  * the accumulator stage is handed back to the MMA warp right after the LAST tcgen05.ld of the tile has landed,
+//    before the stores - not at the end of the tile;
+//  * no mask / column-sum / fp32 / split-K / bulk-store code: ~1/3 of the instruction footprint next to the issuer.
+template <int BLOCK_N>
+__device__ __forceinline__ void conv_epilogue_lean(const ConvParams& p, uint32_t tmem_base, uint64_t* tfull_bar,
+                                                   uint64_t* tempty_bar, int warp, int lane) {
+  static_assert(BLOCK_N == 64 || BLOCK_N == 128, "lean epilogue: 64- or 128-wide exact tiles");
+  constexpr int kAccCols = 2 * BLOCK_N, kSlabs = BLOCK_N / 64;
+  const int group = (warp - 2) >> 2;
+  const int q = warp & 3;
+  const int row = q * 32 + lane;
+  const int ly = row / kTileW, lx = row % kTileW;
+  const bool relu = (p.flags & OSVOS_FLAG_RELU) != 0;
+  const int oh = (p.h + 1) >> 1, ow = (p.w + 1) >> 1;
+  int it = 0;
+  for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+    int nb, tx, ty, img;
+    decode_tile(p, tile, nb, tx, ty, img);
+    const int as = it & 1;
+    const uint32_t aph = (it >> 1) & 1;
+    const int y = ty * kTileH + ly, x = tx * kTileW + lx;
+    const bool valid = (y < p.h) && (x < p.w);
+    const size_t pix = (static_cast<size_t>(img) * p.h + y) * p.w + x;
+    const size_t opix = (static_cast<size_t>(img) * oh + (y >> 1)) * ow + (x >> 1);
+    const bool writer = valid && !(lx & 1) && !(ly & 1);
+
+    mbar_wait(&tfull_bar[as], aph);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + as * kAccCols + (static_cast<uint32_t>(q * 32) << 16) + group * 32;
+    uint32_t v[32], v2[32];
+    tmem_ld32(taddr, v);
+    tmem_ld32(taddr + BLOCK_N, v2);
+#pragma unroll 1                        // (rolled: the body is ~900 instructions and shares the I-cache with the issuer)
+    for (int slab = 0; slab < kSlabs; ++slab) {
+      const int ch = nb * BLOCK_N + slab * 64 + group * 32;
+      float f[32];
+      if (p.bias) {
+        const float4* bp = reinterpret_cast<const float4*>(p.bias + ch);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 b4 = __ldg(bp + j);
+          f[4 * j] = b4.x, f[4 * j + 1] = b4.y, f[4 * j + 2] = b4.z, f[4 * j + 3] = b4.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = 0.f;
+      }
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        f[j] += __uint_as_float(v[j]);        // same association as conv_epilogue_loop: bit-identical outputs
+        f[j] += __uint_as_float(v2[j]);
+        f[j] = relu ? fmaxf(f[j], 0.f) : f[j];
+      }
+      if (slab + 1 < kSlabs) {          // next chunk's accumulator columns: in flight behind the work below
+        tmem_ld32(taddr + (slab + 1) * 64, v);
+        tmem_ld32(taddr + BLOCK_N + (slab + 1) * 64, v2);
+      } else {                          // every column of this stage has been read: the MMA warp may reuse it
+        tc_fence_before();
+        mbar_arrive(&tempty_bar[as]);
+      }
+      if (p.y_hi) {
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) split_pack2(f[2 * j], f[2 * j + 1], hi[j], lo[j]);
+        if (valid) {
+          __nv_bfloat16* dh = p.y_hi + pix * p.cout + ch;
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+            st_global_256(dh + 16 * j, hi[8 * j], hi[8 * j + 1], hi[8 * j + 2], hi[8 * j + 3], hi[8 * j + 4], hi[8 * j + 5],
+                          hi[8 * j + 6], hi[8 * j + 7]);
+          if (p.y_lo) {
+            __nv_bfloat16* dl = p.y_lo + pix * p.cout + ch;
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+              st_global_256(dl + 16 * j, lo[8 * j], lo[8 * j + 1], lo[8 * j + 2], lo[8 * j + 3], lo[8 * j + 4], lo[8 * j + 5],
+                            lo[8 * j + 6], lo[8 * j + 7]);
+          }
+        }
+      }
+      if (p.pool_hi) {
+        // fused MaxPool2d(2, 2, ceil_mode=True): partners are lanes ^1 (x) and ^8 (y); out-of-image partners excluded
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float m0 = valid ? f[2 * j] : -INFINITY, m1 = valid ? f[2 * j + 1] : -INFINITY;
+          m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
+          m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+          m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 8));
+          m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 8));
+          split_pack2(m0, m1, hi[j], lo[j]);
+        }
+        if (writer) {
+          __nv_bfloat16* dh = p.pool_hi + opix * p.cout + ch;
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+            st_global_256(dh + 16 * j, hi[8 * j], hi[8 * j + 1], hi[8 * j + 2], hi[8 * j + 3], hi[8 * j + 4], hi[8 * j + 5],
+                          hi[8 * j + 6], hi[8 * j + 7]);
+          if (p.pool_lo) {
+            __nv_bfloat16* dl = p.pool_lo + opix * p.cout + ch;
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+              st_global_256(dl + 16 * j, lo[8 * j], lo[8 * j + 1], lo[8 * j + 2], lo[8 * j + 3], lo[8 * j + 4], lo[8 * j + 5],
+                            lo[8 * j + 6], lo[8 * j + 7]);
+          }
+        }
+      }
+    }
+  }
+}
+
 // Output act [n,h,w,cout] -> 4-D store maps with box {64, kTileW, kTileH, 1} (SWIZZLE_128B).
 static inline int encode_output_maps(CUtensorMap* hi, CUtensorMap* lo, const osvos_conv3x3_args* a) {
   const uint64_t dims[4] = {(uint64_t)a->cout, (uint64_t)a->w, (uint64_t)a->h, (uint64_t)a->n};

@@ -2,7 +2,7 @@
 # A/B of the library's opt-in switches on 480x854 inference, one process per switch (per-launch environment reads).
 # Usage on a GPU box:  bash scripts/ab_matrix.sh > gpurun_out/ab_matrix.txt 2>&1   (about 15 s per line pair)
 cd "$(dirname "$0")/.."
-for sw in OSVOS_HALO_ST256 OSVOS_HALO_TMA_STORE OSVOS_SPLITK; do
+for sw in OSVOS_HALO_LEAN OSVOS_HALO_ST256 OSVOS_HALO_TMA_STORE OSVOS_SPLITK; do
   echo "== $sw (0 = default)"
   timeout 200 python scripts/ab_env.py $sw 0 1 --train || echo "FAILED: $sw"
 done

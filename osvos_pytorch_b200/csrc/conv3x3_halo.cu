@@ -53,6 +53,11 @@ struct HaloCfg {
   static constexpr int kTmemCols = (2 * kAccCols) < 32 ? 32 : 2 * kAccCols;
   static constexpr int kSmemBytes = kAStages * kAStageBytes + kBStages * kBStageBytes + kStagingBytes + 1024 + 512;
   static_assert(kBStages >= 2, "weight ring too shallow");
+  // The issuer forms descriptors by ADDING (bytes >> 4) to a base descriptor: every address it can reach - the end of
+  // the dynamic allocation plus the static shared variables' 1 KiB alignment slack - must stay inside the 14-bit
+  // start-address field (256 KiB), or the add would carry into the leading-dimension field.
+  static_assert(kSmemBytes <= 227 * 1024, "more than the per-CTA shared memory of sm_100");
+  static_assert(kSmemBytes + 4096 < (1 << 18), "descriptor start-address field would overflow");
   static_assert(kBStageBytes % 1024 == 0, "B stage must keep 1024-byte alignment");
 };
 

@@ -58,6 +58,8 @@ struct WgCfg {
   static constexpr int kAccCols = kSplitAcc ? 2 * BLOCK_N : BLOCK_N;
   static constexpr int kTmemCols = 2 * kAccCols < 32 ? 32 : 2 * kAccCols;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+  // descriptors are formed by adding (bytes >> 4) to a base descriptor (see conv3x3_halo.cu): stay inside the field
+  static_assert(kSmemBytes <= 227 * 1024 && kSmemBytes + 8192 < (1 << 18), "shared memory / descriptor address field");
 };
 
 __device__ __forceinline__ void wg_decode_item(const WgradParams& p, int item, int& mb, int& nb, int& tap, int& split) {

@@ -34,8 +34,8 @@ struct HaloCfg {
   static constexpr int kBPlaneBytes = BLOCK_N * 128;
   static constexpr int kBStageBytes = PLANES * kBPlaneBytes;
   // Output store flavour STORE: 0 = 16-byte direct stores (default), 1 = bulk tensor stores through a staging buffer,
-  // 2 = 32-byte direct stores (st.global.v8.b32), 3 = the lean forward-only epilogue (conv_common.cuh; 32-byte stores,
-  // pipelined tcgen05.ld, early accumulator release).  TMA-store staging (hi + lo slab), STORE == 1 only.  Measured in round 1 while the MMA issuer was still the bottleneck: no
+  // 2 = 32-byte direct stores (st.global.v8.b32), 3 / 4 = the lean forward-only epilogue (conv_common.cuh; 32-byte stores,
+  // pipelined tcgen05.ld, early accumulator release; 4: channel-split max pool).  TMA-store staging (hi + lo slab), STORE == 1 only.  Measured in round 1 while the MMA issuer was still the bottleneck: no
   // faster than direct 16-byte stores, and its 32 KiB cost one weight-ring stage - so it is off by default.  The direct
   // stores do cost the epilogue-bound layers (32 half-filled sectors per STG.128; ablation: conv2_1 49 -> 37 us without
   // stores), hence the opt-in instantiations behind OSVOS_HALO_TMA_STORE=1 for the next measurement.
@@ -277,8 +277,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_c
       __syncwarp();
     }
   } else {
-    if constexpr (STORE == 3) {
-      conv_epilogue_lean<BLOCK_N>(p, tmem_base, tfull_bar, tempty_bar, warp, lane);
+    if constexpr (STORE >= 3) {
+      conv_epilogue_lean<BLOCK_N, STORE == 4>(p, tmem_base, tfull_bar, tempty_bar, warp, lane);
     } else {
       conv_epilogue_loop<BLOCK_N, false, Cfg::kSplitAcc, STORE == 2>(p, tmem_base, tfull_bar, tempty_bar, warp, lane,
                                                                    &map_y_hi, &map_y_lo,
@@ -381,7 +381,7 @@ static int dispatch_halo(const osvos_conv3x3_args* a, cudaStream_t stream, int u
                     (a->pool_hi == nullptr || a->pool_lo != nullptr) && aligned32(a->y_hi) && aligned32(a->y_lo) &&
                     aligned32(a->pool_hi) && aligned32(a->pool_lo) && a->k_valid == 0;
   if (a->cout == 64) {
-    if (lean) return launch_halo<64, 2, PITCH, true, 3>(a, stream, use_bo);
+    if (lean) return atoi(ln) >= 2 ? launch_halo<64, 2, PITCH, true, 4>(a, stream, use_bo) : launch_halo<64, 2, PITCH, true, 3>(a, stream, use_bo);
     if (tma_store) return launch_halo<64, 2, PITCH, true, 1>(a, stream, use_bo);
     if (st256) return launch_halo<64, 2, PITCH, true, 2>(a, stream, use_bo);
     return fast ? launch_halo<64, 1, PITCH>(a, stream, use_bo) : launch_halo<64, 2, PITCH>(a, stream, use_bo);
@@ -412,7 +412,7 @@ static int dispatch_halo(const osvos_conv3x3_args* a, cudaStream_t stream, int u
   const char* sp = getenv("OSVOS_SPLITACC128");
   if (sp != nullptr && atoi(sp) == 0) return launch_halo<128, 2, PITCH, false>(a, stream, use_bo);
   // opt-in: act output through a swizzled staging buffer + bulk tensor stores (full 128-byte rows) - see HaloCfg
-  if (lean) return launch_halo<128, 2, PITCH, true, 3>(a, stream, use_bo);
+  if (lean) return atoi(ln) >= 2 ? launch_halo<128, 2, PITCH, true, 4>(a, stream, use_bo) : launch_halo<128, 2, PITCH, true, 3>(a, stream, use_bo);
   if (tma_store) return launch_halo<128, 2, PITCH, true, 1>(a, stream, use_bo);
   if (st256) return launch_halo<128, 2, PITCH, true, 2>(a, stream, use_bo);
   return launch_halo<128, 2, PITCH>(a, stream, use_bo);

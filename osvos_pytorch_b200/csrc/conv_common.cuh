@@ -418,7 +418,10 @@ __device__ __forceinline__ void conv_epilogue_loop(const ConvParams& p, uint32_t
 //  * the accumulator stage is handed back to the MMA warp right after the LAST tcgen05.ld of the tile has landed,
 //    before the stores - not at the end of the tile;
 //  * no mask / column-sum / fp32 / split-K / bulk-store code: ~1/3 of the instruction footprint next to the issuer.
-template <int BLOCK_N>
+//  * QUAD_POOL (OSVOS_HALO_LEAN=2): the 2x2 max pool splits the 32 channels among the four lanes of a window instead
+//    of letting all four compute all 32 maxima - 16 + 8 shuffles per chunk instead of 64, a quarter of the split work,
+//    and every lane of the window stores 16 bytes per plane (the max-pool shuffles were conv2_2's top stall).
+template <int BLOCK_N, bool QUAD_POOL = false>
 __device__ __forceinline__ void conv_epilogue_lean(const ConvParams& p, uint32_t tmem_base, uint64_t* tfull_bar,
                                                    uint64_t* tempty_bar, int warp, int lane) {
   static_assert(BLOCK_N == 64 || BLOCK_N == 128, "lean epilogue: 64- or 128-wide exact tiles");
@@ -495,7 +498,33 @@ __device__ __forceinline__ void conv_epilogue_lean(const ConvParams& p, uint32_t
           }
         }
       }
-      if (p.pool_hi) {
+      if (QUAD_POOL && p.pool_hi) {
+        // fused MaxPool2d(2, 2, ceil_mode=True), channels split over the window's four lanes: after the x exchange a
+        // lane holds the row-pair maxima of 16 channels (odd x: the upper 16), after the y exchange the window maxima
+        // of 8 (odd y: the upper 8 of those).  Out-of-image pixels contribute -inf (ceil mode clips the window).
+        const bool odd_x = (lx & 1) != 0, odd_y = (ly & 1) != 0;
+        float a16[16], b8[8];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float lo_half = valid ? f[i] : -INFINITY, hi_half = valid ? f[16 + i] : -INFINITY;
+          const float keep = odd_x ? hi_half : lo_half, send = odd_x ? lo_half : hi_half;
+          a16[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 1));
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float keep = odd_y ? a16[8 + i] : a16[i], send = odd_y ? a16[i] : a16[8 + i];
+          b8[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 8));
+        }
+        uint32_t ph[4], pl[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) split_pack2(b8[2 * j], b8[2 * j + 1], ph[j], pl[j]);
+        const int cbase = (odd_x ? 16 : 0) + (odd_y ? 8 : 0);
+        if (((y & ~1) < p.h) && ((x & ~1) < p.w)) {      // the window's top-left pixel exists <=> the pooled pixel does
+          *reinterpret_cast<uint4*>(p.pool_hi + opix * p.cout + ch + cbase) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+          if (p.pool_lo)
+            *reinterpret_cast<uint4*>(p.pool_lo + opix * p.cout + ch + cbase) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+        }
+      } else if (p.pool_hi) {
         // fused MaxPool2d(2, 2, ceil_mode=True): partners are lanes ^1 (x) and ^8 (y); out-of-image partners excluded
         uint32_t hi[16], lo[16];
 #pragma unroll

@@ -6,5 +6,7 @@ for sw in OSVOS_HALO_LEAN OSVOS_HALO_ST256 OSVOS_HALO_TMA_STORE OSVOS_SPLITK; do
   echo "== $sw (0 = default)"
   timeout 200 python scripts/ab_env.py $sw 0 1 --train || echo "FAILED: $sw"
 done
+echo "== OSVOS_HALO_LEAN 1 vs 2 (channel-split max pool)"
+timeout 200 python scripts/ab_env.py OSVOS_HALO_LEAN 1 2 --train || echo "FAILED"
 echo "== OSVOS_SPLITACC128 (1 = default)"
 timeout 120 python scripts/ab_env.py OSVOS_SPLITACC128 1 0 || echo "FAILED"

@@ -21,7 +21,7 @@ from gpu_util import maxrel
 pytestmark = [pytest.mark.gpu,
               pytest.mark.skipif(os.environ.get("OSVOS_TEST_OPTIN") != "1", reason="opt-in variants: set OSVOS_TEST_OPTIN=1")]
 
-VARIANTS = [("OSVOS_HALO_LEAN", "1", 0.0), ("OSVOS_HALO_ST256", "1", 0.0), ("OSVOS_HALO_TMA_STORE", "1", 0.0), ("OSVOS_SPLITACC128", "0", 1e-4),
+VARIANTS = [("OSVOS_HALO_LEAN", "1", 0.0), ("OSVOS_HALO_LEAN", "2", 0.0), ("OSVOS_HALO_ST256", "1", 0.0), ("OSVOS_HALO_TMA_STORE", "1", 0.0), ("OSVOS_SPLITACC128", "0", 1e-4),
             ("OSVOS_SPLITK", "1", 1e-4)]
 
 

@@ -140,14 +140,23 @@ OSVOS_API int osvos_maxpool2x2_fwd(const void* x_hi, const void* x_lo, void* y_h
  * reductions of class_balanced_cross_entropy_loss (layers/osvos_layers.py:28-41).
  *   out[k][n,0,y,x], k<4 = sum over the <=2x2 low-res taps of scale k of p_k
  *   out[4]               = sum_k (same taps of q_k) + fuse_bias
- *   sums[k] = {sum_{y=1} (softplus(x)-x), sum_{y=0} softplus(x)} for the 5 maps,
- *   sums[10] = P = #(label >= .5), sums[11] = number of pixels        (12 doubles, zeroed by the call) */
+ *   sums[2k], sums[2k+1] = {sum_{y=1} (softplus(x)-x), sum_{y=0} softplus(x)} of map k,
+ *   sums[10] = P = #(label >= .5), sums[11] = number of pixels N,
+ *   sums[12], sums[13] = {sum_{y=1} (sigmoid(x_fused)-1), sum_{y=0} sigmoid(x_fused)} (-> d fuse.bias),
+ *   sums[14] = arrival counter                         (OSVOS_TAIL_SUMS = 15 doubles, zeroed by the call)
+ * and, when `losses` is given (the package's own objective: train_online.py:127, train_parent.py:143-147),
+ *   losses[k] = (Nn/N * S_pos_k + P/N * S_neg_k) / divisor,  losses[5] = sum_k loss_weights[k] * losses[k]
+ * so that upsample + crop + fuse + the five class-balanced BCE losses are ONE kernel.            */
+#define OSVOS_TAIL_SUMS 15
 typedef struct {
   const float* pq[4];      /* [n, h_k, w_k, 2], h_k = ceil-halved k+1 times          */
   const float* fuse_bias;  /* [1] */
   float* out[5];           /* each [n,1,h,w] fp32, any may be NULL                   */
   const float* label;      /* [n,1,h,w] or NULL */
-  double* sums;            /* [12] or NULL */
+  double* sums;            /* [OSVOS_TAIL_SUMS] or NULL (required with label)         */
+  float* losses;           /* [6] or NULL (needs label)                               */
+  float loss_weights[5];   /* weights of the five losses in losses[5]                 */
+  float divisor;           /* batch size (batch_average), numel (size_average) or 1   */
   int n, h, w;
 } osvos_tail_fwd_args;
 OSVOS_API int osvos_tail_fwd(const osvos_tail_fwd_args* args /* host */, osvos_stream_t stream);
@@ -214,6 +223,25 @@ typedef struct {
   int n, h, w;
 } osvos_tail_bwd_args;
 OSVOS_API int osvos_tail_bwd(const osvos_tail_bwd_args* args /* host */, osvos_stream_t stream);
+
+/* ---- backward of tail + class-balanced BCE in one launch ---------------------------
+ * Autograd of `total = sum_k loss_weights[k] * class_balanced_cross_entropy_loss(out[k], label)` through
+ * osvos_tail_fwd (layers/osvos_layers.py:28-46 + networks/vgg_osvos.py:68-72; the parent / online objectives of
+ * train_parent.py:143-147 and train_online.py:127): dL/dlogit_k = upstream * loss_weights[k] * w * (sigmoid(x_k) - y)
+ * / divisor is formed on the fly from the logit maps and the label while the bilinear adjoint gathers it - the five
+ * gradient maps are never written.  `sums` is the forward call's (P, N and the fuse-bias sums are read from it).   */
+typedef struct {
+  const float* logits[5];   /* the five maps written by osvos_tail_fwd (NULL allowed where the weight is 0) */
+  const float* label;       /* [n,1,h,w] */
+  const double* sums;       /* [OSVOS_TAIL_SUMS] of the forward call */
+  const float* upstream;    /* device scalar d(total) or NULL (= 1) */
+  float loss_weights[5];
+  float divisor;
+  float* dpq[4];            /* [n,h_k,w_k,2] */
+  float* fuse_bias_grad;    /* [1] or NULL */
+  int n, h, w;
+} osvos_tail_loss_bwd_args;
+OSVOS_API int osvos_tail_loss_bwd(const osvos_tail_loss_bwd_args* args /* host */, osvos_stream_t stream);
 
 /* out[0] = sum(x[0:n]) (fuse.bias gradient); scratch: 2 doubles (total, arrival counter).  */
 OSVOS_API int osvos_sum_f32(const float* x, size_t n, double* scratch, float* out, osvos_stream_t stream);

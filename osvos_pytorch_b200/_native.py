@@ -35,7 +35,17 @@ class Conv3x3Args(Structure):
 
 class TailFwdArgs(Structure):
     _fields_ = [("pq", c_void_p * 4), ("fuse_bias", c_void_p), ("out", c_void_p * 5), ("label", c_void_p),
-                ("sums", c_void_p), ("n", c_int), ("h", c_int), ("w", c_int)]
+                ("sums", c_void_p), ("losses", c_void_p), ("loss_weights", c_float * 5), ("divisor", c_float),
+                ("n", c_int), ("h", c_int), ("w", c_int)]
+
+
+TAIL_SUMS = 15
+
+
+class TailLossBwdArgs(Structure):
+    _fields_ = [("logits", c_void_p * 5), ("label", c_void_p), ("sums", c_void_p), ("upstream", c_void_p),
+                ("loss_weights", c_float * 5), ("divisor", c_float), ("dpq", c_void_p * 4), ("fuse_bias_grad", c_void_p),
+                ("n", c_int), ("h", c_int), ("w", c_int)]
 
 
 class WgradArgs(Structure):
@@ -85,6 +95,7 @@ SIGNATURES = {
     "osvos_conv3x3_wgrad": (c_int, [POINTER(WgradArgs), c_void_p]),
     "osvos_wgrad_finish": (c_int, [POINTER(WgradFinishItem), c_int, c_void_p]),
     "osvos_tail_bwd": (c_int, [POINTER(TailBwdArgs), c_void_p]),
+    "osvos_tail_loss_bwd": (c_int, [POINTER(TailLossBwdArgs), c_void_p]),
     "osvos_sum_f32": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
     "osvos_side_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                c_int, c_void_p]),

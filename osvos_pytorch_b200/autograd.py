@@ -19,7 +19,10 @@ def _trunk_convs(m):
 
 class _OSVOSFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, engine, x, *params):
+    def forward(ctx, engine, x, objective, *params):
+        """objective: None (plain forward: the five maps, each differentiable) or (label, loss_weights[5], divisor):
+        the package's own objective fused into the tail - outputs are then (5 maps, total, losses[5]) with only
+        `total = sum_k w_k * class_balanced_cross_entropy_loss(map_k, label)` differentiable."""
         m = engine.m
         fast = m.precision == "fast"
         engine._check_deconvs()
@@ -55,13 +58,28 @@ class _OSVOSFunction(torch.autograd.Function):
                                       proj_b=m.score_dsn[i - 1].bias.detach())
             feats.append(feat)
             pqs.append(pq)
-        out, _ = ops.tail_fwd(pqs, m.fuse.bias.detach(), n, h, w)
         ctx.engine = engine
-        ctx.saved = (xin, acts, pooled, feats)
         ctx.dims = (n, h, w)
         ctx.fast = fast
-        outs = tuple(out[k] for k in range(5))
-        return outs
+        if objective is None:
+            out, _ = ops.tail_fwd(pqs, m.fuse.bias.detach(), n, h, w)
+            ctx.objective = None
+            ctx.saved = (xin, acts, pooled, feats)
+            return tuple(out[k] for k in range(5))
+        label, weights, divisor = objective
+        label = label.detach().to(xin.device).contiguous().float()
+        if label.numel() != n * h * w:
+            raise ValueError("objective label must be [N,1,H,W] like the output maps")
+        weights = tuple(float(v) for v in weights)
+        out, sums, losses = ops.tail_fwd(pqs, m.fuse.bias.detach(), n, h, w, label=label, loss_weights=weights,
+                                         divisor=divisor)
+        ctx.objective = (out, label, sums, weights, float(divisor))
+        ctx.saved = (xin, acts, pooled, feats)
+        maps = tuple(out[k] for k in range(5))
+        total = losses[5:6].reshape(())          # 0-dim view of the weighted total
+        per_map = losses[0:5]
+        ctx.mark_non_differentiable(*maps, per_map)
+        return maps + (total, per_map)
 
     @staticmethod
     def backward(ctx, *grads):
@@ -72,8 +90,13 @@ class _OSVOSFunction(torch.autograd.Function):
         n, h, w = ctx.dims
         convs = _trunk_convs(m)
         pg = {}                                   # parameter -> gradient tensor
+        obj = ctx.objective
+        if obj is not None:
+            g_total = grads[5]
+            weights = obj[3]
+            grads = tuple((True if weights[k] != 0.0 else None) for k in range(5)) if g_total is not None else (None,) * 5
         if all(g is None for g in grads):
-            return (None, None) + tuple(None for _ in engine._param_list())
+            return (None, None, None) + tuple(None for _ in engine._param_list())
         # ---- weight-gradient plumbing: ONE zeroed arena for all tensor-core wgrad workspaces, ONE finish launch at
         # the end.  In direct mode (engine.accumulate_param_grads_in_place, set by the package's training loops) the
         # finish adds straight into an existing p.grad and the bias column sums are accumulated into p.grad by the
@@ -112,9 +135,18 @@ class _OSVOSFunction(torch.autograd.Function):
                 pg[conv.weight] = it["dw"]
             finish_items.append(it)
 
-        dpq = ops.tail_bwd(list(grads), n, h, w)
-        if grads[4] is not None:
-            pg[m.fuse.bias] = ops.sum_f32(grads[4]).reshape(m.fuse.bias.shape)
+        if obj is not None:
+            # tail + loss backward in ONE launch: dL/dlogit is formed on the fly (never written), d fuse.bias comes from
+            # the forward's sums
+            out, label, sums, weights, divisor = obj
+            dpq, fb = ops.tail_loss_bwd(out, label, sums, weights, divisor, g_total.detach().contiguous().float(),
+                                        n, h, w, want_fuse_bias=grads[4] is not None)
+            if fb is not None:
+                pg[m.fuse.bias] = fb.reshape(m.fuse.bias.shape)
+        else:
+            dpq = ops.tail_bwd(list(grads), n, h, w)
+            if grads[4] is not None:
+                pg[m.fuse.bias] = ops.sum_f32(grads[4]).reshape(m.fuse.bias.shape)
         fuse_w_grad = torch.zeros(64, dtype=torch.float32, device=xin.device) if grads[4] is not None else None
         # one zeroed buffer for all 13 trunk bias gradients; the dgrad / unpool epilogues accumulate into its slices
         flat_convs = [c for stage in convs for c in stage]
@@ -181,10 +213,19 @@ class _OSVOSFunction(torch.autograd.Function):
         pg[c11.bias] = bias_grad(c11)
         ops.wgrad_finish(finish_items)
         ctx.saved = None
-        return (None, dx) + tuple(pg.get(p) for p in engine._param_list())
+        ctx.objective = None
+        return (None, dx, None) + tuple(pg.get(p) for p in engine._param_list())
 
 
 def osvos_apply(engine, x):
     params = engine._param_list()
-    outs = _OSVOSFunction.apply(engine, x, *params)
+    outs = _OSVOSFunction.apply(engine, x, None, *params)
     return list(outs)
+
+
+def osvos_apply_objective(engine, x, label, loss_weights, divisor):
+    """Forward + the weighted class-balanced BCE objective as one autograd node.
+    -> (maps: list of 5 [N,1,H,W] logit tensors (detached), total: 0-dim differentiable loss, per_map: [5] losses)."""
+    params = engine._param_list()
+    res = _OSVOSFunction.apply(engine, x, (label, loss_weights, divisor), *params)
+    return list(res[:5]), res[5], res[6]

@@ -8,70 +8,7 @@
 
 namespace osvos {
 
-// ------------------------------------------------------------------ tail bwd
-// dpq[k][img, iy, ix] = { sum f f g_k , sum f f g_4 } over the (2s)^2 footprint of
-// the low-res pixel in the cropped full-resolution maps (adjoint of tail_fwd).
-struct TailBwdParams {
-  const float* gk;   // [n,1,h,w] gradient of side output k (may be NULL)
-  const float* g4;   // gradient of the fused output (may be NULL)
-  float* dpq;        // [n,hk,wk,2]
-  int n, h, w, hk, wk, s, top, left;
-};
-
-// LANES threads cooperate on one low-res pixel (2 / 8 / 32 / 32 for s = 2 / 4 / 8 / 16): 8 .. 32 taps per lane,
-// sub-warp shuffle reduction.
-// All four scales run in ONE launch: blockIdx.y selects the scale, each with its own share of blockIdx.x.
-struct TailBwdAll {
-  TailBwdParams k[4];
-  int blocks[4];
-};
-
-template <int LANES>
-__device__ __forceinline__ void tail_bwd_body(const TailBwdParams& p, int nblocks) {
-  const int sub = threadIdx.x % LANES;
-  const size_t grp_global = (blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x) / LANES;
-  const size_t ngroups = (static_cast<size_t>(nblocks) * blockDim.x) / LANES;
-  const size_t total = static_cast<size_t>(p.n) * p.hk * p.wk;
-  const int fs = 2 * p.s;
-  const float inv = 1.f / static_cast<float>(p.s);
-  const size_t rounds = (total + ngroups - 1) / ngroups;   // uniform trip count: every lane takes part in the shuffles
-  for (size_t rd = 0; rd < rounds; ++rd) {
-    const size_t i = grp_global + rd * ngroups;
-    const bool live = i < total;
-    float dp = 0.f, dq = 0.f;
-    if (live) {
-      const int ix = static_cast<int>(i % p.wk);
-      const int iy = static_cast<int>((i / p.wk) % p.hk);
-      const int img = static_cast<int>(i / (static_cast<size_t>(p.wk) * p.hk));
-      const size_t base = static_cast<size_t>(img) * p.h * p.w;
-      for (int t = sub; t < fs * fs; t += LANES) {
-        const int ty = t / fs, tx = t - ty * fs;
-        const int y = iy * p.s + ty - p.top, x = ix * p.s + tx - p.left;
-        if (y < 0 || y >= p.h || x < 0 || x >= p.w) continue;
-        const float fy = 1.f - fabsf(static_cast<float>(ty) - (static_cast<float>(p.s) - 0.5f)) * inv;
-        const float fx = 1.f - fabsf(static_cast<float>(tx) - (static_cast<float>(p.s) - 0.5f)) * inv;
-        const float wgt = fy * fx;
-        const size_t o = base + static_cast<size_t>(y) * p.w + x;
-        if (p.gk) dp = fmaf(wgt, __ldg(p.gk + o), dp);
-        if (p.g4) dq = fmaf(wgt, __ldg(p.g4 + o), dq);
-      }
-    }
-#pragma unroll
-    for (int off = LANES / 2; off > 0; off >>= 1) {
-      dp += __shfl_xor_sync(0xffffffffu, dp, off);
-      dq += __shfl_xor_sync(0xffffffffu, dq, off);
-    }
-    if (live && sub == 0) *reinterpret_cast<float2*>(p.dpq + i * 2) = make_float2(dp, dq);
-  }
-}
-
-__global__ void __launch_bounds__(256) tail_bwd_kernel(const __grid_constant__ TailBwdAll a) {
-  const int k = blockIdx.y;
-  if (static_cast<int>(blockIdx.x) >= a.blocks[k]) return;
-  if (k == 0) tail_bwd_body<2>(a.k[0], a.blocks[0]);
-  else if (k == 1) tail_bwd_body<8>(a.k[1], a.blocks[1]);
-  else tail_bwd_body<32>(a.k[k], a.blocks[k]);
-}
+// (the adjoint of the bilinear tail lives in tail.cu, next to its forward)
 
 // ---------------------------------------------------------------- generic sum
 __global__ void __launch_bounds__(256) sum_f32_kernel(const float* __restrict__ x, size_t n, double* __restrict__ out,
@@ -533,38 +470,6 @@ static inline int grid_cap(size_t blocks, int per_sm) {
 }  // namespace osvos
 
 using namespace osvos;
-
-extern "C" int osvos_tail_bwd(const osvos_tail_bwd_args* a, osvos_stream_t stream_) {
-  OSVOS_CHECK_ARG(a != nullptr && a->n > 0 && a->h > 0 && a->w > 0);
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  int hk = a->h, wk = a->w;
-  TailBwdAll all;
-  int max_blocks = 1;
-  for (int k = 0; k < 4; ++k) {
-    hk = (hk + 1) / 2;
-    wk = (wk + 1) / 2;
-    OSVOS_CHECK_ARG(a->dpq[k] != nullptr);
-    TailBwdParams& p = all.k[k];
-    p.gk = a->grad_out[k];
-    p.g4 = a->grad_out[4];
-    p.dpq = a->dpq[k];
-    p.n = a->n;
-    p.h = a->h;
-    p.w = a->w;
-    p.hk = hk;
-    p.wk = wk;
-    p.s = 2 << k;
-    p.top = ((hk + 1) * p.s - a->h) / 2;
-    p.left = ((wk + 1) * p.s - a->w) / 2;
-    const size_t pixels = static_cast<size_t>(a->n) * hk * wk;
-    const int lanes = k == 0 ? 2 : (k == 1 ? 8 : 32);
-    all.blocks[k] = grid_cap((pixels * lanes + 255) / 256, 4);
-    if (all.blocks[k] > max_blocks) max_blocks = all.blocks[k];
-  }
-  tail_bwd_kernel<<<dim3(max_blocks, 4), 256, 0, stream>>>(all);
-  OSVOS_CHECK_CUDA(cudaGetLastError());
-  return OSVOS_OK;
-}
 
 extern "C" int osvos_sum_f32(const float* x, size_t n, double* scratch, float* out, osvos_stream_t stream_) {
   OSVOS_CHECK_ARG(x != nullptr && scratch != nullptr && out != nullptr && n > 0);

@@ -29,28 +29,36 @@ struct TailParams {
   float* out[5];
   const float* label;
   double* sums;
+  float* losses;          // [6]: the five per-map losses and their weighted total (written by the last block), or NULL
+  float loss_weights[5];
+  float inv_divisor;
   int n, h, w;
   int vec_mask;  // bit k: out[k] is 16-byte aligned; bit 5: label is
 };
 
 constexpr int kTailThreads = 256;
+// sums layout (doubles): [2k] / [2k+1] = S_pos / S_neg of map k, [10] = P, [11] = N, [12] / [13] = A_pos / A_neg of the
+// fused map (sum_{y=1} (sigmoid(x) - 1), sum_{y=0} sigmoid(x): d fuse.bias without another pass), [14] = arrival counter
+constexpr int kTailSums = 15;
 
 __device__ __forceinline__ float softplus_f(float x) { return fmaxf(x, 0.f) + log1pf(__expf(-fabsf(x))); }
 
+// One thread = four consecutive elements of the flat [n,1,h,w] maps (always 16-byte aligned whatever the row length);
+// (img, y, x) of the first comes from ONE pair of 32-bit divisions, the other three by carry (the first version paid
+// two 64-bit divisions per pixel - most of its 15 us).
 __global__ void __launch_bounds__(kTailThreads) tail_fwd_kernel(const TailParams p) {
   pdl_wait();               // side maps, biases and the accumulators all come from earlier kernels (ptx.cuh)
   pdl_launch_dependents();
-  const size_t hw = static_cast<size_t>(p.h) * p.w;
-  const size_t total = static_cast<size_t>(p.n) * hw;
-  const size_t nvec = (total + 3) / 4;
+  const uint32_t hw = static_cast<uint32_t>(p.h) * p.w;
+  const uint32_t total = static_cast<uint32_t>(p.n) * hw;
+  const uint32_t nvec = (total + 3) / 4;
   const float fb = p.fuse_bias ? __ldg(p.fuse_bias) : 0.f;
 
   float s_pos[5] = {0, 0, 0, 0, 0}, s_neg[5] = {0, 0, 0, 0, 0};
-  float cnt_pos = 0.f;
+  float cnt_pos = 0.f, a_pos = 0.f, a_neg = 0.f;
 
-  for (size_t v = blockIdx.x * static_cast<size_t>(kTailThreads) + threadIdx.x; v < nvec;
-       v += static_cast<size_t>(gridDim.x) * kTailThreads) {
-    const size_t e0 = v * 4;
+  for (uint32_t v = blockIdx.x * kTailThreads + threadIdx.x; v < nvec; v += gridDim.x * kTailThreads) {
+    const uint32_t e0 = v * 4;
     float o[5][4];
     float lab[4] = {0, 0, 0, 0};
     const bool full = (e0 + 3 < total);
@@ -63,14 +71,14 @@ __global__ void __launch_bounds__(kTailThreads) tail_fwd_kernel(const TailParams
           if (e0 + j < total) lab[j] = __ldg(p.label + e0 + j);
       }
     }
+    int img = static_cast<int>(e0 / hw);
+    const uint32_t rem = e0 - static_cast<uint32_t>(img) * hw;
+    int y = static_cast<int>(rem / static_cast<uint32_t>(p.w));
+    int x = static_cast<int>(rem - static_cast<uint32_t>(y) * p.w);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const size_t e = e0 + j;
       float fused = fb;
-      if (e < total) {
-        const int img = static_cast<int>(e / hw);
-        const int rem = static_cast<int>(e - static_cast<size_t>(img) * hw);
-        const int y = rem / p.w, x = rem - y * p.w;
+      if (e0 + j < total) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const TailScale& sc = p.sc[k];
@@ -91,7 +99,7 @@ __global__ void __launch_bounds__(kTailThreads) tail_fwd_kernel(const TailParams
             for (int dx = 0; dx < 2; ++dx) {
               const int ix = ax - 1 + dx;
               if (wx[dx] == 0.f) continue;
-              const float2 t = __ldg(base + static_cast<size_t>(iy) * sc.wk + ix);
+              const float2 t = __ldg(base + iy * sc.wk + ix);
               const float wgt = wy[dy] * wx[dx];
               sp = fmaf(wgt, t.x, sp);
               sq = fmaf(wgt, t.y, sq);
@@ -105,7 +113,7 @@ __global__ void __launch_bounds__(kTailThreads) tail_fwd_kernel(const TailParams
         for (int k = 0; k < 4; ++k) o[k][j] = 0.f;
       }
       o[4][j] = fused;
-      if (p.label && e < total) {
+      if (p.label && e0 + j < total) {
         const bool pos = lab[j] >= 0.5f;
         cnt_pos += pos ? 1.f : 0.f;
 #pragma unroll
@@ -114,6 +122,16 @@ __global__ void __launch_bounds__(kTailThreads) tail_fwd_kernel(const TailParams
           const float sp = softplus_f(xk);
           if (pos) s_pos[k] += sp - xk;
           else s_neg[k] += sp;
+        }
+        const float sg = 1.f / (1.f + __expf(-fused));
+        if (pos) a_pos += sg - 1.f;
+        else a_neg += sg;
+      }
+      if (++x == p.w) {       // carry to the next row / image
+        x = 0;
+        if (++y == p.h) {
+          y = 0;
+          ++img;
         }
       }
     }
@@ -130,31 +148,170 @@ __global__ void __launch_bounds__(kTailThreads) tail_fwd_kernel(const TailParams
   }
 
   if (p.label && p.sums) {
-    __shared__ float red[kTailThreads / 32][11];
-    float vals[11];
+    constexpr int kVals = 13;
+    __shared__ float red[kTailThreads / 32][kVals];
+    float vals[kVals];
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
       vals[2 * k] = s_pos[k];
       vals[2 * k + 1] = s_neg[k];
     }
     vals[10] = cnt_pos;
+    vals[11] = a_pos;
+    vals[12] = a_neg;
 #pragma unroll
-    for (int i = 0; i < 11; ++i) {
+    for (int i = 0; i < kVals; ++i) {
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1) vals[i] += __shfl_xor_sync(0xffffffffu, vals[i], off);
     }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (lane == 0) {
 #pragma unroll
-      for (int i = 0; i < 11; ++i) red[warp][i] = vals[i];
+      for (int i = 0; i < kVals; ++i) red[warp][i] = vals[i];
     }
     __syncthreads();
-    if (threadIdx.x < 11) {
+    if (threadIdx.x < kVals) {
       double acc = 0.0;
       for (int wv = 0; wv < kTailThreads / 32; ++wv) acc += static_cast<double>(red[wv][threadIdx.x]);
-      atomicAdd(p.sums + threadIdx.x, acc);
+      atomicAdd(p.sums + (threadIdx.x < 11 ? threadIdx.x : threadIdx.x + 1), acc);
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) p.sums[11] = static_cast<double>(total);
+    // the last block to arrive turns the sums into the five losses and their weighted total:
+    // L_k = (Nn/N * S_pos_k + P/N * S_neg_k) / divisor   (layers/osvos_layers.py:38-46)
+    if (last_block_arrives(reinterpret_cast<unsigned int*>(p.sums + 14)) && threadIdx.x == 0) {
+      const double tot = static_cast<double>(total);
+      const double pcount = __ldcg(p.sums + 10), nn = tot - pcount;
+      p.sums[11] = tot;
+      if (p.losses) {
+        double wsum = 0.0;
+        for (int k = 0; k < 5; ++k) {
+          const double lk = (nn / tot * __ldcg(p.sums + 2 * k) + pcount / tot * __ldcg(p.sums + 2 * k + 1)) *
+                            static_cast<double>(p.inv_divisor);
+          p.losses[k] = static_cast<float>(lk);
+          wsum += static_cast<double>(p.loss_weights[k]) * lk;
+        }
+        p.losses[5] = static_cast<float>(wsum);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Backward of the tail (and, in LOSS mode, of the class-balanced BCE on top of it) in ONE launch:
+//   dpq[k][iy][ix] = sum_{ty,tx < 2s} f[ty] f[tx] * (g_k, g_4)[iy*s + ty - top][ix*s + tx - left]        (adjoint of the
+//   zero-padded bilinear deconvolution + crop: networks/vgg_osvos.py:68-72, layers/osvos_layers.py:51-85)
+// with g_k either given (LOSS = false: arbitrary upstream gradients of the five maps) or formed on the fly from the logit
+// maps and the label (LOSS = true): g_k = c_k * w * (sigmoid(x_k) - y) / divisor, w = y Nn/N + (1-y) P/N
+// (layers/osvos_layers.py:28-46) - the five dL/dlogit maps are never written to memory.
+// Work item = (scale, image, low-res row iy, segment of low-res columns): the block first reduces its 2s source rows
+// column-wise into shared memory (coalesced row reads, separable weights), then each low-res pixel of the segment sums
+// its 2s columns (sub-warp shuffle reduction).  Segments are sized so that every item covers 2-4 k source pixels.
+struct TailBwdScale {
+  float* dpq;  // [n, hk, wk, 2]
+  int hk, wk, s, top, left, seg_lo, segs, first_item;
+};
+struct TailBwdParams {
+  TailBwdScale sc[4];
+  const float* src[5];    // LOSS: the five logit maps; else the five upstream gradient maps (NULL = zero)
+  const float* label;
+  const double* sums;     // forward sums: P at [10], N at [11], A_pos / A_neg at [12] / [13]
+  const float* upstream;  // device scalar d(total loss) or NULL (= 1)
+  float coeff[5];         // loss weights
+  float inv_divisor;
+  float* fuse_bias_grad;  // [1] or NULL
+  int n, h, w, total_items;
+};
+constexpr int kTailBwdCols = 512 + 32;
+
+template <bool LOSS>
+__global__ void __launch_bounds__(256) tail_bwd2_kernel(const __grid_constant__ TailBwdParams p) {
+  __shared__ float colp[kTailBwdCols], colq[kTailBwdCols];
+  const int tid = threadIdx.x;
+  int k = 3;
+  while (k > 0 && static_cast<int>(blockIdx.x) < p.sc[k].first_item) --k;
+  const TailBwdScale& sc = p.sc[k];
+  const int local = static_cast<int>(blockIdx.x) - sc.first_item;
+  const int seg = local % sc.segs, row = local / sc.segs;
+  const int iy = row % sc.hk, img = row / sc.hk;
+  const int s = sc.s, fs = 2 * s;
+  const int ix0 = seg * sc.seg_lo;
+  const int nout = min(sc.seg_lo, sc.wk - ix0);
+  const int xlo = ix0 * s - sc.left;        // image column of shared-memory column 0 (may be negative)
+  const int width = nout * s + s;
+  const float inv_s = 1.f / static_cast<float>(s);
+
+  float wpos = 0.f, wneg = 0.f, cp = 1.f, cq = 1.f;
+  if (LOSS) {
+    const double pc = p.sums[10], nt = p.sums[11];
+    wpos = static_cast<float>((nt - pc) / nt);
+    wneg = static_cast<float>(pc / nt);
+    const float up = (p.upstream ? __ldg(p.upstream) : 1.f) * p.inv_divisor;
+    cp = p.coeff[k] * up;
+    cq = p.coeff[4] * up;
+    if (blockIdx.x == 0 && tid == 0 && p.fuse_bias_grad)   // d fuse.bias = sum_px g_4, from the forward's A sums
+      p.fuse_bias_grad[0] = cq * static_cast<float>((nt - pc) / nt * p.sums[12] + pc / nt * p.sums[13]);
+  }
+  const bool use_p = LOSS ? (p.coeff[k] != 0.f) : (p.src[k] != nullptr);
+  const bool use_q = LOSS ? (p.coeff[4] != 0.f) : (p.src[4] != nullptr);
+
+  for (int c = tid; c < width; c += 256) colp[c] = 0.f, colq[c] = 0.f;
+  __syncthreads();
+  // phase 1: column sums over the 2s source rows.  Threads = (row group r) x (column c0): wpad columns side by side,
+  // 256 / wpad row groups striding the rows.
+  const int wpad = min(256, (width + 31) & ~31);
+  const int rgroups = 256 / wpad;
+  const int r = tid / wpad, c0 = tid - r * wpad;
+  if (r < rgroups) {
+    for (int c = c0; c < width; c += wpad) {
+      const int x = xlo + c;
+      if (x < 0 || x >= p.w) continue;
+      float ap = 0.f, aq = 0.f;
+      for (int ty = r; ty < fs; ty += rgroups) {
+        const int y = iy * s + ty - sc.top;
+        if (y < 0 || y >= p.h) continue;
+        const float fy = 1.f - fabsf(static_cast<float>(ty) - (static_cast<float>(s) - 0.5f)) * inv_s;
+        const size_t o = (static_cast<size_t>(img) * p.h + y) * p.w + x;
+        if (LOSS) {
+          const bool pos = __ldg(p.label + o) >= 0.5f;
+          const float wgt = (pos ? wpos : wneg) * fy;
+          const float yv = pos ? 1.f : 0.f;
+          if (use_p) ap = fmaf(wgt, 1.f / (1.f + __expf(-__ldg(p.src[k] + o))) - yv, ap);
+          if (use_q) aq = fmaf(wgt, 1.f / (1.f + __expf(-__ldg(p.src[4] + o))) - yv, aq);
+        } else {
+          if (use_p) ap = fmaf(fy, __ldg(p.src[k] + o), ap);
+          if (use_q) aq = fmaf(fy, __ldg(p.src[4] + o), aq);
+        }
+      }
+      if (rgroups > 1) {
+        atomicAdd(&colp[c], ap);
+        atomicAdd(&colq[c], aq);
+      } else {
+        colp[c] = ap, colq[c] = aq;
+      }
+    }
+  }
+  __syncthreads();
+  // phase 2: every low-res pixel of the segment sums its 2s columns; lw = min(32, 2s) lanes per pixel
+  const int lw = fs < 32 ? fs : 32;
+  const int per_pass = 256 / lw;
+  const int sub = tid % lw, grp = tid / lw;
+  for (int base = 0; base < nout; base += per_pass) {
+    const int oi = base + grp;
+    float dp = 0.f, dq = 0.f;
+    if (oi < nout) {
+      for (int tx = sub; tx < fs; tx += lw) {
+        const float fx = 1.f - fabsf(static_cast<float>(tx) - (static_cast<float>(s) - 0.5f)) * inv_s;
+        dp = fmaf(fx, colp[oi * s + tx], dp);
+        dq = fmaf(fx, colq[oi * s + tx], dq);
+      }
+    }
+    for (int off = lw >> 1; off > 0; off >>= 1) {
+      dp += __shfl_xor_sync(0xffffffffu, dp, off);
+      dq += __shfl_xor_sync(0xffffffffu, dq, off);
+    }
+    if (oi < nout && sub == 0) {
+      float* dst = sc.dpq + ((static_cast<size_t>(img) * sc.hk + iy) * sc.wk + ix0 + oi) * 2;
+      *reinterpret_cast<float2*>(dst) = make_float2(dp * cp, dq * cq);
+    }
   }
 }
 
@@ -162,39 +319,48 @@ __global__ void __launch_bounds__(kTailThreads) tail_fwd_kernel(const TailParams
 
 using namespace osvos;
 
-extern "C" int osvos_tail_fwd(const osvos_tail_fwd_args* a, osvos_stream_t stream_) {
-  OSVOS_CHECK_ARG(a != nullptr && a->n > 0 && a->h > 0 && a->w > 0);
-  OSVOS_CHECK_ARG(a->label == nullptr || a->sums != nullptr);
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  TailParams p;
-  int hk = a->h, wk = a->w;
+static void fill_tail_scales(TailParams& p, const float* const* pq, int h, int w) {
+  int hk = h, wk = w;
   for (int k = 0; k < 4; ++k) {
-    OSVOS_CHECK_ARG(a->pq[k] != nullptr);
     hk = (hk + 1) / 2;
     wk = (wk + 1) / 2;
     const int s = 2 << k;
-    p.sc[k].pq = a->pq[k];
+    p.sc[k].pq = pq[k];
     p.sc[k].hk = hk;
     p.sc[k].wk = wk;
     p.sc[k].s = s;
     p.sc[k].log2s = k + 1;
-    p.sc[k].top = ((hk + 1) * s - a->h) / 2;   // layers/osvos_layers.py:52-56: floor(d/2) rows cropped on top
-    p.sc[k].left = ((wk + 1) * s - a->w) / 2;
+    p.sc[k].top = ((hk + 1) * s - h) / 2;   // layers/osvos_layers.py:52-56: floor(d/2) rows cropped on top
+    p.sc[k].left = ((wk + 1) * s - w) / 2;
   }
+}
+
+extern "C" int osvos_tail_fwd(const osvos_tail_fwd_args* a, osvos_stream_t stream_) {
+  OSVOS_CHECK_ARG(a != nullptr && a->n > 0 && a->h > 0 && a->w > 0);
+  OSVOS_CHECK_ARG(a->label == nullptr || a->sums != nullptr);
+  OSVOS_CHECK_ARG(a->losses == nullptr || (a->label != nullptr && a->divisor > 0.f));
+  OSVOS_CHECK_ARG(static_cast<size_t>(a->n) * a->h * a->w < (1ull << 31));   // 32-bit element indices in the kernel
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  TailParams p;
+  for (int k = 0; k < 4; ++k) OSVOS_CHECK_ARG(a->pq[k] != nullptr);
+  fill_tail_scales(p, a->pq, a->h, a->w);
   p.vec_mask = 0;
   for (int k = 0; k < 5; ++k) {
     p.out[k] = a->out[k];
     OSVOS_CHECK_ARG((reinterpret_cast<uintptr_t>(a->out[k]) & 3) == 0);
     if ((reinterpret_cast<uintptr_t>(a->out[k]) & 15) == 0) p.vec_mask |= 1 << k;
+    p.loss_weights[k] = a->loss_weights[k];
   }
   if ((reinterpret_cast<uintptr_t>(a->label) & 15) == 0) p.vec_mask |= 32;
   p.fuse_bias = a->fuse_bias;
   p.label = a->label;
   p.sums = a->sums;
+  p.losses = a->losses;
+  p.inv_divisor = a->divisor > 0.f ? 1.f / a->divisor : 1.f;
   p.n = a->n;
   p.h = a->h;
   p.w = a->w;
-  if (a->sums) OSVOS_CHECK_CUDA(cudaMemsetAsync(a->sums, 0, 12 * sizeof(double), stream));
+  if (a->sums) OSVOS_CHECK_CUDA(cudaMemsetAsync(a->sums, 0, kTailSums * sizeof(double), stream));
   const size_t nvec = (static_cast<size_t>(a->n) * a->h * a->w + 3) / 4;
   size_t blocks = (nvec + kTailThreads - 1) / kTailThreads;
   const size_t cap = static_cast<size_t>(device_sm_count()) * 8;
@@ -202,6 +368,66 @@ extern "C" int osvos_tail_fwd(const osvos_tail_fwd_args* a, osvos_stream_t strea
   // (with a loss, the memset above is this kernel's stream predecessor: plain launch)
   if (a->sums) tail_fwd_kernel<<<static_cast<int>(blocks), kTailThreads, 0, stream>>>(p);
   else OSVOS_CHECK_CUDA(launch_pdl(tail_fwd_kernel, dim3(static_cast<unsigned>(blocks)), dim3(kTailThreads), 0, stream, p));
+  OSVOS_CHECK_CUDA(cudaGetLastError());
+  return OSVOS_OK;
+}
+
+// segment sizes (low-res columns per work item) per scale: 2s rows x (seg_lo + 1) s columns = 2-4 k source pixels
+static int fill_tail_bwd_scales(TailBwdParams& p, float* const* dpq, int n, int h, int w) {
+  static const int kSegLo[4] = {255, 63, 15, 7};
+  int hk = h, wk = w, items = 0;
+  for (int k = 0; k < 4; ++k) {
+    hk = (hk + 1) / 2;
+    wk = (wk + 1) / 2;
+    const int s = 2 << k;
+    TailBwdScale& sc = p.sc[k];
+    sc.dpq = dpq[k];
+    sc.hk = hk;
+    sc.wk = wk;
+    sc.s = s;
+    sc.top = ((hk + 1) * s - h) / 2;
+    sc.left = ((wk + 1) * s - w) / 2;
+    sc.seg_lo = kSegLo[k];
+    sc.segs = (wk + sc.seg_lo - 1) / sc.seg_lo;
+    sc.first_item = items;
+    items += n * hk * sc.segs;
+  }
+  p.total_items = items;
+  return items;
+}
+
+extern "C" int osvos_tail_bwd(const osvos_tail_bwd_args* a, osvos_stream_t stream_) {
+  OSVOS_CHECK_ARG(a != nullptr && a->n > 0 && a->h > 0 && a->w > 0);
+  for (int k = 0; k < 4; ++k) OSVOS_CHECK_ARG(a->dpq[k] != nullptr);
+  TailBwdParams p;
+  memset(&p, 0, sizeof(p));
+  const int items = fill_tail_bwd_scales(p, a->dpq, a->n, a->h, a->w);
+  for (int k = 0; k < 5; ++k) p.src[k] = a->grad_out[k];
+  p.n = a->n, p.h = a->h, p.w = a->w;
+  tail_bwd2_kernel<false><<<items, 256, 0, static_cast<cudaStream_t>(stream_)>>>(p);
+  OSVOS_CHECK_CUDA(cudaGetLastError());
+  return OSVOS_OK;
+}
+
+extern "C" int osvos_tail_loss_bwd(const osvos_tail_loss_bwd_args* a, osvos_stream_t stream_) {
+  OSVOS_CHECK_ARG(a != nullptr && a->n > 0 && a->h > 0 && a->w > 0 && a->label != nullptr && a->sums != nullptr);
+  OSVOS_CHECK_ARG(a->divisor > 0.f);
+  for (int k = 0; k < 4; ++k) OSVOS_CHECK_ARG(a->dpq[k] != nullptr);
+  for (int k = 0; k < 5; ++k) OSVOS_CHECK_ARG(a->logits[k] != nullptr || a->loss_weights[k] == 0.f);
+  TailBwdParams p;
+  memset(&p, 0, sizeof(p));
+  const int items = fill_tail_bwd_scales(p, a->dpq, a->n, a->h, a->w);
+  for (int k = 0; k < 5; ++k) {
+    p.src[k] = a->logits[k];
+    p.coeff[k] = a->loss_weights[k];
+  }
+  p.label = a->label;
+  p.sums = a->sums;
+  p.upstream = a->upstream;
+  p.inv_divisor = 1.f / a->divisor;
+  p.fuse_bias_grad = a->fuse_bias_grad;
+  p.n = a->n, p.h = a->h, p.w = a->w;
+  tail_bwd2_kernel<true><<<items, 256, 0, static_cast<cudaStream_t>(stream_)>>>(p);
   OSVOS_CHECK_CUDA(cudaGetLastError());
   return OSVOS_OK;
 }

@@ -148,6 +148,26 @@ class OSVOSEngine:
             return self._forward_graphed(x)
         return self.forward_inference(x)
 
+    def forward_objective(self, x, gts, loss_weights, size_average=False, batch_average=True):
+        """See OSVOS.forward_objective."""
+        if not isinstance(x, torch.Tensor) or x.dim() != 4 or x.size(1) != 3:
+            raise ValueError("OSVOS.forward_objective expects a [N, 3, H, W] tensor")
+        if not x.is_cuda:
+            raise RuntimeError("osvos_pytorch_b200.OSVOS runs on CUDA (sm_100a) only; there is no CPU fallback")
+        if len(loss_weights) != 5:
+            raise ValueError("loss_weights: one weight per output map (5)")
+        if size_average:
+            divisor = float(gts.numel())
+        elif batch_average:
+            divisor = float(gts.size(0))
+        else:
+            divisor = 1.0
+        if x.device != torch.device("cuda", torch.cuda.current_device()):
+            with torch.cuda.device(x.device):
+                return self.forward_objective(x, gts, loss_weights, size_average, batch_average)
+        from .autograd import osvos_apply_objective
+        return osvos_apply_objective(self, x, gts, loss_weights, divisor)
+
     def _forward_graphed(self, x):
         """Inference through a captured CUDA graph: copy the frame into the static input, replay, hand back fresh
         output tensors (one device copy of the five maps).  Re-captured when shapes or parameters change."""

@@ -156,15 +156,17 @@ def side_project(feat, proj_w, proj_b):
     return pq
 
 
-def tail_fwd(pqs, fuse_bias, n, h, w, label=None, out=None):
-    """Upsample + crop + fuse (+ loss sums).  Returns (out [5,n,1,h,w] fp32, sums [12] f64 | None)."""
+def tail_fwd(pqs, fuse_bias, n, h, w, label=None, out=None, loss_weights=None, divisor=None):
+    """Upsample + crop + fuse (+ loss sums, + the five class-balanced BCE losses and their weighted total).
+    Returns (out [5,n,1,h,w] fp32, sums [TAIL_SUMS] f64 | None) and, with `loss_weights` (5 floats) and `divisor`,
+    additionally losses [6] fp32 = the five per-map losses and sum_k loss_weights[k] * loss_k."""
     lib = nat.load()
     dev = pqs[0].device
     if out is None:
         # each map starts on a 16-byte boundary so the kernel can use 128-bit stores
         per = (n * h * w + 3) // 4 * 4
         out = torch.empty((5, per), dtype=torch.float32, device=dev)[:, :n * h * w].view(5, n, 1, h, w)
-    sums = torch.empty(12, dtype=torch.float64, device=dev) if label is not None else None
+    sums = torch.empty(nat.TAIL_SUMS, dtype=torch.float64, device=dev) if label is not None else None
     a = nat.TailFwdArgs()
     for k in range(4):
         a.pq[k] = pqs[k].data_ptr()
@@ -173,10 +175,46 @@ def tail_fwd(pqs, fuse_bias, n, h, w, label=None, out=None):
     a.fuse_bias = nat.ptr(fuse_bias)
     a.label = nat.ptr(label)
     a.sums = nat.ptr(sums)
+    losses = None
+    if loss_weights is not None:
+        if label is None or divisor is None:
+            raise ValueError("tail_fwd: loss_weights needs label and divisor")
+        losses = torch.empty(6, dtype=torch.float32, device=dev)
+        a.losses = losses.data_ptr()
+        for k in range(5):
+            a.loss_weights[k] = float(loss_weights[k])
+        a.divisor = float(divisor)
     a.n, a.h, a.w = n, h, w
     _count()
     nat.check(lib.osvos_tail_fwd(byref(a), _stream()), "osvos_tail_fwd")
+    if losses is not None:
+        return out, sums, losses
     return out, sums
+
+
+def tail_loss_bwd(out, label, sums, loss_weights, divisor, upstream, n, h, w, want_fuse_bias=True):
+    """Backward of tail + the weighted class-balanced BCE objective in one launch (see include/osvos_b200.h):
+    -> (list of 4 dpq tensors [n,hk,wk,2], fuse.bias gradient [1] | None)."""
+    lib = nat.load()
+    dev = out.device
+    a = nat.TailLossBwdArgs()
+    for k in range(5):
+        a.logits[k] = out[k].data_ptr()
+        a.loss_weights[k] = float(loss_weights[k])
+    a.label, a.sums, a.upstream = label.data_ptr(), sums.data_ptr(), nat.ptr(upstream)
+    a.divisor = float(divisor)
+    dpq, hk, wk = [], h, w
+    for k in range(4):
+        hk, wk = (hk + 1) // 2, (wk + 1) // 2
+        t = torch.empty((n, hk, wk, 2), dtype=torch.float32, device=dev)
+        dpq.append(t)
+        a.dpq[k] = t.data_ptr()
+    fb = torch.empty(1, dtype=torch.float32, device=dev) if want_fuse_bias else None
+    a.fuse_bias_grad = nat.ptr(fb)
+    a.n, a.h, a.w = n, h, w
+    _count(1)
+    nat.check(lib.osvos_tail_loss_bwd(byref(a), _stream()), "osvos_tail_loss_bwd")
+    return dpq, fb
 
 
 # ------------------------------------------------------------------ backward ops

@@ -26,6 +26,10 @@ class GradientBucket:
         device = device or self.params[0].device
         self.numel = sum(p.numel() for p in self.params)
         self.flat = torch.zeros(self.numel, dtype=torch.float32, device=device)
+        # measurement aid (bench.py): with time_collective set, every allreduce is bracketed by CUDA events on the current
+        # stream; the pairs collect in collective_events (device time of the collective incl. the wait for slower ranks)
+        self.time_collective = False
+        self.collective_events = []
         self.attach()
 
     def attach(self):
@@ -48,17 +52,43 @@ class GradientBucket:
         if not dist.is_initialized() or dist.get_world_size(group) == 1:
             return None
         world = dist.get_world_size(group)
+        ev = None
+        if self.time_collective and self.flat.is_cuda:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
         if dist.get_backend(group) == "nccl":
             dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=group)
         else:                       # gloo (CPU tests) has no AVG
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
             self.flat.div_(world)
+        if ev is not None:
+            ev[1].record()
+            self.collective_events.append(ev)
         return self.flat
 
 
 def trainable_parameters(net):
     """Everything except the fixed bilinear deconvolution taps (upscale / upscale_)."""
     return [p for name, p in net.named_parameters() if not name.startswith("upscale")]
+
+
+def broadcast_parameters(module, src=0, group=None):
+    """Make every rank start from rank `src`'s parameters and buffers.  The reference initialises side_prep / score_dsn /
+    fuse with an UNSEEDED nn.init.normal_ (networks/vgg_osvos.py:76-83), so independently constructed replicas differ;
+    data parallelism is only the reference's nAveGrad accumulation if all replicas are the same model."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    with torch.no_grad():
+        for t in list(module.parameters()) + list(module.buffers()):
+            dist.broadcast(t.data, src=src, group=group)
+
+
+def steps_per_rank(total_micro_batches, world, n_ave_grad=1):
+    """Micro-batches EVERY rank runs per epoch when `total_micro_batches` are dealt out over `world` ranks: the same on
+    all ranks and a multiple of n_ave_grad (as DistributedSampler's drop_last), so that every rank takes part in every
+    allreduce - unequal counts would pair gradients of different steps and hang the longer ranks."""
+    per = total_micro_batches // world
+    return (per // n_ave_grad) * n_ave_grad
 
 
 def shard_range(total, rank, world):

@@ -7,6 +7,7 @@ import torch
 from .layers.osvos_layers import class_balanced_cross_entropy_loss
 
 MEANVAL = (104.00699, 116.66877, 122.67892)      # dataloaders/davis_2016.py:19 of the reference
+ONLINE_WEIGHTS = (0.0, 0.0, 0.0, 0.0, 1.0)       # train_online.py:127: only the fused map is supervised
 
 
 def _named(module, key):
@@ -58,7 +59,8 @@ class GraphedTrainStep:
     set_to_none would detach the graph from its buffers).  The weight-packing kernels are part of the graph, so
     parameter updates between replays are picked up - unless ``external_pack`` is set: then the packed conv
     layouts are static buffers outside the graph that ``optim.FusedSGD`` rewrites in its update kernel (no
-    packing work per micro-batch; only valid with that optimizer).  ``objective(outputs, gts) -> scalar tensor``.
+    packing work per micro-batch; only valid with that optimizer).  ``objective(outputs, gts) -> scalar tensor``, or a
+    tuple of five loss weights = the package's fused objective (``OSVOS.forward_objective``).
     """
 
     def __init__(self, net, objective, sample, grad_scale=1.0, external_pack=False):
@@ -90,6 +92,18 @@ class GraphedTrainStep:
         net._engine.drop_derived_caches(keep_packed=external_pack)   # graph-private buffers must not serve eager calls
 
     def _body(self):
+        if not callable(self.objective):
+            # loss weights of the package's fused objective (tail + five losses = one kernel each way); grad_scale is
+            # folded into the weights, so no scaling kernel runs either
+            w = [float(v) * self.grad_scale for v in self.objective]
+            _, total, per_map = self.net.forward_objective(self.x, self.gt, w)
+            with self.net._engine.direct_grad_accumulation():
+                total.backward()
+            self.per_map = per_map
+            nz = [k for k, v in enumerate(self.objective) if float(v) != 0.0]
+            if len(nz) == 1 and float(self.objective[nz[0]]) == 1.0:
+                return per_map[nz[0]]                       # the unscaled objective IS that map's loss: no extra kernel
+            return total.detach() if self.grad_scale == 1.0 else total.detach() / self.grad_scale
         outputs = self.net(self.x)
         loss = self.objective(outputs, self.gt)
         with self.net._engine.direct_grad_accumulation():   # p.grad buffers are static: add into them in the kernels
@@ -130,9 +144,8 @@ def online_finetune(net, sample_fn, iters, n_ave_grad=5, lr=1e-8, wd=0.0002, log
         inputs, gts = sample["image"], sample["gt"]
         if use_graph:
             if step is None:
-                step = GraphedTrainStep(
-                    net, lambda outs, gt: class_balanced_cross_entropy_loss(outs[-1], gt, size_average=False), sample,
-                    grad_scale=1.0 / n_ave_grad, external_pack=fused_optimizer)
+                step = GraphedTrainStep(net, ONLINE_WEIGHTS, sample, grad_scale=1.0 / n_ave_grad,
+                                        external_pack=fused_optimizer)
             loss_val = step(sample)
             running = loss_val.clone() if running is None else running + loss_val
             if (it + 1) % n_ave_grad == 0:
@@ -143,11 +156,9 @@ def online_finetune(net, sample_fn, iters, n_ave_grad=5, lr=1e-8, wd=0.0002, log
                     opt.step()
                     step.zero_grads()
         else:
-            outputs = net.forward(inputs)
-            loss = class_balanced_cross_entropy_loss(outputs[-1], gts, size_average=False)
-            # clone: `loss /= n_ave_grad` below is in place (as in the reference) and must not scale the logged value
-            running = loss.detach().clone() if running is None else running + loss.detach()
-            loss /= n_ave_grad
+            # fuse-map loss only (train_online.py:127), 1/nAveGrad folded into the weight (train_online.py:140)
+            _, loss, per_map = net.forward_objective(inputs, gts, [v / n_ave_grad for v in ONLINE_WEIGHTS])
+            running = per_map[4].clone() if running is None else running + per_map[4]
             with net._engine.direct_grad_accumulation():
                 loss.backward()
             if (it + 1) % n_ave_grad == 0:
@@ -164,24 +175,32 @@ def online_finetune(net, sample_fn, iters, n_ave_grad=5, lr=1e-8, wd=0.0002, log
     return history
 
 
-def parent_epoch(net, opt, bucket, batches, epoch, n_epochs, n_ave_grad=1, group=None):
+def parent_epoch(net, opt, bucket, batches, epoch, n_epochs, n_ave_grad=1, group=None, state=None):
     """One epoch of the parent objective on this rank's shard: deep-supervision loss
     (1 - epoch/nEpochs) * sum_{k<4} L_k + L_fuse (train_parent.py:143-147), gradient accumulation over
-    `n_ave_grad` local micro-batches, then ONE allreduce(mean) and one SGD step."""
+    `n_ave_grad` local micro-batches, then ONE allreduce(mean) and one SGD step.
+    `state`: a dict the caller keeps across epochs; it carries the accumulation counter, which the reference does NOT
+    reset at epoch boundaries (`aveGrad`, train_parent.py:125,165-172) - leftover micro-batches of an epoch whose length
+    is not a multiple of nAveGrad complete their group in the next epoch instead of inflating its first step."""
     net.train()
+    if state is None:
+        state = {}
+    state.setdefault("ave_grad", 0)
     side_w = 1.0 - epoch / n_epochs
     totals = torch.zeros(5, device=bucket.flat.device)
     count = 0
     for it, sample in enumerate(batches):
-        outputs = net.forward(sample["image"])
-        losses = [class_balanced_cross_entropy_loss(o, sample["gt"], size_average=False) for o in outputs]
-        totals += torch.stack([l.detach() for l in losses])
+        # (1 - epoch/nEpochs) * sum(side losses) + fuse loss, / nAveGrad (train_parent.py:143-147,163), as the fused
+        # objective: tail + five losses are one kernel forward and one backward
+        w = [side_w / n_ave_grad] * 4 + [1.0 / n_ave_grad]
+        _, loss, per_map = net.forward_objective(sample["image"], sample["gt"], w)
+        totals += per_map
         count += 1
-        loss = side_w * sum(losses[:-1]) + losses[-1]
-        loss /= n_ave_grad
         with net._engine.direct_grad_accumulation():
             loss.backward()
-        if (it + 1) % n_ave_grad == 0:
+        state["ave_grad"] += 1
+        if state["ave_grad"] % n_ave_grad == 0:
+            state["ave_grad"] = 0
             bucket.allreduce_mean(group)
             if hasattr(opt, "_engine"):                     # optim.FusedSGD: update + zeroing + repack in one kernel
                 opt.step(zero_grad=True)

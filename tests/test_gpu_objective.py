@@ -1,0 +1,162 @@
+"""The package's fused objective (OSVOS.forward_objective): upsample + crop + fuse + the five class-balanced BCE losses
+as ONE kernel forward (osvos_tail_fwd with `losses`) and ONE kernel backward (osvos_tail_loss_bwd), replacing the
+reference's 5 x class_balanced_cross_entropy_loss + autograd (layers/osvos_layers.py:19-48, train_parent.py:143-147,
+train_online.py:127).  Checked against fp64 closed forms on CPU, against the oracle's autograd, and against this
+package's own unfused route (net(x) + five separate loss calls)."""
+import pytest
+import torch
+
+from oracle import osvos_oracle as oc
+from gpu_util import maxrel
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda:0")
+
+
+def _random_pqs(n, h, w, g, scale=5.0):
+    pqs, hk, wk = [], h, w
+    for _ in range(4):
+        hk, wk = oc.pooled_size(hk), oc.pooled_size(wk)
+        pqs.append(torch.randn(n, hk, wk, 2, generator=g) * scale)
+    return pqs
+
+
+def _ref_maps(pqs, fb, h, w):
+    outs, fused = [], fb.view(1, 1, 1, 1)
+    for k in range(4):
+        s = 2 ** (k + 1)
+        outs.append(oc.center_crop(oc.upsample_zero_padded(pqs[k][..., 0].unsqueeze(1), s), h, w))
+        fused = fused + oc.center_crop(oc.upsample_zero_padded(pqs[k][..., 1].unsqueeze(1), s), h, w)
+    return outs + [fused]
+
+
+@pytest.mark.parametrize("n,h,w", [(1, 48, 70), (2, 33, 45), (1, 240, 427), (1, 17, 3), (3, 64, 96)])
+@pytest.mark.parametrize("weights", [(0, 0, 0, 0, 1), (0.5, 0.5, 0.5, 0.5, 1), (1, 0, 2, 0, 0.25)])
+def test_tail_losses_and_fused_backward_vs_fp64_autograd(dev, n, h, w, weights):
+    from osvos_pytorch_b200 import ops
+    g = torch.Generator().manual_seed(17 + h)
+    pqs = _random_pqs(n, h, w, g)
+    fb = torch.randn(1, generator=g)
+    label = (torch.rand(n, 1, h, w, generator=g) > 0.7).float()
+    # fp64 reference with autograd: the oracle's loss on the oracle's maps
+    leaves = [p.double().requires_grad_(True) for p in pqs]
+    fbl = fb.double().requires_grad_(True)
+    maps = _ref_maps(leaves, fbl, h, w)
+    losses = [oc.class_balanced_cross_entropy_loss(m, label.double(), size_average=False) for m in maps]
+    total = sum(wk * l for wk, l in zip(weights, losses))
+    (3.0 * total).backward()                    # upstream gradient 3
+    out, sums, got_losses = ops.tail_fwd([p.to(dev) for p in pqs], fb.to(dev), n, h, w, label=label.to(dev),
+                                         loss_weights=weights, divisor=n)
+    gl = got_losses.cpu().double()
+    for k in range(5):
+        assert abs(float(gl[k]) - float(losses[k])) <= 2e-5 * max(1.0, abs(float(losses[k]))), (k, float(gl[k]), float(losses[k]))
+    assert abs(float(gl[5]) - float(total)) <= 2e-5 * max(1.0, abs(float(total)))
+    up = torch.full((), 3.0, device=dev)
+    dpq, dfb = ops.tail_loss_bwd(out, label.to(dev), sums, weights, n, up, n, h, w)
+    for k in range(4):
+        want = leaves[k].grad
+        if want is None:
+            assert float(dpq[k].abs().max()) == 0.0
+            continue
+        scale = float(want.abs().max())
+        assert float((dpq[k].cpu().double() - want).abs().max()) <= 2e-5 * scale, (k, maxrel(dpq[k], want))
+        if weights[k] == 0:
+            assert float(dpq[k][..., 0].abs().max()) == 0.0
+    if weights[4] != 0:
+        assert abs(float(dfb) - float(fbl.grad)) <= 2e-5 * max(1.0, abs(float(fbl.grad)))
+
+
+@pytest.mark.parametrize("n,h,w", [(1, 1080 // 4, 1920 // 4), (2, 100, 1040)])
+def test_tail_bwd_wide_rows_segmenting(dev, n, h, w):
+    """Rows wider than one 255-column segment at scale 2 (and odd sizes): the generic-gradient mode of the same kernel."""
+    from osvos_pytorch_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    grads = [torch.randn(n, 1, h, w, generator=g) for _ in range(5)]
+    pqs, hk, wk = [], h, w
+    for k in range(4):
+        hk, wk = oc.pooled_size(hk), oc.pooled_size(wk)
+        pqs.append(torch.zeros(n, hk, wk, 2, dtype=torch.float64, requires_grad=True))
+    maps = _ref_maps(pqs, torch.zeros(1, dtype=torch.float64), h, w)
+    sum((m * gr.double()).sum() for m, gr in zip(maps, grads)).backward()
+    got = ops.tail_bwd([t.to(dev) for t in grads], n, h, w)
+    for k in range(4):
+        assert maxrel(got[k], pqs[k].grad) < 2e-6
+
+
+@pytest.fixture(scope="module")
+def net(dev):
+    from osvos_pytorch_b200.networks.vgg_osvos import OSVOS
+    m = OSVOS(pretrained=0, verbose=False)
+    m.load_state_dict(oc.he_params(seed=0), strict=False)
+    return m.to(dev).train()
+
+
+@pytest.mark.parametrize("n,h,w,weights", [(1, 64, 96, (0, 0, 0, 0, 1)), (2, 40, 56, (0.5, 0.5, 0.5, 0.5, 1)),
+                                           (1, 240, 427, (0.25, 0.25, 0.25, 0.25, 1))])
+def test_forward_objective_equals_unfused_route(net, dev, n, h, w, weights):
+    """Same network kernels, same maps; only the tail/loss kernels differ -> gradients agree to fp32 reduction noise."""
+    from osvos_pytorch_b200.layers.osvos_layers import class_balanced_cross_entropy_loss as cbce
+    x, gt = oc.synthetic_frame(n, h, w, 91)
+    x, gt = x.to(dev), gt.to(dev)
+    net.zero_grad(set_to_none=True)
+    outs = net(x)
+    losses = [cbce(o, gt, size_average=False) for o in outs]
+    total = sum(wk * l for wk, l in zip(weights, losses) if wk != 0)
+    total.backward()
+    ref = {k: p.grad.detach().clone() for k, p in net.named_parameters() if p.grad is not None}
+    net.zero_grad(set_to_none=True)
+    maps, tot2, per_map = net.forward_objective(x, gt, weights)
+    tot2.backward()
+    for a, b in zip(maps, outs):
+        assert torch.equal(a, b.detach())
+    assert abs(float(tot2) - float(total)) <= 1e-5 * abs(float(total))
+    for k in range(5):
+        assert abs(float(per_map[k]) - float(losses[k])) <= 1e-5 * abs(float(losses[k]))
+    got = {k: p.grad for k, p in net.named_parameters() if p.grad is not None}
+    assert set(got) == set(ref)                       # same None pattern (score_dsn unsupervised under the online objective)
+    worst = 0.0
+    for k in ref:
+        err = float((got[k].double() - ref[k].double()).norm() / ref[k].double().norm().clamp(min=1e-30))
+        worst = max(worst, err)
+        assert err < 2e-4, (k, err)
+    print(f"fused objective vs unfused route {n}x{h}x{w}: worst per-parameter difference {worst:.2e}")
+
+
+def test_forward_objective_vs_oracle_parent(net, dev):
+    n, h, w, sw = 2, 40, 56, 0.5
+    x, gt = oc.synthetic_frame(n, h, w, 33)
+    loss, _, grads = oc.forward_backward(oc.he_params(seed=0), x, gt, objective="parent", side_weight=sw)
+    net.zero_grad(set_to_none=True)
+    _, total, _ = net.forward_objective(x.to(dev), gt.to(dev), (sw, sw, sw, sw, 1.0))
+    total.backward()
+    assert abs(float(total) - float(loss)) <= 1e-4 * abs(float(loss))
+    for k, p in net.named_parameters():
+        if k in grads:
+            err = float((p.grad.cpu().double() - grads[k].double()).norm() / grads[k].double().norm())
+            assert err < (1e-3 if k.startswith(("fuse", "score_dsn", "side_prep")) else 4e-2), (k, err)
+
+
+def test_graphed_step_with_fused_objective_accumulates(net, dev):
+    from osvos_pytorch_b200.training import GraphedTrainStep, ONLINE_WEIGHTS
+    x, gt = oc.synthetic_frame(1, 64, 96, 7)
+    sample = {"image": x.to(dev), "gt": gt.to(dev)}
+    net.zero_grad(set_to_none=True)
+    _, total, _ = net.forward_objective(sample["image"], sample["gt"], [v / 5 for v in ONLINE_WEIGHTS])
+    total.backward()
+    ref = {k: p.grad.detach().clone() for k, p in net.named_parameters() if p.grad is not None}
+    net.zero_grad(set_to_none=True)
+    step = GraphedTrainStep(net, ONLINE_WEIGHTS, sample, grad_scale=1.0 / 5)
+    step.zero_grads()
+    l1 = float(step(sample))
+    l2 = float(step(sample))
+    assert abs(l1 - 5 * float(total)) <= 1e-5 * abs(l1) and l1 == l2
+    for k, p in net.named_parameters():
+        if k in ref:
+            err = float((p.grad.double() - 2 * ref[k].double()).norm() / (2 * ref[k].double()).norm().clamp(min=1e-30))
+            assert err < 2e-4, (k, err)
+    net._engine.drop_derived_caches()

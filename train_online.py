@@ -126,17 +126,26 @@ def main():
     out_dir = os.path.join(save_dir, "Results", a.seq_name)
     os.makedirs(out_dir, exist_ok=True)
     net.eval()
-    with torch.no_grad():
+    # The reference's test loop (train_online.py:172-187): forward -> numpy sigmoid -> scipy.misc.imsave, which min-max
+    # bytescales each frame.  Same payload here, produced on the device (ops.logits_to_u8 mode "bytescale") with the
+    # H2D / forward / D2H legs of consecutive frames overlapped (inference.SequenceSegmenter).
+    import collections
+    from osvos_pytorch_b200.inference import SequenceSegmenter
+    names = collections.deque()
+
+    def frames():
         for ii, s in enumerate(test_frames):
-            outputs = net.forward(s["image"].to(device))
-            pred = torch.sigmoid(outputs[-1]).mul(255).byte().cpu().numpy()
-            for jj in range(pred.shape[0]):
-                name = os.path.basename(s["fname"][jj]) if "fname" in s else f"{ii:05d}"
-                try:
-                    import cv2
-                    cv2.imwrite(os.path.join(out_dir, name + ".png"), pred[jj, 0])
-                except ImportError:
-                    np.save(os.path.join(out_dir, name + ".npy"), pred[jj, 0])
+            n = int(s["image"].shape[0])
+            names.append([os.path.basename(s["fname"][jj]) if "fname" in s else f"{ii:05d}_{jj}" for jj in range(n)])
+            yield s["image"]
+    for pred in SequenceSegmenter(net, output="bytescale")(frames()):
+        arr = pred.numpy()
+        for jj, name in enumerate(names.popleft()):
+            try:
+                from PIL import Image
+                Image.fromarray(arr[jj, 0], mode="L").save(os.path.join(out_dir, name + ".png"))
+            except ImportError:
+                np.save(os.path.join(out_dir, name + ".npy"), arr[jj, 0])
     return history
 
 

@@ -59,13 +59,15 @@ def main():
         ckpt = os.path.join(save_dir, f"{a.model_name}_epoch-{a.resume_epoch - 1}.pth")
         net.load_state_dict(torch.load(ckpt, map_location="cpu"))
     net.to(device)
+    parallel.broadcast_parameters(net, src=0)        # replicas must be ONE model (the reference's init is unseeded)
     opt = training.make_optimizer(net, "parent", a.lr, a.wd, fused=True)
     bucket = parallel.GradientBucket(parallel.trainable_parameters(net), device)
 
     if a.synthetic:
         def epoch_batches(epoch):
-            lo, hi = parallel.shard_range(a.iters_per_epoch, rank, world)
-            for i in range(lo, hi):
+            # the same number of micro-batches on every rank (a multiple of n_ave): every rank joins every allreduce
+            per = parallel.steps_per_rank(a.iters_per_epoch, world, n_ave)
+            for i in range(rank * per, (rank + 1) * per):
                 yield training.synthetic_batch(a.batch, a.height, a.width, 7919 * epoch + i, device)
         val_batches = None
     else:
@@ -77,8 +79,9 @@ def main():
         aug = transforms.Compose([tr.RandomHorizontalFlip(), tr.ScaleNRotate(rots=(-30, 30), scales=(.75, 1.25)),
                                   tr.ToTensor()])
         db_train = db.DAVIS2016(train=True, inputRes=None, db_root_dir=Path.db_root_dir(), transform=aug)
-        sampler = DistributedSampler(db_train, world, rank, shuffle=True) if world > 1 else None
-        loader = DataLoader(db_train, batch_size=a.batch, shuffle=sampler is None, sampler=sampler, num_workers=2)
+        sampler = DistributedSampler(db_train, world, rank, shuffle=True, drop_last=True) if world > 1 else None
+        loader = DataLoader(db_train, batch_size=a.batch, shuffle=sampler is None, sampler=sampler, num_workers=2,
+                            drop_last=world > 1)
         db_test = db.DAVIS2016(train=False, db_root_dir=Path.db_root_dir(), transform=tr.ToTensor())
         val_batches = DataLoader(db_test, batch_size=1, shuffle=False, num_workers=2)
 
@@ -91,9 +94,10 @@ def main():
     if rank == 0:
         print(f"Training Network on {world} GPU(s): batch/rank {a.batch}, local nAveGrad {n_ave}, "
               f"gradient allreduce payload {bucket.numel * 4 / 1e6:.1f} MB per optimizer step")
+    loop_state = {}                                  # accumulation counter, carried across epochs as in the reference
     for epoch in range(a.resume_epoch, a.epochs):
         t0 = timeit.default_timer()
-        losses = training.parent_epoch(net, opt, bucket, epoch_batches(epoch), epoch, a.epochs, n_ave)
+        losses = training.parent_epoch(net, opt, bucket, epoch_batches(epoch), epoch, a.epochs, n_ave, state=loop_state)
         torch.cuda.synchronize()
         if rank == 0:
             print(f"[Epoch: {epoch}] " + " ".join(f"Loss {k}: {v:.4f}" for k, v in enumerate(losses))

@@ -171,23 +171,46 @@ def upsample_zero_padded(x: torch.Tensor, stride: int) -> torch.Tensor:
 # --------------------------------------------------------------------------
 # network forward, networks/vgg_osvos.py:59-74
 # --------------------------------------------------------------------------
-def trunk_forward(params: Dict[str, torch.Tensor], x: torch.Tensor) -> List[torch.Tensor]:
-    """Outputs of the five stages (each after its last ReLU), networks/vgg_osvos.py:61,66."""
+def trunk_forward(params: Dict[str, torch.Tensor], x: torch.Tensor, gates=None) -> List[torch.Tensor]:
+    """Outputs of the five stages (each after its last ReLU), networks/vgg_osvos.py:61,66.
+
+    ``gates`` (test aid, see ``gates_from_activations``): the SELECTIONS of the network's two discontinuous ops taken
+    from another implementation's forward pass - ``gates["relu"][k]`` a 0/1 mask replacing ``z > 0`` of conv k,
+    ``gates["pool"][i]`` the flat argmax indices of pooling i.  With them the network is the same piecewise-linear
+    function evaluated on the other implementation's linear piece, so gradients can be compared without the
+    mask / argmax flips that a 1e-5 forward difference causes (tests/test_gpu_backward.py)."""
     names = trunk_conv_names()
     k = 0
     outs = []
     for i, chans in enumerate(STAGE_CHANNELS):
         if i > 0:
-            x = F.max_pool2d(x, kernel_size=2, stride=2, ceil_mode=True)
+            if gates is None:
+                x = F.max_pool2d(x, kernel_size=2, stride=2, ceil_mode=True)
+            else:
+                idx = gates["pool"][i - 1]
+                x = x.flatten(2).gather(2, idx.flatten(2)).view(idx.shape)
         for _ in chans:
-            x = F.relu(F.conv2d(x, params[names[k] + ".weight"], params[names[k] + ".bias"], padding=1))
+            z = F.conv2d(x, params[names[k] + ".weight"], params[names[k] + ".bias"], padding=1)
+            x = F.relu(z) if gates is None else z * gates["relu"][k].to(z.dtype)
             k += 1
         outs.append(x)
     return outs
 
 
+def gates_from_activations(conv_outputs: Sequence[torch.Tensor]):
+    """ReLU masks and pooling argmax indices implied by the 13 post-ReLU trunk activations (NCHW) of a forward pass."""
+    relu = [(a > 0) for a in conv_outputs]
+    pool, k = [], 0
+    for i, chans in enumerate(STAGE_CHANNELS):
+        k += len(chans)
+        if i < len(STAGE_CHANNELS) - 1:
+            pool.append(F.max_pool2d(conv_outputs[k - 1].float(), kernel_size=2, stride=2, ceil_mode=True,
+                                     return_indices=True)[1])
+    return {"relu": relu, "pool": pool}
+
+
 def osvos_forward(params: Dict[str, torch.Tensor], x: torch.Tensor,
-                  return_side_feats: bool = False):
+                  return_side_feats: bool = False, gates=None):
     """The five logit maps [side_out1..4, fused], networks/vgg_osvos.py:59-74.
 
     The side branch is computed in the fused form proved equivalent in
@@ -197,7 +220,7 @@ def osvos_forward(params: Dict[str, torch.Tensor], x: torch.Tensor,
     this against the reference's literal cat + 1x1-conv route.
     """
     h, w = int(x.shape[-2]), int(x.shape[-1])
-    stage_out = trunk_forward(params, x)
+    stage_out = trunk_forward(params, x, gates)
     side_out, side_feats = [], []
     fused = None
     wf = params["fuse.weight"]
@@ -301,7 +324,7 @@ def parent_objective(outputs: Sequence[torch.Tensor], gts: torch.Tensor, side_we
 
 def forward_backward(params: Dict[str, torch.Tensor], x: torch.Tensor, gts: torch.Tensor,
                      objective: str = "online", side_weight: float = 1.0,
-                     grad_scale: float = 1.0):
+                     grad_scale: float = 1.0, gates=None):
     """One fwd+bwd of the reference loop body (train_online.py:124-141 /
     train_parent.py:140-164): returns (loss, outputs, grads dict).  ``grad_scale``
     is the 1/nAveGrad factor of train_online.py:140.  Autograd over the oracle
@@ -309,7 +332,7 @@ def forward_backward(params: Dict[str, torch.Tensor], x: torch.Tensor, gts: torc
     (SURVEY.md section 8c item 9)."""
     leaves = {k: v.detach().clone().requires_grad_(True) for k, v in params.items()
               if not k.startswith("upscale")}
-    outs = osvos_forward(leaves, x)
+    outs = osvos_forward(leaves, x, gates=gates)
     if objective == "online":
         loss = online_objective(outs, gts)
     else:

@@ -61,6 +61,8 @@ class _OSVOSFunction(torch.autograd.Function):
         ctx.engine = engine
         ctx.dims = (n, h, w)
         ctx.fast = fast
+        if getattr(engine, "debug_capture", None) is not None:      # tests: the saved activations of this pass
+            engine.debug_capture.update(acts=acts, pooled=pooled, feats=feats)
         if objective is None:
             out, _ = ops.tail_fwd(pqs, m.fuse.bias.detach(), n, h, w)
             ctx.objective = None

@@ -19,7 +19,7 @@ pytestmark = pytest.mark.gpu
 # flip moves the gradient norm by ~sqrt(eps) per layer (scripts/grad_debug.py shows the step-wise jumps; feeding
 # the oracle's exact dL/dlogit changes nothing).  Measured 1e-3 .. 7e-3 per trunk parameter; any two fp32
 # implementations with different summation orders show the same effect at a slightly lower level.
-GRAD_TOL = 1e-2
+GRAD_TOL = 2e-3
 # On the 40x56 / 64x96 fixtures the deepest maps hold only 3x4x512 .. 4x6x512 values: ONE flipped ReLU mask there
 # moves a gradient norm by ~sqrt(1/3000) = 1.8e-2 (scripts/grad_debug.py counts the flips), so the tiny cases get
 # a looser bound; the 480x854 case (8e-4 measured) keeps GRAD_TOL.
@@ -349,3 +349,74 @@ def test_direct_grad_accumulation_equals_autograd_accumulation():
     with net._engine.direct_grad_accumulation():
         cbce(net(x)[-1], gt, size_average=False).backward()
     assert net.stages[2][1].weight.grad is not None and net.score_dsn[0].weight.grad is None
+
+
+def _gated_oracle_grads(net, x, gt, objective, side_weight=1.0):
+    """One CUDA fwd+bwd with its saved activations captured, then the oracle's fwd+bwd evaluated ON THE SAME LINEAR PIECE
+    of the network: the CUDA pass's ReLU masks and pooling argmax are injected into the oracle (oc.trunk_forward `gates`),
+    which removes the only discontinuities between input and loss.  What remains is the backward arithmetic itself."""
+    from osvos_pytorch_b200 import ops
+    from osvos_pytorch_b200.layers.osvos_layers import class_balanced_cross_entropy_loss as cbce
+    params = {k: v.detach().cpu() for k, v in net.state_dict().items() if not k.startswith("upscale")}
+    cap = {}
+    net._engine.debug_capture = cap
+    try:
+        net.zero_grad()
+        outs = net(x.cuda())
+        if objective == "online":
+            loss = cbce(outs[-1], gt.cuda(), size_average=False)
+        else:
+            ls = [cbce(o, gt.cuda(), size_average=False) for o in outs]
+            loss = side_weight * sum(ls[:-1]) + ls[-1]
+        loss.backward()
+    finally:
+        net._engine.debug_capture = None
+    conv_outs = [ops.act_to_nchw(a).cpu() for stage in cap["acts"] for a in stage]
+    assert len(conv_outs) == 13
+    gates = oc.gates_from_activations(conv_outs)
+    ref_loss, _, ograds = oc.forward_backward(params, x, gt, objective=objective, side_weight=side_weight, gates=gates)
+    _, _, free = oc.forward_backward(params, x, gt, objective=objective, side_weight=side_weight)
+    flips = [int((g != (f > 0)).sum()) for g, f in zip(gates["relu"], _oracle_conv_outputs(params, x))]
+    errs = {n: relnorm(p.grad, ograds[n]) for n, p in net.named_parameters() if n in ograds}
+    errs_free = {n: relnorm(p.grad, free[n]) for n, p in net.named_parameters() if n in free}
+    return float(loss), float(ref_loss), errs, errs_free, flips
+
+
+def _oracle_conv_outputs(params, x):
+    names = oc.trunk_conv_names()
+    outs, k, a = [], 0, x
+    with torch.no_grad():
+        for i, chans in enumerate(oc.STAGE_CHANNELS):
+            if i > 0:
+                a = F.max_pool2d(a, 2, 2, ceil_mode=True)
+            for _ in chans:
+                a = F.relu(F.conv2d(a, params[names[k] + ".weight"], params[names[k] + ".bias"], padding=1))
+                outs.append(a)
+                k += 1
+    return outs
+
+
+# Gradient bound with the discontinuities removed (ReLU masks / pool argmax of the CUDA pass injected into the oracle):
+# only fp32-class arithmetic differences remain.
+GATED_TOL = 2e-4
+
+
+@pytest.mark.parametrize("n,h,w,objective", [(1, 40, 56, "online"), (2, 40, 56, "parent"), (1, 64, 96, "online")])
+def test_backward_with_injected_gates_small(net, n, h, w, objective):
+    x, gt = oc.synthetic_frame(n, h, w, 311)
+    loss, ref_loss, errs, errs_free, flips = _gated_oracle_grads(net, x, gt, objective, side_weight=0.5)
+    worst = max(errs, key=errs.get)
+    print(f"gated {objective} {n}x{h}x{w}: worst {errs[worst]:.2e} ({worst}); ungated worst {max(errs_free.values()):.2e}; "
+          f"ReLU mask flips per conv (CUDA vs oracle forward): {flips}")
+    assert abs(loss - ref_loss) < 1e-4 * abs(ref_loss)
+    assert errs[worst] < GATED_TOL, (worst, errs[worst])
+
+
+def test_backward_with_injected_gates_480p(net):
+    x, gt = oc.synthetic_frame(1, 480, 854, 1234)
+    loss, ref_loss, errs, errs_free, flips = _gated_oracle_grads(net, x, gt, "online")
+    worst, worst_free = max(errs, key=errs.get), max(errs_free, key=errs_free.get)
+    print(f"gated online 480p: worst {errs[worst]:.2e} ({worst}); ungated worst {errs_free[worst_free]:.2e} ({worst_free}); "
+          f"ReLU mask flips per conv: {flips} of {[480 * 854 * 64] * 2 + [240 * 427 * 128] * 2} ... elements")
+    assert errs[worst] < GATED_TOL, (worst, errs[worst])
+    assert errs_free[worst_free] < 2e-3, (worst_free, errs_free[worst_free])      # the ungated bound at 480p (8e-4 measured)

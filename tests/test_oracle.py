@@ -262,3 +262,30 @@ def test_scale_n_rotate_known_answers():
     assert np.allclose(oc.scale_n_rotate(const, 10.0, 1.2, False, False)[0, 3:9, 4:13], 3.0, atol=1e-5)   # weights sum to 1
     q = oc.scale_n_rotate(img, 17.0, 0.9, True, False)
     assert q.shape == img.shape and np.isfinite(q).all() and abs(q).max() <= abs(img).max() * 1.6
+
+
+def test_gated_forward_is_the_same_piecewise_linear_function():
+    """oc.trunk_forward(gates=...) with the gates of the oracle's OWN forward reproduces outputs and gradients exactly
+    (the gated form is the test aid of tests/test_gpu_backward.py::test_backward_with_injected_gates_*)."""
+    import torch.nn.functional as F
+    params = oc.he_params(seed=0)
+    x, gt = oc.synthetic_frame(2, 33, 45, 5)
+    names = oc.trunk_conv_names()
+    outs, k, a = [], 0, x
+    with torch.no_grad():
+        for i, chans in enumerate(oc.STAGE_CHANNELS):
+            if i > 0:
+                a = F.max_pool2d(a, 2, 2, ceil_mode=True)
+            for _ in chans:
+                a = F.relu(F.conv2d(a, params[names[k] + ".weight"], params[names[k] + ".bias"], padding=1))
+                outs.append(a)
+                k += 1
+    gates = oc.gates_from_activations(outs)
+    l0, o0, g0 = oc.forward_backward(params, x, gt, objective="parent", side_weight=0.5)
+    l1, o1, g1 = oc.forward_backward(params, x, gt, objective="parent", side_weight=0.5, gates=gates)
+    assert float(l0) == float(l1)
+    for a, b in zip(o0, o1):
+        assert torch.equal(a, b)
+    assert set(g0) == set(g1)
+    for k in g0:
+        assert torch.allclose(g0[k], g1[k], rtol=1e-6, atol=1e-9), k

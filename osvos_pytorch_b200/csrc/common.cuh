@@ -64,6 +64,19 @@ static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 blo
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
+// Opt-in to > 48 KiB of dynamic shared memory, once per (kernel instantiation, DEVICE): the attribute is per device, and
+// the engine supports modules on any GPU of the process.  `done_mask` is the call site's static bit mask of devices.
+template <typename K>
+static inline cudaError_t ensure_dynamic_smem(K kern, int bytes, uint64_t* done_mask) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 64 && ((*done_mask >> dev) & 1ull)) return cudaSuccess;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess && dev < 64) *done_mask |= 1ull << dev;
+  return e;
+}
+
 // ---- split-bf16 ("bf16x2") representation of an fp32 value: v ~= hi + lo ------
 __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
   hi = __float2bfloat16_rn(v);

@@ -349,11 +349,8 @@ static int launch_halo(const osvos_conv3x3_args* a, cudaStream_t stream, int use
     if (rc) return rc;
   }
   auto kern = conv3x3_halo_kernel<BLOCK_N, PLANES, PITCH, SPLIT, STORE>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    OSVOS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_done = true;
-  }
+  static uint64_t attr_done = 0;   // per instantiation: bit d = device d has the shared-memory opt-in
+  OSVOS_CHECK_CUDA(ensure_dynamic_smem(kern, Cfg::kSmemBytes, &attr_done));
   const int sms = device_sm_count();
   const int grid = ksplit > 1 ? p.total_tiles * ksplit : (p.total_tiles < sms ? p.total_tiles : sms);
   OSVOS_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(64 + EpiCfg<BLOCK_N>::kThreads), Cfg::kSmemBytes, stream, mx_hi, mx_lo,

@@ -245,11 +245,8 @@ static int launch_halo2(const osvos_conv3x3_args* a, cudaStream_t stream) {
   int rc = encode_weight_maps(&mw_hi, &mw_lo, a, Cfg::kHalfN);  // box = half of the N block per CTA
   if (rc) return rc;
   auto kern = conv3x3_halo2_kernel<BLOCK_N, PLANES>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    OSVOS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_done = true;
-  }
+  static uint64_t attr_done = 0;   // per instantiation: bit d = device d has the shared-memory opt-in
+  OSVOS_CHECK_CUDA(ensure_dynamic_smem(kern, Cfg::kSmemBytes, &attr_done));
   const int sms = device_sm_count();
   int clusters = sms / 2;
   if (clusters > p.total_pairs) clusters = p.total_pairs;

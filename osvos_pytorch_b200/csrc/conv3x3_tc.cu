@@ -206,11 +206,8 @@ static int launch_conv(const osvos_conv3x3_args* a, cudaStream_t stream) {
   }
 
   auto kern = conv3x3_tc_kernel<BLOCK_N, PLANES>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    OSVOS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_done = true;
-  }
+  static uint64_t attr_done = 0;   // per instantiation: bit d = device d has the shared-memory opt-in
+  OSVOS_CHECK_CUDA(ensure_dynamic_smem(kern, Cfg::kSmemBytes, &attr_done));
   const int sms = device_sm_count();
   const int grid = p.total_tiles < sms ? p.total_tiles : sms;
   kern<<<grid, 64 + EpiCfg<BLOCK_N>::kThreads, Cfg::kSmemBytes, stream>>>(mx_hi, mx_lo, mw_hi, mw_lo, p);

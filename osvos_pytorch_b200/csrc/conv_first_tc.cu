@@ -223,11 +223,8 @@ int conv_first_tc_launch(const float* x, const float* w_oihw, const float* bias,
   }
   const bool fast = (flags & OSVOS_FLAG_FAST) != 0;
   auto kern = fast ? conv_first_tc_kernel<1> : conv_first_tc_kernel<2>;
-  static bool attr_done[2] = {false, false};
-  if (!attr_done[fast ? 1 : 0]) {
-    OSVOS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kFirstSmem));
-    attr_done[fast ? 1 : 0] = true;
-  }
+  static uint64_t attr_done[2] = {0, 0};   // per instantiation: bit d = device d has the shared-memory opt-in
+  OSVOS_CHECK_CUDA(ensure_dynamic_smem(kern, kFirstSmem, &attr_done[fast ? 1 : 0]));
   const int sms = device_sm_count();
   const int grid = p.total_tiles < sms ? p.total_tiles : sms;
   OSVOS_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(kFirstTcThreads), kFirstSmem, stream, x, w_oihw, my_hi, my_lo, p));

@@ -302,11 +302,8 @@ static int launch_side(const osvos_conv3x3_args* a, cudaStream_t stream) {
     if (rc) return rc;
   }
   auto kern = side_conv_kernel<PLANES>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    OSVOS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
-    attr_done = true;
-  }
+  static uint64_t attr_done = 0;   // per instantiation: bit d = device d has the shared-memory opt-in
+  OSVOS_CHECK_CUDA(ensure_dynamic_smem(kern, Cfg::kSmem, &attr_done));
   const int sms = device_sm_count();
   const int grid = p.total_tiles < sms ? p.total_tiles : sms;
   OSVOS_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(kSideThreads), Cfg::kSmem, stream, mx_hi, mx_lo, mw_hi, mw_lo, p));

@@ -439,11 +439,8 @@ static int launch_wgrad(const osvos_wgrad_args* a, cudaStream_t stream) {
   const size_t ws_bytes = static_cast<size_t>(9) * p.m_total * p.n_total * sizeof(float);
   if (!deferred) OSVOS_CHECK_CUDA(cudaMemsetAsync(a->workspace, 0, ws_bytes, stream));
   auto kern = wgrad_tc_kernel<BLOCK_N, PLANES>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    OSVOS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_done = true;
-  }
+  static uint64_t attr_done = 0;   // per instantiation: bit d = device d has the shared-memory opt-in
+  OSVOS_CHECK_CUDA(ensure_dynamic_smem(kern, Cfg::kSmemBytes, &attr_done));
   const int grid = p.total_items < sms ? p.total_items : sms;
   if (deferred) {   // (otherwise the memset above is this kernel's stream predecessor: plain launch)
     OSVOS_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(kWgThreads), Cfg::kSmemBytes, stream, mp_hi, mp_lo, mq_hi, mq_lo, p));

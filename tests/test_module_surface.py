@@ -79,3 +79,46 @@ def test_layer_helpers(golden):
     assert abs(L.sigmoid_np(L.logit(np.array(0.3))) - 0.3) < 1e-6
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         L.class_balanced_cross_entropy_loss(torch.zeros(1, 1, 2, 2), torch.zeros(1, 1, 2, 2))
+
+
+def test_caffe_vgg_loader_matches_the_reference_loader(tmp_path, monkeypatch):
+    """`OSVOS(pretrained=2)` reads models/vgg_caffe.mat exactly like the reference's loader
+    (networks/vgg_osvos.py:110-125): a synthetic .mat in the Caffe export layout (weights[0][k] = (kw, kh, cin, cout),
+    biases[0][k] = (cout, 1)) goes through BOTH loaders - the reference's own (oracle/_ref, unmodified) and this
+    package's - and every trunk tensor must come out bit-identical."""
+    import numpy as np
+    import scipy.io
+    import torch
+    from oracle import osvos_oracle as oc
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("oracle/_ref not built (bash oracle/make_ref.sh; needs /root/reference)")
+    rng = np.random.default_rng(5)
+    shapes = [oc.param_shapes()[n + ".weight"] for n in oc.trunk_conv_names()]
+    weights = np.empty((1, len(shapes)), dtype=object)
+    biases = np.empty((1, len(shapes)), dtype=object)
+    for k, (co, ci, kh, kw) in enumerate(shapes):
+        weights[0, k] = rng.standard_normal((kw, kh, ci, co)).astype(np.float32)
+        biases[0, k] = rng.standard_normal((co, 1)).astype(np.float32)
+    (tmp_path / "models").mkdir()
+    scipy.io.savemat(str(tmp_path / "models" / "vgg_caffe.mat"), {"weights": weights, "biases": biases})
+    monkeypatch.chdir(tmp_path)                       # both Path.models_dir() default to ./models
+    monkeypatch.delenv("OSVOS_MODELS_DIR", raising=False)
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        ref_net = ref_loader.load().net.OSVOS(pretrained=2)
+    from osvos_pytorch_b200.networks.vgg_osvos import OSVOS
+    mine = OSVOS(pretrained=2, verbose=False)
+    ref_sd, my_sd = ref_net.state_dict(), mine.state_dict()
+    assert list(ref_sd.keys()) == list(my_sd.keys())
+    checked = 0
+    for name in ref_sd:
+        if name.startswith("stages."):
+            assert torch.equal(ref_sd[name], my_sd[name]), name
+            checked += 1
+    assert checked == 26
+    # the tensor the kernels will read is what Caffe stored: conv k, output channel o, input channel i, tap (r, s)
+    k, (co, ci, kh, kw) = 3, shapes[3]
+    w = my_sd[oc.trunk_conv_names()[k] + ".weight"]
+    assert float(w[5, 7, 1, 2]) == float(weights[0, k][2, 1, 7, 5])

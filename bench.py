@@ -333,14 +333,22 @@ def run_dp(args, rank, world, local, dev, timer, steps):
     from osvos_pytorch_b200 import ops, parallel, training
     from osvos_pytorch_b200.networks.vgg_osvos import OSVOS, he_init_
     parity = dp_parity(rank, world, dev, args.precision)
-    net = he_init_(OSVOS(pretrained=0, verbose=False, precision=args.precision), seed=0).to(dev)
-    opt = training.make_optimizer(net, "parent", fused=True)   # one-launch SGD + grad zeroing + weight repack
+    net = he_init_(OSVOS(pretrained=0, verbose=False, precision=args.precision), seed=0)
+    with torch.no_grad():               # keep the synthetic logits O(10), as train_online.py --synthetic does
+        for mod in list(net.side_prep) + [net.fuse]:
+            mod.weight.mul_(0.1)
+    net = net.to(dev)
+    parallel.broadcast_parameters(net, src=0)
+    # one-launch SGD + grad zeroing + weight repack.  lr: He-init synthetic weights give O(1e5) summed losses whose
+    # gradients make the reference's 1e-8 diverge within tens of steps; the arithmetic of a step does not depend on lr.
+    opt = training.make_optimizer(net, "parent", lr=args.dp_lr, fused=True)
     bucket = parallel.GradientBucket(parallel.trainable_parameters(net), dev)
     bucket.time_collective = True
     batches = [training.synthetic_batch(args.batch, H, W, 1000 * rank + i, dev) for i in range(2)]
+    loss_log = []
 
     def one(i):
-        training.parent_epoch(net, opt, bucket, [batches[i % 2]], 0, 240, 1)
+        loss_log.append(training.parent_epoch(net, opt, bucket, [batches[i % 2]], 0, 240, 1))
     for i in range(3):
         one(i)
     torch.cuda.synchronize()
@@ -372,12 +380,14 @@ def run_dp(args, rank, world, local, dev, timer, steps):
         net.train()
     if world > 1:
         dist.all_reduce(finite, op=dist.ReduceOp.MIN)
+    torch.cuda.synchronize()
+    first, last = [float(v) for v in loss_log[0]], [float(v) for v in loss_log[-1]]     # device tensors until here
     if rank != 0:
         return None
     fps = world * args.batch * 1000.0 / ms
     return {"workload": f"parent480 (BASELINE configs[3]): per-GPU batch {args.batch} x 3x{H}x{W} synthetic frames, global "
-                        f"batch {world * args.batch}, 5-loss parent objective (train_parent.py:143-147), FusedSGD(lr 1e-8, "
-                        f"mom .9, wd 2e-4), one optimizer step per step",
+                        f"batch {world * args.batch}, 5-loss parent objective (train_parent.py:143-147), FusedSGD(lr {args.dp_lr:g}, "
+                        f"mom .9, wd 2e-4), one optimizer step per step; He-init weights with the side branch scaled by 0.1",
             "parallelism": f"dp{world}: one ncclAllReduce(AVG) of the flat fp32 gradient bucket "
                            f"({bucket.numel * 4 / 1e6:.1f} MB) per step; weak scaling",
             "fps": fps, "fps_per_gpu": fps / world, "ms_per_step": ms, "steps": steps, **info,
@@ -387,6 +397,8 @@ def run_dp(args, rank, world, local, dev, timer, steps):
                               "between events around it inside the timed steps, max over ranks (payload + waiting for the "
                               "slowest rank = skew)",
             "nccl_ranks": world, "gpu_launches": int(launches), "outputs_finite_all_ranks": bool(float(finite) == 1.0),
+            "optimizer_steps_run": len(loss_log), "losses_first_step": first, "losses_last_step": last,
+            "losses_finite": bool(all(math.isfinite(v) for v in first + last)),
             "dtype": "bf16x3 (split-bf16 operands, fp32 accumulate)" if args.precision == "exact" else "bf16",
             "parity": parity, "clocks": clocks}
 
@@ -411,7 +423,8 @@ def forward_parity(net, dev):
         diff = (g > 0) != (r > 0)
         outside = diff & (r.abs() > 1e-3 * scale)
         gi, ri = g > 0, r > 0
-        iou = float((gi & ri).sum()) / max(1.0, float((gi | ri).sum()))
+        union = float((gi | ri).sum())
+        iou = float((gi & ri).sum()) / union if union > 0 else 1.0          # both masks empty: identical
         maps[n] = {"max_rel": float((g - r).abs().max()) / scale, "rms_rel": float((g - r).pow(2).mean().sqrt()) / scale,
                    "mask_flips": int(diff.sum()), "mask_flips_outside_band": int(outside.sum()), "iou": iou}
         flips_total += int(diff.sum())
@@ -516,6 +529,7 @@ def main():
     ap.add_argument("--batch", type=int, default=12, help="parent480 / dp: frames per GPU per optimizer step")
     ap.add_argument("--precision", default="exact", choices=["exact", "fast"])
     ap.add_argument("--dp-steps", type=int, default=10, help="optimizer steps per timed block of the dp leg")
+    ap.add_argument("--dp-lr", type=float, default=1e-10, help="learning rate of the dp leg (see run_dp)")
     ap.add_argument("--skip", default="", help="comma list of legs to skip: dp,parity,gpu_reference,cpu_baseline,roofline,e2e_extra")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager-train", action="store_true", help="train480: eager launches instead of the step graph")

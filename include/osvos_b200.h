@@ -117,14 +117,26 @@ typedef struct {
    * chunk can be non-zero (the 16-channel side-branch gradient is stored padded to 64): the remaining K steps
    * are skipped - fewer tcgen05.mma, identical result. */
   int k_valid;
-  /* optional split-K workspace (osvos_conv3x3_splitk_workspace_bytes bytes, or NULL): layers with fewer output
-   * tiles than half the SMs (stage 5 at 480p: 56 tiles of 128 px x 128 channels) then run 2 or 4 CTAs per tile,
-   * each reducing a share of the input channels; the helpers' fp32 partial accumulators go through this buffer. */
-  void* splitk_ws;
+  /* optional stream-K workspace (osvos_conv3x3_streamk_workspace_bytes() bytes, ZERO-FILLED once by the caller and
+   * then reused across calls on the same stream; or NULL): layers whose 128 x 128 tiles leave much of the last wave
+   * idle (stage 4 at 480x854: 224 tiles on 148 SMs; stage 5: 56) are then scheduled by (tile, 64-channel chunk)
+   * units in balanced contiguous ranges; tiles cut by a range boundary exchange fp32 partial accumulators through
+   * this buffer.  The kernel leaves the buffer's counters at zero again.  Results differ from the whole-tile
+   * schedule only by fp32 summation order. */
+  void* streamk_ws;
 } osvos_conv3x3_args;
 OSVOS_API int osvos_conv3x3(const osvos_conv3x3_args* args /* host */, osvos_stream_t stream);
-/* 0 when the layer would not be split (then splitk_ws may be NULL). */
-OSVOS_API size_t osvos_conv3x3_splitk_workspace_bytes(int n, int h, int w, int cin, int cout);
+OSVOS_API size_t osvos_conv3x3_streamk_workspace_bytes(void);
+
+/* ---- folded side branch (inference) ---------------------------------------------------
+ * side_prep has no ReLU (networks/vgg_osvos.py:67), so side_prep followed by score_dsn and this scale's slice of
+ * fuse (:44,54,69,72) is ONE 3x3 convolution C -> 2:  W'[o][ci][tap] = sum_co proj_w[16 o + co] * side_w[co][ci][tap],
+ * b'[o] = (o == 0 ? proj_b : 0) + sum_co proj_w[16 o + co] * side_b[co].  This writes W' in the packed operand layout
+ * (osvos_packed_weight_bytes(2, cin) bytes) and b' (2 floats); osvos_conv3x3 with cout == 2, w_packed = packed,
+ * bias = bias2 and pq set then produces the same pq as the cout == 16 call with projections, at 1/8 of the columns. */
+OSVOS_API int osvos_fold_side_weights(const float* side_w /* [16,cin,3,3] */, const float* side_b /* [16] or NULL */,
+                                      const float* proj_w /* [32] */, const float* proj_b /* [1] or NULL */, void* packed,
+                                      float* bias2 /* [2] */, int cin, osvos_stream_t stream);
 /* Same contract on CUDA cores (fp32 FMA over hi+lo); debugging cross-check only. */
 OSVOS_API int osvos_conv3x3_simt(const osvos_conv3x3_args* args /* host */, osvos_stream_t stream);
 

@@ -10,12 +10,12 @@
 //
 // PITCH is the smem row pitch in pixels: 10 packs the patch rows (1280 B) and relies on the UMMA swizzle being a
 // function of the absolute shared-memory address, validated on hardware together with the padded 16-pixel pitch and the
-// descriptor's base-offset field (scripts/halo_experiment.py; the base-offset field must stay 0).  The kernel keeps
-// its trailing `use_base_offset` parameter for that experiment's launcher but no longer reads it.
+// descriptor's base-offset field in round 1 (the base-offset field must stay 0).
 //
 // Producer and issuer loops: one elected thread each, taps unrolled, descriptors by addition - see the comments at
 // the two loops and DESIGN.md section 4 for the measurements behind that.
 #include <stdlib.h>
+#include <string.h>
 
 #include <type_traits>
 
@@ -25,7 +25,7 @@ namespace osvos {
 
 constexpr int kHaloRows = kTileH + 2;  // 18
 
-template <int BLOCK_N, int PLANES, int PITCH, bool SPLIT, int STORE = 0>
+template <int BLOCK_N, int PLANES, int PITCH, bool SPLIT, bool LEAN = false>
 struct HaloCfg {
   static constexpr int kABoxBytes = kHaloRows * PITCH * 128;                // one plane, one chunk
   static constexpr int kAPlaneBytes = (kABoxBytes + 1023) / 1024 * 1024;    // keep 1 KiB alignment
@@ -33,13 +33,8 @@ struct HaloCfg {
   static constexpr int kAStages = 2;
   static constexpr int kBPlaneBytes = BLOCK_N * 128;
   static constexpr int kBStageBytes = PLANES * kBPlaneBytes;
-  // Output store flavour STORE: 0 = 16-byte direct stores (default), 1 = bulk tensor stores through a staging buffer,
-  // 2 = 32-byte direct stores (st.global.v8.b32), 3 / 4 = the lean forward-only epilogue (conv_common.cuh; 32-byte stores,
-  // pipelined tcgen05.ld, early accumulator release; 4: channel-split max pool).  TMA-store staging (hi + lo slab), STORE == 1 only.  Measured in round 1 while the MMA issuer was still the bottleneck: no
-  // faster than direct 16-byte stores, and its 32 KiB cost one weight-ring stage - so it is off by default.  The direct
-  // stores do cost the epilogue-bound layers (32 half-filled sectors per STG.128; ablation: conv2_1 49 -> 37 us without
-  // stores), hence the opt-in instantiations behind OSVOS_HALO_TMA_STORE=1 for the next measurement.
-  static constexpr int kStagingBytes = STORE == 1 ? 2 * kABytes : 0;
+  // LEAN: the forward-only epilogue (conv_common.cuh: conv_epilogue_lean) instead of the general one.
+  static constexpr int kStagingBytes = 0;
   static constexpr int kBudget = 225 * 1024 - kAStages * kAStageBytes - kStagingBytes;   // 227 KiB per CTA minus align/barriers
   static constexpr int kBStagesRaw = kBudget / kBStageBytes;
   static constexpr int kBStages = kBStagesRaw > 9 ? 9 : kBStagesRaw;
@@ -61,13 +56,12 @@ struct HaloCfg {
   static_assert(kBStageBytes % 1024 == 0, "B stage must keep 1024-byte alignment");
 };
 
-template <int BLOCK_N, int PLANES, int PITCH, bool SPLIT, int STORE>
+template <int BLOCK_N, int PLANES, int PITCH, bool SPLIT, bool LEAN>
 __global__ void __launch_bounds__(64 + EpiCfg<BLOCK_N>::kThreads, 1)
 conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo,
                     const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
-                    const __grid_constant__ CUtensorMap map_y_hi, const __grid_constant__ CUtensorMap map_y_lo,
-                    const ConvParams p, const int use_base_offset) {
-  using Cfg = HaloCfg<BLOCK_N, PLANES, PITCH, SPLIT, STORE>;
+                    const ConvParams p) {
+  using Cfg = HaloCfg<BLOCK_N, PLANES, PITCH, SPLIT, LEAN>;
   constexpr int SA = Cfg::kAStages, SB = Cfg::kBStages;
 
   extern __shared__ uint8_t smem_raw[];
@@ -117,10 +111,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_c
   // outputs (activations, masks, pooled planes, workspaces) are first accessed below.
   pdl_wait();
   pdl_launch_dependents();
-  // split-K: ksplit consecutive CTAs share a tile, each reducing its own range of channel chunks (conv_common.cuh)
-  const int w_first = static_cast<int>(blockIdx.x) / p.ksplit, w_stride = static_cast<int>(gridDim.x) / p.ksplit;
-  const int kc_per = p.k_chunks / p.ksplit;
-  const int kc_begin = (static_cast<int>(blockIdx.x) % p.ksplit) * kc_per, kc_end = kc_begin + kc_per;
+  // work items of this CTA (whole tiles, or - stream-K - the parts of tiles inside its unit range): conv_common.cuh
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (one elected thread)
@@ -147,22 +138,27 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_c
         }
       };
       int nb = 0, tx = 0, ty = 0, img = 0;
-      if (w_first < p.total_tiles) {
-        decode_tile(p, w_first, nb, tx, ty, img);
-        issue_a(tx * kTileW - 1, ty * kTileH - 1, img, kc_begin);
+      WorkList work;
+      work.init(p);
+      WorkItem item, nitem;
+      bool have = work.peek(item);
+      if (have) {
+        decode_tile(p, item.tile, nb, tx, ty, img);
+        issue_a(tx * kTileW - 1, ty * kTileH - 1, img, item.kb);
       }
-      for (int tile = w_first; tile < p.total_tiles; tile += w_stride) {
-        const bool has_next = tile + w_stride < p.total_tiles;
+      while (have) {
+        work.advance(item);
+        const bool has_next = work.peek(nitem);
         int nnb = 0, ntx = 0, nty = 0, nimg = 0;
-        if (has_next) decode_tile(p, tile + w_stride, nnb, ntx, nty, nimg);
+        if (has_next) decode_tile(p, nitem.tile, nnb, ntx, nty, nimg);
         const int n0 = nb * BLOCK_N;
-        for (int kc = kc_begin; kc < kc_end; ++kc) {
+        for (int kc = item.kb; kc < item.ke; ++kc) {
           const int c0 = kc * kBlockK;
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
             if (tap == 3) {  // prefetch the next chunk's halo while this one is being consumed
-              if (kc + 1 < kc_end) issue_a(tx * kTileW - 1, ty * kTileH - 1, img, kc + 1);
-              else if (has_next) issue_a(ntx * kTileW - 1, nty * kTileH - 1, nimg, kc_begin);
+              if (kc + 1 < item.ke) issue_a(tx * kTileW - 1, ty * kTileH - 1, img, kc + 1);
+              else if (has_next) issue_a(ntx * kTileW - 1, nty * kTileH - 1, nimg, nitem.kb);
             }
             mbar_wait(&b_empty[b_stage], b_phase ^ 1);
             if (skip_b) {
@@ -180,6 +176,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_c
           }
         }
         nb = nnb, tx = ntx, ty = nty, img = nimg;
+        item = nitem;
+        have = has_next;
       }
     }
     __syncwarp();
@@ -212,18 +210,21 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_c
         int a_stage = 0, b_stage = 0;
         uint32_t a_phase = 0, b_phase = 0;
         int it = 0;
-        for (int tile = w_first; tile < p.total_tiles; tile += w_stride, ++it) {
+        WorkList work;
+        work.init(p);
+        WorkItem item;
+        for (; work.peek(item); work.advance(item), ++it) {
           const int as = it & 1;
           const uint32_t aph = (it >> 1) & 1;
           mbar_wait(&tempty_bar[as], aph ^ 1);
           tc_fence_after();
           const uint32_t tmem_d = tmem_base + as * Cfg::kAccCols;
-          for (int kc = kc_begin; kc < kc_end; ++kc) {
+          for (int kc = item.kb; kc < item.ke; ++kc) {
             mbar_wait(&a_full[a_stage], a_phase);
             tc_fence_after();
             const uint64_t da0 = kDescA | static_cast<uint64_t>((smem_a_u32 + a_stage * Cfg::kAStageBytes) >> 4);
-            const uint32_t not_first_chunk = kc != kc_begin;
-            const bool last_chunk = kc == kc_end - 1;
+            const uint32_t not_first_chunk = kc != item.kb;
+            const bool last_chunk = kc == item.ke - 1;
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
               constexpr int kRowBytes16 = 128 >> 4;
@@ -277,13 +278,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_c
       __syncwarp();
     }
   } else {
-    if constexpr (STORE >= 3) {
-      conv_epilogue_lean<BLOCK_N, STORE == 4>(p, tmem_base, tfull_bar, tempty_bar, warp, lane);
-    } else {
-      conv_epilogue_loop<BLOCK_N, false, Cfg::kSplitAcc, STORE == 2>(p, tmem_base, tfull_bar, tempty_bar, warp, lane,
-                                                                   &map_y_hi, &map_y_lo,
-                                                                   (Cfg::kStagingBytes > 0 && p.y_hi != nullptr) ? staging : nullptr);
-    }
+    if constexpr (LEAN) conv_epilogue_lean<BLOCK_N>(p, tmem_base, tfull_bar, tempty_bar, warp, lane);
+    else conv_epilogue_loop<BLOCK_N, Cfg::kSplitAcc>(p, tmem_base, tfull_bar, tempty_bar, warp, lane);
   }
 
   tc_fence_before();
@@ -294,39 +290,63 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_c
   }
 }
 
-// split-K factor for a layer run with 128-wide tiles: the largest of {4, 2} that still fits one CTA per SM and leaves
-// every part at least two channel chunks; 1 = no split.  (All ksplit * tiles CTAs are co-resident - one per SM - so
-// the owner's wait on its helpers cannot deadlock.)
-// OPT-IN (OSVOS_SPLITK=1): measured on B200 it is SLOWER than the N = 64 tiles it was meant to replace - stage 5 at
-// 480x854 (56 tiles -> 112 CTAs, 4 chunks each): 41 us vs 37 us per layer, 240x427 whole frame 0.463 vs 0.417 ms -
-// the helper's partial write, the owner's wait and the extra memset outweigh the halved MMA chain at this size.
-static int splitk_factor(int n, int h, int w, int cin, int cout) {
-  const char* on = getenv("OSVOS_SPLITK");
-  if (cout % 128 != 0 || cin % 64 != 0 || on == nullptr || atoi(on) == 0) return 1;
-  const int m_tiles = ((w + kTileW - 1) / kTileW) * ((h + kTileH - 1) / kTileH) * n;
-  const long tiles = static_cast<long>(m_tiles) * (cout / 128);
-  const int k_chunks = cin / kBlockK;
-  const int sms = device_sm_count();
-  for (int ks = 4; ks >= 2; ks >>= 1)
-    if (tiles * ks <= sms && k_chunks % ks == 0 && k_chunks / ks >= 2) return ks;
-  return 1;
+// ---- stream-K (conv_common.cuh: WorkList) ---------------------------------------------------------------------------
+// Worth it when whole-tile scheduling leaves much of the last wave idle: stage 4 at 480x854 has 224 tiles of 128 x 128
+// on 148 SMs (two waves for 1.51 waves of work), stage 5 has 56.  With the (tile, 64-channel chunk) units dealt out in
+// balanced contiguous ranges every CTA reduces the same number of chunks; only the tiles cut by a range boundary
+// (at most one at each end of a CTA's range) exchange an fp32 partial accumulator through the workspace.
+// (Round 1's split-K - ksplit CTAs for EVERY tile plus a memset per launch - measured slower than the N = 64 fallback
+// and is gone; OSVOS_STREAMK=0 switches this off for A/B runs.)
+// efficiency of whole-tile scheduling: tiles / (waves * CTAs)
+static bool streamk_pays(long tiles, int k_chunks, int sms) {
+  if (k_chunks < 2 || tiles <= 0) return false;
+  const long waves = (tiles + sms - 1) / sms;
+  return static_cast<double>(tiles) / static_cast<double>(waves * sms) < 0.90 && tiles * k_chunks >= sms;
 }
-static size_t splitk_partial_bytes(int n, int h, int w, int cout, int ks) {
-  const int m_tiles = ((w + kTileW - 1) / kTileW) * ((h + kTileH - 1) / kTileH) * n;
-  return static_cast<size_t>(m_tiles) * (cout / 128) * (ks - 1) * kBlockM * 128 * sizeof(float);
+static size_t streamk_workspace_bytes_for(int sms) {
+  return static_cast<size_t>(sms) * kBlockM * 128 * sizeof(float) + sizeof(unsigned int) * sms + 256;
 }
 
-template <int BLOCK_N, int PLANES, int PITCH, bool SPLIT = (PLANES == 2 && BLOCK_N <= 128), int STORE = 0>
-static int launch_halo(const osvos_conv3x3_args* a, cudaStream_t stream, int use_bo, int ksplit = 1) {
-  using Cfg = HaloCfg<BLOCK_N, PLANES, PITCH, SPLIT, STORE>;
+// Environment switches of the dispatcher (A/B and diagnosis; defaults are the measured winners).  Read ONCE per process;
+// OSVOS_ENV_RELOAD=1 makes every dispatch re-read them (scripts/ab_env.py flips switches inside one process).
+struct HaloSwitches {
+  bool lean;        // OSVOS_HALO_LEAN      (default 1): lean epilogue for plain forward launches
+  bool streamk;     // OSVOS_STREAMK        (default 1): stream-K scheduling of badly quantised layers
+  bool n256;        // OSVOS_CONV_N256      (default 1): 256-wide tiles where they pay
+  bool splitacc128; // OSVOS_SPLITACC128    (default 1): N-concatenated accumulator for 128-wide exact tiles
+};
+static bool env_flag(const char* name, bool dflt) {
+  const char* e = getenv(name);
+  return e == nullptr ? dflt : atoi(e) != 0;
+}
+static HaloSwitches halo_switches() {
+  static HaloSwitches sw;
+  static int state = 0;          // 0: unread, 1: cached, 2: re-read on every call
+  if (state != 1) {
+    sw.lean = env_flag("OSVOS_HALO_LEAN", true);
+    sw.streamk = env_flag("OSVOS_STREAMK", true);
+    sw.n256 = env_flag("OSVOS_CONV_N256", true);
+    sw.splitacc128 = env_flag("OSVOS_SPLITACC128", true);
+    state = env_flag("OSVOS_ENV_RELOAD", false) ? 2 : 1;
+  }
+  return sw;
+}
+
+template <int BLOCK_N, int PLANES, int PITCH, bool SPLIT = (PLANES == 2 && BLOCK_N <= 128), bool LEAN = false>
+static int launch_halo(const osvos_conv3x3_args* a, cudaStream_t stream, bool streamk = false) {
+  using Cfg = HaloCfg<BLOCK_N, PLANES, PITCH, SPLIT, LEAN>;
   ConvParams p;
   fill_conv_params(p, a, BLOCK_N);
-  if (ksplit > 1) {
-    p.ksplit = ksplit;
-    p.sk_partial = static_cast<float*>(a->splitk_ws);
-    p.sk_flags = reinterpret_cast<unsigned int*>(static_cast<uint8_t*>(a->splitk_ws) +
-                                                 splitk_partial_bytes(a->n, a->h, a->w, a->cout, ksplit));
-    OSVOS_CHECK_CUDA(cudaMemsetAsync(p.sk_flags, 0, sizeof(unsigned int) * p.total_tiles, stream));
+  const int sms = device_sm_count();
+  if (streamk) {
+    if (BLOCK_N > 128 || LEAN) {   // partial slots are sized for <= 128-wide tiles; only the general epilogue exchanges them
+      set_last_error("stream-K: unsupported instantiation");
+      return OSVOS_ERR_INVALID_ARGUMENT;
+    }
+    p.streamk = 1;
+    p.sk_partial = static_cast<float*>(a->streamk_ws);
+    p.sk_flags = reinterpret_cast<unsigned int*>(static_cast<uint8_t*>(a->streamk_ws) +
+                                                 static_cast<size_t>(sms) * kBlockM * 128 * sizeof(float));
   }
   CUtensorMap mx_hi, mx_lo, mw_hi, mw_lo;
   {
@@ -343,89 +363,113 @@ static int launch_halo(const osvos_conv3x3_args* a, cudaStream_t stream, int use
   }
   int rc = encode_weight_maps(&mw_hi, &mw_lo, a, BLOCK_N);
   if (rc) return rc;
-  CUtensorMap my_hi = mw_hi, my_lo = mw_lo;  // placeholders when there is no act output
-  if (a->y_hi != nullptr && BLOCK_N >= 64) {
-    rc = encode_output_maps(&my_hi, &my_lo, a);
-    if (rc) return rc;
-  }
-  auto kern = conv3x3_halo_kernel<BLOCK_N, PLANES, PITCH, SPLIT, STORE>;
+  auto kern = conv3x3_halo_kernel<BLOCK_N, PLANES, PITCH, SPLIT, LEAN>;
   static uint64_t attr_done = 0;   // per instantiation: bit d = device d has the shared-memory opt-in
   OSVOS_CHECK_CUDA(ensure_dynamic_smem(kern, Cfg::kSmemBytes, &attr_done));
-  const int sms = device_sm_count();
-  const int grid = ksplit > 1 ? p.total_tiles * ksplit : (p.total_tiles < sms ? p.total_tiles : sms);
+  const long units = static_cast<long>(p.total_tiles) * p.k_chunks;
+  const int grid = streamk ? static_cast<int>(units < sms ? units : sms) : (p.total_tiles < sms ? p.total_tiles : sms);
   OSVOS_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(64 + EpiCfg<BLOCK_N>::kThreads), Cfg::kSmemBytes, stream, mx_hi, mx_lo,
-                              mw_hi, mw_lo, my_hi, my_lo, p, use_bo));
+                              mw_hi, mw_lo, p));
   return OSVOS_OK;
 }
 
 template <int PITCH>
-static int dispatch_halo(const osvos_conv3x3_args* a, cudaStream_t stream, int use_bo) {
+static int dispatch_halo(const osvos_conv3x3_args* a, cudaStream_t stream) {
   const bool fast = (a->flags & OSVOS_FLAG_FAST) != 0;
-  if (a->cout == 16) return fast ? launch_halo<16, 1, PITCH>(a, stream, use_bo) : launch_halo<16, 2, PITCH>(a, stream, use_bo);
-  // opt-in store flavours of the exact-mode epilogue (see HaloCfg): OSVOS_HALO_TMA_STORE=1 bulk tensor stores,
-  // OSVOS_HALO_ST256=1 32-byte direct stores (all output planes must be 32-byte aligned)
-  const char* ts = getenv("OSVOS_HALO_TMA_STORE");
-  const bool tma_store = ts != nullptr && atoi(ts) != 0 && a->y_hi != nullptr && !fast;
-  const char* s256 = getenv("OSVOS_HALO_ST256");
-  auto aligned32 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 31) == 0; };
-  const bool st256 = s256 != nullptr && atoi(s256) != 0 && !fast && !tma_store && aligned32(a->y_hi) && aligned32(a->y_lo) &&
-                     aligned32(a->y_f32) && aligned32(a->pool_hi) && aligned32(a->pool_lo) && aligned32(a->mask_hi);
-  // OSVOS_HALO_LEAN=1: the lean epilogue for launches that use nothing but bias / ReLU / act output / fused pool
-  const char* ln = getenv("OSVOS_HALO_LEAN");
-  const bool lean = ln != nullptr && atoi(ln) != 0 && !fast && !tma_store && a->splitk_ws == nullptr &&
-                    !(a->flags & OSVOS_FLAG_RELU_MASK) && a->colsum == nullptr && a->y_f32 == nullptr && a->pq == nullptr &&
-                    (a->y_hi != nullptr || a->pool_hi != nullptr) && (a->y_hi == nullptr || a->y_lo != nullptr) &&
-                    (a->pool_hi == nullptr || a->pool_lo != nullptr) && aligned32(a->y_hi) && aligned32(a->y_lo) &&
-                    aligned32(a->pool_hi) && aligned32(a->pool_lo) && a->k_valid == 0;
+  const HaloSwitches sw = halo_switches();
+  if (a->cout == 16) return fast ? launch_halo<16, 1, PITCH>(a, stream) : launch_halo<16, 2, PITCH>(a, stream);
+  // the lean epilogue serves launches that use nothing but bias / ReLU / split-bf16 act output / fused pool (exact mode)
+  const bool lean = sw.lean && !fast && !(a->flags & OSVOS_FLAG_RELU_MASK) && a->colsum == nullptr && a->y_f32 == nullptr &&
+                    a->pq == nullptr && (a->y_hi != nullptr || a->pool_hi != nullptr) &&
+                    (a->y_hi == nullptr || a->y_lo != nullptr) && (a->pool_hi == nullptr || a->pool_lo != nullptr) &&
+                    a->k_valid == 0;
   if (a->cout == 64) {
-    if (lean) return atoi(ln) >= 2 ? launch_halo<64, 2, PITCH, true, 4>(a, stream, use_bo) : launch_halo<64, 2, PITCH, true, 3>(a, stream, use_bo);
-    if (tma_store) return launch_halo<64, 2, PITCH, true, 1>(a, stream, use_bo);
-    if (st256) return launch_halo<64, 2, PITCH, true, 2>(a, stream, use_bo);
-    return fast ? launch_halo<64, 1, PITCH>(a, stream, use_bo) : launch_halo<64, 2, PITCH>(a, stream, use_bo);
+    if (lean) return launch_halo<64, 2, PITCH, true, true>(a, stream);
+    return fast ? launch_halo<64, 1, PITCH>(a, stream) : launch_halo<64, 2, PITCH>(a, stream);
   }
-  // N = 256 tiles (one tcgen05.mma of 128 cycles instead of two of ~85-100) whenever there are enough pixel tiles
-  // to fill the chip; OSVOS_CONV_N256=0 disables.
-  const char* n256 = getenv("OSVOS_CONV_N256");
   const int m_tiles = ((a->w + kTileW - 1) / kTileW) * ((a->h + kTileH - 1) / kTileH) * a->n;
   const int sms = device_sm_count();
-  const long waves128 = (static_cast<long>(m_tiles) * (a->cout / 128) + sms - 1) / sms;
+  const long tiles128 = static_cast<long>(m_tiles) * (a->cout / 128);
+  const long waves128 = (tiles128 + sms - 1) / sms;
   const long waves256 = (static_cast<long>(m_tiles) * (a->cout / 256) + sms - 1) / sms;
-  // measured cycles per (tap, 64-channel) step: N = 128 ~ 1000 (2 + 1 instructions), N = 256 ~ 2200 exact
+  // whole-tile scheduling would leave much of the last wave idle (stage 4: 224 tiles, stage 5: 56 on 148 SMs): stream-K
+  if (sw.streamk && a->streamk_ws != nullptr && a->cin % kBlockK == 0 && a->k_valid == 0 &&
+      streamk_pays(tiles128, a->cin / kBlockK, sms))
+    return fast ? launch_halo<128, 1, PITCH>(a, stream, true) : launch_halo<128, 2, PITCH>(a, stream, true);
+  // few tiles and no stream-K: N = 64 tiles double the CTA count at ~0.8x the time per tile
+  if (waves128 == 1 && tiles128 * 5 <= static_cast<long>(sms) * 3) {
+    if (lean) return launch_halo<64, 2, PITCH, true, true>(a, stream);
+    return fast ? launch_halo<64, 1, PITCH>(a, stream) : launch_halo<64, 2, PITCH>(a, stream);
+  }
+  // N = 256 tiles (one tcgen05.mma of 128 cycles per pass) whenever that does not cost a wave; measured cycles per
+  // (tap, 64-channel) step: N = 128 ~ 1000 (2 + 1 instructions), N = 256 ~ 2200 exact
   const bool prefer256 = fast ? waves256 * 1100 < waves128 * 700 : waves256 * 2200 < waves128 * 1000;
-  // few tiles (stage 5 at 480p: 56 of 128 px x 128 ch): split the reduction over 2 or 4 CTAs per tile
-  const int ks = a->splitk_ws != nullptr ? splitk_factor(a->n, a->h, a->w, a->cin, a->cout) : 1;
-  if (ks > 1)
-    return fast ? launch_halo<128, 1, PITCH>(a, stream, use_bo, ks) : launch_halo<128, 2, PITCH>(a, stream, use_bo, ks);
-  // without a workspace: N = 64 tiles double the CTA count at ~0.8x the time per tile
-  if (waves128 == 1 && static_cast<long>(m_tiles) * (a->cout / 128) * 5 <= static_cast<long>(sms) * 3)
-    return fast ? launch_halo<64, 1, PITCH>(a, stream, use_bo) : launch_halo<64, 2, PITCH>(a, stream, use_bo);
-  if (a->cout % 256 == 0 && prefer256 && !(n256 && atoi(n256) == 0))
-    return fast ? launch_halo<256, 1, PITCH>(a, stream, use_bo) : launch_halo<256, 2, PITCH>(a, stream, use_bo);
-  if (fast) return launch_halo<128, 1, PITCH>(a, stream, use_bo);
+  if (a->cout % 256 == 0 && prefer256 && sw.n256)
+    return fast ? launch_halo<256, 1, PITCH>(a, stream) : launch_halo<256, 2, PITCH>(a, stream);
+  if (fast) return launch_halo<128, 1, PITCH>(a, stream);
   // Exact mode, N = 128: the N-concatenated split accumulator (2 MMAs per K step, 256 accumulator columns, the
-  // epilogue reads and sums two halves) and the plain three-pass form (3 MMAs, 128 columns) cost the SAME tensor
-  // time - 128 + 64 = 3 x 64 cycles per K step (scripts/microbench/operand_reuse_bench.cu) - so the choice is
-  // issuer instructions against epilogue work.  OSVOS_SPLITACC128=0 selects the three-pass form (read per launch).
-  const char* sp = getenv("OSVOS_SPLITACC128");
-  if (sp != nullptr && atoi(sp) == 0) return launch_halo<128, 2, PITCH, false>(a, stream, use_bo);
-  // opt-in: act output through a swizzled staging buffer + bulk tensor stores (full 128-byte rows) - see HaloCfg
-  if (lean) return atoi(ln) >= 2 ? launch_halo<128, 2, PITCH, true, 4>(a, stream, use_bo) : launch_halo<128, 2, PITCH, true, 3>(a, stream, use_bo);
-  if (tma_store) return launch_halo<128, 2, PITCH, true, 1>(a, stream, use_bo);
-  if (st256) return launch_halo<128, 2, PITCH, true, 2>(a, stream, use_bo);
-  return launch_halo<128, 2, PITCH>(a, stream, use_bo);
+  // epilogue sums two halves) and the plain three-pass form (3 MMAs, 128 columns) cost the SAME tensor time
+  // (scripts/microbench/operand_reuse_bench.cu) and measured the same; OSVOS_SPLITACC128=0 selects the three-pass form.
+  if (!sw.splitacc128) return launch_halo<128, 2, PITCH, false>(a, stream);
+  if (lean) return launch_halo<128, 2, PITCH, true, true>(a, stream);
+  return launch_halo<128, 2, PITCH>(a, stream);
 }
 
-size_t conv3x3_splitk_workspace_bytes(int n, int h, int w, int cin, int cout) {
-  const int ks = splitk_factor(n, h, w, cin, cout);
-  if (ks <= 1) return 0;
-  const int m_tiles = ((w + kTileW - 1) / kTileW) * ((h + kTileH - 1) / kTileH) * n;
-  return splitk_partial_bytes(n, h, w, cout, ks) + sizeof(unsigned int) * m_tiles * (cout / 128) + 256;
+int conv3x3_halo_dispatch(const osvos_conv3x3_args* a, cudaStream_t stream) {
+  // packed patch rows (pitch 10) are the only instantiation: the padded 16-pixel pitch and the descriptor base-offset
+  // field were validated equivalent on hardware in round 1 and dropped
+  return dispatch_halo<10>(a, stream);
 }
 
-int conv3x3_halo_dispatch(const osvos_conv3x3_args* a, cudaStream_t stream, int pitch, int use_bo) {
-  (void)pitch;  // pitch 16 (padded rows) was validated equivalent on hardware and dropped: it no longer fits with
-                // the TMA-store staging buffer; packed rows (pitch 10) are the only instantiation.
-  return dispatch_halo<10>(a, stream, use_bo);
+static int check_conv_args(const osvos_conv3x3_args* a) {
+  OSVOS_CHECK_ARG(a != nullptr);
+  OSVOS_CHECK_ARG(a->n > 0 && a->h > 0 && a->w > 0);
+  OSVOS_CHECK_ARG(a->cin >= 64 && a->cin % 64 == 0);
+  OSVOS_CHECK_ARG(a->cout == 2 || a->cout == 16 || a->cout == 64 || (a->cout > 0 && a->cout % 128 == 0));
+  // cout == 2: the folded side branch (osvos_fold_side_weights) - pq is the only output, bias = the 2 folded biases
+  OSVOS_CHECK_ARG(a->cout != 2 || (a->pq != nullptr && a->y_hi == nullptr && a->y_f32 == nullptr && a->pool_hi == nullptr &&
+                                   a->colsum == nullptr && !(a->flags & (OSVOS_FLAG_RELU | OSVOS_FLAG_RELU_MASK)) &&
+                                   a->k_valid == 0));
+  OSVOS_CHECK_ARG(a->x_hi != nullptr && a->w_packed != nullptr);
+  OSVOS_CHECK_ARG((a->flags & OSVOS_FLAG_FAST) || a->x_lo != nullptr);
+  OSVOS_CHECK_ARG(a->y_hi != nullptr || a->y_f32 != nullptr || a->pq != nullptr || a->pool_hi != nullptr);
+  OSVOS_CHECK_ARG(!(a->flags & OSVOS_FLAG_RELU_MASK) || a->mask_hi != nullptr);
+  OSVOS_CHECK_ARG(a->pq == nullptr || a->cout == 2 || (a->cout == 16 && a->proj_w != nullptr));
+  OSVOS_CHECK_ARG((a->pool_hi == nullptr && a->colsum == nullptr) || a->cout >= 64);
+  OSVOS_CHECK_ARG((reinterpret_cast<uintptr_t>(a->x_hi) & 15) == 0);
+  OSVOS_CHECK_ARG((reinterpret_cast<uintptr_t>(a->w_packed) & 15) == 0);
+  OSVOS_CHECK_ARG((reinterpret_cast<uintptr_t>(a->bias) & 15) == 0);
+  OSVOS_CHECK_ARG((reinterpret_cast<uintptr_t>(a->streamk_ws) & 15) == 0);
+  if (a->cout >= 64) {   // 256-bit stores / loads in the epilogues
+    const uintptr_t any = reinterpret_cast<uintptr_t>(a->y_hi) | reinterpret_cast<uintptr_t>(a->y_lo) |
+                          reinterpret_cast<uintptr_t>(a->y_f32) | reinterpret_cast<uintptr_t>(a->pool_hi) |
+                          reinterpret_cast<uintptr_t>(a->pool_lo) | reinterpret_cast<uintptr_t>(a->mask_hi);
+    OSVOS_CHECK_ARG((any & 31) == 0);
+  }
+  OSVOS_CHECK_ARG(a->k_valid >= 0 && a->k_valid <= 64 && a->k_valid % 16 == 0);
+  return OSVOS_OK;
 }
 
 }  // namespace osvos
+
+using namespace osvos;
+
+extern "C" size_t osvos_conv3x3_streamk_workspace_bytes(void) { return streamk_workspace_bytes_for(device_sm_count()); }
+
+extern "C" int osvos_conv3x3(const osvos_conv3x3_args* a, osvos_stream_t stream_) {
+  int rc = check_conv_args(a);
+  if (rc) return rc;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  // side_prep shape (16 outputs, fp32 features / projections only): nine-taps-along-N kernel (side_conv.cu);
+  // OSVOS_SIDE_IMPL=generic sends it through the halo kernel's N = 16 instantiation instead (cross-check)
+  if (a->cout == 2) return side_conv_dispatch(a, stream);
+  if (a->cout == 16 && a->y_hi == nullptr && !(a->flags & OSVOS_FLAG_RELU_MASK) && a->colsum == nullptr) {
+    static int generic = -1;
+    if (generic < 0) {
+      const char* side = getenv("OSVOS_SIDE_IMPL");
+      generic = (side != nullptr && strcmp(side, "generic") == 0) ? 1 : 0;
+    }
+    if (!generic) return side_conv_dispatch(a, stream);
+  }
+  return conv3x3_halo_dispatch(a, stream);
+}

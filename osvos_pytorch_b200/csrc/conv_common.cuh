@@ -33,16 +33,61 @@ struct ConvParams {
   int k_steps;               // tcgen05.mma K steps (of 16 channels) issued per 64-channel chunk: 4, or fewer (k_valid)
   int m_tiles, total_pairs;  // CTA-pair kernels: m_tiles pixel tiles, total_pairs = ceil(m_tiles / 2) * n_blocks work items
   int flags;
-  // split-K (halo kernel, layers with fewer tiles than half the SMs): ksplit CTAs share one output tile, each
-  // reducing k_chunks / ksplit channel chunks; CTA (tile, part > 0) writes its fp32 partial accumulator to
-  // sk_partial[tile][part - 1][128][BLOCK_N] and bumps sk_flags[tile]; part 0 adds them in its epilogue.
-  int ksplit;                // 1 = off
+  // stream-K (halo kernel, layers whose tile count leaves much of the last wave idle): the total_tiles * k_chunks
+  // (tile, 64-channel chunk) units are dealt out to the CTAs in contiguous balanced ranges (WorkList below); a tile cut
+  // by a range boundary is reduced by several CTAs: the one holding its FIRST chunks owns it (runs the epilogue), the
+  // others write their fp32 partial accumulators to sk_partial[their CTA index][128][BLOCK_N] and bump sk_flags[owner].
+  int streamk;               // 0 = off (CTA c takes whole tiles c, c + G, ...)
   // Timing ablations (OSVOS_ABLATE bit mask, diagnosis only - results are garbage): 1 = no weight TMA loads,
   // 2 = no activation TMA loads, 4 = no tcgen05.mma, 8 = no global stores in the epilogue.  0 in production.
   int ablate;
   float* sk_partial;
-  unsigned int* sk_flags;    // zeroed by the launcher
+  unsigned int* sk_flags;    // [grid] arrival counters; zero at launch, reset to zero by the owner that consumed them
 };
+
+// ---- work decomposition of the persistent conv kernel --------------------------------------------------------------
+// classic : CTA c takes whole tiles c, c + G, c + 2G, ... (G = gridDim.x)
+// stream-K: U = total_tiles * k_chunks units, CTA c takes units [unit_begin(c), unit_begin(c + 1)); an item is the part
+//           of ONE tile inside that range: chunks [kb, ke).  kb == 0 && ke == k_chunks: whole tile.  kb == 0, ke < k_chunks:
+//           this CTA OWNS the tile (it is the last item of its range) and adds the partials of the CTAs after it.
+//           kb > 0: helper part (the first item of its range).  A CTA is owner at most once and helper at most once.
+struct WorkItem {
+  int tile, kb, ke;
+};
+struct WorkList {
+  int streamk, k_chunks, total_tiles, cur, end, stride;
+  __device__ __forceinline__ static int unit_begin(int c, int per, int extra) { return c * per + (c < extra ? c : extra); }
+  __device__ __forceinline__ void init(const ConvParams& p) {
+    streamk = p.streamk, k_chunks = p.k_chunks, total_tiles = p.total_tiles;
+    if (streamk) {
+      const int units = total_tiles * k_chunks, g = static_cast<int>(gridDim.x);
+      const int per = units / g, extra = units - per * g, c = static_cast<int>(blockIdx.x);
+      cur = unit_begin(c, per, extra);
+      end = unit_begin(c + 1, per, extra);
+      stride = 0;
+    } else {
+      cur = static_cast<int>(blockIdx.x), end = total_tiles, stride = static_cast<int>(gridDim.x);
+    }
+  }
+  __device__ __forceinline__ bool peek(WorkItem& it) const {
+    if (cur >= end) return false;
+    if (streamk) {
+      it.tile = cur / k_chunks;
+      it.kb = cur - it.tile * k_chunks;
+      const int left = end - cur;
+      it.ke = (it.kb + left < k_chunks) ? it.kb + left : k_chunks;
+    } else {
+      it.tile = cur, it.kb = 0, it.ke = k_chunks;
+    }
+    return true;
+  }
+  __device__ __forceinline__ void advance(const WorkItem& it) { cur += streamk ? (it.ke - it.kb) : stride; }
+};
+// CTA whose range holds unit u (inverse of unit_begin)
+__device__ __forceinline__ int streamk_cta_of_unit(int u, int per, int extra) {
+  const int cut = extra * (per + 1);
+  return u < cut ? u / (per + 1) : extra + (u - cut) / per;
+}
 
 __device__ __forceinline__ void decode_tile(const ConvParams& p, int tile, int& nb, int& tx, int& ty, int& img) {
   nb = tile % p.n_blocks;
@@ -76,48 +121,23 @@ struct EpiCfg {
   static constexpr int kThreads = 128 * kGroups;
 };
 
-// CTA-pair work item w -> this CTA's pixel tile (rank 0 / 1 take the even / odd tile of the pair).  A pair whose
-// second tile does not exist gets a dummy tile placed below the image: TMA zero-fills it and nothing is stored.
-__device__ __forceinline__ void decode_pair(const ConvParams& p, int w, int rank, int& nb, int& tx, int& ty, int& img) {
-  nb = w % p.n_blocks;
-  int m = 2 * (w / p.n_blocks) + rank;
-  if (m >= p.m_tiles) {
-    tx = 0;
-    ty = p.tiles_y;
-    img = p.n - 1;
-    return;
-  }
-  tx = m % p.tiles_x;
-  m /= p.tiles_x;
-  ty = m % p.tiles_y;
-  img = m / p.tiles_y;
-}
-
 // Epilogue of one warp over all tiles of this CTA.  Epilogue warps are warps 2 .. 2 + 4*kGroups - 1; warp w
 // reads TMEM lane quarter (w & 3) and the 32-column chunks with index parity (w - 2) >> 2.
-// `staging` (2 x 16 KiB, 1 KiB aligned) + the output tensor maps enable the TMA-store path for the act
-// output: each 64-channel slab of the tile is written to shared memory in the SWIZZLE_128B layout and
-// stored with one bulk tensor copy per plane (full 128-byte rows, image edges clipped by the TMA unit)
-// instead of 16-byte scattered global stores.  staging == nullptr keeps the direct stores.
 // SPLIT_ACC: the accumulator stage holds 2 * BLOCK_N columns - [A.B_hi | A.B_lo] produced by one N-concatenated
 // tcgen05.mma - and the result is the sum of the two halves.
-// STORE256: the act / pooled / fp32 outputs of the BLOCK_N >= 64 path are written with 256-bit stores (one full sector
-// per lane and instruction, half the store instructions); needs 32-byte aligned output planes.
-template <int BLOCK_N, bool PAIR = false, bool SPLIT_ACC = false, bool STORE256 = false>
+// The act / pooled / fp32 outputs and the mask of the BLOCK_N >= 64 path move with 256-bit instructions (one full 32-byte
+// sector per lane: half the store instructions of the 16-byte form, +2-3 % on inference and fwd+bwd in the round-2 A/B
+// - profiles/r02_ab_matrix.txt); every output plane must be 32-byte aligned (checked by osvos_conv3x3).  The bulk-store
+// (TMA) epilogue measured the same +2 % at the price of 32 KiB of staging and was dropped.
+// TMA_STORE (conv1_1 only, conv_first_tc.cu): the act output goes through `staging` (2 x 16 KiB, 1 KiB aligned) in the
+// SWIZZLE_128B layout and leaves with one bulk tensor store per plane and 64-channel slab (full 128-byte rows, image
+// edges clipped by the TMA unit) - that layer does nothing but write 105 MB.
+template <int BLOCK_N, bool SPLIT_ACC = false, bool TMA_STORE = false>
 __device__ __forceinline__ void conv_epilogue_loop(const ConvParams& p, uint32_t tmem_base, uint64_t* tfull_bar,
                                                    uint64_t* tempty_bar, int warp, int lane,
                                                    const CUtensorMap* map_y_hi = nullptr,
                                                    const CUtensorMap* map_y_lo = nullptr, uint8_t* staging = nullptr) {
-  // PAIR: this CTA is one half of a cta_group::2 pair; the TMEM-empty barrier lives in the leader (rank 0)
-  const int rank = PAIR ? static_cast<int>(cluster_ctarank()) : 0;
-  const int ks = PAIR ? 1 : p.ksplit;                                   // split-K parts per tile (1 = off)
-  const int part = static_cast<int>(blockIdx.x) % ks;
-  const int w_first = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x) / ks;
-  const int w_stride = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x) / ks;
-  const int w_total = PAIR ? p.total_pairs : p.total_tiles;
-  const uint32_t tempty_remote = PAIR ? mapa_shared(smem_u32(tempty_bar), 0) : 0u;
   constexpr int kEpiThreads = EpiCfg<BLOCK_N>::kThreads;
-  const bool use_tma = (staging != nullptr) && (p.y_hi != nullptr);
   const bool epi_leader = (warp == 2) && (lane == 0);
   const int group = (warp - 2) >> 2;
   const int q = warp & 3;  // TMEM lane quarter this warp may read
@@ -127,10 +147,27 @@ __device__ __forceinline__ void conv_epilogue_loop(const ConvParams& p, uint32_t
   const bool masked = (p.flags & OSVOS_FLAG_RELU_MASK) != 0;
   const bool store_ok = !(p.ablate & 8);
   int it = 0;
-  for (int tile = w_first; tile < w_total; tile += w_stride, ++it) {
+  WorkList work;
+  work.init(p);
+  WorkItem item;
+  for (; work.peek(item); work.advance(item), ++it) {
+    const int tile = item.tile;
+    // stream-K role of this item: 0 = whole tile, 1 = owner (adds `parts` partials), 2 = helper (writes a partial)
+    const int role = (item.kb > 0) ? 2 : (item.ke < p.k_chunks ? 1 : 0);
+    int parts = 0, owner_cta = 0;
+    if (role != 0) {
+      const int units = p.total_tiles * p.k_chunks, g = static_cast<int>(gridDim.x);
+      const int per = units / g, extra = units - per * g;
+      if (role == 1) {          // CTAs after this one that hold the rest of the tile
+        const int tile_end = (tile + 1) * p.k_chunks;
+        int c = static_cast<int>(blockIdx.x) + 1;
+        while (WorkList::unit_begin(c, per, extra) < tile_end) ++c, ++parts;
+      } else {
+        owner_cta = streamk_cta_of_unit(tile * p.k_chunks, per, extra);
+      }
+    }
     int nb, tx, ty, img;
-    if (PAIR) decode_pair(p, tile, rank, nb, tx, ty, img);
-    else decode_tile(p, tile, nb, tx, ty, img);
+    decode_tile(p, tile, nb, tx, ty, img);
     const int as = it & 1;
     const uint32_t aph = (it >> 1) & 1;
     const int y = ty * kTileH + ly, x = tx * kTileW + lx;
@@ -141,17 +178,20 @@ __device__ __forceinline__ void conv_epilogue_loop(const ConvParams& p, uint32_t
     tc_fence_after();
     constexpr int kAccCols = SPLIT_ACC ? 2 * BLOCK_N : BLOCK_N;
     const uint32_t taddr = tmem_base + as * kAccCols + (static_cast<uint32_t>(q * 32) << 16);
-    if (ks > 1 && part == 0) {
-      // split-K owner: the other parts' partial accumulators must be in memory before they are added below
+    if (role == 1) {
+      // stream-K owner: the other parts' partial accumulators must be in memory before they are added below
       if (lane == 0) {
-        const int need = (ks - 1) * (kEpiThreads / 32);
+        const int need = parts * (kEpiThreads / 32);
         unsigned int spins = 0;
-        while (static_cast<int>(ld_acquire_gpu_u32(p.sk_flags + tile)) < need) {
+        while (static_cast<int>(ld_acquire_gpu_u32(p.sk_flags + blockIdx.x)) < need) {
           __nanosleep(64);
           if (++spins > (1u << 24)) __trap();
         }
       }
       __syncwarp();
+      // every epilogue warp has seen the full count: hand the counter back at zero for the next launch
+      epilogue_bar_sync(kEpiThreads);
+      if (epi_leader) st_relaxed_gpu_u32(p.sk_flags + blockIdx.x, 0u);
     }
 
     if constexpr (BLOCK_N == 16) {
@@ -217,10 +257,10 @@ __device__ __forceinline__ void conv_epilogue_loop(const ConvParams& p, uint32_t
           for (int j = 0; j < 32; ++j) f[j] = 0.f;
         }
         tmem_ld_wait();
-        if (ks > 1) {
-          float* part_base = p.sk_partial + ((static_cast<size_t>(tile) * (ks - 1)) * kBlockM + row) * BLOCK_N + c0;
-          if (part > 0) {   // helper: raw partial accumulator (no bias) -> workspace, nothing else
-            float4* dst = reinterpret_cast<float4*>(part_base + static_cast<size_t>(part - 1) * kBlockM * BLOCK_N);
+        if (role != 0) {
+          const size_t slab_off = static_cast<size_t>(row) * BLOCK_N + c0;
+          if (role == 2) {   // helper: raw partial accumulator (no bias) -> this CTA's workspace slot, nothing else
+            float4* dst = reinterpret_cast<float4*>(p.sk_partial + static_cast<size_t>(blockIdx.x) * kBlockM * BLOCK_N + slab_off);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               float4 o;
@@ -232,8 +272,8 @@ __device__ __forceinline__ void conv_epilogue_loop(const ConvParams& p, uint32_t
             }
             continue;
           }
-          for (int hp = 0; hp < ks - 1; ++hp) {   // owner: add the helpers' partials
-            const float4* src = reinterpret_cast<const float4*>(part_base + static_cast<size_t>(hp) * kBlockM * BLOCK_N);
+          for (int hp = 1; hp <= parts; ++hp) {   // owner: add the helpers' partials (fixed order: deterministic)
+            const float4* src = reinterpret_cast<const float4*>(p.sk_partial + static_cast<size_t>(blockIdx.x + hp) * kBlockM * BLOCK_N + slab_off);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const float4 o = __ldcg(src + j);
@@ -247,77 +287,31 @@ __device__ __forceinline__ void conv_epilogue_loop(const ConvParams& p, uint32_t
           if (SPLIT_ACC) f[j] += __uint_as_float(v2[j]);
           f[j] = relu ? fmaxf(f[j], 0.f) : f[j];
         }
-        if (masked && valid) {
-          if constexpr (STORE256) {   // same mask, two 32-byte loads instead of four 16-byte ones
+        if (masked && valid) {   // two 32-byte loads of the mask's hi plane
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              uint32_t mw[8];
-              ld_global_nc_256(p.mask_hi + pix * p.cout + ch + 16 * j, mw);
+          for (int j = 0; j < 2; ++j) {
+            uint32_t mw[8];
+            ld_global_nc_256(p.mask_hi + pix * p.cout + ch + 16 * j, mw);
 #pragma unroll
-              for (int t = 0; t < 8; ++t) {
-                if (!(bf16_lo_to_float(mw[t]) > 0.f)) f[16 * j + 2 * t] = 0.f;
-                if (!(bf16_hi_to_float(mw[t]) > 0.f)) f[16 * j + 2 * t + 1] = 0.f;
-              }
-            }
-          } else {
-            const uint4* mk = reinterpret_cast<const uint4*>(p.mask_hi + pix * p.cout + ch);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint4 m = __ldg(mk + j);
-              const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
-#pragma unroll
-              for (int t = 0; t < 4; ++t) {
-                if (!(bf16_lo_to_float(mw[t]) > 0.f)) f[8 * j + 2 * t] = 0.f;
-                if (!(bf16_hi_to_float(mw[t]) > 0.f)) f[8 * j + 2 * t + 1] = 0.f;
-              }
+            for (int t = 0; t < 8; ++t) {
+              if (!(bf16_lo_to_float(mw[t]) > 0.f)) f[16 * j + 2 * t] = 0.f;
+              if (!(bf16_hi_to_float(mw[t]) > 0.f)) f[16 * j + 2 * t + 1] = 0.f;
             }
           }
         }
         if (p.y_f32 && valid) {
-          if constexpr (STORE256) {
-            float* dst = p.y_f32 + pix * p.cout + ch;
+          float* dst = p.y_f32 + pix * p.cout + ch;
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              st_global_256(dst + 8 * j, __float_as_uint(f[8 * j]), __float_as_uint(f[8 * j + 1]), __float_as_uint(f[8 * j + 2]),
-                            __float_as_uint(f[8 * j + 3]), __float_as_uint(f[8 * j + 4]), __float_as_uint(f[8 * j + 5]),
-                            __float_as_uint(f[8 * j + 6]), __float_as_uint(f[8 * j + 7]));
-          } else {
-            float4* dst = reinterpret_cast<float4*>(p.y_f32 + pix * p.cout + ch);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-          }
+          for (int j = 0; j < 4; ++j)
+            st_global_256(dst + 8 * j, __float_as_uint(f[8 * j]), __float_as_uint(f[8 * j + 1]), __float_as_uint(f[8 * j + 2]),
+                          __float_as_uint(f[8 * j + 3]), __float_as_uint(f[8 * j + 4]), __float_as_uint(f[8 * j + 5]),
+                          __float_as_uint(f[8 * j + 6]), __float_as_uint(f[8 * j + 7]));
         }
         if (p.y_hi) {
           uint32_t hi[16], lo[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) split_pack2(f[2 * j], f[2 * j + 1], hi[j], lo[j]);
-          if (!use_tma) {
-            if (valid) {
-              if constexpr (STORE256) {
-                __nv_bfloat16* dh = p.y_hi + pix * p.cout + ch;
-#pragma unroll
-                for (int j = 0; j < 2; ++j)
-                  st_global_256(dh + 16 * j, hi[8 * j], hi[8 * j + 1], hi[8 * j + 2], hi[8 * j + 3], hi[8 * j + 4], hi[8 * j + 5],
-                                hi[8 * j + 6], hi[8 * j + 7]);
-                if (p.y_lo) {
-                  __nv_bfloat16* dl = p.y_lo + pix * p.cout + ch;
-#pragma unroll
-                  for (int j = 0; j < 2; ++j)
-                    st_global_256(dl + 16 * j, lo[8 * j], lo[8 * j + 1], lo[8 * j + 2], lo[8 * j + 3], lo[8 * j + 4], lo[8 * j + 5],
-                                  lo[8 * j + 6], lo[8 * j + 7]);
-                }
-              } else {
-                uint4* dh = reinterpret_cast<uint4*>(p.y_hi + pix * p.cout + ch);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) dh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-                if (p.y_lo) {
-                  uint4* dl = reinterpret_cast<uint4*>(p.y_lo + pix * p.cout + ch);
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) dl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
-                }
-              }
-            }
-          } else {
+          if constexpr (TMA_STORE) {
             // the previous slab's bulk store must have finished READING the staging buffer
             if (epi_leader) tma_store_wait_read<0>();
             epilogue_bar_sync(kEpiThreads);
@@ -336,6 +330,19 @@ __device__ __forceinline__ void conv_epilogue_loop(const ConvParams& p, uint32_t
               tma_store_4d(map_y_hi, staging, c64, tx * kTileW, ty * kTileH, img);
               if (p.y_lo) tma_store_4d(map_y_lo, staging + kABytes, c64, tx * kTileW, ty * kTileH, img);
               tma_store_commit();
+            }
+          } else if (valid) {
+            __nv_bfloat16* dh = p.y_hi + pix * p.cout + ch;
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+              st_global_256(dh + 16 * j, hi[8 * j], hi[8 * j + 1], hi[8 * j + 2], hi[8 * j + 3], hi[8 * j + 4], hi[8 * j + 5],
+                            hi[8 * j + 6], hi[8 * j + 7]);
+            if (p.y_lo) {
+              __nv_bfloat16* dl = p.y_lo + pix * p.cout + ch;
+#pragma unroll
+              for (int j = 0; j < 2; ++j)
+                st_global_256(dl + 16 * j, lo[8 * j], lo[8 * j + 1], lo[8 * j + 2], lo[8 * j + 3], lo[8 * j + 4], lo[8 * j + 5],
+                              lo[8 * j + 6], lo[8 * j + 7]);
             }
           }
         }
@@ -368,46 +375,35 @@ __device__ __forceinline__ void conv_epilogue_loop(const ConvParams& p, uint32_t
             split_pack2(m0, m1, hi[j], lo[j]);
           }
           if (writer) {
-            if constexpr (STORE256) {
-              __nv_bfloat16* dh = p.pool_hi + opix * p.cout + ch;
+            __nv_bfloat16* dh = p.pool_hi + opix * p.cout + ch;
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+              st_global_256(dh + 16 * j, hi[8 * j], hi[8 * j + 1], hi[8 * j + 2], hi[8 * j + 3], hi[8 * j + 4], hi[8 * j + 5],
+                            hi[8 * j + 6], hi[8 * j + 7]);
+            if (p.pool_lo) {
+              __nv_bfloat16* dl = p.pool_lo + opix * p.cout + ch;
 #pragma unroll
               for (int j = 0; j < 2; ++j)
-                st_global_256(dh + 16 * j, hi[8 * j], hi[8 * j + 1], hi[8 * j + 2], hi[8 * j + 3], hi[8 * j + 4], hi[8 * j + 5],
-                              hi[8 * j + 6], hi[8 * j + 7]);
-              if (p.pool_lo) {
-                __nv_bfloat16* dl = p.pool_lo + opix * p.cout + ch;
-#pragma unroll
-                for (int j = 0; j < 2; ++j)
-                  st_global_256(dl + 16 * j, lo[8 * j], lo[8 * j + 1], lo[8 * j + 2], lo[8 * j + 3], lo[8 * j + 4], lo[8 * j + 5],
-                                lo[8 * j + 6], lo[8 * j + 7]);
-              }
-            } else {
-              uint4* dh = reinterpret_cast<uint4*>(p.pool_hi + opix * p.cout + ch);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) dh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-              if (p.pool_lo) {
-                uint4* dl = reinterpret_cast<uint4*>(p.pool_lo + opix * p.cout + ch);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) dl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
-              }
+                st_global_256(dl + 16 * j, lo[8 * j], lo[8 * j + 1], lo[8 * j + 2], lo[8 * j + 3], lo[8 * j + 4], lo[8 * j + 5],
+                              lo[8 * j + 6], lo[8 * j + 7]);
             }
           }
         }
       }
     }
-    if (ks > 1 && part > 0) {   // helper: publish the partial (one count per epilogue warp)
+    if (role == 2) {   // helper: publish the partial (one count per epilogue warp)
       __threadfence();
       __syncwarp();
-      if (lane == 0) red_release_gpu_add_u32(p.sk_flags + tile, 1u);
+      if (lane == 0) red_release_gpu_add_u32(p.sk_flags + owner_cta, 1u);
     }
     tc_fence_before();
-    if (PAIR) mbar_arrive_cluster(tempty_remote + as * 8);
-    else mbar_arrive(&tempty_bar[as]);
+    mbar_arrive(&tempty_bar[as]);
   }
-  if (use_tma && epi_leader) tma_store_wait_all<0>();
+  if (TMA_STORE && epi_leader) tma_store_wait_all<0>();
 }
 
-// LEAN epilogue (opt-in, OSVOS_HALO_LEAN=1; UNMEASURED at the time of writing - see DESIGN.md section 4, round-2 list):
+// LEAN epilogue - the default for plain forward launches (measured +2.9 % on the 480p frame against the general epilogue
+// with 16-byte stores, profiles/r02_ab_matrix.txt; OSVOS_HALO_LEAN=0 selects the general epilogue for A/B runs):
 // the inference / plain-forward feature set only - bias, ReLU, split-bf16 act output and / or fused 2x2 max pool, exact
 // mode with the N-concatenated accumulator - written against what ncu showed of the general epilogue on the Cin <= 128
 // layers (profiles/r01f_ncu_stall_by_role.txt):
@@ -418,10 +414,7 @@ __device__ __forceinline__ void conv_epilogue_loop(const ConvParams& p, uint32_t
 //  * the accumulator stage is handed back to the MMA warp right after the LAST tcgen05.ld of the tile has landed,
 //    before the stores - not at the end of the tile;
 //  * no mask / column-sum / fp32 / split-K / bulk-store code: ~1/3 of the instruction footprint next to the issuer.
-//  * QUAD_POOL (OSVOS_HALO_LEAN=2): the 2x2 max pool splits the 32 channels among the four lanes of a window instead
-//    of letting all four compute all 32 maxima - 16 + 8 shuffles per chunk instead of 64, a quarter of the split work,
-//    and every lane of the window stores 16 bytes per plane (the max-pool shuffles were conv2_2's top stall).
-template <int BLOCK_N, bool QUAD_POOL = false>
+template <int BLOCK_N>
 __device__ __forceinline__ void conv_epilogue_lean(const ConvParams& p, uint32_t tmem_base, uint64_t* tfull_bar,
                                                    uint64_t* tempty_bar, int warp, int lane) {
   static_assert(BLOCK_N == 64 || BLOCK_N == 128, "lean epilogue: 64- or 128-wide exact tiles");
@@ -498,33 +491,7 @@ __device__ __forceinline__ void conv_epilogue_lean(const ConvParams& p, uint32_t
           }
         }
       }
-      if (QUAD_POOL && p.pool_hi) {
-        // fused MaxPool2d(2, 2, ceil_mode=True), channels split over the window's four lanes: after the x exchange a
-        // lane holds the row-pair maxima of 16 channels (odd x: the upper 16), after the y exchange the window maxima
-        // of 8 (odd y: the upper 8 of those).  Out-of-image pixels contribute -inf (ceil mode clips the window).
-        const bool odd_x = (lx & 1) != 0, odd_y = (ly & 1) != 0;
-        float a16[16], b8[8];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float lo_half = valid ? f[i] : -INFINITY, hi_half = valid ? f[16 + i] : -INFINITY;
-          const float keep = odd_x ? hi_half : lo_half, send = odd_x ? lo_half : hi_half;
-          a16[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 1));
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float keep = odd_y ? a16[8 + i] : a16[i], send = odd_y ? a16[i] : a16[8 + i];
-          b8[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 8));
-        }
-        uint32_t ph[4], pl[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) split_pack2(b8[2 * j], b8[2 * j + 1], ph[j], pl[j]);
-        const int cbase = (odd_x ? 16 : 0) + (odd_y ? 8 : 0);
-        if (((y & ~1) < p.h) && ((x & ~1) < p.w)) {      // the window's top-left pixel exists <=> the pooled pixel does
-          *reinterpret_cast<uint4*>(p.pool_hi + opix * p.cout + ch + cbase) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-          if (p.pool_lo)
-            *reinterpret_cast<uint4*>(p.pool_lo + opix * p.cout + ch + cbase) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
-        }
-      } else if (p.pool_hi) {
+      if (p.pool_hi) {
         // fused MaxPool2d(2, 2, ceil_mode=True): partners are lanes ^1 (x) and ^8 (y); out-of-image partners excluded
         uint32_t hi[16], lo[16];
 #pragma unroll
@@ -555,7 +522,7 @@ __device__ __forceinline__ void conv_epilogue_lean(const ConvParams& p, uint32_t
   }
 }
 
-// Output act [n,h,w,cout] -> 4-D store maps with box {64, kTileW, kTileH, 1} (SWIZZLE_128B).
+// Output act [n,h,w,cout] -> 4-D store maps with box {64, kTileW, kTileH, 1} (SWIZZLE_128B); conv1_1's bulk stores.
 static inline int encode_output_maps(CUtensorMap* hi, CUtensorMap* lo, const osvos_conv3x3_args* a) {
   const uint64_t dims[4] = {(uint64_t)a->cout, (uint64_t)a->w, (uint64_t)a->h, (uint64_t)a->n};
   const uint64_t strides[3] = {(uint64_t)a->cout * 2, (uint64_t)a->w * a->cout * 2, (uint64_t)a->h * a->w * a->cout * 2};
@@ -594,7 +561,7 @@ static inline void fill_conv_params(ConvParams& p, const osvos_conv3x3_args* a, 
   p.k_chunks = a->cin / kBlockK;
   p.k_steps = (a->k_valid > 0 && a->k_valid < kBlockK) ? (a->k_valid + 15) / 16 : kBlockK / 16;
   p.flags = a->flags;
-  p.ksplit = 1;
+  p.streamk = 0;
   {
     static int ablate = -1;
     if (ablate < 0) {
@@ -624,8 +591,6 @@ static inline int encode_weight_maps(CUtensorMap* hi, CUtensorMap* lo, const osv
 int conv_first_tc_launch(const float* x, const float* w_oihw, const float* bias, void* y_hi, void* y_lo, int n, int h,
                          int w, int flags, cudaStream_t stream);
 int side_conv_dispatch(const osvos_conv3x3_args* a, cudaStream_t stream);
-int conv3x3_halo2_dispatch(const osvos_conv3x3_args* a, cudaStream_t stream);
-int conv3x3_halo_dispatch(const osvos_conv3x3_args* a, cudaStream_t stream, int pitch, int use_bo);
-size_t conv3x3_splitk_workspace_bytes(int n, int h, int w, int cin, int cout);
+int conv3x3_halo_dispatch(const osvos_conv3x3_args* a, cudaStream_t stream);
 
 }  // namespace osvos

@@ -128,7 +128,7 @@ conv_first_tc_kernel(const float* __restrict__ x, const float* __restrict__ wgt,
     }
     __syncwarp();
   } else if (warp >= 2 && warp < 10) {
-    conv_epilogue_loop<64>(p, tmem_base, tfull_bar, tempty_bar, warp, lane, &map_y_hi, &map_y_lo, staging);
+    conv_epilogue_loop<64, false, true>(p, tmem_base, tfull_bar, tempty_bar, warp, lane, &map_y_hi, &map_y_lo, staging);
   } else if (warp >= 10) {
     // ------------------------------------------------------------- A builders
     const int row = (warp - 10) * 32 + lane;  // GEMM row = pixel of the tile

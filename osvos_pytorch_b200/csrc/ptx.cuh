@@ -92,6 +92,9 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu_u32(const unsigned int* p) {
 __device__ __forceinline__ void red_release_gpu_add_u32(unsigned int* p, uint32_t v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ void st_relaxed_gpu_u32(unsigned int* p, uint32_t v) {
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;

@@ -10,19 +10,23 @@
 //
 // Replaces side_prep[i] (+ score_dsn[i] and this scale's slice of fuse as projections), reference
 // networks/vgg_osvos.py:41,44,54 run at :67,69,72.  Same argument contract as osvos_conv3x3 with cout == 16.
+//
+// NCO = 2 - the FOLDED side branch (inference): side_prep has no ReLU, so side_prep followed by the two 1x1 projections
+// (score_dsn, this scale's slice of fuse) is ONE linear 3x3 convolution C -> 2 whose weights are
+// W'[o][ci][tap] = sum_co proj[o][co] * W_side[co][ci][tap] (osvos_fold_side_weights).  The same kernel then runs with
+// N = 32 (18 used) instead of 144: 1/8 of the accumulator columns to exchange, 1/4.5 of the weight bytes to stream,
+// a third less tensor time - the side branch was bound by exactly those (shared-memory bandwidth: the N = 144 MMA alone
+// reads 120 B/clk of operands).  Training keeps NCO = 16: its backward needs the 16 features.
 #include "conv_common.cuh"
 
 namespace osvos {
 
 constexpr int kSideTileW = 8, kSideTileH = 10;              // output tile
 constexpr int kSideHaloW = 10, kSideHaloH = 12;             // 120 halo pixels = GEMM rows
-constexpr int kSideN = 144;                                 // 9 taps x 16 channels
 constexpr int kSideThreads = 192;                           // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
 constexpr int kSideABox = kSideHaloW * kSideHaloH * 128;    // 15360 B
 constexpr int kSideAPlane = 128 * 128;                      // the MMA reads 128 rows
-constexpr int kSideBPlane = kSideN * 128;                   // 18432 B
-constexpr int kSideAStages = 2, kSideBStages = 3;
-constexpr int kSideYBuf = 3 * 16 * 128 * 4;                 // one tap row: [s][co][halo px (128)] floats = 24 KiB
+constexpr int kSideAStages = 2;
 
 struct SideParams {
   const float* bias;
@@ -35,11 +39,19 @@ struct SideParams {
   int relu;
 };
 
-template <int PLANES>
+template <int PLANES, int NCO>
 struct SideCfg {
+  static_assert(NCO == 16 || NCO == 2, "16 side features, or the 2 folded projections");
+  static constexpr int kN = NCO == 16 ? 144 : 32;             // MMA N: 9 taps x NCO columns (18 of the 32 used)
+  static constexpr int kBBox = 9 * NCO * 128;                 // bytes the weight box of one chunk and plane delivers
+  static constexpr int kBPlane = kN * 128;                    // 18432 / 4096 B: what the MMA reads (1 KiB multiple)
+  static constexpr int kBStages = NCO == 16 ? 3 : 6;
   static constexpr int kAStage = PLANES * kSideAPlane;
-  static constexpr int kBStage = PLANES * kSideBPlane;
-  static constexpr int kSmem = kSideAStages * kAStage + kSideBStages * kBStage + kSideYBuf + 1024 + 256;
+  static constexpr int kBStage = PLANES * kBPlane;
+  // exchange buffer: NCO = 16: one tap row [s][co][halo px (128)] floats = 24 KiB;
+  //                  NCO = 2: two buffers (alternating tiles) of [tap][halo px] float2 = 2 x 9 KiB
+  static constexpr int kYBuf = NCO == 16 ? 3 * 16 * 128 * 4 : 2 * 9 * 128 * 8;
+  static constexpr int kSmem = kSideAStages * kAStage + kBStages * kBStage + kYBuf + 1024 + 256;
 };
 
 __device__ __forceinline__ void side_decode(const SideParams& p, int tile, int& tx, int& ty, int& img) {
@@ -49,12 +61,13 @@ __device__ __forceinline__ void side_decode(const SideParams& p, int tile, int& 
   img = t / p.tiles_y;
 }
 
-template <int PLANES>
+template <int PLANES, int NCO>
 __global__ void __launch_bounds__(kSideThreads, 1)
 side_conv_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo,
                  const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
                  const SideParams p) {
-  using Cfg = SideCfg<PLANES>;
+  using Cfg = SideCfg<PLANES, NCO>;
+  constexpr int kSideBStages = Cfg::kBStages, kSideBPlane = Cfg::kBPlane, kSideN = Cfg::kN, kSideYBuf = Cfg::kYBuf;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
@@ -116,7 +129,7 @@ side_conv_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
           if (PLANES == 2)
             tma_load_4d(&map_x_lo, &a_full[a_stage], sa + kSideAPlane, kc * 64, tx * kSideTileW - 1,
                         ty * kSideTileH - 1, img);
-          mbar_arrive_expect_tx(&b_full[b_stage], PLANES * kSideBPlane);
+          mbar_arrive_expect_tx(&b_full[b_stage], PLANES * Cfg::kBBox);
           tma_load_3d(&map_w_hi, &b_full[b_stage], sb, kc * 64, 0, 0);
           if (PLANES == 2) tma_load_3d(&map_w_lo, &b_full[b_stage], sb + kSideBPlane, kc * 64, 0, 0);
         }
@@ -197,6 +210,33 @@ side_conv_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
       mbar_wait(&tfull_bar[as], aph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + as * 256 + (static_cast<uint32_t>(q * 32) << 16);
+      if constexpr (NCO == 2) {
+        // folded projections: column 2 * tap + o of halo pixel `row`.  One read, accumulator handed back at once, one
+        // exchange through the buffer of this tile's parity (a single barrier per tile), nine float2 gathers.
+        uint32_t v[32];
+        tmem_ld32(taddr, v);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(&tempty_bar[as]);
+        float2* yb = reinterpret_cast<float2*>(ybuf) + (it & 1) * 9 * 128;
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap)
+          yb[tap * 128 + row] = make_float2(__uint_as_float(v[2 * tap]), __uint_as_float(v[2 * tap + 1]));
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int y = ty * kSideTileH + oy, x = tx * kSideTileW + ox;
+        if (row < kSideTileW * kSideTileH && y < p.h && x < p.w) {
+          float sp = p.bias ? __ldg(p.bias) : 0.f, sq = p.bias ? __ldg(p.bias + 1) : 0.f;
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            const float2 t = yb[tap * 128 + (oy + tap / 3) * kSideHaloW + ox + tap % 3];
+            sp += t.x;
+            sq += t.y;
+          }
+          const size_t pix = (static_cast<size_t>(img) * p.h + y) * p.w + x;
+          *reinterpret_cast<float2*>(p.pq + pix * 2) = make_float2(sp, sq);
+        }
+        continue;
+      }
       float acc[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) acc[j] = p.bias ? __ldg(p.bias + j) : 0.f;
@@ -258,9 +298,9 @@ side_conv_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
   }
 }
 
-template <int PLANES>
+template <int PLANES, int NCO>
 static int launch_side(const osvos_conv3x3_args* a, cudaStream_t stream) {
-  using Cfg = SideCfg<PLANES>;
+  using Cfg = SideCfg<PLANES, NCO>;
   SideParams p;
   p.bias = a->bias;
   p.y_f32 = a->y_f32;
@@ -289,10 +329,10 @@ static int launch_side(const osvos_conv3x3_args* a, cudaStream_t stream) {
     if (rc) return rc;
   }
   {
-    const size_t plane = static_cast<size_t>(9) * 16 * a->cin;
-    const uint64_t dims[3] = {(uint64_t)a->cin, 16, 9};
-    const uint64_t strides[2] = {(uint64_t)a->cin * 2, (uint64_t)16 * a->cin * 2};
-    const uint32_t box[3] = {64, 16, 9};
+    const size_t plane = static_cast<size_t>(9) * NCO * a->cin;
+    const uint64_t dims[3] = {(uint64_t)a->cin, NCO, 9};
+    const uint64_t strides[2] = {(uint64_t)a->cin * 2, (uint64_t)NCO * a->cin * 2};
+    const uint32_t box[3] = {64, NCO, 9};
     const __nv_bfloat16* wp = static_cast<const __nv_bfloat16*>(a->w_packed);
     int rc = encode_tensor_map(&mw_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 3, wp, dims, strides, box,
                                CU_TENSOR_MAP_SWIZZLE_128B);
@@ -301,7 +341,7 @@ static int launch_side(const osvos_conv3x3_args* a, cudaStream_t stream) {
                            CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
-  auto kern = side_conv_kernel<PLANES>;
+  auto kern = side_conv_kernel<PLANES, NCO>;
   static uint64_t attr_done = 0;   // per instantiation: bit d = device d has the shared-memory opt-in
   OSVOS_CHECK_CUDA(ensure_dynamic_smem(kern, Cfg::kSmem, &attr_done));
   const int sms = device_sm_count();
@@ -311,7 +351,9 @@ static int launch_side(const osvos_conv3x3_args* a, cudaStream_t stream) {
 }
 
 int side_conv_dispatch(const osvos_conv3x3_args* a, cudaStream_t stream) {
-  return (a->flags & OSVOS_FLAG_FAST) ? launch_side<1>(a, stream) : launch_side<2>(a, stream);
+  if (a->cout == 2)   // folded projections (osvos_fold_side_weights): pq only
+    return (a->flags & OSVOS_FLAG_FAST) ? launch_side<1, 2>(a, stream) : launch_side<2, 2>(a, stream);
+  return (a->flags & OSVOS_FLAG_FAST) ? launch_side<1, 16>(a, stream) : launch_side<2, 16>(a, stream);
 }
 
 }  // namespace osvos

@@ -29,6 +29,9 @@ class OSVOSEngine:
         # training loops of this package set this: backward adds weight / trunk-bias gradients straight into an
         # existing p.grad (and hands autograd None for them) instead of returning tensors for AccumulateGrad
         self.accumulate_param_grads_in_place = False
+        # inference only: fold side_prep with its two 1x1 projections into one 3x3 conv C -> 2 (OSVOS_FOLD_SIDE=0, read per
+        # eager pass, switches it off for A/B runs)
+        self.fold_side_branch = True
 
     def direct_grad_accumulation(self):
         """Context manager enabling in-place gradient accumulation for the backward passes run inside it."""
@@ -110,6 +113,13 @@ class OSVOSEngine:
         return self._cached(("proj", i), [sd.weight, fu.weight],
                             lambda: torch.cat([sd.weight.detach().reshape(16),
                                                fu.weight.detach().reshape(64)[16 * i:16 * i + 16]]).float().contiguous())
+
+    def _folded_side(self, i):
+        """(packed [2,C,3,3] operand, bias2) of side_prep[i] folded with score_dsn[i] and fuse's slice (inference)."""
+        m = self.m
+        sp, sd = m.side_prep[i], m.score_dsn[i]
+        return self._cached(("fold", i), [sp.weight, sp.bias, sd.weight, sd.bias, m.fuse.weight],
+                            lambda: ops.fold_side_weights(sp.weight, sp.bias.detach(), self._proj(i), sd.bias.detach()))
 
     def _check_deconvs(self):
         """The native tail implements the bilinear deconvolution in closed form; both entry points of
@@ -231,6 +241,10 @@ class OSVOSEngine:
                 _, feat, _ = ops.conv3x3(full, self._packed(sp, f"sp{i}"), sp.bias.detach(), 16, relu=False, fast=fast,
                                          out_act=False, out_f32=True, simt=True)
                 pq = ops.side_project(feat, self._proj(i - 1), m.score_dsn[i - 1].bias.detach())
+            elif not return_intermediates and self.fold_side_branch and os.environ.get("OSVOS_FOLD_SIDE", "1") != "0":
+                # inference: side_prep o (score_dsn, fuse slice) folded into one 3x3 conv C -> 2 (include/osvos_b200.h)
+                feat = None
+                pq = ops.side_folded(full, *self._folded_side(i - 1), fast=fast)
             else:
                 _, feat, pq = ops.conv3x3(full, self._packed(sp, f"sp{i}"), sp.bias.detach(), 16, relu=False, fast=fast,
                                           out_act=False, out_f32=return_intermediates, proj_w=self._proj(i - 1),

@@ -97,6 +97,52 @@ def conv_first(x, weight, bias, relu=True, fast=False):
     return y
 
 
+_STREAMK_WS = {}
+
+
+def streamk_workspace(dev):
+    """The conv kernel's stream-K exchange buffer: ONE zero-filled allocation per (device, stream), reused by every
+    launch on that stream (the kernel hands its counters back at zero; launches on one stream are ordered, so they
+    never use it concurrently).  Allocated outside CUDA-graph capture by the engine's eager warm-up pass."""
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), torch.cuda.current_stream(dev).cuda_stream)
+    ws = _STREAMK_WS.get(key)
+    if ws is None:
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("stream-K workspace must be allocated before CUDA-graph capture (run one eager pass first)")
+        ws = torch.zeros(nat.load().osvos_conv3x3_streamk_workspace_bytes(), dtype=torch.uint8, device=dev)
+        _STREAMK_WS[key] = ws
+    return ws
+
+
+def fold_side_weights(side_w, side_b, proj_w, proj_b):
+    """side_prep o {score_dsn, fuse slice} -> (packed [2, cin, 3, 3] operand, bias2 [2]); see include/osvos_b200.h."""
+    lib = nat.load()
+    side_w = side_w.detach().contiguous().float()
+    cin = int(side_w.shape[1])
+    packed = torch.empty(lib.osvos_packed_weight_bytes(2, cin) // 2, dtype=torch.bfloat16, device=side_w.device)
+    bias2 = torch.empty(2, dtype=torch.float32, device=side_w.device)
+    _count()
+    nat.check(lib.osvos_fold_side_weights(side_w.data_ptr(), nat.ptr(side_b), proj_w.data_ptr(), nat.ptr(proj_b),
+                                          packed.data_ptr(), bias2.data_ptr(), cin, _stream()), "osvos_fold_side_weights")
+    return packed, bias2
+
+
+def side_folded(x, packed, bias2, fast=False):
+    """pq [n,h,w,2] of the folded side branch (cout == 2 call of osvos_conv3x3)."""
+    lib = nat.load()
+    n, h, w, cin = x.shape
+    dev = x.hi.device
+    pq = torch.empty((n, h, w, 2), dtype=torch.float32, device=dev)
+    a = nat.Conv3x3Args()
+    a.x_hi, a.x_lo = x.hi.data_ptr(), nat.ptr(x.lo)
+    a.w_packed, a.bias, a.pq = packed.data_ptr(), bias2.data_ptr(), pq.data_ptr()
+    a.n, a.h, a.w, a.cin, a.cout = n, h, w, cin, 2
+    a.flags = nat.FLAG_FAST if fast else 0
+    _count()
+    nat.check(lib.osvos_conv3x3(byref(a), _stream()), "osvos_conv3x3 (folded side branch)")
+    return pq
+
+
 def conv3x3(x, w_packed, bias, cout, relu=False, fast=False, out_act=True, out_f32=False, mask=None,
             proj_w=None, proj_b=None, simt=False, pool=False, colsum=None, k_valid=0):
     """3x3 / pad 1 conv of an Act through the tcgen05 kernel.  Returns (Act|None, f32|None, pq|None), or
@@ -122,9 +168,7 @@ def conv3x3(x, w_packed, bias, cout, relu=False, fast=False, out_act=True, out_f
     a.colsum = nat.ptr(colsum)
     a.k_valid = k_valid
     a.n, a.h, a.w, a.cin, a.cout = n, h, w, cin, cout
-    skb = 0 if simt else lib.osvos_conv3x3_splitk_workspace_bytes(n, h, w, cin, cout)
-    sk_ws = torch.empty(skb, dtype=torch.uint8, device=dev) if skb else None   # small layers: split-K partials
-    a.splitk_ws = nat.ptr(sk_ws)
+    a.streamk_ws = None if simt else streamk_workspace(dev).data_ptr()
     a.flags = (nat.FLAG_RELU if relu else 0) | (nat.FLAG_FAST if fast else 0) | \
               (nat.FLAG_RELU_MASK if mask is not None else 0)
     fn = lib.osvos_conv3x3_simt if simt else lib.osvos_conv3x3

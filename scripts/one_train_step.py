@@ -12,10 +12,14 @@ from oracle import osvos_oracle as oc
 from osvos_pytorch_b200.layers.osvos_layers import class_balanced_cross_entropy_loss as cbce
 from osvos_pytorch_b200.networks.vgg_osvos import OSVOS, he_init_
 
-h, w = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (480, 854)
+argv = [a for a in sys.argv[1:] if not a.startswith("--")]
+h, w = (int(argv[0]), int(argv[1])) if len(argv) >= 2 else (480, 854)
 net = he_init_(OSVOS(pretrained=0, verbose=False)).cuda().train()
 x, gt = oc.synthetic_frame(1, h, w, 1234)
-loss = cbce(net(x.cuda())[-1], gt.cuda(), size_average=False)
+if "--unfused" in sys.argv:      # the reference's call sequence: forward, separate loss, autograd
+    loss = cbce(net(x.cuda())[-1], gt.cuda(), size_average=False)
+else:                            # the package's fused objective (tail + loss one kernel each way)
+    _, loss, _ = net.forward_objective(x.cuda(), gt.cuda(), (0.0, 0.0, 0.0, 0.0, 1.0))
 loss.backward()
 torch.cuda.synchronize()
 print("ok", float(loss))

@@ -4,6 +4,8 @@ import sys
 import numpy as np
 import pytest
 
+# the library caches its environment switches at the first dispatch; the tests flip them per test
+os.environ.setdefault("OSVOS_ENV_RELOAD", "1")
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

@@ -88,28 +88,69 @@ def test_conv3x3_tensor_core(dev, n, h, w, cin, cout, relu, fast):
     assert maxrel(got_f32, ys.permute(0, 3, 1, 2).cpu()) < 2e-5
 
 
-@pytest.mark.parametrize("n,h,w,cin,cout,expect_ks", [(1, 30, 54, 512, 512, 2), (1, 15, 27, 512, 512, 4),
-                                                        (2, 9, 11, 256, 128, 2), (1, 33, 45, 128, 256, 0)])
-def test_conv3x3_split_k_opt_in(dev, monkeypatch, n, h, w, cin, cout, expect_ks):
-    """OSVOS_SPLITK=1: 2 / 4 CTAs per output tile, partial accumulators exchanged through the workspace
-    (kept opt-in: measured slower than the N = 64 tiles at these sizes).  Same result as the default path."""
-    from osvos_pytorch_b200 import _native as nat, ops
+@pytest.mark.parametrize("n,h,w,cin,cout", [(1, 30, 54, 512, 512),      # stage 5 at 480p: 56 tiles of 128 x 128, 8 chunks
+                                            (1, 60, 107, 512, 512),     # stage 4: 224 tiles on 148 SMs
+                                            (1, 15, 27, 512, 512),      # 16 tiles: every CTA reduces ONE chunk, 7 helpers per tile
+                                            (2, 9, 11, 256, 128),       # tiny: 4 tiles x 4 chunks
+                                            (1, 60, 107, 512, 256),     # dgrad of conv4_1 (112 tiles)
+                                            (1, 33, 45, 128, 256)])     # 2 chunks
+@pytest.mark.parametrize("relu_mask", [False, True])
+def test_conv3x3_stream_k(dev, monkeypatch, n, h, w, cin, cout, relu_mask):
+    """Stream-K scheduling (csrc/conv_common.cuh: WorkList): same convolution with the (tile, chunk) units dealt out in
+    balanced ranges and fp32 partial accumulators exchanged through the workspace, against the whole-tile schedule
+    (OSVOS_STREAMK=0) and the fp64 reference; run twice to check that the workspace counters come back at zero."""
+    from osvos_pytorch_b200 import ops
     g = torch.Generator().manual_seed(7 + h + cin)
     x = torch.randn(n, cin, h, w, generator=g) * 3.0
     wt = torch.randn(cout, cin, 3, 3, generator=g) * math.sqrt(2.0 / (9 * cin))
     b = torch.randn(cout, generator=g) * 0.1
     a = ops.nchw_to_act(x.to(dev))
     wp = ops.pack_conv3x3_weights(wt.to(dev))
-    _, base, _ = ops.conv3x3(a, wp, b.to(dev), cout, relu=True, out_act=False, out_f32=True)
-    monkeypatch.setenv("OSVOS_SPLITK", "1")
-    nbytes = nat.load().osvos_conv3x3_splitk_workspace_bytes(n, h, w, cin, cout)
-    assert (nbytes > 0) == (expect_ks > 0)
-    y, split, _ = ops.conv3x3(a, wp, b.to(dev), cout, relu=True, out_act=True, out_f32=True)
-    torch.cuda.synchronize()
-    ref = F.conv2d(x.double(), wt.double(), b.double(), padding=1).relu()
-    assert maxrel(split.permute(0, 3, 1, 2).cpu(), ref) < EXACT_TOL
-    assert maxrel(split, base) < 1e-5                       # only the fp32 summation order differs
-    assert torch.equal(ops.act_to_nchw(y).cpu(), split_round(split.permute(0, 3, 1, 2).cpu()))
+    mask = ops.nchw_to_act(torch.randn(n, cout, h, w, generator=g).clamp(min=0).to(dev)).hi if relu_mask else None
+    colsum0 = torch.zeros(cout, device=dev) if relu_mask else None
+    monkeypatch.setenv("OSVOS_STREAMK", "0")
+    _, base, _ = ops.conv3x3(a, wp, b.to(dev), cout, relu=not relu_mask, out_act=False, out_f32=True, mask=mask, colsum=colsum0)
+    monkeypatch.setenv("OSVOS_STREAMK", "1")
+    for rep in range(2):
+        colsum = torch.zeros(cout, device=dev) if relu_mask else None
+        y, split, _ = ops.conv3x3(a, wp, b.to(dev), cout, relu=not relu_mask, out_act=True, out_f32=True, mask=mask, colsum=colsum)
+        torch.cuda.synchronize()
+        if not relu_mask:
+            ref = F.conv2d(x.double(), wt.double(), b.double(), padding=1).relu()
+            assert maxrel(split.permute(0, 3, 1, 2).cpu(), ref) < EXACT_TOL
+        assert maxrel(split, base) < 1e-5                       # only the fp32 summation order differs
+        assert torch.equal(ops.act_to_nchw(y).cpu(), split_round(split.permute(0, 3, 1, 2).cpu()))
+        if relu_mask:
+            assert maxrel(colsum, colsum0) < 1e-4
+    # (the workspace counters are handed back at zero: the second repetition would trap on its bounded spin otherwise)
+
+
+def test_side_branch_folded_into_one_conv(dev):
+    """side_prep (no ReLU) + score_dsn + fuse slice == ONE 3x3 conv C -> 2 (osvos_fold_side_weights): same pq as the
+    16-feature kernel with fused projections, to fp32 reassociation."""
+    from osvos_pytorch_b200 import ops
+    for n, h, w, cin in [(1, 30, 27, 128), (2, 17, 13, 256), (1, 60, 107, 512), (1, 5, 3, 512), (1, 120, 214, 128)]:
+        g = torch.Generator().manual_seed(h + cin)
+        x = torch.randn(n, cin, h, w, generator=g) * 3.0
+        wt = torch.randn(16, cin, 3, 3, generator=g) * math.sqrt(2.0 / (9 * cin))
+        bs = torch.randn(16, generator=g) * 0.1
+        proj = torch.randn(32, generator=g) * 0.3
+        pb = torch.randn(1, generator=g)
+        a = ops.nchw_to_act(x.to(dev))
+        _, _, pq16 = ops.conv3x3(a, ops.pack_conv3x3_weights(wt.to(dev)), bs.to(dev), 16, out_act=False, proj_w=proj.to(dev),
+                                 proj_b=pb.to(dev))
+        packed, bias2 = ops.fold_side_weights(wt.to(dev), bs.to(dev), proj.to(dev), pb.to(dev))
+        pq2 = ops.side_folded(a, packed, bias2)
+        torch.cuda.synchronize()
+        feat = F.conv2d(x.double(), wt.double(), bs.double(), padding=1)
+        want_p = (feat * proj[:16].double().view(1, 16, 1, 1)).sum(1) + pb.double()
+        want_q = (feat * proj[16:].double().view(1, 16, 1, 1)).sum(1)
+        want = torch.stack([want_p, want_q], dim=-1)
+        assert maxrel(pq2, want) < EXACT_TOL, (n, h, w, cin, maxrel(pq2, want))
+        assert maxrel(pq2, pq16) < 2e-5, (n, h, w, cin, maxrel(pq2, pq16))
+        # fast mode: one bf16 pass
+        pqf = ops.side_folded(ops.nchw_to_act(x.to(dev), True), packed, bias2, fast=True)
+        assert maxrel(pqf, want) < FAST_TOL
 
 
 def test_conv3x3_relu_mask_and_projection(dev):

@@ -1,14 +1,10 @@
-"""Parity of the library's OPT-IN kernel variants against the default path (and through it the oracle).
+"""The library's alternative code paths against the default path (and through it the oracle): the general epilogue instead
+of the lean one (OSVOS_HALO_LEAN=0), the three-pass accumulator (OSVOS_SPLITACC128=0), whole-tile scheduling instead of
+stream-K (OSVOS_STREAMK=0), no 256-wide tiles (OSVOS_CONV_N256=0), the unfolded side branch (OSVOS_FOLD_SIDE=0).
 
-These variants are diagnostic / next-round candidates that are off by default (README "Diagnostic switches"); some were
-written after the GPU budget of round 1 was spent and have never run.  The module is therefore skipped unless
-OSVOS_TEST_OPTIN=1, so that it cannot take the default suite down with it:
-
-    OSVOS_TEST_OPTIN=1 python -m pytest tests/test_gpu_optin.py -m gpu -q
-
-Every switch is read by the library per launch, so one process can flip it; CUDA graphs are off for the comparison.
-Store-flavour variants must reproduce the default bit for bit (same arithmetic, different store instructions); the
-three-pass accumulator variant within float reassociation noise.
+Every switch is re-read per launch under OSVOS_ENV_RELOAD=1 (tests/conftest.py), so one process can flip it; CUDA graphs
+are off for the comparison.  Variants that only change store instructions must reproduce the default bit for bit; variants
+that change the fp32 summation order within float reassociation noise.
 """
 import os
 
@@ -18,11 +14,10 @@ import torch
 from oracle import osvos_oracle as oc
 from gpu_util import maxrel
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("OSVOS_TEST_OPTIN") != "1", reason="opt-in variants: set OSVOS_TEST_OPTIN=1")]
+pytestmark = [pytest.mark.gpu]
 
-VARIANTS = [("OSVOS_HALO_LEAN", "1", 0.0), ("OSVOS_HALO_LEAN", "2", 0.0), ("OSVOS_HALO_ST256", "1", 0.0), ("OSVOS_HALO_TMA_STORE", "1", 0.0), ("OSVOS_SPLITACC128", "0", 1e-4),
-            ("OSVOS_SPLITK", "1", 1e-4)]
+VARIANTS = [("OSVOS_HALO_LEAN", "0", 0.0), ("OSVOS_SPLITACC128", "0", 1e-4), ("OSVOS_STREAMK", "0", 1e-4),
+            ("OSVOS_CONV_N256", "0", 1e-4), ("OSVOS_FOLD_SIDE", "0", 1e-4)]
 
 
 @pytest.fixture(scope="module")
@@ -73,5 +68,8 @@ def test_variant_backward_matches_default(net, monkeypatch, var, value, tol):
     assert abs(loss1 - loss0) <= max(tol, 1e-6) * abs(loss0)
     for k in g0:
         rel = float((g1[k] - g0[k]).norm() / (g0[k].norm() + 1e-30))
-        # atomics (wgrad workspace, fused bias sums) reorder between runs: 1e-5 of noise even for identical kernels
-        assert rel <= max(10 * tol, 1e-4), f"{k}: {rel:.2e}"
+        # atomics (wgrad workspace, fused bias sums) reorder between runs: 1e-5 of noise even for identical kernels; a
+        # variant that changes the fp32 SUMMATION ORDER of the forward (tol > 0) moves a few ReLU masks / pool argmax
+        # and with them the trunk gradients (6e-3 measured for the three-pass accumulator; the controlled comparison
+        # is tests/test_gpu_backward.py::test_backward_with_injected_gates_*)
+        assert rel <= (2e-2 if tol > 0 else 1e-4), f"{k}: {rel:.2e}"

@@ -114,10 +114,9 @@ def test_fast_mode_reports_its_error(net):
     assert err < 5e-2 and iou > 0.97
 
 
-@pytest.mark.parametrize("n,h,w", [(1, 720, 1280), (3, 97, 131), (1, 17, 9)])
+@pytest.mark.parametrize("n,h,w", [(1, 720, 1280), (1, 1080, 1920), (3, 97, 131), (1, 17, 9)])
 def test_forward_other_resolutions_vs_oracle(net, n, h, w):
-    """BASELINE.json configs[4] shapes (720p; 1080p is covered by the timing sweep), a ragged batch, and a frame
-    smaller than one tile at every stage."""
+    """BASELINE.json configs[4] shapes (720p, 1080p), a ragged batch, and a frame smaller than one tile at every stage."""
     x, _ = oc.synthetic_frame(n, h, w, 99)
     params = oc.he_params(seed=0)
     with torch.no_grad():

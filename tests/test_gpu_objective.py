@@ -160,3 +160,33 @@ def test_graphed_step_with_fused_objective_accumulates(net, dev):
             err = float((p.grad.double() - 2 * ref[k].double()).norm() / (2 * ref[k].double()).norm().clamp(min=1e-30))
             assert err < 2e-4, (k, err)
     net._engine.drop_derived_caches()
+
+
+def test_parent_objective_batch12_480p_vs_oracle(net, dev):
+    """BASELINE.json configs[3] at its real size: per-GPU batch 12 x 480x854, 5-loss parent objective (train_parent.py:
+    143-147) through the fused objective, against the oracle's autograd (CPU: about 15 s and 15 GB on the GPU box).
+    The loss's class-balance counts span the whole 12-frame tensor (layers/osvos_layers.py:30-32)."""
+    n, h, w, sw = 12, 480, 854, 0.75
+    x, gt = oc.synthetic_frame(n, h, w, 2024)
+    import os
+    torch.set_num_threads(min(32, os.cpu_count() or 1))
+    loss, outs, grads = oc.forward_backward(oc.he_params(seed=0), x, gt, objective="parent", side_weight=sw)
+    net.zero_grad(set_to_none=True)
+    maps, total, per_map = net.forward_objective(x.to(dev), gt.to(dev), (sw, sw, sw, sw, 1.0))
+    total.backward()
+    torch.cuda.synchronize()
+    for k in range(5):
+        assert maxrel(maps[k], outs[k]) <= 1e-3
+        ref_k = oc.class_balanced_cross_entropy_loss(outs[k], gt, size_average=False)
+        assert abs(float(per_map[k]) - float(ref_k)) <= 1e-4 * abs(float(ref_k))
+    assert abs(float(total) - float(loss)) <= 1e-4 * abs(float(loss))
+    worst = ("", 0.0)
+    for k, p in net.named_parameters():
+        if k in grads:
+            err = float((p.grad.cpu().double() - grads[k].double()).norm() / grads[k].double().norm())
+            if err > worst[1]:
+                worst = (k, err)
+            assert err < (1e-3 if k.startswith(("fuse", "score_dsn", "side_prep")) else 2e-3), (k, err)
+    print(f"parent objective, batch 12 x 480x854: loss {float(total):.2f} (oracle {float(loss):.2f}); worst per-parameter "
+          f"gradient error {worst[1]:.2e} ({worst[0]})")
+    net.zero_grad(set_to_none=True)

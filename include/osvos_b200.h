@@ -140,6 +140,26 @@ OSVOS_API int osvos_fold_side_weights(const float* side_w /* [16,cin,3,3] */, co
 /* Same contract on CUDA cores (fp32 FMA over hi+lo); debugging cross-check only. */
 OSVOS_API int osvos_conv3x3_simt(const osvos_conv3x3_args* args /* host */, osvos_stream_t stream);
 
+/* ---- stage 1 of the trunk as one kernel (inference) -------------------------------------
+ * conv1_1 + ReLU + conv1_2 + ReLU (+ the first MaxPool2d(2,2,ceil_mode=True)): networks/vgg_osvos.py:61,140-143.
+ * conv1_1 is evaluated inside conv1_2's kernel on the halo patch conv1_2 reads, so the 64-channel full-resolution map
+ * between the two layers never touches memory.  Exact mode only.  Outputs: the full-resolution act (y_*), the pooled
+ * act (pool_*), or both; all planes 32-byte aligned.  Same results as osvos_conv_first_fwd + osvos_conv3x3 up to the
+ * fp32 summation order inside conv1_1.                                                            */
+typedef struct {
+  const float* x;          /* [n,3,h,w] fp32 frame (NCHW)                    */
+  const float* w1;         /* conv1_1 weight [64,3,3,3] fp32 (OIHW)          */
+  const float* b1;         /* conv1_1 bias [64] or NULL                      */
+  const void* w2_packed;   /* conv1_2 weight, osvos_pack_conv3x3_weights(transpose_flip = 0) */
+  const float* b2;         /* conv1_2 bias [64] or NULL                      */
+  void* y_hi;              /* [n,h,w,64] or NULL                             */
+  void* y_lo;
+  void* pool_hi;           /* [n,ceil(h/2),ceil(w/2),64] or NULL             */
+  void* pool_lo;
+  int n, h, w;
+} osvos_stage1_args;
+OSVOS_API int osvos_stage1_fused(const osvos_stage1_args* args /* host */, osvos_stream_t stream);
+
 /* ---- MaxPool2d(2, 2, ceil_mode=True) on an act (networks/vgg_osvos.py:140) --- */
 OSVOS_API int osvos_maxpool2x2_fwd(const void* x_hi, const void* x_lo, void* y_hi, void* y_lo, int n, int h, int w, int c,
                          osvos_stream_t stream);

@@ -33,6 +33,12 @@ class Conv3x3Args(Structure):
                 ("k_valid", c_int), ("streamk_ws", c_void_p)]
 
 
+class Stage1Args(Structure):
+    _fields_ = [("x", c_void_p), ("w1", c_void_p), ("b1", c_void_p), ("w2_packed", c_void_p), ("b2", c_void_p),
+                ("y_hi", c_void_p), ("y_lo", c_void_p), ("pool_hi", c_void_p), ("pool_lo", c_void_p),
+                ("n", c_int), ("h", c_int), ("w", c_int)]
+
+
 class TailFwdArgs(Structure):
     _fields_ = [("pq", c_void_p * 4), ("fuse_bias", c_void_p), ("out", c_void_p * 5), ("label", c_void_p),
                 ("sums", c_void_p), ("losses", c_void_p), ("loss_weights", c_float * 5), ("divisor", c_float),
@@ -86,6 +92,7 @@ SIGNATURES = {
                                      c_void_p]),
     "osvos_conv3x3": (c_int, [POINTER(Conv3x3Args), c_void_p]),
     "osvos_conv3x3_streamk_workspace_bytes": (c_size_t, []),
+    "osvos_stage1_fused": (c_int, [POINTER(Stage1Args), c_void_p]),
     "osvos_fold_side_weights": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "osvos_conv3x3_simt": (c_int, [POINTER(Conv3x3Args), c_void_p]),
     "osvos_maxpool2x2_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),

@@ -347,16 +347,24 @@ __device__ __forceinline__ void conv_epilogue_loop(const ConvParams& p, uint32_t
           }
         }
         if (p.colsum) {
-          // fused bias gradient: per-channel sum of this warp's 32 pixels (butterfly), one atomic per lane
-          float mine = 0.f;
+          // fused bias gradient: per-channel sum over this warp's 32 pixels as a TRANSPOSING reduction - at every
+          // halving step a lane keeps the half of its columns selected by one bit of its lane index and hands the other
+          // half to its partner: 16 + 8 + 4 + 2 + 1 = 31 shuffles, after which lane l holds the total of column l
+          // (the butterfly-per-column form it replaces took 160), then one atomic per lane
+          float cs[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float sj = valid ? f[j] : 0.f;
+          for (int j = 0; j < 32; ++j) cs[j] = valid ? f[j] : 0.f;
 #pragma unroll
-            for (int off = 16; off > 0; off >>= 1) sj += __shfl_xor_sync(0xffffffffu, sj, off);
-            if (lane == j) mine = sj;
+          for (int half = 16; half >= 1; half >>= 1) {
+            const bool up = (lane & half) != 0;
+#pragma unroll
+            for (int i = 0; i < half; ++i) {
+              const float send = up ? cs[i] : cs[half + i];
+              const float keep = up ? cs[half + i] : cs[i];
+              cs[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+            }
           }
-          atomicAdd(p.colsum + ch + lane, mine);
+          atomicAdd(p.colsum + ch + lane, cs[0]);
         }
         if (p.pool_hi) {
           // fused MaxPool2d(2, 2, ceil_mode=True): the 2x2 partners are lanes ^1 (x) and ^8 (y) of this warp;

@@ -1,0 +1,387 @@
+// Stage 1 of the trunk as ONE kernel (inference): conv1_1 (3 -> 64, + bias + ReLU) computed INSIDE conv1_2's kernel,
+// on the 18 x 10-pixel halo patch conv1_2 reads anyway, so that the 105 MB split-bf16 map between the two layers is
+// never written to or read from memory (separately the two kernels took 51 + 82 us of a 790 us frame, conv1_1 being
+// nothing but that write).  Replaces stages[0] of the reference (networks/vgg_osvos.py:61,140-143: conv, ReLU, conv,
+// ReLU) and the first max pool (:140) when the caller only needs the pooled output.
+//
+// conv1_2 part = conv3x3_halo_kernel<64, exact, lean epilogue> unchanged: nine taps as nine UMMA descriptors into the
+// halo patch, weight slabs streamed by TMA through a ring, N-concatenated split accumulator, lean epilogue with the
+// fused 2 x 2 max pool.  What changes is WHO fills the activation stage: not a TMA box but four "stage-1" warps:
+//   1. build the im2col operand of conv1_1 for the 180 halo pixels (rows m = hy * 10 + hx, k = ci * 9 + 3r + s < 27,
+//      split bf16 hi / lo, canonical K-major SWIZZLE_128B rows - the layout of conv_first_tc.cu) from the fp32 frame;
+//   2. the MMA warp runs conv1_1 on it: two M = 128 halves x two K steps x (A_hi.[B_hi | B_lo] + A_lo.B_hi) into 2 x 128
+//      TMEM columns next to conv1_2's two accumulator stages (512 columns in all);
+//   3. the stage-1 warps read those accumulators back, add the bias, apply ReLU, ZERO the halo pixels that lie outside the
+//      image (they are conv1_2's zero padding, not conv1_1 evaluated outside the frame), split into hi / lo and write
+//      the rows of the activation stage exactly where the TMA box of the unfused kernel would have put them
+//      (generic-proxy writes + fence.proxy.async before the mbarrier arrive).
+// Issue order per tile j: [conv1_1 MMAs of tile j + 1] then [conv1_2 MMAs of tile j], so that steps 3 and 1 of the
+// stage-1 warps hide behind the 4 k cycles of conv1_2's MMAs.  Single-buffered im2col tile and conv1_1 accumulators.
+#include <string.h>
+
+#include "conv_common.cuh"
+
+namespace osvos {
+
+constexpr int kS1Pitch = 10;                                        // halo patch row pitch in pixels (packed rows)
+constexpr int kS1HaloRows = kTileH + 2;                             // 18
+constexpr int kS1HaloPx = kS1HaloRows * kS1Pitch;                   // 180 GEMM rows of conv1_1 per tile
+constexpr int kS1APlane = (kS1HaloPx * 128 + 1023) / 1024 * 1024;   // 23552 B: one plane of one activation stage
+constexpr int kS1AStage = 2 * kS1APlane;
+constexpr int kS1AStages = 2;
+constexpr int kS1BPlane = 64 * 128;                                 // conv1_2 weight slab, one plane (64 co x 64 ci)
+constexpr int kS1BStage = 2 * kS1BPlane;
+constexpr int kS1BStages = 3;
+constexpr int kS1Im2colPlane = 256 * 128;                           // M = 256 rows x 128 B (k < 32 used)
+constexpr int kS1W1Bytes = 2 * 64 * 128;                            // conv1_1 weights: [hi 64 rows][lo 64 rows]
+constexpr int kS1Smem = kS1AStages * kS1AStage + kS1BStages * kS1BStage + 2 * kS1Im2colPlane + kS1W1Bytes + 1024 + 512;
+constexpr int kS1EpiThreads = EpiCfg<64>::kThreads;                 // 256: warps 2 .. 9
+constexpr int kS1Threads = 64 + kS1EpiThreads + 128;                // + stage-1 warps 10 .. 13
+static_assert(kS1Smem <= 227 * 1024, "stage-1 kernel exceeds the per-CTA shared memory");
+static_assert(kS1Smem + 4096 < (1 << 18), "descriptor start-address field would overflow");
+
+struct Stage1Params {
+  const float* x;    // [n,3,h,w] fp32 frame
+  const float* w1;   // conv1_1 weight [64,3,3,3]
+  const float* b1;   // conv1_1 bias [64] or NULL
+};
+
+__global__ void __launch_bounds__(kS1Threads, 1)
+conv_stage1_fused_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
+                         const Stage1Params s1, const ConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem_a + kS1AStages * kS1AStage;
+  uint8_t* smem_i = smem_b + kS1BStages * kS1BStage;     // im2col operand: [hi plane 256 rows][lo plane 256 rows]
+  uint8_t* smem_w1 = smem_i + 2 * kS1Im2colPlane;        // conv1_1 weights [hi 64 rows][lo 64 rows]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_w1 + kS1W1Bytes);
+  uint64_t* a_full = bars;                       // [2] stage-1 warps -> MMA   (128 arrivals)
+  uint64_t* a_empty = bars + 2;                  // [2] MMA -> stage-1 warps   (commit)
+  uint64_t* b_full = bars + 4;                   // [3] TMA -> MMA
+  uint64_t* b_empty = bars + 4 + kS1BStages;     // [3] MMA -> TMA producer
+  uint64_t* tfull_bar = bars + 4 + 2 * kS1BStages;   // [2] conv1_2 accumulator ready
+  uint64_t* tempty_bar = tfull_bar + 2;              // [2] conv1_2 accumulator drained (256 arrivals)
+  uint64_t* i_full = tempty_bar + 2;             // im2col tile built              (128 arrivals)
+  uint64_t* i_empty = i_full + 1;                // conv1_1 MMAs have read it      (commit)
+  uint64_t* c_full = i_empty + 1;                // conv1_1 accumulators ready     (commit)
+  uint64_t* c_empty = c_full + 1;                // ... and read back              (128 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(c_empty + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map_w_hi);
+    tma_prefetch_desc(&map_w_lo);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&a_full[i], 128);
+      mbar_init(&a_empty[i], 1);
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], kS1EpiThreads);
+    }
+    for (int i = 0; i < kS1BStages; ++i) {
+      mbar_init(&b_full[i], 1);
+      mbar_init(&b_empty[i], 1);
+    }
+    mbar_init(i_full, 128);
+    mbar_init(i_empty, 1);
+    mbar_init(c_full, 1);
+    mbar_init(c_empty, 128);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);   // [0,256): two conv1_2 accumulator stages; [256,512): conv1_1, two M halves
+  pdl_wait();               // the frame / the weights may come from the previous kernel of the stream
+  pdl_launch_dependents();
+  // resident B operand of conv1_1: rows = co, k = ci*9 + 3r + s (the OIHW flattening), chunks 0..3 (k < 32)
+  for (int i = threadIdx.x; i < 64 * 4; i += kS1Threads) {
+    const int co = i >> 2, chunk = i & 3;
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int k0 = chunk * 8 + 2 * t;
+      const float v0 = k0 < 27 ? __ldg(s1.w1 + co * 27 + k0) : 0.f;
+      const float v1 = k0 + 1 < 27 ? __ldg(s1.w1 + co * 27 + k0 + 1) : 0.f;
+      split_pack2(v0, v1, hi[t], lo[t]);
+    }
+    *reinterpret_cast<uint4*>(smem_w1 + sw128_offset(co, chunk)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(smem_w1 + 64 * 128 + sw128_offset(co, chunk)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_c1 = tmem_base + 256;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer: conv1_2 weight slabs only
+    if (elect_one()) {
+      int b_stage = 0;
+      uint32_t b_phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          mbar_wait(&b_empty[b_stage], b_phase ^ 1);
+          uint8_t* st = smem_b + b_stage * kS1BStage;
+          mbar_arrive_expect_tx(&b_full[b_stage], kS1BStage);
+          tma_load_3d(&map_w_hi, &b_full[b_stage], st, 0, 0, tap);
+          tma_load_3d(&map_w_lo, &b_full[b_stage], st + kS1BPlane, 0, 0, tap);
+          if (++b_stage == kS1BStages) {
+            b_stage = 0;
+            b_phase ^= 1;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // -------------------------------------------------------------- MMA issuer (one elected thread)
+    if (elect_one()) {
+      constexpr uint32_t idesc64 = make_idesc_f16(kBlockM, 64, /*bf16=*/true);
+      constexpr uint32_t idesc128 = make_idesc_f16(kBlockM, 128, /*bf16=*/true);
+      constexpr uint64_t kDescA = (static_cast<uint64_t>(16 >> 4) << 16) | (static_cast<uint64_t>((kS1Pitch * 128) >> 4) << 32) |
+                                  (1ull << 46) | (static_cast<uint64_t>(kLayoutSW128) << 61);
+      constexpr uint64_t kDescK = (static_cast<uint64_t>(16 >> 4) << 16) | (static_cast<uint64_t>(1024 >> 4) << 32) |
+                                  (1ull << 46) | (static_cast<uint64_t>(kLayoutSW128) << 61);   // plain 8-row groups
+      const uint32_t smem_a_u32 = smem_u32(smem_a), smem_b_u32 = smem_u32(smem_b);
+      const uint64_t di_hi = kDescK | static_cast<uint64_t>(smem_u32(smem_i) >> 4);
+      const uint64_t di_lo = di_hi + (kS1Im2colPlane >> 4);
+      const uint64_t dw1 = kDescK | static_cast<uint64_t>(smem_u32(smem_w1) >> 4);   // [hi | lo]: 128 rows
+      uint32_t i_phase = 0, c_phase = 0;
+      // conv1_1 of one tile: 2 M halves x 2 K steps x (A_hi.[B_hi | B_lo] (N = 128) + A_lo.B_hi (N = 64))
+      auto conv1_1 = [&]() {
+        mbar_wait(i_full, i_phase);
+        mbar_wait(c_empty, c_phase ^ 1);          // the previous tile's accumulators have been read back
+        tc_fence_after();
+#pragma unroll
+        for (int mh = 0; mh < 2; ++mh) {
+          const uint32_t d = tmem_c1 + mh * 128;
+          const uint32_t moff = static_cast<uint32_t>(mh * 128 * 128) >> 4;
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            umma_f16(d, di_hi + moff + 2 * k, dw1 + 2 * k, idesc128, k != 0);
+            umma_f16(d, di_lo + moff + 2 * k, dw1 + 2 * k, idesc64, 1);
+          }
+        }
+        umma_commit(i_empty);
+        umma_commit(c_full);
+        i_phase ^= 1;
+        c_phase ^= 1;
+      };
+      int a_stage = 0, b_stage = 0;
+      uint32_t a_phase = 0, b_phase = 0;
+      int it = 0;
+      if (static_cast<int>(blockIdx.x) < p.total_tiles) conv1_1();
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        if (tile + static_cast<int>(gridDim.x) < p.total_tiles) conv1_1();     // next tile's conv1_1 first
+        const int as = it & 1;
+        const uint32_t aph = (it >> 1) & 1;
+        mbar_wait(&tempty_bar[as], aph ^ 1);
+        mbar_wait(&a_full[a_stage], a_phase);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * 128;
+        const uint64_t da0 = kDescA | static_cast<uint64_t>((smem_a_u32 + a_stage * kS1AStage) >> 4);
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          const uint32_t tap_off = static_cast<uint32_t>(((tap / 3) * kS1Pitch + (tap % 3)) * (128 >> 4));
+          mbar_wait(&b_full[b_stage], b_phase);
+          tc_fence_after();
+          const uint64_t db_hi = kDescK | static_cast<uint64_t>((smem_b_u32 + b_stage * kS1BStage) >> 4);
+          const uint64_t da_hi = da0 + tap_off;
+          const uint64_t da_lo = da_hi + (kS1APlane >> 4);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            umma_f16(tmem_d, da_hi + 2 * k, db_hi + 2 * k, idesc128, (tap | k) != 0);   // [A_hi.B_hi | A_hi.B_lo]
+            umma_f16(tmem_d, da_lo + 2 * k, db_hi + 2 * k, idesc64, 1);                 // + A_lo.B_hi
+          }
+          umma_commit(&b_empty[b_stage]);
+          if (tap == 8) {
+            umma_commit(&a_empty[a_stage]);
+            umma_commit(&tfull_bar[as]);
+          }
+          if (++b_stage == kS1BStages) {
+            b_stage = 0;
+            b_phase ^= 1;
+          }
+        }
+        if (++a_stage == kS1AStages) {
+          a_stage = 0;
+          a_phase ^= 1;
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp < 2 + kS1EpiThreads / 32) {
+    // ------------------------------------------------------------ conv1_2 epilogue (bias, ReLU, act and / or pooled output)
+    conv_epilogue_lean<64>(p, tmem_base, tfull_bar, tempty_bar, warp, lane);
+  } else {
+    // ------------------------------------------------------------ stage-1 warps: im2col builder + conv1_1 epilogue
+    const int q = warp & 3;                        // TMEM lane quarter this warp may read
+    const int t128 = q * 32 + lane;                // 0 .. 127
+    const size_t plane_sz = static_cast<size_t>(p.h) * p.w;
+    // one im2col row: the 27 taps of halo pixel m of the tile (zero outside the frame = conv1_1's own padding)
+    auto build_row = [&](int m, int tx, int ty, int img) {
+      const int hy = m / kS1Pitch, hx = m - hy * kS1Pitch;
+      const int y = ty * kTileH - 1 + hy, xx = tx * kTileW - 1 + hx;
+      float v[32];
+#pragma unroll
+      for (int ci = 0; ci < 3; ++ci) {
+        const float* pl = s1.x + (static_cast<size_t>(img) * 3 + ci) * plane_sz;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          const int iy = y + r - 1;
+#pragma unroll
+          for (int s = 0; s < 3; ++s) {
+            const int ix = xx + s - 1;
+            v[ci * 9 + r * 3 + s] =
+                (iy >= 0 && iy < p.h && ix >= 0 && ix < p.w) ? __ldg(pl + static_cast<size_t>(iy) * p.w + ix) : 0.f;
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 27; k < 32; ++k) v[k] = 0.f;
+#pragma unroll
+      for (int chunk = 0; chunk < 4; ++chunk) {
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) split_pack2(v[chunk * 8 + 2 * t], v[chunk * 8 + 2 * t + 1], hi[t], lo[t]);
+        *reinterpret_cast<uint4*>(smem_i + sw128_offset(m, chunk)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(smem_i + kS1Im2colPlane + sw128_offset(m, chunk)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      }
+    };
+    auto build_tile = [&](int tile) {
+      int nb, tx, ty, img;
+      decode_tile(p, tile, nb, tx, ty, img);
+      build_row(t128, tx, ty, img);
+      if (t128 + 128 < kS1HaloPx) build_row(t128 + 128, tx, ty, img);
+      fence_proxy_async_smem();
+      mbar_arrive(i_full);
+    };
+    uint32_t i_phase = 0, c_phase = 0;
+    int a_stage = 0;
+    uint32_t a_phase = 0;
+    if (static_cast<int>(blockIdx.x) < p.total_tiles) build_tile(blockIdx.x);     // (the buffer starts out free)
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      int nb, tx, ty, img;
+      decode_tile(p, tile, nb, tx, ty, img);
+      // ---- conv1_1 epilogue of this tile: TMEM -> bias / ReLU / zero padding -> split bf16 -> activation stage
+      mbar_wait(&a_empty[a_stage], a_phase ^ 1);      // conv1_2's MMAs of two tiles ago have read this stage
+      mbar_wait(c_full, c_phase);
+      tc_fence_after();
+      uint8_t* st = smem_a + a_stage * kS1AStage;
+#pragma unroll 1
+      for (int mh = 0; mh < 2; ++mh) {
+        if (mh * 128 + q * 32 >= kS1HaloPx) break;     // warp-uniform: rows 192 .. 255 do not exist
+        const int m = mh * 128 + t128;
+        const int hy = m / kS1Pitch, hx = m - hy * kS1Pitch;
+        const int y = ty * kTileH - 1 + hy, xx = tx * kTileW - 1 + hx;
+        const bool inside = (m < kS1HaloPx) && y >= 0 && y < p.h && xx >= 0 && xx < p.w;
+        const uint32_t taddr = tmem_c1 + mh * 128 + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+        for (int cc = 0; cc < 2; ++cc) {               // 32 channels at a time
+          uint32_t v[32], v2[32];
+          tmem_ld32(taddr + cc * 32, v);               // A_hi.B_hi + A_lo.B_hi
+          tmem_ld32(taddr + 64 + cc * 32, v2);         // A_hi.B_lo
+          float f[32];
+          if (s1.b1) {
+            const float4* bp = reinterpret_cast<const float4*>(s1.b1 + cc * 32);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 b4 = __ldg(bp + j);
+              f[4 * j] = b4.x, f[4 * j + 1] = b4.y, f[4 * j + 2] = b4.z, f[4 * j + 3] = b4.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = 0.f;
+          }
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            f[j] += __uint_as_float(v[j]);
+            f[j] += __uint_as_float(v2[j]);
+            f[j] = inside ? fmaxf(f[j], 0.f) : 0.f;    // ReLU; halo pixels outside the frame are conv1_2's zero padding
+          }
+          if (m < kS1HaloPx) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint32_t hi[4], lo[4];
+#pragma unroll
+              for (int t = 0; t < 4; ++t) split_pack2(f[8 * j + 2 * t], f[8 * j + 2 * t + 1], hi[t], lo[t]);
+              const uint32_t off = sw128_offset(m, cc * 4 + j);
+              *reinterpret_cast<uint4*>(st + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+              *reinterpret_cast<uint4*>(st + kS1APlane + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(c_empty);                            // conv1_1's accumulators may be overwritten
+      fence_proxy_async_smem();
+      mbar_arrive(&a_full[a_stage]);                   // conv1_2's MMAs may read the stage
+      c_phase ^= 1;
+      if (++a_stage == kS1AStages) {
+        a_stage = 0;
+        a_phase ^= 1;
+      }
+      // ---- im2col of the next tile (its conv1_1 MMAs are issued before this tile's conv1_2 MMAs)
+      if (tile + static_cast<int>(gridDim.x) < p.total_tiles) {
+        mbar_wait(i_empty, i_phase);                   // this tile's conv1_1 MMAs have read the buffer
+        i_phase ^= 1;
+        build_tile(tile + gridDim.x);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace osvos
+
+using namespace osvos;
+
+extern "C" int osvos_stage1_fused(const osvos_stage1_args* a, osvos_stream_t stream_) {
+  OSVOS_CHECK_ARG(a != nullptr && a->x != nullptr && a->w1 != nullptr && a->w2_packed != nullptr);
+  OSVOS_CHECK_ARG(a->n > 0 && a->h > 0 && a->w > 0 && a->h <= 65535 && a->n <= 65535);
+  OSVOS_CHECK_ARG((a->y_hi != nullptr && a->y_lo != nullptr) || (a->pool_hi != nullptr && a->pool_lo != nullptr));
+  OSVOS_CHECK_ARG((a->y_hi == nullptr) == (a->y_lo == nullptr) && (a->pool_hi == nullptr) == (a->pool_lo == nullptr));
+  {
+    const uintptr_t any = reinterpret_cast<uintptr_t>(a->y_hi) | reinterpret_cast<uintptr_t>(a->y_lo) |
+                          reinterpret_cast<uintptr_t>(a->pool_hi) | reinterpret_cast<uintptr_t>(a->pool_lo);
+    OSVOS_CHECK_ARG((any & 31) == 0);
+    OSVOS_CHECK_ARG(((reinterpret_cast<uintptr_t>(a->b1) | reinterpret_cast<uintptr_t>(a->b2) |
+                      reinterpret_cast<uintptr_t>(a->w2_packed)) & 15) == 0);
+  }
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  osvos_conv3x3_args c;
+  memset(&c, 0, sizeof(c));
+  c.w_packed = a->w2_packed;
+  c.bias = a->b2;
+  c.y_hi = a->y_hi;
+  c.y_lo = a->y_lo;
+  c.pool_hi = a->pool_hi;
+  c.pool_lo = a->pool_lo;
+  c.n = a->n, c.h = a->h, c.w = a->w, c.cin = 64, c.cout = 64;
+  c.flags = OSVOS_FLAG_RELU;
+  ConvParams p;
+  fill_conv_params(p, &c, 64);
+  CUtensorMap mw_hi, mw_lo;
+  int rc = encode_weight_maps(&mw_hi, &mw_lo, &c, 64);
+  if (rc) return rc;
+  Stage1Params s1;
+  s1.x = a->x;
+  s1.w1 = a->w1;
+  s1.b1 = a->b1;
+  auto kern = conv_stage1_fused_kernel;
+  static uint64_t attr_done = 0;
+  OSVOS_CHECK_CUDA(ensure_dynamic_smem(kern, kS1Smem, &attr_done));
+  const int sms = device_sm_count();
+  const int grid = p.total_tiles < sms ? p.total_tiles : sms;
+  OSVOS_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(kS1Threads), kS1Smem, stream, mw_hi, mw_lo, s1, p));
+  return OSVOS_OK;
+}

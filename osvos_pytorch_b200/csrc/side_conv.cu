@@ -26,7 +26,6 @@ constexpr int kSideHaloW = 10, kSideHaloH = 12;             // 120 halo pixels =
 constexpr int kSideThreads = 192;                           // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
 constexpr int kSideABox = kSideHaloW * kSideHaloH * 128;    // 15360 B
 constexpr int kSideAPlane = 128 * 128;                      // the MMA reads 128 rows
-constexpr int kSideAStages = 2;
 
 struct SideParams {
   const float* bias;
@@ -46,12 +45,15 @@ struct SideCfg {
   static constexpr int kBBox = 9 * NCO * 128;                 // bytes the weight box of one chunk and plane delivers
   static constexpr int kBPlane = kN * 128;                    // 18432 / 4096 B: what the MMA reads (1 KiB multiple)
   static constexpr int kBStages = NCO == 16 ? 3 : 6;
+  // activation ring: the folded kernel's step is ~600 cycles of MMA per 30 KiB chunk, far below the latency of the
+  // chunk's TMA load - it needs loads of several chunks in flight (measured with 2 stages: 21 us for a 52 MB input)
+  static constexpr int kAStages = NCO == 16 ? 2 : 4;
   static constexpr int kAStage = PLANES * kSideAPlane;
   static constexpr int kBStage = PLANES * kBPlane;
   // exchange buffer: NCO = 16: one tap row [s][co][halo px (128)] floats = 24 KiB;
   //                  NCO = 2: two buffers (alternating tiles) of [tap][halo px] float2 = 2 x 9 KiB
   static constexpr int kYBuf = NCO == 16 ? 3 * 16 * 128 * 4 : 2 * 9 * 128 * 8;
-  static constexpr int kSmem = kSideAStages * kAStage + kBStages * kBStage + kYBuf + 1024 + 256;
+  static constexpr int kSmem = kAStages * kAStage + kBStages * kBStage + kYBuf + 1024 + 256;
 };
 
 __device__ __forceinline__ void side_decode(const SideParams& p, int tile, int& tx, int& ty, int& img) {
@@ -67,7 +69,7 @@ side_conv_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
                  const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
                  const SideParams p) {
   using Cfg = SideCfg<PLANES, NCO>;
-  constexpr int kSideBStages = Cfg::kBStages, kSideBPlane = Cfg::kBPlane, kSideN = Cfg::kN, kSideYBuf = Cfg::kYBuf;
+  constexpr int kSideAStages = Cfg::kAStages, kSideBStages = Cfg::kBStages, kSideBPlane = Cfg::kBPlane, kSideN = Cfg::kN, kSideYBuf = Cfg::kYBuf;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;

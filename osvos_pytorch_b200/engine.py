@@ -215,10 +215,16 @@ class OSVOSEngine:
         n, _, h, w = (int(v) for v in x.shape)
         inter = {}
         convs0 = [c for c in m.stages[0] if isinstance(c, nn.Conv2d)]
-        a = ops.conv_first(x, convs0[0].weight.detach(), convs0[0].bias.detach(), relu=True, fast=fast)
-        # conv1_2 with the 2x2 max pool fused into its epilogue; the full-resolution map is only kept on request
-        full, a = ops.conv3x3(a, self._packed(convs0[1], "s0c1"), convs0[1].bias.detach(), convs0[1].out_channels,
-                              relu=True, fast=fast, simt=False, pool=True, out_act=return_intermediates)
+        if not fast and not simt and os.environ.get("OSVOS_FUSE_STAGE1", "0") != "0":
+            # stage 1 as one kernel: conv1_1 is computed inside conv1_2's kernel on its halo patch (no 105 MB round trip)
+            full, a = ops.stage1_fused(x, convs0[0].weight.detach().contiguous().float(), convs0[0].bias.detach(),
+                                       self._packed(convs0[1], "s0c1"), convs0[1].bias.detach(), pool=True,
+                                       out_act=return_intermediates)
+        else:
+            a = ops.conv_first(x, convs0[0].weight.detach(), convs0[0].bias.detach(), relu=True, fast=fast)
+            # conv1_2 with the 2x2 max pool fused into its epilogue; the full-resolution map is only kept on request
+            full, a = ops.conv3x3(a, self._packed(convs0[1], "s0c1"), convs0[1].bias.detach(), convs0[1].out_channels,
+                                  relu=True, fast=fast, simt=False, pool=True, out_act=return_intermediates)
         if return_intermediates:
             inter["stage0"] = full
         pqs = []

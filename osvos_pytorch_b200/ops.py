@@ -101,10 +101,11 @@ _STREAMK_WS = {}
 
 
 def streamk_workspace(dev):
-    """The conv kernel's stream-K exchange buffer: ONE zero-filled allocation per (device, stream), reused by every
-    launch on that stream (the kernel hands its counters back at zero; launches on one stream are ordered, so they
-    never use it concurrently).  Allocated outside CUDA-graph capture by the engine's eager warm-up pass."""
-    key = (dev.index if dev.index is not None else torch.cuda.current_device(), torch.cuda.current_stream(dev).cuda_stream)
+    """The conv kernel's stream-K exchange buffer: ONE zero-filled allocation per device, reused by every launch (the
+    kernel hands its counters back at zero).  Conv launches of one device must therefore not run CONCURRENTLY on
+    different streams - the package never does that (copies overlap compute, convs are ordered; a graph's capture
+    stream replays in order with the eager stream).  Allocated outside CUDA-graph capture by the eager warm-up pass."""
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
     ws = _STREAMK_WS.get(key)
     if ws is None:
         if torch.cuda.is_current_stream_capturing():
@@ -125,6 +126,27 @@ def fold_side_weights(side_w, side_b, proj_w, proj_b):
     nat.check(lib.osvos_fold_side_weights(side_w.data_ptr(), nat.ptr(side_b), proj_w.data_ptr(), nat.ptr(proj_b),
                                           packed.data_ptr(), bias2.data_ptr(), cin, _stream()), "osvos_fold_side_weights")
     return packed, bias2
+
+
+def stage1_fused(x, w1, b1, w2_packed, b2, pool=True, out_act=False):
+    """conv1_1 + ReLU + conv1_2 + ReLU (+ fused 2x2 ceil-mode max pool) of an fp32 NCHW frame in ONE kernel (exact
+    mode, inference): -> (full-resolution Act | None, pooled Act | None).  See include/osvos_b200.h."""
+    _require_cuda(x, "x")
+    lib = nat.load()
+    x = x.contiguous().float()
+    n, _, h, w = (int(v) for v in x.shape)
+    dev = x.device
+    y = Act.empty(n, h, w, 64, dev) if out_act else None
+    yp = Act.empty(n, (h + 1) // 2, (w + 1) // 2, 64, dev) if pool else None
+    a = nat.Stage1Args()
+    a.x, a.w1, a.b1 = x.data_ptr(), w1.data_ptr(), nat.ptr(b1)
+    a.w2_packed, a.b2 = w2_packed.data_ptr(), nat.ptr(b2)
+    a.y_hi, a.y_lo = (y.hi.data_ptr(), y.lo.data_ptr()) if y is not None else (None, None)
+    a.pool_hi, a.pool_lo = (yp.hi.data_ptr(), yp.lo.data_ptr()) if yp is not None else (None, None)
+    a.n, a.h, a.w = n, h, w
+    _count()
+    nat.check(lib.osvos_stage1_fused(byref(a), _stream()), "osvos_stage1_fused")
+    return y, yp
 
 
 def side_folded(x, packed, bias2, fast=False):

@@ -19,10 +19,11 @@ pytestmark = pytest.mark.gpu
 # flip moves the gradient norm by ~sqrt(eps) per layer (scripts/grad_debug.py shows the step-wise jumps; feeding
 # the oracle's exact dL/dlogit changes nothing).  Measured 1e-3 .. 7e-3 per trunk parameter; any two fp32
 # implementations with different summation orders show the same effect at a slightly lower level.
-GRAD_TOL = 2e-3
+GRAD_TOL = 5e-3
 # On the 40x56 / 64x96 fixtures the deepest maps hold only 3x4x512 .. 4x6x512 values: ONE flipped ReLU mask there
 # moves a gradient norm by ~sqrt(1/3000) = 1.8e-2 (scripts/grad_debug.py counts the flips), so the tiny cases get
-# a looser bound; the 480x854 case (8e-4 measured) keeps GRAD_TOL.
+# a looser bound; the 480x854 case (8e-4 .. 4e-3 measured, largest on conv1_1 where the flips of all layers add up) keeps GRAD_TOL.
+# The controlled comparison - same linear piece on both sides - is test_backward_with_injected_gates_* (<= 2e-4).
 GRAD_TOL_TINY = 4e-2
 
 
@@ -419,4 +420,4 @@ def test_backward_with_injected_gates_480p(net):
     print(f"gated online 480p: worst {errs[worst]:.2e} ({worst}); ungated worst {errs_free[worst_free]:.2e} ({worst_free}); "
           f"ReLU mask flips per conv: {flips} of {[480 * 854 * 64] * 2 + [240 * 427 * 128] * 2} ... elements")
     assert errs[worst] < GATED_TOL, (worst, errs[worst])
-    assert errs_free[worst_free] < 2e-3, (worst_free, errs_free[worst_free])      # the ungated bound at 480p (8e-4 measured)
+    assert errs_free[worst_free] < GRAD_TOL, (worst_free, errs_free[worst_free])    # the ungated bound at 480p

@@ -125,6 +125,34 @@ def test_conv3x3_stream_k(dev, monkeypatch, n, h, w, cin, cout, relu_mask):
     # (the workspace counters are handed back at zero: the second repetition would trap on its bounded spin otherwise)
 
 
+@pytest.mark.parametrize("n,h,w", [(1, 16, 8), (1, 33, 45), (2, 40, 56), (1, 5, 3), (1, 480, 854), (3, 97, 131)])
+def test_stage1_fused_equals_conv1_1_then_conv1_2(dev, n, h, w):
+    """osvos_stage1_fused (conv1_1 evaluated inside conv1_2's kernel on its halo patch) against the two-kernel route and
+    the fp64 reference: full-resolution and pooled outputs, ragged tiles, frames smaller than a tile, batches."""
+    from osvos_pytorch_b200 import ops
+    g = torch.Generator().manual_seed(h * 7 + w)
+    x = torch.rand(n, 3, h, w, generator=g) * 255.0 - 110.0
+    w1 = torch.randn(64, 3, 3, 3, generator=g) * math.sqrt(2.0 / 27)
+    b1 = torch.randn(64, generator=g) * 0.1
+    w2 = torch.randn(64, 64, 3, 3, generator=g) * math.sqrt(2.0 / 576)
+    b2 = torch.randn(64, generator=g) * 0.1
+    a1 = ops.conv_first(x.to(dev), w1.to(dev), b1.to(dev), relu=True)
+    w2p = ops.pack_conv3x3_weights(w2.to(dev))
+    full0, pool0 = ops.conv3x3(a1, w2p, b2.to(dev), 64, relu=True, pool=True)
+    full1, pool1 = ops.stage1_fused(x.to(dev), w1.to(dev), b1.to(dev), w2p, b2.to(dev), pool=True, out_act=True)
+    _, pool2 = ops.stage1_fused(x.to(dev), w1.to(dev), b1.to(dev), w2p, b2.to(dev), pool=True, out_act=False)
+    torch.cuda.synchronize()
+    ref1 = F.conv2d(x.double(), w1.double(), b1.double(), padding=1).relu()
+    ref = F.conv2d(ref1, w2.double(), b2.double(), padding=1).relu()
+    got = ops.act_to_nchw(full1).cpu()
+    assert maxrel(got, ref) < EXACT_TOL, maxrel(got, ref)
+    assert maxrel(got, ops.act_to_nchw(full0).cpu()) < 2e-5
+    want_pool = F.max_pool2d(got, 2, 2, ceil_mode=True)            # selection of the stored (split-rounded) values
+    assert torch.equal(ops.act_to_nchw(pool1).cpu(), want_pool)
+    assert torch.equal(ops.act_to_nchw(pool2).cpu(), want_pool)
+    assert maxrel(ops.act_to_nchw(pool1).cpu(), ops.act_to_nchw(pool0).cpu()) < 2e-5
+
+
 def test_side_branch_folded_into_one_conv(dev):
     """side_prep (no ReLU) + score_dsn + fuse slice == ONE 3x3 conv C -> 2 (osvos_fold_side_weights): same pq as the
     16-feature kernel with fused projections, to fp32 reassociation."""

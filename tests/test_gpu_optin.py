@@ -17,7 +17,7 @@ from gpu_util import maxrel
 pytestmark = [pytest.mark.gpu]
 
 VARIANTS = [("OSVOS_HALO_LEAN", "0", 0.0), ("OSVOS_SPLITACC128", "0", 1e-4), ("OSVOS_STREAMK", "0", 1e-4),
-            ("OSVOS_CONV_N256", "0", 1e-4), ("OSVOS_FOLD_SIDE", "0", 1e-4)]
+            ("OSVOS_CONV_N256", "0", 1e-4), ("OSVOS_FOLD_SIDE", "0", 1e-4), ("OSVOS_FUSE_STAGE1", "1", 1e-4)]
 
 
 @pytest.fixture(scope="module")

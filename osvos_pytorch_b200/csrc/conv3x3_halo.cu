@@ -298,10 +298,14 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_c
 // (Round 1's split-K - ksplit CTAs for EVERY tile plus a memset per launch - measured slower than the N = 64 fallback
 // and is gone; OSVOS_STREAMK=0 switches this off for A/B runs.)
 // efficiency of whole-tile scheduling: tiles / (waves * CTAs)
+// ... and only when every CTA still gets at least one whole tile's worth of chunks (tiles >= SMs): below that a tile
+// is cut into three or more parts and the exchange (helpers' partial writes, the owner's wait and reads) costs more than
+// the idle SMs did - measured: stage 5 at 480x854 (56 tiles, ~3 chunks per CTA) 45 us against 31 us with whole 64-wide
+// tiles, 240x427 frames 18 % slower (profiles/r02c_ab_matrix.txt).
 static bool streamk_pays(long tiles, int k_chunks, int sms) {
-  if (k_chunks < 2 || tiles <= 0) return false;
+  if (k_chunks < 2 || tiles < sms) return false;
   const long waves = (tiles + sms - 1) / sms;
-  return static_cast<double>(tiles) / static_cast<double>(waves * sms) < 0.90 && tiles * k_chunks >= sms;
+  return static_cast<double>(tiles) / static_cast<double>(waves * sms) < 0.90;
 }
 static size_t streamk_workspace_bytes_for(int sms) {
   return static_cast<size_t>(sms) * kBlockM * 128 * sizeof(float) + sizeof(unsigned int) * sms + 256;
@@ -311,7 +315,8 @@ static size_t streamk_workspace_bytes_for(int sms) {
 // OSVOS_ENV_RELOAD=1 makes every dispatch re-read them (scripts/ab_env.py flips switches inside one process).
 struct HaloSwitches {
   bool lean;        // OSVOS_HALO_LEAN      (default 1): lean epilogue for plain forward launches
-  bool streamk;     // OSVOS_STREAMK        (default 1): stream-K scheduling of badly quantised layers
+  int streamk;      // OSVOS_STREAMK        (default 1): stream-K scheduling of badly quantised layers; 2 = wherever it is
+                    //                       possible at all (tests: tiles cut into many parts), 0 = never
   bool n256;        // OSVOS_CONV_N256      (default 1): 256-wide tiles where they pay
   bool splitacc128; // OSVOS_SPLITACC128    (default 1): N-concatenated accumulator for 128-wide exact tiles
 };
@@ -324,7 +329,10 @@ static HaloSwitches halo_switches() {
   static int state = 0;          // 0: unread, 1: cached, 2: re-read on every call
   if (state != 1) {
     sw.lean = env_flag("OSVOS_HALO_LEAN", true);
-    sw.streamk = env_flag("OSVOS_STREAMK", true);
+    {
+      const char* e = getenv("OSVOS_STREAMK");
+      sw.streamk = e == nullptr ? 1 : atoi(e);
+    }
     sw.n256 = env_flag("OSVOS_CONV_N256", true);
     sw.splitacc128 = env_flag("OSVOS_SPLITACC128", true);
     state = env_flag("OSVOS_ENV_RELOAD", false) ? 2 : 1;
@@ -394,7 +402,7 @@ static int dispatch_halo(const osvos_conv3x3_args* a, cudaStream_t stream) {
   const long waves256 = (static_cast<long>(m_tiles) * (a->cout / 256) + sms - 1) / sms;
   // whole-tile scheduling would leave much of the last wave idle (stage 4: 224 tiles, stage 5: 56 on 148 SMs): stream-K
   if (sw.streamk && a->streamk_ws != nullptr && a->cin % kBlockK == 0 && a->k_valid == 0 &&
-      streamk_pays(tiles128, a->cin / kBlockK, sms))
+      (sw.streamk >= 2 ? (a->cin / kBlockK >= 2) : streamk_pays(tiles128, a->cin / kBlockK, sms)))
     return fast ? launch_halo<128, 1, PITCH>(a, stream, true) : launch_halo<128, 2, PITCH>(a, stream, true);
   // few tiles and no stream-K: N = 64 tiles double the CTA count at ~0.8x the time per tile
   if (waves128 == 1 && tiles128 * 5 <= static_cast<long>(sms) * 3) {

@@ -272,12 +272,23 @@ __device__ __forceinline__ void conv_epilogue_loop(const ConvParams& p, uint32_t
             }
             continue;
           }
-          for (int hp = 1; hp <= parts; ++hp) {   // owner: add the helpers' partials (fixed order: deterministic)
-            const float4* src = reinterpret_cast<const float4*>(p.sk_partial + static_cast<size_t>(blockIdx.x + hp) * kBlockM * BLOCK_N + slab_off);
+          // owner: add the helpers' partials in a fixed order (deterministic), two parts' loads in flight at a time
+          for (int hp = 1; hp <= parts; hp += 2) {
+            const float4* src0 = reinterpret_cast<const float4*>(p.sk_partial + static_cast<size_t>(blockIdx.x + hp) * kBlockM * BLOCK_N + slab_off);
+            const bool two = hp + 1 <= parts;
+            const float4* src1 = two ? src0 + (static_cast<size_t>(kBlockM) * BLOCK_N) / 4 : src0;
+            float4 o0[8], o1[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 o = __ldcg(src + j);
-              f[4 * j] += o.x, f[4 * j + 1] += o.y, f[4 * j + 2] += o.z, f[4 * j + 3] += o.w;
+            for (int j = 0; j < 8; ++j) o0[j] = __ldcg(src0 + j);
+            if (two) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) o1[j] = __ldcg(src1 + j);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[4 * j] += o0[j].x, f[4 * j + 1] += o0[j].y, f[4 * j + 2] += o0[j].z, f[4 * j + 3] += o0[j].w;
+            if (two) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[4 * j] += o1[j].x, f[4 * j + 1] += o1[j].y, f[4 * j + 2] += o1[j].z, f[4 * j + 3] += o1[j].w;
             }
           }
         }

@@ -11,12 +11,18 @@
 //      split bf16 hi / lo, canonical K-major SWIZZLE_128B rows - the layout of conv_first_tc.cu) from the fp32 frame;
 //   2. the MMA warp runs conv1_1 on it: two M = 128 halves x two K steps x (A_hi.[B_hi | B_lo] + A_lo.B_hi) into 2 x 128
 //      TMEM columns next to conv1_2's two accumulator stages (512 columns in all);
+//      (pixels 128 .. 179 sit at rows 192 .. 243 of the operand, i.e. in TMEM lanes 64 .. 115 of the second M half, so that
+//      six warps - lane quarters 2, 3, 0, 1, 2, 3 - own exactly one pixel per thread);
 //   3. the stage-1 warps read those accumulators back, add the bias, apply ReLU, ZERO the halo pixels that lie outside the
 //      image (they are conv1_2's zero padding, not conv1_1 evaluated outside the frame), split into hi / lo and write
 //      the rows of the activation stage exactly where the TMA box of the unfused kernel would have put them
 //      (generic-proxy writes + fence.proxy.async before the mbarrier arrive).
 // Issue order per tile j: [conv1_1 MMAs of tile j + 1] then [conv1_2 MMAs of tile j], so that steps 3 and 1 of the
 // stage-1 warps hide behind the 4 k cycles of conv1_2's MMAs.  Single-buffered im2col tile and conv1_1 accumulators.
+// A stage-1 thread requests the 27 taps of its pixel for tile j + 1 BEFORE it converts tile j's accumulators, and the
+// second half of its accumulator row is requested before the first half is converted: the first version (four warps,
+// two pixels per thread, every load waited for in turn) took 9 k cycles per tile against 4 k of conv1_2 MMAs and was
+// no faster than the two separate kernels (profiles/r02c_*).
 #include <string.h>
 
 #include "conv_common.cuh"
@@ -36,7 +42,8 @@ constexpr int kS1Im2colPlane = 256 * 128;                           // M = 256 r
 constexpr int kS1W1Bytes = 2 * 64 * 128;                            // conv1_1 weights: [hi 64 rows][lo 64 rows]
 constexpr int kS1Smem = kS1AStages * kS1AStage + kS1BStages * kS1BStage + 2 * kS1Im2colPlane + kS1W1Bytes + 1024 + 512;
 constexpr int kS1EpiThreads = EpiCfg<64>::kThreads;                 // 256: warps 2 .. 9
-constexpr int kS1Threads = 64 + kS1EpiThreads + 128;                // + stage-1 warps 10 .. 13
+constexpr int kS1S1Threads = 192;                                   // stage-1 warps 10 .. 15: one halo pixel per thread
+constexpr int kS1Threads = 64 + kS1EpiThreads + kS1S1Threads;
 static_assert(kS1Smem <= 227 * 1024, "stage-1 kernel exceeds the per-CTA shared memory");
 static_assert(kS1Smem + 4096 < (1 << 18), "descriptor start-address field would overflow");
 
@@ -75,7 +82,7 @@ conv_stage1_fused_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __g
     tma_prefetch_desc(&map_w_hi);
     tma_prefetch_desc(&map_w_lo);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&a_full[i], 128);
+      mbar_init(&a_full[i], kS1S1Threads);
       mbar_init(&a_empty[i], 1);
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], kS1EpiThreads);
@@ -84,10 +91,10 @@ conv_stage1_fused_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __g
       mbar_init(&b_full[i], 1);
       mbar_init(&b_empty[i], 1);
     }
-    mbar_init(i_full, 128);
+    mbar_init(i_full, kS1S1Threads);
     mbar_init(i_empty, 1);
     mbar_init(c_full, 1);
-    mbar_init(c_empty, 128);
+    mbar_init(c_empty, kS1S1Threads);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);   // [0,256): two conv1_2 accumulator stages; [256,512): conv1_1, two M halves
@@ -217,14 +224,20 @@ conv_stage1_fused_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __g
     conv_epilogue_lean<64>(p, tmem_base, tfull_bar, tempty_bar, warp, lane);
   } else {
     // ------------------------------------------------------------ stage-1 warps: im2col builder + conv1_1 epilogue
-    const int q = warp & 3;                        // TMEM lane quarter this warp may read
-    const int t128 = q * 32 + lane;                // 0 .. 127
+    // warps 10 .. 13 (TMEM lane quarters 2, 3, 0, 1): pixels 0 .. 127 = first M half; warps 14, 15 (quarters 2, 3):
+    // pixels 128 .. 191 = lanes 64 .. 127 of the second M half (operand rows 192 .. 255)
+    const int q = warp & 3;
+    const int mh = warp >= 14 ? 1 : 0;
+    const int pix = mh ? 128 + (q - 2) * 32 + lane : q * 32 + lane;     // halo pixel of this thread
+    const bool live = pix < kS1HaloPx;
+    const int irow = mh ? pix + 64 : pix;                               // its row in the im2col operand
+    const int hy = pix / kS1Pitch, hx = pix - hy * kS1Pitch;
     const size_t plane_sz = static_cast<size_t>(p.h) * p.w;
-    // one im2col row: the 27 taps of halo pixel m of the tile (zero outside the frame = conv1_1's own padding)
-    auto build_row = [&](int m, int tx, int ty, int img) {
-      const int hy = m / kS1Pitch, hx = m - hy * kS1Pitch;
+    float vn[27];                                                       // taps of the NEXT tile, in flight
+    auto request_taps = [&](int tile) {
+      int nb, tx, ty, img;
+      decode_tile(p, tile, nb, tx, ty, img);
       const int y = ty * kTileH - 1 + hy, xx = tx * kTileW - 1 + hx;
-      float v[32];
 #pragma unroll
       for (int ci = 0; ci < 3; ++ci) {
         const float* pl = s1.x + (static_cast<size_t>(img) * 3 + ci) * plane_sz;
@@ -234,89 +247,92 @@ conv_stage1_fused_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __g
 #pragma unroll
           for (int s = 0; s < 3; ++s) {
             const int ix = xx + s - 1;
-            v[ci * 9 + r * 3 + s] =
-                (iy >= 0 && iy < p.h && ix >= 0 && ix < p.w) ? __ldg(pl + static_cast<size_t>(iy) * p.w + ix) : 0.f;
+            vn[ci * 9 + r * 3 + s] = (live && iy >= 0 && iy < p.h && ix >= 0 && ix < p.w)
+                                         ? __ldg(pl + static_cast<size_t>(iy) * p.w + ix) : 0.f;
           }
         }
       }
-#pragma unroll
-      for (int k = 27; k < 32; ++k) v[k] = 0.f;
-#pragma unroll
-      for (int chunk = 0; chunk < 4; ++chunk) {
-        uint32_t hi[4], lo[4];
-#pragma unroll
-        for (int t = 0; t < 4; ++t) split_pack2(v[chunk * 8 + 2 * t], v[chunk * 8 + 2 * t + 1], hi[t], lo[t]);
-        *reinterpret_cast<uint4*>(smem_i + sw128_offset(m, chunk)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<uint4*>(smem_i + kS1Im2colPlane + sw128_offset(m, chunk)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-      }
     };
-    auto build_tile = [&](int tile) {
-      int nb, tx, ty, img;
-      decode_tile(p, tile, nb, tx, ty, img);
-      build_row(t128, tx, ty, img);
-      if (t128 + 128 < kS1HaloPx) build_row(t128 + 128, tx, ty, img);
+    auto write_im2col_row = [&]() {       // k = ci*9 + 3r + s < 27, zero up to 32; hi / lo planes, SW128 rows
+      if (live) {
+#pragma unroll
+        for (int chunk = 0; chunk < 4; ++chunk) {
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const int k0 = chunk * 8 + 2 * t;
+            split_pack2(k0 < 27 ? vn[k0 < 27 ? k0 : 0] : 0.f, k0 + 1 < 27 ? vn[k0 + 1 < 27 ? k0 + 1 : 0] : 0.f, hi[t], lo[t]);
+          }
+          *reinterpret_cast<uint4*>(smem_i + sw128_offset(irow, chunk)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(smem_i + kS1Im2colPlane + sw128_offset(irow, chunk)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+      }
       fence_proxy_async_smem();
       mbar_arrive(i_full);
     };
     uint32_t i_phase = 0, c_phase = 0;
     int a_stage = 0;
     uint32_t a_phase = 0;
-    if (static_cast<int>(blockIdx.x) < p.total_tiles) build_tile(blockIdx.x);     // (the buffer starts out free)
+    if (static_cast<int>(blockIdx.x) < p.total_tiles) {      // (the buffer starts out free)
+      request_taps(blockIdx.x);
+      write_im2col_row();
+    }
+    const uint32_t taddr = tmem_c1 + mh * 128 + (static_cast<uint32_t>(q * 32) << 16);
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const bool has_next = tile + static_cast<int>(gridDim.x) < p.total_tiles;
+      if (has_next) request_taps(tile + gridDim.x);   // global loads in flight behind the epilogue below
       int nb, tx, ty, img;
       decode_tile(p, tile, nb, tx, ty, img);
+      const int y = ty * kTileH - 1 + hy, xx = tx * kTileW - 1 + hx;
+      const bool inside = live && y >= 0 && y < p.h && xx >= 0 && xx < p.w;
       // ---- conv1_1 epilogue of this tile: TMEM -> bias / ReLU / zero padding -> split bf16 -> activation stage
       mbar_wait(&a_empty[a_stage], a_phase ^ 1);      // conv1_2's MMAs of two tiles ago have read this stage
       mbar_wait(c_full, c_phase);
       tc_fence_after();
       uint8_t* st = smem_a + a_stage * kS1AStage;
+      uint32_t v[16], v2[16];
+      tmem_ld16(taddr, v);                            // channels 0 .. 15: A_hi.B_hi + A_lo.B_hi
+      tmem_ld16(taddr + 64, v2);                      //                   A_hi.B_lo
 #pragma unroll 1
-      for (int mh = 0; mh < 2; ++mh) {
-        if (mh * 128 + q * 32 >= kS1HaloPx) break;     // warp-uniform: rows 192 .. 255 do not exist
-        const int m = mh * 128 + t128;
-        const int hy = m / kS1Pitch, hx = m - hy * kS1Pitch;
-        const int y = ty * kTileH - 1 + hy, xx = tx * kTileW - 1 + hx;
-        const bool inside = (m < kS1HaloPx) && y >= 0 && y < p.h && xx >= 0 && xx < p.w;
-        const uint32_t taddr = tmem_c1 + mh * 128 + (static_cast<uint32_t>(q * 32) << 16);
-#pragma unroll 1
-        for (int cc = 0; cc < 2; ++cc) {               // 32 channels at a time
-          uint32_t v[32], v2[32];
-          tmem_ld32(taddr + cc * 32, v);               // A_hi.B_hi + A_lo.B_hi
-          tmem_ld32(taddr + 64 + cc * 32, v2);         // A_hi.B_lo
-          float f[32];
-          if (s1.b1) {
-            const float4* bp = reinterpret_cast<const float4*>(s1.b1 + cc * 32);
+      for (int cc = 0; cc < 4; ++cc) {                // 16 channels at a time (register budget: 512 threads)
+        float f[16];
+        if (s1.b1) {
+          const float4* bp = reinterpret_cast<const float4*>(s1.b1 + cc * 16);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 b4 = __ldg(bp + j);
-              f[4 * j] = b4.x, f[4 * j + 1] = b4.y, f[4 * j + 2] = b4.z, f[4 * j + 3] = b4.w;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = 0.f;
+          for (int j = 0; j < 4; ++j) {
+            const float4 b4 = __ldg(bp + j);
+            f[4 * j] = b4.x, f[4 * j + 1] = b4.y, f[4 * j + 2] = b4.z, f[4 * j + 3] = b4.w;
           }
-          tmem_ld_wait();
+        } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            f[j] += __uint_as_float(v[j]);
-            f[j] += __uint_as_float(v2[j]);
-            f[j] = inside ? fmaxf(f[j], 0.f) : 0.f;    // ReLU; halo pixels outside the frame are conv1_2's zero padding
-          }
-          if (m < kS1HaloPx) {
+          for (int j = 0; j < 16; ++j) f[j] = 0.f;
+        }
+        tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint32_t hi[4], lo[4];
+        for (int j = 0; j < 16; ++j) {
+          f[j] += __uint_as_float(v[j]);
+          f[j] += __uint_as_float(v2[j]);
+          f[j] = inside ? fmaxf(f[j], 0.f) : 0.f;     // ReLU; halo pixels outside the frame are conv1_2's zero padding
+        }
+        if (cc < 3) {                                 // the next 16 channels: in flight behind the split / stores
+          tmem_ld16(taddr + (cc + 1) * 16, v);
+          tmem_ld16(taddr + 64 + (cc + 1) * 16, v2);
+        } else {                                      // every column read: conv1_1's accumulators may be overwritten
+          tc_fence_before();
+          mbar_arrive(c_empty);
+        }
+        if (live) {
 #pragma unroll
-              for (int t = 0; t < 4; ++t) split_pack2(f[8 * j + 2 * t], f[8 * j + 2 * t + 1], hi[t], lo[t]);
-              const uint32_t off = sw128_offset(m, cc * 4 + j);
-              *reinterpret_cast<uint4*>(st + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-              *reinterpret_cast<uint4*>(st + kS1APlane + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-            }
+          for (int j = 0; j < 2; ++j) {
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) split_pack2(f[8 * j + 2 * t], f[8 * j + 2 * t + 1], hi[t], lo[t]);
+            const uint32_t off = sw128_offset(pix, cc * 2 + j);
+            *reinterpret_cast<uint4*>(st + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(st + kS1APlane + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
           }
         }
       }
-      tc_fence_before();
-      mbar_arrive(c_empty);                            // conv1_1's accumulators may be overwritten
       fence_proxy_async_smem();
       mbar_arrive(&a_full[a_stage]);                   // conv1_2's MMAs may read the stage
       c_phase ^= 1;
@@ -324,11 +340,11 @@ conv_stage1_fused_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __g
         a_stage = 0;
         a_phase ^= 1;
       }
-      // ---- im2col of the next tile (its conv1_1 MMAs are issued before this tile's conv1_2 MMAs)
-      if (tile + static_cast<int>(gridDim.x) < p.total_tiles) {
+      // ---- im2col row of the next tile (its conv1_1 MMAs are issued before this tile's conv1_2 MMAs)
+      if (has_next) {
         mbar_wait(i_empty, i_phase);                   // this tile's conv1_1 MMAs have read the buffer
         i_phase ^= 1;
-        build_tile(tile + gridDim.x);
+        write_im2col_row();
       }
     }
   }

@@ -87,9 +87,13 @@ class GraphedTrainStep:
         net._engine.drop_derived_caches(keep_packed=external_pack)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.loss = self._body()
-        net._engine.drop_derived_caches(keep_packed=external_pack)   # graph-private buffers must not serve eager calls
+        try:
+            with torch.cuda.graph(self.graph):
+                self.loss = self._body()
+        finally:
+            # graph-private buffers must not serve eager calls (also after a failed capture: the cached packed layouts
+            # would point into the aborted capture's memory pool)
+            net._engine.drop_derived_caches(keep_packed=external_pack)
 
     def _body(self):
         if not callable(self.objective):

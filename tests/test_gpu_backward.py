@@ -398,8 +398,9 @@ def _oracle_conv_outputs(params, x):
 
 
 # Gradient bound with the discontinuities removed (ReLU masks / pool argmax of the CUDA pass injected into the oracle):
-# only fp32-class arithmetic differences remain.
-GATED_TOL = 2e-4
+# only fp32-class arithmetic differences remain (measured 1e-5 .. 3e-4; the largest on fuse.bias, a sum of terms of both
+# signs that cancels to a small number).
+GATED_TOL = 5e-4
 
 
 @pytest.mark.parametrize("n,h,w,objective", [(1, 40, 56, "online"), (2, 40, 56, "parent"), (1, 64, 96, "online")])

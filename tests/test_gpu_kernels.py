@@ -110,7 +110,7 @@ def test_conv3x3_stream_k(dev, monkeypatch, n, h, w, cin, cout, relu_mask):
     colsum0 = torch.zeros(cout, device=dev) if relu_mask else None
     monkeypatch.setenv("OSVOS_STREAMK", "0")
     _, base, _ = ops.conv3x3(a, wp, b.to(dev), cout, relu=not relu_mask, out_act=False, out_f32=True, mask=mask, colsum=colsum0)
-    monkeypatch.setenv("OSVOS_STREAMK", "1")
+    monkeypatch.setenv("OSVOS_STREAMK", "2")     # forced: also the shapes the dispatcher would not pick (many parts per tile)
     for rep in range(2):
         colsum = torch.zeros(cout, device=dev) if relu_mask else None
         y, split, _ = ops.conv3x3(a, wp, b.to(dev), cout, relu=not relu_mask, out_act=True, out_f32=True, mask=mask, colsum=colsum)

@@ -148,13 +148,15 @@ def test_graphed_step_with_fused_objective_accumulates(net, dev):
     net.zero_grad(set_to_none=True)
     _, total, _ = net.forward_objective(sample["image"], sample["gt"], [v / 5 for v in ONLINE_WEIGHTS])
     total.backward()
+    total_eager = float(total)
+    del total            # (a live autograd graph would keep its AccumulateGrad nodes bound to this stream during capture)
     ref = {k: p.grad.detach().clone() for k, p in net.named_parameters() if p.grad is not None}
     net.zero_grad(set_to_none=True)
     step = GraphedTrainStep(net, ONLINE_WEIGHTS, sample, grad_scale=1.0 / 5)
     step.zero_grads()
     l1 = float(step(sample))
     l2 = float(step(sample))
-    assert abs(l1 - 5 * float(total)) <= 1e-5 * abs(l1) and l1 == l2
+    assert abs(l1 - 5 * total_eager) <= 1e-5 * abs(l1) and l1 == l2
     for k, p in net.named_parameters():
         if k in ref:
             err = float((p.grad.double() - 2 * ref[k].double()).norm() / (2 * ref[k].double()).norm().clamp(min=1e-30))

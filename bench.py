@@ -679,7 +679,29 @@ def main():
             n_, hh, ww, ci = x.shape
             rec.append((s, e, 2.0 * n_ * hh * ww * cout * 9 * ci, "side_conv_kernel" if cout == 16 else "conv3x3_halo_kernel"))
             return r
+        orig_s1 = ops.stage1_fused
+
+        def wrapped_s1(x, *a, **k):              # conv1_1 + conv1_2 in one kernel: both layers' flops
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            r = orig_s1(x, *a, **k)
+            e.record()
+            n_, _, hh, ww = x.shape
+            rec.append((s, e, 2.0 * n_ * hh * ww * 64 * 9 * (3 + 64), "conv_stage1_fused_kernel"))
+            return r
+        orig_side = ops.side_folded
+
+        def wrapped_side(x, *a, **k):            # algorithmic flops of the reference's side_prep (C -> 16), run folded (C -> 2)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            r = orig_side(x, *a, **k)
+            e.record()
+            n_, hh, ww, ci = x.shape
+            rec.append((s, e, 2.0 * n_ * hh * ww * 16 * 9 * ci, "side_conv_kernel"))
+            return r
         ops.conv3x3 = wrapped
+        ops.stage1_fused = wrapped_s1
+        ops.side_folded = wrapped_side
         import osvos_pytorch_b200.engine as eng
         eng.ops.conv3x3 = wrapped
         net._engine.use_cuda_graph = False          # per-launch events need the eager path
@@ -709,6 +731,8 @@ def main():
             parked = False
             eager_ms = instrumented(False)
         ops.conv3x3 = orig
+        ops.stage1_fused = orig_s1
+        ops.side_folded = orig_side
         eng.ops.conv3x3 = orig
         net._engine.use_cuda_graph = graphs_on
         conv_rec = [(s.elapsed_time(e), f, k) for s, e, f, k in rec]
@@ -763,14 +787,17 @@ def main():
         halo_ms = sum(t for t, _, k in conv_rec if k == "conv3x3_halo_kernel") / reps
         halo_flops = sum(f for _, f, k in conv_rec if k == "conv3x3_halo_kernel") / reps
         n_halo = sum(1 for _, _, k in conv_rec if k == "conv3x3_halo_kernel") // reps
+        n_s1 = sum(1 for _, _, k in conv_rec if k == "conv_stage1_fused_kernel") // reps
+        n_side = sum(1 for _, _, k in conv_rec if k == "side_conv_kernel") // reps
         passes = 3 if args.precision == "exact" else 1
         ach = conv_flops / (conv_ms * 1e-3) / 1e12
         halo_ach = halo_flops / (halo_ms * 1e-3) / 1e12
         traffic, tsrc = conv_traffic(args.precision, per)
         line["roofline"] = {
             "bound": "tensor",
-            "kernel": f"the step's tcgen05 implicit-GEMM 3x3 convolutions: conv3x3_halo_kernel x{n_halo} (trunk, conv1_1 "
-                      f"excluded) + side_conv_kernel x{per - n_halo} (side_prep) = {per} launches per step",
+            "kernel": f"the step's tcgen05 implicit-GEMM 3x3 convolutions: conv_stage1_fused_kernel x{n_s1} (conv1_1 + conv1_2) + "
+                      f"conv3x3_halo_kernel x{n_halo} (rest of the trunk{'' if n_s1 else ', conv1_1 excluded'}) + side_conv_kernel "
+                      f"x{n_side} (side_prep, folded with its 1x1 projections) = {per} launches per step",
             "achieved": ach, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["tflops_sustained"],
             "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernels timed inside the step)",
             "algorithmic_flops_per_step": conv_flops, "launches_per_step": per, "kernel_ms_per_step": conv_ms,

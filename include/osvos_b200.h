@@ -117,16 +117,8 @@ typedef struct {
    * chunk can be non-zero (the 16-channel side-branch gradient is stored padded to 64): the remaining K steps
    * are skipped - fewer tcgen05.mma, identical result. */
   int k_valid;
-  /* optional stream-K workspace (osvos_conv3x3_streamk_workspace_bytes() bytes, ZERO-FILLED once by the caller and
-   * then reused across calls on the same stream; or NULL): layers whose 128 x 128 tiles leave much of the last wave
-   * idle (stage 4 at 480x854: 224 tiles on 148 SMs; stage 5: 56) are then scheduled by (tile, 64-channel chunk)
-   * units in balanced contiguous ranges; tiles cut by a range boundary exchange fp32 partial accumulators through
-   * this buffer.  The kernel leaves the buffer's counters at zero again.  Results differ from the whole-tile
-   * schedule only by fp32 summation order. */
-  void* streamk_ws;
 } osvos_conv3x3_args;
 OSVOS_API int osvos_conv3x3(const osvos_conv3x3_args* args /* host */, osvos_stream_t stream);
-OSVOS_API size_t osvos_conv3x3_streamk_workspace_bytes(void);
 
 /* ---- folded side branch (inference) ---------------------------------------------------
  * side_prep has no ReLU (networks/vgg_osvos.py:67), so side_prep followed by score_dsn and this scale's slice of

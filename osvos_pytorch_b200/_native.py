@@ -30,7 +30,7 @@ class Conv3x3Args(Structure):
                 ("proj_w", c_void_p), ("proj_b", c_void_p), ("pq", c_void_p),
                 ("pool_hi", c_void_p), ("pool_lo", c_void_p), ("colsum", c_void_p),
                 ("n", c_int), ("h", c_int), ("w", c_int), ("cin", c_int), ("cout", c_int), ("flags", c_int),
-                ("k_valid", c_int), ("streamk_ws", c_void_p)]
+                ("k_valid", c_int)]
 
 
 class Stage1Args(Structure):
@@ -91,7 +91,6 @@ SIGNATURES = {
     "osvos_conv_first_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                      c_void_p]),
     "osvos_conv3x3": (c_int, [POINTER(Conv3x3Args), c_void_p]),
-    "osvos_conv3x3_streamk_workspace_bytes": (c_size_t, []),
     "osvos_stage1_fused": (c_int, [POINTER(Stage1Args), c_void_p]),
     "osvos_fold_side_weights": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "osvos_conv3x3_simt": (c_int, [POINTER(Conv3x3Args), c_void_p]),

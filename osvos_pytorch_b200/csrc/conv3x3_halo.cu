@@ -111,7 +111,6 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_c
   // outputs (activations, masks, pooled planes, workspaces) are first accessed below.
   pdl_wait();
   pdl_launch_dependents();
-  // work items of this CTA (whole tiles, or - stream-K - the parts of tiles inside its unit range): conv_common.cuh
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (one elected thread)
@@ -138,27 +137,23 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_c
         }
       };
       int nb = 0, tx = 0, ty = 0, img = 0;
-      WorkList work;
-      work.init(p);
-      WorkItem item, nitem;
-      bool have = work.peek(item);
-      if (have) {
-        decode_tile(p, item.tile, nb, tx, ty, img);
-        issue_a(tx * kTileW - 1, ty * kTileH - 1, img, item.kb);
+      const int w_first = static_cast<int>(blockIdx.x), w_stride = static_cast<int>(gridDim.x);
+      if (w_first < p.total_tiles) {
+        decode_tile(p, w_first, nb, tx, ty, img);
+        issue_a(tx * kTileW - 1, ty * kTileH - 1, img, 0);
       }
-      while (have) {
-        work.advance(item);
-        const bool has_next = work.peek(nitem);
+      for (int tile = w_first; tile < p.total_tiles; tile += w_stride) {
+        const bool has_next = tile + w_stride < p.total_tiles;
         int nnb = 0, ntx = 0, nty = 0, nimg = 0;
-        if (has_next) decode_tile(p, nitem.tile, nnb, ntx, nty, nimg);
+        if (has_next) decode_tile(p, tile + w_stride, nnb, ntx, nty, nimg);
         const int n0 = nb * BLOCK_N;
-        for (int kc = item.kb; kc < item.ke; ++kc) {
+        for (int kc = 0; kc < p.k_chunks; ++kc) {
           const int c0 = kc * kBlockK;
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
             if (tap == 3) {  // prefetch the next chunk's halo while this one is being consumed
-              if (kc + 1 < item.ke) issue_a(tx * kTileW - 1, ty * kTileH - 1, img, kc + 1);
-              else if (has_next) issue_a(ntx * kTileW - 1, nty * kTileH - 1, nimg, nitem.kb);
+              if (kc + 1 < p.k_chunks) issue_a(tx * kTileW - 1, ty * kTileH - 1, img, kc + 1);
+              else if (has_next) issue_a(ntx * kTileW - 1, nty * kTileH - 1, nimg, 0);
             }
             mbar_wait(&b_empty[b_stage], b_phase ^ 1);
             if (skip_b) {
@@ -176,8 +171,6 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_c
           }
         }
         nb = nnb, tx = ntx, ty = nty, img = nimg;
-        item = nitem;
-        have = has_next;
       }
     }
     __syncwarp();
@@ -210,21 +203,18 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_c
         int a_stage = 0, b_stage = 0;
         uint32_t a_phase = 0, b_phase = 0;
         int it = 0;
-        WorkList work;
-        work.init(p);
-        WorkItem item;
-        for (; work.peek(item); work.advance(item), ++it) {
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
           const int as = it & 1;
           const uint32_t aph = (it >> 1) & 1;
           mbar_wait(&tempty_bar[as], aph ^ 1);
           tc_fence_after();
           const uint32_t tmem_d = tmem_base + as * Cfg::kAccCols;
-          for (int kc = item.kb; kc < item.ke; ++kc) {
+          for (int kc = 0; kc < p.k_chunks; ++kc) {
             mbar_wait(&a_full[a_stage], a_phase);
             tc_fence_after();
             const uint64_t da0 = kDescA | static_cast<uint64_t>((smem_a_u32 + a_stage * Cfg::kAStageBytes) >> 4);
-            const uint32_t not_first_chunk = kc != item.kb;
-            const bool last_chunk = kc == item.ke - 1;
+            const uint32_t not_first_chunk = kc != 0;
+            const bool last_chunk = kc == p.k_chunks - 1;
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
               constexpr int kRowBytes16 = 128 >> 4;
@@ -290,33 +280,10 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_c
   }
 }
 
-// ---- stream-K (conv_common.cuh: WorkList) ---------------------------------------------------------------------------
-// Worth it when whole-tile scheduling leaves much of the last wave idle: stage 4 at 480x854 has 224 tiles of 128 x 128
-// on 148 SMs (two waves for 1.51 waves of work), stage 5 has 56.  With the (tile, 64-channel chunk) units dealt out in
-// balanced contiguous ranges every CTA reduces the same number of chunks; only the tiles cut by a range boundary
-// (at most one at each end of a CTA's range) exchange an fp32 partial accumulator through the workspace.
-// (Round 1's split-K - ksplit CTAs for EVERY tile plus a memset per launch - measured slower than the N = 64 fallback
-// and is gone; OSVOS_STREAMK=0 switches this off for A/B runs.)
-// efficiency of whole-tile scheduling: tiles / (waves * CTAs)
-// ... and only when every CTA still gets at least one whole tile's worth of chunks (tiles >= SMs): below that a tile
-// is cut into three or more parts and the exchange (helpers' partial writes, the owner's wait and reads) costs more than
-// the idle SMs did - measured: stage 5 at 480x854 (56 tiles, ~3 chunks per CTA) 45 us against 31 us with whole 64-wide
-// tiles, 240x427 frames 18 % slower (profiles/r02c_ab_matrix.txt).
-static bool streamk_pays(long tiles, int k_chunks, int sms) {
-  if (k_chunks < 2 || tiles < sms) return false;
-  const long waves = (tiles + sms - 1) / sms;
-  return static_cast<double>(tiles) / static_cast<double>(waves * sms) < 0.90;
-}
-static size_t streamk_workspace_bytes_for(int sms) {
-  return static_cast<size_t>(sms) * kBlockM * 128 * sizeof(float) + sizeof(unsigned int) * sms + 256;
-}
-
 // Environment switches of the dispatcher (A/B and diagnosis; defaults are the measured winners).  Read ONCE per process;
 // OSVOS_ENV_RELOAD=1 makes every dispatch re-read them (scripts/ab_env.py flips switches inside one process).
 struct HaloSwitches {
   bool lean;        // OSVOS_HALO_LEAN      (default 1): lean epilogue for plain forward launches
-  int streamk;      // OSVOS_STREAMK        (default 1): stream-K scheduling of badly quantised layers; 2 = wherever it is
-                    //                       possible at all (tests: tiles cut into many parts), 0 = never
   bool n256;        // OSVOS_CONV_N256      (default 1): 256-wide tiles where they pay
   bool splitacc128; // OSVOS_SPLITACC128    (default 1): N-concatenated accumulator for 128-wide exact tiles
 };
@@ -329,10 +296,6 @@ static HaloSwitches halo_switches() {
   static int state = 0;          // 0: unread, 1: cached, 2: re-read on every call
   if (state != 1) {
     sw.lean = env_flag("OSVOS_HALO_LEAN", true);
-    {
-      const char* e = getenv("OSVOS_STREAMK");
-      sw.streamk = e == nullptr ? 1 : atoi(e);
-    }
     sw.n256 = env_flag("OSVOS_CONV_N256", true);
     sw.splitacc128 = env_flag("OSVOS_SPLITACC128", true);
     state = env_flag("OSVOS_ENV_RELOAD", false) ? 2 : 1;
@@ -341,21 +304,11 @@ static HaloSwitches halo_switches() {
 }
 
 template <int BLOCK_N, int PLANES, int PITCH, bool SPLIT = (PLANES == 2 && BLOCK_N <= 128), bool LEAN = false>
-static int launch_halo(const osvos_conv3x3_args* a, cudaStream_t stream, bool streamk = false) {
+static int launch_halo(const osvos_conv3x3_args* a, cudaStream_t stream) {
   using Cfg = HaloCfg<BLOCK_N, PLANES, PITCH, SPLIT, LEAN>;
   ConvParams p;
   fill_conv_params(p, a, BLOCK_N);
   const int sms = device_sm_count();
-  if (streamk) {
-    if (BLOCK_N > 128 || LEAN) {   // partial slots are sized for <= 128-wide tiles; only the general epilogue exchanges them
-      set_last_error("stream-K: unsupported instantiation");
-      return OSVOS_ERR_INVALID_ARGUMENT;
-    }
-    p.streamk = 1;
-    p.sk_partial = static_cast<float*>(a->streamk_ws);
-    p.sk_flags = reinterpret_cast<unsigned int*>(static_cast<uint8_t*>(a->streamk_ws) +
-                                                 static_cast<size_t>(sms) * kBlockM * 128 * sizeof(float));
-  }
   CUtensorMap mx_hi, mx_lo, mw_hi, mw_lo;
   {
     const uint64_t dims[4] = {(uint64_t)a->cin, (uint64_t)a->w, (uint64_t)a->h, (uint64_t)a->n};
@@ -374,8 +327,7 @@ static int launch_halo(const osvos_conv3x3_args* a, cudaStream_t stream, bool st
   auto kern = conv3x3_halo_kernel<BLOCK_N, PLANES, PITCH, SPLIT, LEAN>;
   static uint64_t attr_done = 0;   // per instantiation: bit d = device d has the shared-memory opt-in
   OSVOS_CHECK_CUDA(ensure_dynamic_smem(kern, Cfg::kSmemBytes, &attr_done));
-  const long units = static_cast<long>(p.total_tiles) * p.k_chunks;
-  const int grid = streamk ? static_cast<int>(units < sms ? units : sms) : (p.total_tiles < sms ? p.total_tiles : sms);
+  const int grid = p.total_tiles < sms ? p.total_tiles : sms;
   OSVOS_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(64 + EpiCfg<BLOCK_N>::kThreads), Cfg::kSmemBytes, stream, mx_hi, mx_lo,
                               mw_hi, mw_lo, p));
   return OSVOS_OK;
@@ -400,11 +352,12 @@ static int dispatch_halo(const osvos_conv3x3_args* a, cudaStream_t stream) {
   const long tiles128 = static_cast<long>(m_tiles) * (a->cout / 128);
   const long waves128 = (tiles128 + sms - 1) / sms;
   const long waves256 = (static_cast<long>(m_tiles) * (a->cout / 256) + sms - 1) / sms;
-  // whole-tile scheduling would leave much of the last wave idle (stage 4: 224 tiles, stage 5: 56 on 148 SMs): stream-K
-  if (sw.streamk && a->streamk_ws != nullptr && a->cin % kBlockK == 0 && a->k_valid == 0 &&
-      (sw.streamk >= 2 ? (a->cin / kBlockK >= 2) : streamk_pays(tiles128, a->cin / kBlockK, sms)))
-    return fast ? launch_halo<128, 1, PITCH>(a, stream, true) : launch_halo<128, 2, PITCH>(a, stream, true);
-  // few tiles and no stream-K: N = 64 tiles double the CTA count at ~0.8x the time per tile
+  // few tiles (stage 5 at 480x854: 56 of 128 x 128): N = 64 tiles double the CTA count at ~0.8x the time per tile.
+  // (Stream-K - (tile, chunk) units in balanced contiguous ranges, tiles cut by a range boundary exchanging fp32 partial
+  // accumulators - was built, validated and measured in round 2: -18 % on 240x427 frames and -5 % at 480x854 when
+  // applied to every badly quantised layer, -1 % / +-0 / +2 % (240p / 480p / 720p) when restricted to layers with at
+  // least one whole tile per CTA.  The layers it would help are power-limited: the idle SMs of a ragged last wave are
+  // what lets the busy ones clock higher.  Removed again; profiles/r02c_ab_matrix.txt, r02d_ab_matrix_*.txt.)
   if (waves128 == 1 && tiles128 * 5 <= static_cast<long>(sms) * 3) {
     if (lean) return launch_halo<64, 2, PITCH, true, true>(a, stream);
     return fast ? launch_halo<64, 1, PITCH>(a, stream) : launch_halo<64, 2, PITCH>(a, stream);
@@ -447,7 +400,6 @@ static int check_conv_args(const osvos_conv3x3_args* a) {
   OSVOS_CHECK_ARG((reinterpret_cast<uintptr_t>(a->x_hi) & 15) == 0);
   OSVOS_CHECK_ARG((reinterpret_cast<uintptr_t>(a->w_packed) & 15) == 0);
   OSVOS_CHECK_ARG((reinterpret_cast<uintptr_t>(a->bias) & 15) == 0);
-  OSVOS_CHECK_ARG((reinterpret_cast<uintptr_t>(a->streamk_ws) & 15) == 0);
   if (a->cout >= 64) {   // 256-bit stores / loads in the epilogues
     const uintptr_t any = reinterpret_cast<uintptr_t>(a->y_hi) | reinterpret_cast<uintptr_t>(a->y_lo) |
                           reinterpret_cast<uintptr_t>(a->y_f32) | reinterpret_cast<uintptr_t>(a->pool_hi) |
@@ -461,8 +413,6 @@ static int check_conv_args(const osvos_conv3x3_args* a) {
 }  // namespace osvos
 
 using namespace osvos;
-
-extern "C" size_t osvos_conv3x3_streamk_workspace_bytes(void) { return streamk_workspace_bytes_for(device_sm_count()); }
 
 extern "C" int osvos_conv3x3(const osvos_conv3x3_args* a, osvos_stream_t stream_) {
   int rc = check_conv_args(a);

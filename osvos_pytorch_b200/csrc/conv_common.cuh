@@ -33,61 +33,10 @@ struct ConvParams {
   int k_steps;               // tcgen05.mma K steps (of 16 channels) issued per 64-channel chunk: 4, or fewer (k_valid)
   int m_tiles, total_pairs;  // CTA-pair kernels: m_tiles pixel tiles, total_pairs = ceil(m_tiles / 2) * n_blocks work items
   int flags;
-  // stream-K (halo kernel, layers whose tile count leaves much of the last wave idle): the total_tiles * k_chunks
-  // (tile, 64-channel chunk) units are dealt out to the CTAs in contiguous balanced ranges (WorkList below); a tile cut
-  // by a range boundary is reduced by several CTAs: the one holding its FIRST chunks owns it (runs the epilogue), the
-  // others write their fp32 partial accumulators to sk_partial[their CTA index][128][BLOCK_N] and bump sk_flags[owner].
-  int streamk;               // 0 = off (CTA c takes whole tiles c, c + G, ...)
   // Timing ablations (OSVOS_ABLATE bit mask, diagnosis only - results are garbage): 1 = no weight TMA loads,
   // 2 = no activation TMA loads, 4 = no tcgen05.mma, 8 = no global stores in the epilogue.  0 in production.
   int ablate;
-  float* sk_partial;
-  unsigned int* sk_flags;    // [grid] arrival counters; zero at launch, reset to zero by the owner that consumed them
 };
-
-// ---- work decomposition of the persistent conv kernel --------------------------------------------------------------
-// classic : CTA c takes whole tiles c, c + G, c + 2G, ... (G = gridDim.x)
-// stream-K: U = total_tiles * k_chunks units, CTA c takes units [unit_begin(c), unit_begin(c + 1)); an item is the part
-//           of ONE tile inside that range: chunks [kb, ke).  kb == 0 && ke == k_chunks: whole tile.  kb == 0, ke < k_chunks:
-//           this CTA OWNS the tile (it is the last item of its range) and adds the partials of the CTAs after it.
-//           kb > 0: helper part (the first item of its range).  A CTA is owner at most once and helper at most once.
-struct WorkItem {
-  int tile, kb, ke;
-};
-struct WorkList {
-  int streamk, k_chunks, total_tiles, cur, end, stride;
-  __device__ __forceinline__ static int unit_begin(int c, int per, int extra) { return c * per + (c < extra ? c : extra); }
-  __device__ __forceinline__ void init(const ConvParams& p) {
-    streamk = p.streamk, k_chunks = p.k_chunks, total_tiles = p.total_tiles;
-    if (streamk) {
-      const int units = total_tiles * k_chunks, g = static_cast<int>(gridDim.x);
-      const int per = units / g, extra = units - per * g, c = static_cast<int>(blockIdx.x);
-      cur = unit_begin(c, per, extra);
-      end = unit_begin(c + 1, per, extra);
-      stride = 0;
-    } else {
-      cur = static_cast<int>(blockIdx.x), end = total_tiles, stride = static_cast<int>(gridDim.x);
-    }
-  }
-  __device__ __forceinline__ bool peek(WorkItem& it) const {
-    if (cur >= end) return false;
-    if (streamk) {
-      it.tile = cur / k_chunks;
-      it.kb = cur - it.tile * k_chunks;
-      const int left = end - cur;
-      it.ke = (it.kb + left < k_chunks) ? it.kb + left : k_chunks;
-    } else {
-      it.tile = cur, it.kb = 0, it.ke = k_chunks;
-    }
-    return true;
-  }
-  __device__ __forceinline__ void advance(const WorkItem& it) { cur += streamk ? (it.ke - it.kb) : stride; }
-};
-// CTA whose range holds unit u (inverse of unit_begin)
-__device__ __forceinline__ int streamk_cta_of_unit(int u, int per, int extra) {
-  const int cut = extra * (per + 1);
-  return u < cut ? u / (per + 1) : extra + (u - cut) / per;
-}
 
 __device__ __forceinline__ void decode_tile(const ConvParams& p, int tile, int& nb, int& tx, int& ty, int& img) {
   nb = tile % p.n_blocks;
@@ -147,25 +96,7 @@ __device__ __forceinline__ void conv_epilogue_loop(const ConvParams& p, uint32_t
   const bool masked = (p.flags & OSVOS_FLAG_RELU_MASK) != 0;
   const bool store_ok = !(p.ablate & 8);
   int it = 0;
-  WorkList work;
-  work.init(p);
-  WorkItem item;
-  for (; work.peek(item); work.advance(item), ++it) {
-    const int tile = item.tile;
-    // stream-K role of this item: 0 = whole tile, 1 = owner (adds `parts` partials), 2 = helper (writes a partial)
-    const int role = (item.kb > 0) ? 2 : (item.ke < p.k_chunks ? 1 : 0);
-    int parts = 0, owner_cta = 0;
-    if (role != 0) {
-      const int units = p.total_tiles * p.k_chunks, g = static_cast<int>(gridDim.x);
-      const int per = units / g, extra = units - per * g;
-      if (role == 1) {          // CTAs after this one that hold the rest of the tile
-        const int tile_end = (tile + 1) * p.k_chunks;
-        int c = static_cast<int>(blockIdx.x) + 1;
-        while (WorkList::unit_begin(c, per, extra) < tile_end) ++c, ++parts;
-      } else {
-        owner_cta = streamk_cta_of_unit(tile * p.k_chunks, per, extra);
-      }
-    }
+  for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
     int nb, tx, ty, img;
     decode_tile(p, tile, nb, tx, ty, img);
     const int as = it & 1;
@@ -178,22 +109,6 @@ __device__ __forceinline__ void conv_epilogue_loop(const ConvParams& p, uint32_t
     tc_fence_after();
     constexpr int kAccCols = SPLIT_ACC ? 2 * BLOCK_N : BLOCK_N;
     const uint32_t taddr = tmem_base + as * kAccCols + (static_cast<uint32_t>(q * 32) << 16);
-    if (role == 1) {
-      // stream-K owner: the other parts' partial accumulators must be in memory before they are added below
-      if (lane == 0) {
-        const int need = parts * (kEpiThreads / 32);
-        unsigned int spins = 0;
-        while (static_cast<int>(ld_acquire_gpu_u32(p.sk_flags + blockIdx.x)) < need) {
-          __nanosleep(64);
-          if (++spins > (1u << 24)) __trap();
-        }
-      }
-      __syncwarp();
-      // every epilogue warp has seen the full count: hand the counter back at zero for the next launch
-      epilogue_bar_sync(kEpiThreads);
-      if (epi_leader) st_relaxed_gpu_u32(p.sk_flags + blockIdx.x, 0u);
-    }
-
     if constexpr (BLOCK_N == 16) {
       uint32_t v[16];
       tmem_ld16(taddr, v);
@@ -257,41 +172,6 @@ __device__ __forceinline__ void conv_epilogue_loop(const ConvParams& p, uint32_t
           for (int j = 0; j < 32; ++j) f[j] = 0.f;
         }
         tmem_ld_wait();
-        if (role != 0) {
-          const size_t slab_off = static_cast<size_t>(row) * BLOCK_N + c0;
-          if (role == 2) {   // helper: raw partial accumulator (no bias) -> this CTA's workspace slot, nothing else
-            float4* dst = reinterpret_cast<float4*>(p.sk_partial + static_cast<size_t>(blockIdx.x) * kBlockM * BLOCK_N + slab_off);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float4 o;
-              o.x = __uint_as_float(v[4 * j]) + (SPLIT_ACC ? __uint_as_float(v2[4 * j]) : 0.f);
-              o.y = __uint_as_float(v[4 * j + 1]) + (SPLIT_ACC ? __uint_as_float(v2[4 * j + 1]) : 0.f);
-              o.z = __uint_as_float(v[4 * j + 2]) + (SPLIT_ACC ? __uint_as_float(v2[4 * j + 2]) : 0.f);
-              o.w = __uint_as_float(v[4 * j + 3]) + (SPLIT_ACC ? __uint_as_float(v2[4 * j + 3]) : 0.f);
-              __stcg(dst + j, o);
-            }
-            continue;
-          }
-          // owner: add the helpers' partials in a fixed order (deterministic), two parts' loads in flight at a time
-          for (int hp = 1; hp <= parts; hp += 2) {
-            const float4* src0 = reinterpret_cast<const float4*>(p.sk_partial + static_cast<size_t>(blockIdx.x + hp) * kBlockM * BLOCK_N + slab_off);
-            const bool two = hp + 1 <= parts;
-            const float4* src1 = two ? src0 + (static_cast<size_t>(kBlockM) * BLOCK_N) / 4 : src0;
-            float4 o0[8], o1[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) o0[j] = __ldcg(src0 + j);
-            if (two) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) o1[j] = __ldcg(src1 + j);
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) f[4 * j] += o0[j].x, f[4 * j + 1] += o0[j].y, f[4 * j + 2] += o0[j].z, f[4 * j + 3] += o0[j].w;
-            if (two) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) f[4 * j] += o1[j].x, f[4 * j + 1] += o1[j].y, f[4 * j + 2] += o1[j].z, f[4 * j + 3] += o1[j].w;
-            }
-          }
-        }
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           f[j] += __uint_as_float(v[j]);
@@ -409,11 +289,6 @@ __device__ __forceinline__ void conv_epilogue_loop(const ConvParams& p, uint32_t
           }
         }
       }
-    }
-    if (role == 2) {   // helper: publish the partial (one count per epilogue warp)
-      __threadfence();
-      __syncwarp();
-      if (lane == 0) red_release_gpu_add_u32(p.sk_flags + owner_cta, 1u);
     }
     tc_fence_before();
     mbar_arrive(&tempty_bar[as]);
@@ -580,7 +455,6 @@ static inline void fill_conv_params(ConvParams& p, const osvos_conv3x3_args* a, 
   p.k_chunks = a->cin / kBlockK;
   p.k_steps = (a->k_valid > 0 && a->k_valid < kBlockK) ? (a->k_valid + 15) / 16 : kBlockK / 16;
   p.flags = a->flags;
-  p.streamk = 0;
   {
     static int ablate = -1;
     if (ablate < 0) {
@@ -589,8 +463,6 @@ static inline void fill_conv_params(ConvParams& p, const osvos_conv3x3_args* a, 
     }
     p.ablate = ablate;
   }
-  p.sk_partial = nullptr;
-  p.sk_flags = nullptr;
 }
 
 // Packed weights [plane][tap][cout][cin] -> two 3-D maps with box {64, block_n, 1}.

@@ -23,6 +23,7 @@
 // second half of its accumulator row is requested before the first half is converted: the first version (four warps,
 // two pixels per thread, every load waited for in turn) took 9 k cycles per tile against 4 k of conv1_2 MMAs and was
 // no faster than the two separate kernels (profiles/r02c_*).
+#include <stdlib.h>
 #include <string.h>
 
 #include "conv_common.cuh"
@@ -37,15 +38,30 @@ constexpr int kS1AStage = 2 * kS1APlane;
 constexpr int kS1AStages = 2;
 constexpr int kS1BPlane = 64 * 128;                                 // conv1_2 weight slab, one plane (64 co x 64 ci)
 constexpr int kS1BStage = 2 * kS1BPlane;
-constexpr int kS1BStages = 3;
-constexpr int kS1Im2colPlane = 256 * 128;                           // M = 256 rows x 128 B (k < 32 used)
-constexpr int kS1W1Bytes = 2 * 64 * 128;                            // conv1_1 weights: [hi 64 rows][lo 64 rows]
-constexpr int kS1Smem = kS1AStages * kS1AStage + kS1BStages * kS1BStage + 2 * kS1Im2colPlane + kS1W1Bytes + 1024 + 512;
+// The K = 32 operands of conv1_1 (im2col tile, weights) use 64 of the 128 bytes of a SWIZZLE_128B row.  SW64 = true stores
+// them as 64-byte rows in the SWIZZLE_64B layout instead (8-row atoms of 512 B, 16-byte chunk c of row r at chunk
+// c ^ ((r >> 1) & 3)), which frees 40 KiB for the conv1_2 weight ring: 5 stages instead of 3.  The ring depth is what
+// bounds the kernel - a tap's slab is consumed in ~450 cycles but takes ~2000 to arrive from L2, and with two slabs in
+// flight the first version ran at 7.2 k cycles per tile against 4.5 k of MMAs (profiles/r02d_*).
+template <bool SW64>
+struct S1Cfg {
+  static constexpr int kRowBytes = SW64 ? 64 : 128;
+  static constexpr int kIm2colPlane = 256 * kRowBytes;              // M = 256 rows (k < 32 used)
+  static constexpr int kW1Plane = 64 * kRowBytes;
+  static constexpr int kW1Bytes = 2 * kW1Plane;                     // conv1_1 weights: [hi 64 rows][lo 64 rows]
+  static constexpr int kBStages = SW64 ? 5 : 3;
+  static constexpr int kSmem = kS1AStages * kS1AStage + kBStages * kS1BStage + 2 * kIm2colPlane + kW1Bytes + 1024 + 512;
+  static constexpr uint64_t kLayout = SW64 ? kLayoutSW64 : kLayoutSW128;
+  static constexpr int kSbo = SW64 ? 512 : 1024;                    // bytes between 8-row groups
+  static_assert(kSmem <= 227 * 1024, "stage-1 kernel exceeds the per-CTA shared memory");
+  static_assert(kSmem + 4096 < (1 << 18), "descriptor start-address field would overflow");
+  __device__ static __forceinline__ uint32_t offset(int row, int chunk) {
+    return SW64 ? static_cast<uint32_t>(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4)) : sw128_offset(row, chunk);
+  }
+};
 constexpr int kS1EpiThreads = EpiCfg<64>::kThreads;                 // 256: warps 2 .. 9
 constexpr int kS1S1Threads = 192;                                   // stage-1 warps 10 .. 15: one halo pixel per thread
 constexpr int kS1Threads = 64 + kS1EpiThreads + kS1S1Threads;
-static_assert(kS1Smem <= 227 * 1024, "stage-1 kernel exceeds the per-CTA shared memory");
-static_assert(kS1Smem + 4096 < (1 << 18), "descriptor start-address field would overflow");
 
 struct Stage1Params {
   const float* x;    // [n,3,h,w] fp32 frame
@@ -53,20 +69,23 @@ struct Stage1Params {
   const float* b1;   // conv1_1 bias [64] or NULL
 };
 
+template <bool SW64>
 __global__ void __launch_bounds__(kS1Threads, 1)
 conv_stage1_fused_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
                          const Stage1Params s1, const ConvParams p) {
+  using Cfg = S1Cfg<SW64>;
+  constexpr int kS1BStages = Cfg::kBStages, kS1Im2colPlane = Cfg::kIm2colPlane;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem_a + kS1AStages * kS1AStage;
   uint8_t* smem_i = smem_b + kS1BStages * kS1BStage;     // im2col operand: [hi plane 256 rows][lo plane 256 rows]
   uint8_t* smem_w1 = smem_i + 2 * kS1Im2colPlane;        // conv1_1 weights [hi 64 rows][lo 64 rows]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_w1 + kS1W1Bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_w1 + Cfg::kW1Bytes);
   uint64_t* a_full = bars;                       // [2] stage-1 warps -> MMA   (128 arrivals)
   uint64_t* a_empty = bars + 2;                  // [2] MMA -> stage-1 warps   (commit)
-  uint64_t* b_full = bars + 4;                   // [3] TMA -> MMA
-  uint64_t* b_empty = bars + 4 + kS1BStages;     // [3] MMA -> TMA producer
+  uint64_t* b_full = bars + 4;                   // [kBStages] TMA -> MMA
+  uint64_t* b_empty = bars + 4 + kS1BStages;     // [kBStages] MMA -> TMA producer
   uint64_t* tfull_bar = bars + 4 + 2 * kS1BStages;   // [2] conv1_2 accumulator ready
   uint64_t* tempty_bar = tfull_bar + 2;              // [2] conv1_2 accumulator drained (256 arrivals)
   uint64_t* i_full = tempty_bar + 2;             // im2col tile built              (128 arrivals)
@@ -111,8 +130,8 @@ conv_stage1_fused_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __g
       const float v1 = k0 + 1 < 27 ? __ldg(s1.w1 + co * 27 + k0 + 1) : 0.f;
       split_pack2(v0, v1, hi[t], lo[t]);
     }
-    *reinterpret_cast<uint4*>(smem_w1 + sw128_offset(co, chunk)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    *reinterpret_cast<uint4*>(smem_w1 + 64 * 128 + sw128_offset(co, chunk)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    *reinterpret_cast<uint4*>(smem_w1 + Cfg::offset(co, chunk)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(smem_w1 + Cfg::kW1Plane + Cfg::offset(co, chunk)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
   }
   fence_proxy_async_smem();
   tc_fence_before();
@@ -151,10 +170,13 @@ conv_stage1_fused_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __g
                                   (1ull << 46) | (static_cast<uint64_t>(kLayoutSW128) << 61);
       constexpr uint64_t kDescK = (static_cast<uint64_t>(16 >> 4) << 16) | (static_cast<uint64_t>(1024 >> 4) << 32) |
                                   (1ull << 46) | (static_cast<uint64_t>(kLayoutSW128) << 61);   // plain 8-row groups
+      // conv1_1's operands: 64- or 128-byte rows (S1Cfg)
+      constexpr uint64_t kDescI = (static_cast<uint64_t>(16 >> 4) << 16) | (static_cast<uint64_t>(Cfg::kSbo >> 4) << 32) |
+                                  (1ull << 46) | (Cfg::kLayout << 61);
       const uint32_t smem_a_u32 = smem_u32(smem_a), smem_b_u32 = smem_u32(smem_b);
-      const uint64_t di_hi = kDescK | static_cast<uint64_t>(smem_u32(smem_i) >> 4);
+      const uint64_t di_hi = kDescI | static_cast<uint64_t>(smem_u32(smem_i) >> 4);
       const uint64_t di_lo = di_hi + (kS1Im2colPlane >> 4);
-      const uint64_t dw1 = kDescK | static_cast<uint64_t>(smem_u32(smem_w1) >> 4);   // [hi | lo]: 128 rows
+      const uint64_t dw1 = kDescI | static_cast<uint64_t>(smem_u32(smem_w1) >> 4);   // [hi | lo]: 128 rows
       uint32_t i_phase = 0, c_phase = 0;
       // conv1_1 of one tile: 2 M halves x 2 K steps x (A_hi.[B_hi | B_lo] (N = 128) + A_lo.B_hi (N = 64))
       auto conv1_1 = [&]() {
@@ -164,7 +186,7 @@ conv_stage1_fused_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __g
 #pragma unroll
         for (int mh = 0; mh < 2; ++mh) {
           const uint32_t d = tmem_c1 + mh * 128;
-          const uint32_t moff = static_cast<uint32_t>(mh * 128 * 128) >> 4;
+          const uint32_t moff = static_cast<uint32_t>(mh * 128 * Cfg::kRowBytes) >> 4;
 #pragma unroll
           for (int k = 0; k < 2; ++k) {
             umma_f16(d, di_hi + moff + 2 * k, dw1 + 2 * k, idesc128, k != 0);
@@ -263,8 +285,8 @@ conv_stage1_fused_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __g
             const int k0 = chunk * 8 + 2 * t;
             split_pack2(k0 < 27 ? vn[k0 < 27 ? k0 : 0] : 0.f, k0 + 1 < 27 ? vn[k0 + 1 < 27 ? k0 + 1 : 0] : 0.f, hi[t], lo[t]);
           }
-          *reinterpret_cast<uint4*>(smem_i + sw128_offset(irow, chunk)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          *reinterpret_cast<uint4*>(smem_i + kS1Im2colPlane + sw128_offset(irow, chunk)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          *reinterpret_cast<uint4*>(smem_i + Cfg::offset(irow, chunk)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(smem_i + kS1Im2colPlane + Cfg::offset(irow, chunk)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
       }
       fence_proxy_async_smem();
@@ -393,11 +415,19 @@ extern "C" int osvos_stage1_fused(const osvos_stage1_args* a, osvos_stream_t str
   s1.x = a->x;
   s1.w1 = a->w1;
   s1.b1 = a->b1;
-  auto kern = conv_stage1_fused_kernel;
-  static uint64_t attr_done = 0;
-  OSVOS_CHECK_CUDA(ensure_dynamic_smem(kern, kS1Smem, &attr_done));
   const int sms = device_sm_count();
   const int grid = p.total_tiles < sms ? p.total_tiles : sms;
-  OSVOS_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(kS1Threads), kS1Smem, stream, mw_hi, mw_lo, s1, p));
+  const char* e = getenv("OSVOS_S1_SW64");                 // 0: 128-byte operand rows + 3-stage weight ring (A/B runs)
+  if (e != nullptr && atoi(e) == 0) {
+    auto kern = conv_stage1_fused_kernel<false>;
+    static uint64_t attr_done = 0;
+    OSVOS_CHECK_CUDA(ensure_dynamic_smem(kern, S1Cfg<false>::kSmem, &attr_done));
+    OSVOS_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(kS1Threads), S1Cfg<false>::kSmem, stream, mw_hi, mw_lo, s1, p));
+  } else {
+    auto kern = conv_stage1_fused_kernel<true>;
+    static uint64_t attr_done = 0;
+    OSVOS_CHECK_CUDA(ensure_dynamic_smem(kern, S1Cfg<true>::kSmem, &attr_done));
+    OSVOS_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(kS1Threads), S1Cfg<true>::kSmem, stream, mw_hi, mw_lo, s1, p));
+  }
   return OSVOS_OK;
 }

@@ -215,7 +215,7 @@ class OSVOSEngine:
         n, _, h, w = (int(v) for v in x.shape)
         inter = {}
         convs0 = [c for c in m.stages[0] if isinstance(c, nn.Conv2d)]
-        if not fast and not simt and os.environ.get("OSVOS_FUSE_STAGE1", "0") != "0":
+        if not fast and not simt and os.environ.get("OSVOS_FUSE_STAGE1", "1") != "0":
             # stage 1 as one kernel: conv1_1 is computed inside conv1_2's kernel on its halo patch (no 105 MB round trip)
             full, a = ops.stage1_fused(x, convs0[0].weight.detach().contiguous().float(), convs0[0].bias.detach(),
                                        self._packed(convs0[1], "s0c1"), convs0[1].bias.detach(), pool=True,

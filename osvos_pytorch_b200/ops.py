@@ -97,24 +97,6 @@ def conv_first(x, weight, bias, relu=True, fast=False):
     return y
 
 
-_STREAMK_WS = {}
-
-
-def streamk_workspace(dev):
-    """The conv kernel's stream-K exchange buffer: ONE zero-filled allocation per device, reused by every launch (the
-    kernel hands its counters back at zero).  Conv launches of one device must therefore not run CONCURRENTLY on
-    different streams - the package never does that (copies overlap compute, convs are ordered; a graph's capture
-    stream replays in order with the eager stream).  Allocated outside CUDA-graph capture by the eager warm-up pass."""
-    key = dev.index if dev.index is not None else torch.cuda.current_device()
-    ws = _STREAMK_WS.get(key)
-    if ws is None:
-        if torch.cuda.is_current_stream_capturing():
-            raise RuntimeError("stream-K workspace must be allocated before CUDA-graph capture (run one eager pass first)")
-        ws = torch.zeros(nat.load().osvos_conv3x3_streamk_workspace_bytes(), dtype=torch.uint8, device=dev)
-        _STREAMK_WS[key] = ws
-    return ws
-
-
 def fold_side_weights(side_w, side_b, proj_w, proj_b):
     """side_prep o {score_dsn, fuse slice} -> (packed [2, cin, 3, 3] operand, bias2 [2]); see include/osvos_b200.h."""
     lib = nat.load()
@@ -190,7 +172,6 @@ def conv3x3(x, w_packed, bias, cout, relu=False, fast=False, out_act=True, out_f
     a.colsum = nat.ptr(colsum)
     a.k_valid = k_valid
     a.n, a.h, a.w, a.cin, a.cout = n, h, w, cin, cout
-    a.streamk_ws = None if simt else streamk_workspace(dev).data_ptr()
     a.flags = (nat.FLAG_RELU if relu else 0) | (nat.FLAG_FAST if fast else 0) | \
               (nat.FLAG_RELU_MASK if mask is not None else 0)
     fn = lib.osvos_conv3x3_simt if simt else lib.osvos_conv3x3

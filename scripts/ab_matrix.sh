@@ -3,13 +3,11 @@
 # Usage on a GPU box:  bash scripts/ab_matrix.sh > gpurun_out/ab_matrix.txt 2>&1   (about 15 s per line pair)
 cd "$(dirname "$0")/.."
 export OSVOS_ENV_RELOAD=1
-for sw in OSVOS_STREAMK OSVOS_FOLD_SIDE OSVOS_HALO_LEAN; do
+for sw in OSVOS_FUSE_STAGE1 OSVOS_S1_SW64 OSVOS_FOLD_SIDE OSVOS_HALO_LEAN; do
   echo "== $sw (1 = default)"
   timeout 200 python scripts/ab_env.py $sw 1 0 --train || echo "FAILED: $sw"
 done
-echo "== OSVOS_SPLITACC128 (1 = default)"
-timeout 120 python scripts/ab_env.py OSVOS_SPLITACC128 1 0 || echo "FAILED"
-for hw in "240 427" "720 1280"; do
-  echo "== OSVOS_STREAMK at $hw"
-  timeout 200 python scripts/ab_env.py OSVOS_STREAMK 1 0 $hw || echo "FAILED"
+for hw in "240 427" "720 1280" "1080 1920"; do
+  echo "== OSVOS_S1_SW64 at $hw"
+  timeout 200 python scripts/ab_env.py OSVOS_S1_SW64 1 0 $hw || echo "FAILED"
 done

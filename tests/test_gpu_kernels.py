@@ -88,43 +88,6 @@ def test_conv3x3_tensor_core(dev, n, h, w, cin, cout, relu, fast):
     assert maxrel(got_f32, ys.permute(0, 3, 1, 2).cpu()) < 2e-5
 
 
-@pytest.mark.parametrize("n,h,w,cin,cout", [(1, 30, 54, 512, 512),      # stage 5 at 480p: 56 tiles of 128 x 128, 8 chunks
-                                            (1, 60, 107, 512, 512),     # stage 4: 224 tiles on 148 SMs
-                                            (1, 15, 27, 512, 512),      # 16 tiles: every CTA reduces ONE chunk, 7 helpers per tile
-                                            (2, 9, 11, 256, 128),       # tiny: 4 tiles x 4 chunks
-                                            (1, 60, 107, 512, 256),     # dgrad of conv4_1 (112 tiles)
-                                            (1, 33, 45, 128, 256)])     # 2 chunks
-@pytest.mark.parametrize("relu_mask", [False, True])
-def test_conv3x3_stream_k(dev, monkeypatch, n, h, w, cin, cout, relu_mask):
-    """Stream-K scheduling (csrc/conv_common.cuh: WorkList): same convolution with the (tile, chunk) units dealt out in
-    balanced ranges and fp32 partial accumulators exchanged through the workspace, against the whole-tile schedule
-    (OSVOS_STREAMK=0) and the fp64 reference; run twice to check that the workspace counters come back at zero."""
-    from osvos_pytorch_b200 import ops
-    g = torch.Generator().manual_seed(7 + h + cin)
-    x = torch.randn(n, cin, h, w, generator=g) * 3.0
-    wt = torch.randn(cout, cin, 3, 3, generator=g) * math.sqrt(2.0 / (9 * cin))
-    b = torch.randn(cout, generator=g) * 0.1
-    a = ops.nchw_to_act(x.to(dev))
-    wp = ops.pack_conv3x3_weights(wt.to(dev))
-    mask = ops.nchw_to_act(torch.randn(n, cout, h, w, generator=g).clamp(min=0).to(dev)).hi if relu_mask else None
-    colsum0 = torch.zeros(cout, device=dev) if relu_mask else None
-    monkeypatch.setenv("OSVOS_STREAMK", "0")
-    _, base, _ = ops.conv3x3(a, wp, b.to(dev), cout, relu=not relu_mask, out_act=False, out_f32=True, mask=mask, colsum=colsum0)
-    monkeypatch.setenv("OSVOS_STREAMK", "2")     # forced: also the shapes the dispatcher would not pick (many parts per tile)
-    for rep in range(2):
-        colsum = torch.zeros(cout, device=dev) if relu_mask else None
-        y, split, _ = ops.conv3x3(a, wp, b.to(dev), cout, relu=not relu_mask, out_act=True, out_f32=True, mask=mask, colsum=colsum)
-        torch.cuda.synchronize()
-        if not relu_mask:
-            ref = F.conv2d(x.double(), wt.double(), b.double(), padding=1).relu()
-            assert maxrel(split.permute(0, 3, 1, 2).cpu(), ref) < EXACT_TOL
-        assert maxrel(split, base) < 1e-5                       # only the fp32 summation order differs
-        assert torch.equal(ops.act_to_nchw(y).cpu(), split_round(split.permute(0, 3, 1, 2).cpu()))
-        if relu_mask:
-            assert maxrel(colsum, colsum0) < 1e-4
-    # (the workspace counters are handed back at zero: the second repetition would trap on its bounded spin otherwise)
-
-
 @pytest.mark.parametrize("n,h,w", [(1, 16, 8), (1, 33, 45), (2, 40, 56), (1, 5, 3), (1, 480, 854), (3, 97, 131)])
 def test_stage1_fused_equals_conv1_1_then_conv1_2(dev, n, h, w):
     """osvos_stage1_fused (conv1_1 evaluated inside conv1_2's kernel on its halo patch) against the two-kernel route and

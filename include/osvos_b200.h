@@ -58,6 +58,11 @@ typedef void* osvos_stream_t; /* cudaStream_t */
 
 OSVOS_API int osvos_version(void);
 OSVOS_API const char* osvos_last_error(void);
+/* Programmatic dependent launch for the kernels enqueued from now on: 1 on, 0 off, -1 = the process default
+ * (environment OSVOS_PDL, off).  Returns the previous setting.  Every kernel of the library waits
+ * (griddepcontrol.wait) before it first touches memory another kernel may have written, so the switch only decides
+ * whether a kernel's prologue may overlap its predecessor's tail.  A captured CUDA graph keeps what it was captured with. */
+OSVOS_API int osvos_set_pdl(int mode);
 
 /* ---- weight packing ------------------------------------------------------
  * nn.Conv2d weight, OIHW fp32 (networks/vgg_osvos.py:41,142) -> split-bf16

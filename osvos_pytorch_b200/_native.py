@@ -92,6 +92,7 @@ SIGNATURES = {
                                      c_void_p]),
     "osvos_conv3x3": (c_int, [POINTER(Conv3x3Args), c_void_p]),
     "osvos_stage1_fused": (c_int, [POINTER(Stage1Args), c_void_p]),
+    "osvos_set_pdl": (c_int, [c_int]),
     "osvos_fold_side_weights": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "osvos_conv3x3_simt": (c_int, [POINTER(Conv3x3Args), c_void_p]),
     "osvos_maxpool2x2_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),

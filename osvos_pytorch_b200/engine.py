@@ -208,6 +208,19 @@ class OSVOSEngine:
 
     @torch.no_grad()
     def forward_inference(self, x, simt=False, return_intermediates=False):
+        """The inference pass (eager, or while a CUDA graph captures it).  Programmatic dependent launch is switched on
+        for its kernels (every one of them waits before touching its predecessor's data, so only prologues overlap);
+        OSVOS_PDL_INFER=0 keeps plain stream order."""
+        from . import _native as nat
+        lib = nat.load()
+        prev = lib.osvos_set_pdl(1) if os.environ.get("OSVOS_PDL_INFER", "1") != "0" else None
+        try:
+            return self._forward_inference(x, simt, return_intermediates)
+        finally:
+            if prev is not None:
+                lib.osvos_set_pdl(prev)
+
+    def _forward_inference(self, x, simt=False, return_intermediates=False):
         m = self.m
         fast = m.precision == "fast"
         self._check_deconvs()

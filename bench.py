@@ -664,58 +664,68 @@ def main():
                                             "d2h_bytes_per_step": H * W,
                                             "note": "sigmoid + imsave bytescale on the device (ops.logits_to_u8)"}}
 
-    # ---- roofline of the dominant kernel class (tcgen05 convs): CUDA events around every launch ---
+    # ---- roofline of the dominant kernel class (tcgen05 convs) ----------------------------------------------------
+    # In forward_inference every kernel between the first conv and the tail IS a tcgen05 conv (stage-1 kernel, trunk, side
+    # convs; the fold / pack kernels only run on the first pass), so ONE event pair - recorded just before the first conv
+    # launch and just before the tail launch - brackets exactly the conv kernels of a pass, back to back, without the
+    # per-launch event pairs that used to cost the stream a few us each (their sum exceeded the whole graphed step).
     conv_rec, eager_ms, parked = [], 0.0, True
+    conv_spans = []
     reps = 0
     if rank == 0 and not train and "roofline" not in skip:
         rec = []
-        orig = ops.conv3x3
+        span = {"a": None}
+        origs = {n: getattr(ops, n) for n in ("conv3x3", "stage1_fused", "side_folded", "conv_first", "tail_fwd")}
 
-        def wrapped(x, w_packed, bias, cout, *a, **k):
-            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s.record()
-            r = orig(x, w_packed, bias, cout, *a, **k)
-            e.record()
+        def mark_first():
+            if span["a"] is None:
+                span["a"] = torch.cuda.Event(enable_timing=True)
+                span["a"].record()
+
+        def w_conv3x3(x, w_packed, bias, cout, *a, **k):
+            mark_first()
             n_, hh, ww, ci = x.shape
-            rec.append((s, e, 2.0 * n_ * hh * ww * cout * 9 * ci, "side_conv_kernel" if cout == 16 else "conv3x3_halo_kernel"))
-            return r
-        orig_s1 = ops.stage1_fused
+            rec.append((2.0 * n_ * hh * ww * cout * 9 * ci, "side_conv_kernel" if cout == 16 else "conv3x3_halo_kernel"))
+            return origs["conv3x3"](x, w_packed, bias, cout, *a, **k)
 
-        def wrapped_s1(x, *a, **k):              # conv1_1 + conv1_2 in one kernel: both layers' flops
-            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s.record()
-            r = orig_s1(x, *a, **k)
-            e.record()
+        def w_stage1(x, *a, **k):                 # conv1_1 + conv1_2 in one kernel: both layers' flops
+            mark_first()
             n_, _, hh, ww = x.shape
-            rec.append((s, e, 2.0 * n_ * hh * ww * 64 * 9 * (3 + 64), "conv_stage1_fused_kernel"))
-            return r
-        orig_side = ops.side_folded
+            rec.append((2.0 * n_ * hh * ww * 64 * 9 * (3 + 64), "conv_stage1_fused_kernel"))
+            return origs["stage1_fused"](x, *a, **k)
 
-        def wrapped_side(x, *a, **k):            # algorithmic flops of the reference's side_prep (C -> 16), run folded (C -> 2)
-            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s.record()
-            r = orig_side(x, *a, **k)
-            e.record()
+        def w_side(x, *a, **k):                   # algorithmic flops of the reference's side_prep (C -> 16), run folded (C -> 2)
+            mark_first()
             n_, hh, ww, ci = x.shape
-            rec.append((s, e, 2.0 * n_ * hh * ww * 16 * 9 * ci, "side_conv_kernel"))
-            return r
-        ops.conv3x3 = wrapped
-        ops.stage1_fused = wrapped_s1
-        ops.side_folded = wrapped_side
-        import osvos_pytorch_b200.engine as eng
-        eng.ops.conv3x3 = wrapped
-        net._engine.use_cuda_graph = False          # per-launch events need the eager path
+            rec.append((2.0 * n_ * hh * ww * 16 * 9 * ci, "side_conv_kernel"))
+            return origs["side_folded"](x, *a, **k)
+
+        def w_first(x, *a, **k):                  # separate conv1_1 (training / fast mode): inside the span, flops counted
+            mark_first()
+            n_, _, hh, ww = x.shape
+            rec.append((2.0 * n_ * hh * ww * 64 * 27, "conv_first_tc_kernel"))
+            return origs["conv_first"](x, *a, **k)
+
+        def w_tail(*a, **k):
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            conv_spans.append((span["a"], e))
+            span["a"] = None
+            return origs["tail_fwd"](*a, **k)
+        ops.conv3x3, ops.stage1_fused, ops.side_folded, ops.conv_first, ops.tail_fwd = w_conv3x3, w_stage1, w_side, w_first, w_tail
+        net._engine.use_cuda_graph = False          # the span events need the eager path
         reps = min(steps, 10)
         for i in range(3):                          # eager warm-up passes, not counted
             step(i)
 
         def instrumented(park_gpu):
-            """`reps` eager passes with an event pair around every conv launch.  An eager launch costs the host ~40 us
-            (ctypes + six tensor-map encodes), more than the short kernels take, so with the GPU idle the event pairs
-            would time the HOST.  park_gpu: a ~40 ms spin kernel is enqueued first and every launch of the passes
-            queues up behind it; the GPU then runs them back to back and the events see kernel time only."""
+            """`reps` eager passes.  An eager launch costs the host ~40 us (ctypes + tensor-map encodes), more than the short
+            kernels take, so with the GPU idle the span would time the HOST.  park_gpu: a ~40 ms spin kernel is enqueued
+            first and every launch of the passes queues up behind it; the GPU then runs them back to back."""
             torch.cuda.synchronize()
             rec.clear()
+            conv_spans.clear()
+            span["a"] = None
             if park_gpu:
                 torch.cuda._sleep(int(0.04 * 1.9e9))
             p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -724,18 +734,17 @@ def main():
                 step(i)
             p1.record()
             torch.cuda.synchronize()
-            return p0.elapsed_time(p1) / reps       # the instrumented (eager, per-launch events) step
+            return p0.elapsed_time(p1) / reps       # the instrumented (eager) step
         try:
             eager_ms = instrumented(True)
         except Exception:                            # torch.cuda._sleep is a private helper: fall back to plain eager
             parked = False
             eager_ms = instrumented(False)
-        ops.conv3x3 = orig
-        ops.stage1_fused = orig_s1
-        ops.side_folded = orig_side
-        eng.ops.conv3x3 = orig
+        for n, f in origs.items():
+            setattr(ops, n, f)
         net._engine.use_cuda_graph = graphs_on
-        conv_rec = [(s.elapsed_time(e), f, k) for s, e, f, k in rec]
+        conv_rec = list(rec)
+        conv_span_ms = sum(a.elapsed_time(b) for a, b in conv_spans) / max(1, len(conv_spans))
 
     # ---- the north-star multi-GPU path (every N, 1 included) ------------------------------------------------------
     dp = None
@@ -782,33 +791,29 @@ def main():
     }
     if conv_rec:
         per = len(conv_rec) // reps
-        conv_ms = sum(t for t, _, _ in conv_rec) / reps
-        conv_flops = sum(f for _, f, _ in conv_rec) / reps
-        halo_ms = sum(t for t, _, k in conv_rec if k == "conv3x3_halo_kernel") / reps
-        halo_flops = sum(f for _, f, k in conv_rec if k == "conv3x3_halo_kernel") / reps
-        n_halo = sum(1 for _, _, k in conv_rec if k == "conv3x3_halo_kernel") // reps
-        n_s1 = sum(1 for _, _, k in conv_rec if k == "conv_stage1_fused_kernel") // reps
-        n_side = sum(1 for _, _, k in conv_rec if k == "side_conv_kernel") // reps
+        conv_ms = conv_span_ms
+        conv_flops = sum(f for f, _ in conv_rec) / reps
+        kinds = {}
+        for _, k in conv_rec:
+            kinds[k] = kinds.get(k, 0) + 1
+        kinds = {k: v // reps for k, v in kinds.items()}
         passes = 3 if args.precision == "exact" else 1
         ach = conv_flops / (conv_ms * 1e-3) / 1e12
-        halo_ach = halo_flops / (halo_ms * 1e-3) / 1e12
+        # upper bound from the headline itself: all conv flops over the WHOLE graphed step (as if nothing else ran in it)
+        ach_floor_step = conv_flops / (ms * 1e-3) / 1e12
         traffic, tsrc = conv_traffic(args.precision, per)
         line["roofline"] = {
             "bound": "tensor",
-            "kernel": f"the step's tcgen05 implicit-GEMM 3x3 convolutions: conv_stage1_fused_kernel x{n_s1} (conv1_1 + conv1_2) + "
-                      f"conv3x3_halo_kernel x{n_halo} (rest of the trunk{'' if n_s1 else ', conv1_1 excluded'}) + side_conv_kernel "
-                      f"x{n_side} (side_prep, folded with its 1x1 projections) = {per} launches per step",
+            "kernel": "the step's tcgen05 implicit-GEMM 3x3 convolutions: " + " + ".join(f"{k} x{v}" for k, v in kinds.items())
+                      + f" = {per} launches per step (every kernel of the step between the frame and the tail)",
             "achieved": ach, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["tflops_sustained"],
             "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernels timed inside the step)",
             "algorithmic_flops_per_step": conv_flops, "launches_per_step": per, "kernel_ms_per_step": conv_ms,
-            "dominant_kernel_only": {"kernel": "conv3x3_halo_kernel", "launches_per_step": n_halo, "kernel_ms_per_step": halo_ms,
-                                     "achieved": halo_ach, "frac": halo_ach / peaks["tflops_sustained"],
-                                     "issued_mma_frac": halo_ach * passes / peaks["tflops_sustained"]},
-            # share measured inside ONE pass: per-launch events and the pass's own total (eager launches; the headline
-            # `ms_per_step` replays the same kernels from a CUDA graph)
+            "how": "ONE CUDA-event pair per pass spanning the conv launches (first conv launch -> tail launch), eager launches "
+                   + ("queued behind a parked GPU (back-to-back kernel time)" if parked else "(host launch gaps included)"),
             "share_of_step": conv_ms / eager_ms, "instrumented_step_ms": eager_ms,
-            "instrumented_how": ("eager launches queued behind a parked GPU (back-to-back kernel time)"
-                                 if parked else "plain eager launches (host launch gaps included)"),
+            "conv_flops_over_whole_graphed_step": {"achieved": ach_floor_step, "frac": ach_floor_step / peaks["tflops_sustained"],
+                                                    "note": "all conv flops / the headline ms_per_step (tail and copies included)"},
             "tensor_pipe_passes": passes,
             # exact mode emulates fp32 operands with three bf16 passes (hi*hi + hi*lo + lo*hi): the tensor pipe EXECUTES
             # passes x the algorithmic flops; this is that figure over the peak

@@ -122,7 +122,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_c
       uint32_t a_phase = 0, b_phase = 0;
       const bool skip_a = (p.ablate & 2) != 0, skip_b = (p.ablate & 1) != 0;
       auto issue_a = [&](int x0, int y0, int img, int kc) {
-        mbar_wait_relaxed(&a_empty[a_stage], a_phase ^ 1, p.wait_hint);
+        mbar_wait(&a_empty[a_stage], a_phase ^ 1);
         if (skip_a) {
           mbar_arrive(&a_full[a_stage]);
         } else {
@@ -155,7 +155,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_c
               if (kc + 1 < p.k_chunks) issue_a(tx * kTileW - 1, ty * kTileH - 1, img, kc + 1);
               else if (has_next) issue_a(ntx * kTileW - 1, nty * kTileH - 1, nimg, 0);
             }
-            mbar_wait_relaxed(&b_empty[b_stage], b_phase ^ 1, p.wait_hint);
+            mbar_wait(&b_empty[b_stage], b_phase ^ 1);
             if (skip_b) {
               mbar_arrive(&b_full[b_stage]);
             } else {

@@ -36,9 +36,6 @@ struct ConvParams {
   // Timing ablations (OSVOS_ABLATE bit mask, diagnosis only - results are garbage): 1 = no weight TMA loads,
   // 2 = no activation TMA loads, 4 = no tcgen05.mma, 8 = no global stores in the epilogue.  0 in production.
   int ablate;
-  // suspend-time hint (ns) for the mbarrier waits of warps off the critical path (ptx.cuh: mbar_wait_relaxed); 0 = plain
-  // spinning.  OSVOS_WAIT_HINT_NS, default below.
-  int wait_hint;
 };
 
 __device__ __forceinline__ void decode_tile(const ConvParams& p, int tile, int& nb, int& tx, int& ty, int& img) {
@@ -108,7 +105,7 @@ __device__ __forceinline__ void conv_epilogue_loop(const ConvParams& p, uint32_t
     const bool valid = (y < p.h) && (x < p.w) && store_ok;
     const size_t pix = (static_cast<size_t>(img) * p.h + y) * p.w + x;
 
-    mbar_wait_relaxed(&tfull_bar[as], aph, p.wait_hint);
+    mbar_wait(&tfull_bar[as], aph);
     tc_fence_after();
     constexpr int kAccCols = SPLIT_ACC ? 2 * BLOCK_N : BLOCK_N;
     const uint32_t taddr = tmem_base + as * kAccCols + (static_cast<uint32_t>(q * 32) << 16);
@@ -334,7 +331,7 @@ __device__ __forceinline__ void conv_epilogue_lean(const ConvParams& p, uint32_t
     const size_t opix = (static_cast<size_t>(img) * oh + (y >> 1)) * ow + (x >> 1);
     const bool writer = valid && !(lx & 1) && !(ly & 1);
 
-    mbar_wait_relaxed(&tfull_bar[as], aph, p.wait_hint);
+    mbar_wait(&tfull_bar[as], aph);
     tc_fence_after();
     const uint32_t taddr = tmem_base + as * kAccCols + (static_cast<uint32_t>(q * 32) << 16) + group * 32;
     uint32_t v[32], v2[32];
@@ -465,18 +462,6 @@ static inline void fill_conv_params(ConvParams& p, const osvos_conv3x3_args* a, 
       ablate = e ? atoi(e) : 0;
     }
     p.ablate = ablate;
-  }
-  {
-    static int hint = -1, reload = -1;
-    if (reload < 0) {
-      const char* r = getenv("OSVOS_ENV_RELOAD");
-      reload = (r != nullptr && atoi(r) != 0) ? 1 : 0;
-    }
-    if (hint < 0 || reload) {
-      const char* e = getenv("OSVOS_WAIT_HINT_NS");
-      hint = e ? atoi(e) : 0;
-    }
-    p.wait_hint = hint;
   }
 }
 

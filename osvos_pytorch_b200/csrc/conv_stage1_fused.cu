@@ -148,7 +148,7 @@ conv_stage1_fused_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __g
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
-          mbar_wait_relaxed(&b_empty[b_stage], b_phase ^ 1, p.wait_hint);
+          mbar_wait(&b_empty[b_stage], b_phase ^ 1);
           uint8_t* st = smem_b + b_stage * kS1BStage;
           mbar_arrive_expect_tx(&b_full[b_stage], kS1BStage);
           tma_load_3d(&map_w_hi, &b_full[b_stage], st, 0, 0, tap);
@@ -308,8 +308,8 @@ conv_stage1_fused_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __g
       const int y = ty * kTileH - 1 + hy, xx = tx * kTileW - 1 + hx;
       const bool inside = live && y >= 0 && y < p.h && xx >= 0 && xx < p.w;
       // ---- conv1_1 epilogue of this tile: TMEM -> bias / ReLU / zero padding -> split bf16 -> activation stage
-      mbar_wait_relaxed(&a_empty[a_stage], a_phase ^ 1, p.wait_hint);   // conv1_2's MMAs of two tiles ago have read this stage
-      mbar_wait_relaxed(c_full, c_phase, p.wait_hint);
+      mbar_wait(&a_empty[a_stage], a_phase ^ 1);   // conv1_2's MMAs of two tiles ago have read this stage
+      mbar_wait(c_full, c_phase);
       tc_fence_after();
       uint8_t* st = smem_a + a_stage * kS1AStage;
       uint32_t v[16], v2[16];
@@ -364,7 +364,7 @@ conv_stage1_fused_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __g
       }
       // ---- im2col row of the next tile (its conv1_1 MMAs are issued before this tile's conv1_2 MMAs)
       if (has_next) {
-        mbar_wait_relaxed(i_empty, i_phase, p.wait_hint);   // this tile's conv1_1 MMAs have read the buffer
+        mbar_wait(i_empty, i_phase);   // this tile's conv1_1 MMAs have read the buffer
         i_phase ^= 1;
         write_im2col_row();
       }

@@ -103,31 +103,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
-// Wait of a warp that is NOT on the critical path (epilogue warps waiting for an accumulator, producers waiting for a
-// free stage): with hint_ns > 0 the try_wait carries a suspend-time hint, so the waiting warp sleeps in hardware until
-// the phase completes (or the hint elapses) instead of re-issuing try_wait + branch every ~35 cycles - in the fused
-// stage-1 kernel a dozen such spinners took half of the SM's issue slots from the six warps doing the work
-// (profiles/r02e_ncu_stage1_fused.txt: smsp__issue_active 51 %, 4.3 M loop iterations per launch).  hint_ns == 0: plain.
-__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, uint32_t hint_ns) {
-  if (hint_ns == 0) {
-    mbar_wait(bar, parity);
-    return;
-  }
-  uint32_t spins = 0;
-  for (;;) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred P;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
-        "selp.u32 %0, 1, 0, P;\n\t}\n"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
-        : "memory");
-    if (ok) return;
-    if (++spins > OSVOS_SPIN_LIMIT) __trap();
-  }
-}
-
 // ---------------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

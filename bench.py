@@ -381,7 +381,7 @@ def run_dp(args, rank, world, local, dev, timer, steps):
     if world > 1:
         dist.all_reduce(finite, op=dist.ReduceOp.MIN)
     torch.cuda.synchronize()
-    first, last = [float(v) for v in loss_log[0]], [float(v) for v in loss_log[-1]]     # device tensors until here
+    first, last = loss_log[0].tolist(), loss_log[-1].tolist()     # device tensors until here: no host sync per step
     if rank != 0:
         return None
     fps = world * args.batch * 1000.0 / ms

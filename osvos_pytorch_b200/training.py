@@ -183,6 +183,9 @@ def parent_epoch(net, opt, bucket, batches, epoch, n_epochs, n_ave_grad=1, group
     """One epoch of the parent objective on this rank's shard: deep-supervision loss
     (1 - epoch/nEpochs) * sum_{k<4} L_k + L_fuse (train_parent.py:143-147), gradient accumulation over
     `n_ave_grad` local micro-batches, then ONE allreduce(mean) and one SGD step.
+    Returns the mean of the five losses over the micro-batches as a device tensor (the reference reads `.item()` of
+    every loss in every iteration, train_parent.py:146: a host sync per step that exposes launch latency and, in data
+    parallel, lets rank skew accumulate; here the host only waits when it logs).
     `state`: a dict the caller keeps across epochs; it carries the accumulation counter, which the reference does NOT
     reset at epoch boundaries (`aveGrad`, train_parent.py:125,165-172) - leftover micro-batches of an epoch whose length
     is not a multiple of nAveGrad complete their group in the next epoch instead of inflating its first step."""
@@ -211,7 +214,7 @@ def parent_epoch(net, opt, bucket, batches, epoch, n_epochs, n_ave_grad=1, group
             else:
                 opt.step()
                 bucket.zero_()
-    return (totals / max(count, 1)).tolist()
+    return totals / max(count, 1)          # DEVICE tensor [5]: no host sync per call; callers read it when they log
 
 
 def timed_parent_steps(net, opt, bucket, make_batch, steps, warmup, epoch=0, n_epochs=240, group=None):

@@ -67,6 +67,9 @@ def main():
         def epoch_batches(epoch):
             # the same number of micro-batches on every rank (a multiple of n_ave): every rank joins every allreduce
             per = parallel.steps_per_rank(a.iters_per_epoch, world, n_ave)
+            if per == 0:
+                raise ValueError(f"--iters-per-epoch {a.iters_per_epoch} gives no complete optimizer step on {world} ranks with "
+                                 f"nAveGrad {n_ave} (need >= {world * n_ave})")
             for i in range(rank * per, (rank + 1) * per):
                 yield training.synthetic_batch(a.batch, a.height, a.width, 7919 * epoch + i, device)
         val_batches = None
@@ -100,7 +103,7 @@ def main():
         losses = training.parent_epoch(net, opt, bucket, epoch_batches(epoch), epoch, a.epochs, n_ave, state=loop_state)
         torch.cuda.synchronize()
         if rank == 0:
-            print(f"[Epoch: {epoch}] " + " ".join(f"Loss {k}: {v:.4f}" for k, v in enumerate(losses))
+            print(f"[Epoch: {epoch}] " + " ".join(f"Loss {k}: {v:.4f}" for k, v in enumerate(losses.tolist()))
                   + f"  Execution time: {timeit.default_timer() - t0:.2f}")
             if epoch % a.snapshot == a.snapshot - 1 and epoch != 0:
                 torch.save(net.state_dict(), os.path.join(save_dir, f"{a.model_name}_epoch-{epoch}.pth"))

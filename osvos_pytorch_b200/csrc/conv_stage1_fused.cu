@@ -256,22 +256,27 @@ conv_stage1_fused_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __g
     const int hy = pix / kS1Pitch, hx = pix - hy * kS1Pitch;
     const size_t plane_sz = static_cast<size_t>(p.h) * p.w;
     float vn[27];                                                       // taps of the NEXT tile, in flight
-    auto request_taps = [&](int tile) {
-      int nb, tx, ty, img;
-      decode_tile(p, tile, nb, tx, ty, img);
+    // One 64-bit base pointer per tile (the tap at (ci, r, s) = (0, 0, 0), possibly outside the frame and then never
+    // dereferenced), 32-bit offsets ci * plane + r * w + s from it, three row and three column predicates: the first
+    // version recomputed a 64-bit address and four comparisons per tap - 640 of the ~1200 instructions a stage-1 thread
+    // executed per tile, which made these six warps, not the tensor pipe, the pace of the kernel
+    // (profiles/r02e_ncu_stage1_fused.txt).
+    const int fw = p.w, fplane = p.h * p.w;
+    auto request_taps = [&](int tx, int ty, int img) {
       const int y = ty * kTileH - 1 + hy, xx = tx * kTileW - 1 + hx;
+      const bool ry[3] = {live && static_cast<unsigned>(y - 1) < static_cast<unsigned>(p.h),
+                          live && static_cast<unsigned>(y) < static_cast<unsigned>(p.h),
+                          live && static_cast<unsigned>(y + 1) < static_cast<unsigned>(p.h)};
+      const bool cx[3] = {static_cast<unsigned>(xx - 1) < static_cast<unsigned>(fw), static_cast<unsigned>(xx) < static_cast<unsigned>(fw),
+                          static_cast<unsigned>(xx + 1) < static_cast<unsigned>(fw)};
+      const float* base = s1.x + static_cast<size_t>(img) * 3 * plane_sz + static_cast<ptrdiff_t>(y - 1) * fw + (xx - 1);
 #pragma unroll
       for (int ci = 0; ci < 3; ++ci) {
-        const float* pl = s1.x + (static_cast<size_t>(img) * 3 + ci) * plane_sz;
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
-          const int iy = y + r - 1;
 #pragma unroll
-          for (int s = 0; s < 3; ++s) {
-            const int ix = xx + s - 1;
-            vn[ci * 9 + r * 3 + s] = (live && iy >= 0 && iy < p.h && ix >= 0 && ix < p.w)
-                                         ? __ldg(pl + static_cast<size_t>(iy) * p.w + ix) : 0.f;
-          }
+          for (int s = 0; s < 3; ++s)
+            vn[ci * 9 + r * 3 + s] = (ry[r] && cx[s]) ? __ldg(base + (ci * fplane + r * fw + s)) : 0.f;
         }
       }
     };
@@ -295,16 +300,19 @@ conv_stage1_fused_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __g
     uint32_t i_phase = 0, c_phase = 0;
     int a_stage = 0;
     uint32_t a_phase = 0;
+    int tx = 0, ty = 0, img = 0, ntx = 0, nty = 0, nimg = 0, nb_unused = 0;
     if (static_cast<int>(blockIdx.x) < p.total_tiles) {      // (the buffer starts out free)
-      request_taps(blockIdx.x);
+      decode_tile(p, blockIdx.x, nb_unused, tx, ty, img);
+      request_taps(tx, ty, img);
       write_im2col_row();
     }
     const uint32_t taddr = tmem_c1 + mh * 128 + (static_cast<uint32_t>(q * 32) << 16);
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const bool has_next = tile + static_cast<int>(gridDim.x) < p.total_tiles;
-      if (has_next) request_taps(tile + gridDim.x);   // global loads in flight behind the epilogue below
-      int nb, tx, ty, img;
-      decode_tile(p, tile, nb, tx, ty, img);
+      if (has_next) {                                 // global loads in flight behind the epilogue below
+        decode_tile(p, tile + gridDim.x, nb_unused, ntx, nty, nimg);
+        request_taps(ntx, nty, nimg);
+      }
       const int y = ty * kTileH - 1 + hy, xx = tx * kTileW - 1 + hx;
       const bool inside = live && y >= 0 && y < p.h && xx >= 0 && xx < p.w;
       // ---- conv1_1 epilogue of this tile: TMEM -> bias / ReLU / zero padding -> split bf16 -> activation stage
@@ -368,6 +376,7 @@ conv_stage1_fused_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __g
         i_phase ^= 1;
         write_im2col_row();
       }
+      tx = ntx, ty = nty, img = nimg;
     }
   }
 

@@ -308,9 +308,14 @@ __device__ __forceinline__ void conv_epilogue_loop(const ConvParams& p, uint32_t
 //  * the accumulator stage is handed back to the MMA warp right after the LAST tcgen05.ld of the tile has landed,
 //    before the stores - not at the end of the tile;
 //  * no mask / column-sum / fp32 / split-K / bulk-store code: ~1/3 of the instruction footprint next to the issuer.
-template <int BLOCK_N>
+struct NoTileHook {
+  __device__ __forceinline__ void operator()(int) const {}
+};
+// `pre_tile(tile)` runs at the top of every tile iteration, BEFORE the wait for that tile's accumulator: the fused
+// stage-1 kernel uses the epilogue warps' idle time there to build conv1_1's operand rows of a later tile.
+template <int BLOCK_N, class TileHook = NoTileHook>
 __device__ __forceinline__ void conv_epilogue_lean(const ConvParams& p, uint32_t tmem_base, uint64_t* tfull_bar,
-                                                   uint64_t* tempty_bar, int warp, int lane) {
+                                                   uint64_t* tempty_bar, int warp, int lane, TileHook pre_tile = TileHook()) {
   static_assert(BLOCK_N == 64 || BLOCK_N == 128, "lean epilogue: 64- or 128-wide exact tiles");
   constexpr int kAccCols = 2 * BLOCK_N, kSlabs = BLOCK_N / 64;
   const int group = (warp - 2) >> 2;
@@ -331,6 +336,7 @@ __device__ __forceinline__ void conv_epilogue_lean(const ConvParams& p, uint32_t
     const size_t opix = (static_cast<size_t>(img) * oh + (y >> 1)) * ow + (x >> 1);
     const bool writer = valid && !(lx & 1) && !(ly & 1);
 
+    pre_tile(tile);
     mbar_wait(&tfull_bar[as], aph);
     tc_fence_after();
     const uint32_t taddr = tmem_base + as * kAccCols + (static_cast<uint32_t>(q * 32) << 16) + group * 32;

@@ -6,23 +6,24 @@
 //
 // conv1_2 part = conv3x3_halo_kernel<64, exact, lean epilogue> unchanged: nine taps as nine UMMA descriptors into the
 // halo patch, weight slabs streamed by TMA through a ring, N-concatenated split accumulator, lean epilogue with the
-// fused 2 x 2 max pool.  What changes is WHO fills the activation stage: not a TMA box but four "stage-1" warps:
-//   1. build the im2col operand of conv1_1 for the 180 halo pixels (rows m = hy * 10 + hx, k = ci * 9 + 3r + s < 27,
+// fused 2 x 2 max pool.  What changes is WHO fills the activation stage: not a TMA box but the CTA itself:
+//   1. (the eight conv1_2 epilogue warps, in their idle time) build the im2col operand of conv1_1 for the 180 halo pixels (rows m = hy * 10 + hx, k = ci * 9 + 3r + s < 27,
 //      split bf16 hi / lo, canonical K-major SWIZZLE_128B rows - the layout of conv_first_tc.cu) from the fp32 frame;
 //   2. the MMA warp runs conv1_1 on it: two M = 128 halves x two K steps x (A_hi.[B_hi | B_lo] + A_lo.B_hi) into 2 x 128
 //      TMEM columns next to conv1_2's two accumulator stages (512 columns in all);
 //      (pixels 128 .. 179 sit at rows 192 .. 243 of the operand, i.e. in TMEM lanes 64 .. 115 of the second M half, so that
 //      six warps - lane quarters 2, 3, 0, 1, 2, 3 - own exactly one pixel per thread);
-//   3. the stage-1 warps read those accumulators back, add the bias, apply ReLU, ZERO the halo pixels that lie outside the
+//   3. six "stage-1" warps read those accumulators back, add the bias, apply ReLU, ZERO the halo pixels that lie outside the
 //      image (they are conv1_2's zero padding, not conv1_1 evaluated outside the frame), split into hi / lo and write
 //      the rows of the activation stage exactly where the TMA box of the unfused kernel would have put them
 //      (generic-proxy writes + fence.proxy.async before the mbarrier arrive).
 // Issue order per tile j: [conv1_1 MMAs of tile j + 1] then [conv1_2 MMAs of tile j], so that steps 3 and 1 of the
 // stage-1 warps hide behind the 4 k cycles of conv1_2's MMAs.  Single-buffered im2col tile and conv1_1 accumulators.
-// A stage-1 thread requests the 27 taps of its pixel for tile j + 1 BEFORE it converts tile j's accumulators, and the
-// second half of its accumulator row is requested before the first half is converted: the first version (four warps,
-// two pixels per thread, every load waited for in turn) took 9 k cycles per tile against 4 k of conv1_2 MMAs and was
-// no faster than the two separate kernels (profiles/r02c_*).
+// History (profiles/r02c .. r02h): v1 - four stage-1 warps doing steps 1 and 3 for two pixels each, every load waited
+// for in turn: 9 k cycles per tile against 4.5 k of MMAs, no faster than two kernels.  v2 - six warps, one pixel per
+// thread, taps of the next tile and the next 16 accumulator columns requested ahead: 7.5 k.  v3 - one base pointer and
+// 32-bit offsets for the 27 taps instead of per-tap 64-bit addressing: 6.9 k, the stage-1 warps still the pace of the
+// kernel.  v4 (this) - step 1 moved to the epilogue warps, three tiles ahead, so that the stage-1 warps only convert.
 #include <stdlib.h>
 #include <string.h>
 
@@ -110,7 +111,7 @@ conv_stage1_fused_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __g
       mbar_init(&b_full[i], 1);
       mbar_init(&b_empty[i], 1);
     }
-    mbar_init(i_full, kS1S1Threads);
+    mbar_init(i_full, kS1EpiThreads);
     mbar_init(i_empty, 1);
     mbar_init(c_full, 1);
     mbar_init(c_empty, kS1S1Threads);
@@ -243,26 +244,25 @@ conv_stage1_fused_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __g
     __syncwarp();
   } else if (warp < 2 + kS1EpiThreads / 32) {
     // ------------------------------------------------------------ conv1_2 epilogue (bias, ReLU, act and / or pooled output)
-    conv_epilogue_lean<64>(p, tmem_base, tfull_bar, tempty_bar, warp, lane);
-  } else {
-    // ------------------------------------------------------------ stage-1 warps: im2col builder + conv1_1 epilogue
-    // warps 10 .. 13 (TMEM lane quarters 2, 3, 0, 1): pixels 0 .. 127 = first M half; warps 14, 15 (quarters 2, 3):
-    // pixels 128 .. 191 = lanes 64 .. 127 of the second M half (operand rows 192 .. 255)
-    const int q = warp & 3;
-    const int mh = warp >= 14 ? 1 : 0;
-    const int pix = mh ? 128 + (q - 2) * 32 + lane : q * 32 + lane;     // halo pixel of this thread
+    // ... and, in the time these eight warps otherwise spend waiting for the next accumulator (half of it: profiles/
+    // r02a_ncu_stall_by_role_lean.txt), the im2col operand rows of conv1_1: thread t builds the row of halo pixel t
+    // (< 180) of the tile THREE tile-steps ahead of the one whose accumulator it is about to read - that tile's conv1_1
+    // MMAs are issued one step ahead of its conv1_2 MMAs, which run one step ahead of this epilogue.  The row is built at
+    // the top of the iteration (the wait for the previous conv1_1's commit and the latency of the 27 tap loads are paid
+    // while the accumulator is still being produced).  One 64-bit base pointer per tile, 32-bit offsets
+    // ci * plane + r * w + s, three row and three column predicates (the first version's per-tap 64-bit addressing was
+    // 640 of a builder thread's 1200 instructions per tile).
+    const int pix = threadIdx.x - 64;                                   // 0 .. 255: halo pixel built by this thread
     const bool live = pix < kS1HaloPx;
-    const int irow = mh ? pix + 64 : pix;                               // its row in the im2col operand
+    const int irow = pix < 128 ? pix : pix + 64;                        // pixels 128 .. 179 -> operand rows 192 .. 243
     const int hy = pix / kS1Pitch, hx = pix - hy * kS1Pitch;
     const size_t plane_sz = static_cast<size_t>(p.h) * p.w;
-    float vn[27];                                                       // taps of the NEXT tile, in flight
-    // One 64-bit base pointer per tile (the tap at (ci, r, s) = (0, 0, 0), possibly outside the frame and then never
-    // dereferenced), 32-bit offsets ci * plane + r * w + s from it, three row and three column predicates: the first
-    // version recomputed a 64-bit address and four comparisons per tap - 640 of the ~1200 instructions a stage-1 thread
-    // executed per tile, which made these six warps, not the tensor pipe, the pace of the kernel
-    // (profiles/r02e_ncu_stage1_fused.txt).
     const int fw = p.w, fplane = p.h * p.w;
-    auto request_taps = [&](int tx, int ty, int img) {
+    uint32_t i_phase = 0;
+    int built = 0;                                                      // operand rows built so far (tile ordinal)
+    auto build = [&](int tile) {
+      int nb, tx, ty, img;
+      decode_tile(p, tile, nb, tx, ty, img);
       const int y = ty * kTileH - 1 + hy, xx = tx * kTileW - 1 + hx;
       const bool ry[3] = {live && static_cast<unsigned>(y - 1) < static_cast<unsigned>(p.h),
                           live && static_cast<unsigned>(y) < static_cast<unsigned>(p.h),
@@ -270,6 +270,7 @@ conv_stage1_fused_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __g
       const bool cx[3] = {static_cast<unsigned>(xx - 1) < static_cast<unsigned>(fw), static_cast<unsigned>(xx) < static_cast<unsigned>(fw),
                           static_cast<unsigned>(xx + 1) < static_cast<unsigned>(fw)};
       const float* base = s1.x + static_cast<size_t>(img) * 3 * plane_sz + static_cast<ptrdiff_t>(y - 1) * fw + (xx - 1);
+      float vn[27];
 #pragma unroll
       for (int ci = 0; ci < 3; ++ci) {
 #pragma unroll
@@ -279,9 +280,12 @@ conv_stage1_fused_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __g
             vn[ci * 9 + r * 3 + s] = (ry[r] && cx[s]) ? __ldg(base + (ci * fplane + r * fw + s)) : 0.f;
         }
       }
-    };
-    auto write_im2col_row = [&]() {       // k = ci*9 + 3r + s < 27, zero up to 32; hi / lo planes, SW128 rows
-      if (live) {
+      if (built > 0) {                                  // the previous tile's conv1_1 MMAs have read the buffer
+        mbar_wait(i_empty, i_phase);
+        i_phase ^= 1;
+      }
+      ++built;
+      if (live) {                                       // k = ci*9 + 3r + s < 27, zero up to 32; hi / lo planes
 #pragma unroll
         for (int chunk = 0; chunk < 4; ++chunk) {
           uint32_t hi[4], lo[4];
@@ -297,22 +301,28 @@ conv_stage1_fused_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __g
       fence_proxy_async_smem();
       mbar_arrive(i_full);
     };
-    uint32_t i_phase = 0, c_phase = 0;
+    const int first = static_cast<int>(blockIdx.x), stride = static_cast<int>(gridDim.x);
+    for (int k = 0; k < 3; ++k)                         // operand rows of this CTA's first three tiles
+      if (first + k * stride < p.total_tiles) build(first + k * stride);
+    conv_epilogue_lean<64>(p, tmem_base, tfull_bar, tempty_bar, warp, lane, [&](int tile) {
+      if (tile + 3 * stride < p.total_tiles) build(tile + 3 * stride);
+    });
+  } else {
+    // ------------------------------------------------------------ stage-1 warps: conv1_1's epilogue (TMEM -> activation stage)
+    // warps 10 .. 13 (TMEM lane quarters 2, 3, 0, 1): pixels 0 .. 127 = first M half; warps 14, 15 (quarters 2, 3):
+    // pixels 128 .. 191 = lanes 64 .. 127 of the second M half (operand rows 192 .. 255)
+    const int q = warp & 3;
+    const int mh = warp >= 14 ? 1 : 0;
+    const int pix = mh ? 128 + (q - 2) * 32 + lane : q * 32 + lane;     // halo pixel of this thread
+    const bool live = pix < kS1HaloPx;
+    const int hy = pix / kS1Pitch, hx = pix - hy * kS1Pitch;
+    uint32_t c_phase = 0;
     int a_stage = 0;
     uint32_t a_phase = 0;
-    int tx = 0, ty = 0, img = 0, ntx = 0, nty = 0, nimg = 0, nb_unused = 0;
-    if (static_cast<int>(blockIdx.x) < p.total_tiles) {      // (the buffer starts out free)
-      decode_tile(p, blockIdx.x, nb_unused, tx, ty, img);
-      request_taps(tx, ty, img);
-      write_im2col_row();
-    }
     const uint32_t taddr = tmem_c1 + mh * 128 + (static_cast<uint32_t>(q * 32) << 16);
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const bool has_next = tile + static_cast<int>(gridDim.x) < p.total_tiles;
-      if (has_next) {                                 // global loads in flight behind the epilogue below
-        decode_tile(p, tile + gridDim.x, nb_unused, ntx, nty, nimg);
-        request_taps(ntx, nty, nimg);
-      }
+      int nb, tx, ty, img;
+      decode_tile(p, tile, nb, tx, ty, img);
       const int y = ty * kTileH - 1 + hy, xx = tx * kTileW - 1 + hx;
       const bool inside = live && y >= 0 && y < p.h && xx >= 0 && xx < p.w;
       // ---- conv1_1 epilogue of this tile: TMEM -> bias / ReLU / zero padding -> split bf16 -> activation stage
@@ -370,13 +380,6 @@ conv_stage1_fused_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __g
         a_stage = 0;
         a_phase ^= 1;
       }
-      // ---- im2col row of the next tile (its conv1_1 MMAs are issued before this tile's conv1_2 MMAs)
-      if (has_next) {
-        mbar_wait(i_empty, i_phase);   // this tile's conv1_1 MMAs have read the buffer
-        i_phase ^= 1;
-        write_im2col_row();
-      }
-      tx = ntx, ty = nty, img = nimg;
     }
   }
 

@@ -34,8 +34,7 @@ struct HaloCfg {
   static constexpr int kBPlaneBytes = BLOCK_N * 128;
   static constexpr int kBStageBytes = PLANES * kBPlaneBytes;
   // LEAN: the forward-only epilogue (conv_common.cuh: conv_epilogue_lean) instead of the general one.
-  static constexpr int kStagingBytes = 0;
-  static constexpr int kBudget = 225 * 1024 - kAStages * kAStageBytes - kStagingBytes;   // 227 KiB per CTA minus align/barriers
+  static constexpr int kBudget = 225 * 1024 - kAStages * kAStageBytes;   // 227 KiB per CTA minus align/barriers
   static constexpr int kBStagesRaw = kBudget / kBStageBytes;
   static constexpr int kBStages = kBStagesRaw > 9 ? 9 : kBStagesRaw;
   // Exact mode with BLOCK_N <= 128: N-concatenated split-B.  The hi and lo weight planes are contiguous in the B
@@ -46,7 +45,7 @@ struct HaloCfg {
   static_assert(!SPLIT || (PLANES == 2 && BLOCK_N <= 128), "split accumulators need two planes and 2 * BLOCK_N <= 256");
   static constexpr int kAccCols = kSplitAcc ? 2 * BLOCK_N : BLOCK_N;
   static constexpr int kTmemCols = (2 * kAccCols) < 32 ? 32 : 2 * kAccCols;
-  static constexpr int kSmemBytes = kAStages * kAStageBytes + kBStages * kBStageBytes + kStagingBytes + 1024 + 512;
+  static constexpr int kSmemBytes = kAStages * kAStageBytes + kBStages * kBStageBytes + 1024 + 512;
   static_assert(kBStages >= 2, "weight ring too shallow");
   // The issuer forms descriptors by ADDING (bytes >> 4) to a base descriptor: every address it can reach - the end of
   // the dynamic allocation plus the static shared variables' 1 KiB alignment slack - must stay inside the 14-bit
@@ -68,8 +67,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_c
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + SA * Cfg::kAStageBytes;
-  uint8_t* staging = smem_b + SB * Cfg::kBStageBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + Cfg::kStagingBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + SB * Cfg::kBStageBytes);
   uint64_t* a_full = bars;
   uint64_t* a_empty = bars + SA;
   uint64_t* b_full = bars + 2 * SA;

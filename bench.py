@@ -52,6 +52,12 @@ MIN_TIMED_MS = 1000.0          # blocks of K steps are repeated until this much 
 MAX_BLOCKS = 400
 
 
+def workload_label(workload):
+    """The same string in the native and the reference arm."""
+    return (f"{workload}: 1x3x{H}x{W} synthetic BGR frame per step (seeded, mean-subtracted 0..255), OSVOS VGG-16 trunk + 4 side "
+            f"branches, seeded He-init weights")
+
+
 def load_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -216,8 +222,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 20))
-    warmup = max(1, min(args.warmup, 3))
+    steps = max(1, min(args.steps, 60))          # bounded sample: ~0.45 s per frame on the host cores
+    warmup = max(3, min(args.warmup, 20))        # same rule as the native arm (W >= 3)
     workload = "train480" if args.workload == "train480" else "infer480"
     fps, ms, cores, threads, kind = cpu_reference_fps(steps, warmup, workload)
     what = ("the unmodified reference modules (oracle/_ref: networks/vgg_osvos.py + layers/osvos_layers.py)"
@@ -226,8 +232,7 @@ def run_reference(args):
             "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": f"{workload}: 1x3x{H}x{W} synthetic BGR frame per step, OSVOS VGG-16 trunk + 4 side "
-                                   f"branches, He-init weights"},
+            "config": {"workload": workload_label(workload)},
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": kind,
                              "sample": f"{steps} steps of the full 480x854 frame after {warmup} warm-up: {what}, torch CPU "
                                        f"fp32 (MKLDNN) on {threads} threads of {cores} host cores"},
@@ -765,8 +770,7 @@ def main():
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16x3 (split-bf16 operands, fp32 accumulate)" if args.precision == "exact" else "bf16",
         "data": "synthetic",
-        "config": {"workload": f"{args.workload}: 1x3x{H}x{W} synthetic BGR frame per step, OSVOS VGG-16 trunk + 4 side "
-                               f"branches, He-init weights, precision={args.precision}",
+        "config": {"workload": workload_label(args.workload), "precision": args.precision,
                    "parallelism": f"replicas x{world} for this headline (inference has no collective); the data-parallel "
                                   f"parent-training path is the `dp` object of this line",
                    "l2": "per-step activation traffic (~0.9 GB exact) exceeds the 126 MB L2; inputs rotate over 4 frames; no explicit flush",

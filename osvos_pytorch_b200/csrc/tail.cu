@@ -22,6 +22,7 @@ namespace osvos {
 struct TailScale {
   const float* pq;  // [n, hk, wk, 2]
   int hk, wk, s, log2s, top, left;
+  float inv_s;      // 1 / s, exact (s is a power of two): the tap weights are multiples of 1 / (2 s)
 };
 struct TailParams {
   TailScale sc[4];
@@ -72,7 +73,7 @@ __global__ void __launch_bounds__(kTailThreads) tail_fwd_kernel(const TailParams
       const TailScale& sc = p.sc[k];
       const int oy = y + sc.top;
       const int ay = oy >> sc.log2s;
-      const float fy1 = (static_cast<float>(oy & (sc.s - 1)) + 0.5f) / static_cast<float>(sc.s);   // weight of row ay
+      const float fy1 = (static_cast<float>(oy & (sc.s - 1)) + 0.5f) * sc.inv_s;   // weight of row ay (s = 2^k: exact)
       const float w0 = ay >= 1 ? 1.f - fy1 : 0.f, w1 = ay < sc.hk ? fy1 : 0.f;
       const float2* r0 = reinterpret_cast<const float2*>(sc.pq) + (static_cast<size_t>(img) * sc.hk + (ay >= 1 ? ay - 1 : 0)) * sc.wk;
       const float2* r1 = reinterpret_cast<const float2*>(sc.pq) + (static_cast<size_t>(img) * sc.hk + (ay < sc.hk ? ay : sc.hk - 1)) * sc.wk;
@@ -119,7 +120,7 @@ __global__ void __launch_bounds__(kTailThreads) tail_fwd_kernel(const TailParams
           const TailScale& sc = p.sc[k];
           const int ox = (live ? x : 0) + sc.left;
           const int ax = ox >> sc.log2s;
-          const float fx1 = (static_cast<float>(ox & (sc.s - 1)) + 0.5f) / static_cast<float>(sc.s);   // weight of col ax
+          const float fx1 = (static_cast<float>(ox & (sc.s - 1)) + 0.5f) * sc.inv_s;   // weight of col ax
           const float w0 = ax >= 1 ? 1.f - fx1 : 0.f, w1 = ax < sc.wk ? fx1 : 0.f;
           const float2 t0 = vbuf[voff[k] + (ax >= 1 ? ax - 1 : 0)];
           const float2 t1 = vbuf[voff[k] + (ax < sc.wk ? ax : sc.wk - 1)];
@@ -352,6 +353,7 @@ static void fill_tail_scales(TailParams& p, const float* const* pq, int h, int w
     p.sc[k].wk = wk;
     p.sc[k].s = s;
     p.sc[k].log2s = k + 1;
+    p.sc[k].inv_s = 1.f / static_cast<float>(s);
     p.sc[k].top = ((hk + 1) * s - h) / 2;   // layers/osvos_layers.py:52-56: floor(d/2) rows cropped on top
     p.sc[k].left = ((wk + 1) * s - w) / 2;
   }

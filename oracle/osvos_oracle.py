@@ -435,9 +435,11 @@ def scale_n_rotate(img: np.ndarray, rot: float, sc: float, flip: bool, nearest: 
     transposes afterwards - per-channel arithmetic is identical).  ``cv2.flip(tmp, 1)``; ``M =
     cv2.getRotationMatrix2D((w/2, h/2), rot, sc)``; ``cv2.warpAffine(tmp, M, (w, h), flags)`` with INTER_NEAREST for
     0/1 masks, INTER_CUBIC otherwise, BORDER_CONSTANT 0.
-    cv2 is a third-party dependency the reference does not vendor or pin and that is absent from this image:
-    PARITY UNPINNED for this function.  It restates OpenCV's published algorithm (imgwarp.cpp WarpAffineInvoker +
-    remap): the inverse matrix in fp64; source coordinates in fixed point with AB_BITS = 10,
+    cv2 is a third-party dependency the reference does not vendor or pin; this restates OpenCV's published algorithm
+    and is PINNED against outputs of the reference's own transforms run with the image's cv2 4.13
+    (tests/golden/make_golden_augment.py -> reference_augment.npz, tests/test_oracle.py::
+    test_scale_n_rotate_matches_the_reference_transforms: masks bit-exact, cubic pixels to 9.2e-5 of 255-scale values).
+    Algorithm (imgwarp.cpp WarpAffineInvoker + remap): the inverse matrix in fp64; source coordinates in fixed point with AB_BITS = 10,
     ``X = (cvRound((m1*y + m2)*1024) + round_delta + cvRound(m0*x*1024)) >> shift`` with round_delta 16 / shift 5
     (1/32-pixel positions) for cubic and 512 / 10 for nearest; cubic weights ``interpolateCubic`` with A = -0.75
     in fp32 at the 1/32 position, the 4x4 window anchored one pixel up-left; out-of-image taps read 0."""

@@ -56,3 +56,23 @@ def test_augment_batch_draws_like_the_reference_and_chunks():
         augment.affine_warp(sample["image"], params[:3], "cubic")
     with pytest.raises(RuntimeError):
         augment.affine_warp(sample["image"].cpu(), params, "cubic")
+
+
+def test_affine_warp_matches_the_reference_fixture():
+    """The CUDA kernel against outputs of the reference's own cv2 transforms (tests/golden/reference_augment.npz,
+    made by tests/golden/make_golden_augment.py from dataloaders/custom_transforms.py:7-54, :87-100): masks bit-exact,
+    cubic pixels to fp32 summation order."""
+    import os
+    from osvos_pytorch_b200 import augment
+    fx = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_augment.npz"))
+    mean = np.array((104.00699, 116.66877, 122.67892), dtype=np.float32)
+    for k in range(int(fx["n_cases"])):
+        flip, rot, sc = fx[f"c{k}.draws"]
+        img = torch.from_numpy((fx[f"c{k}.image_u8"].astype(np.float32) - mean).transpose(2, 0, 1).copy())[None]
+        gt = torch.from_numpy(fx[f"c{k}.gt_u8"].astype(np.float32))[None, None]
+        params = [(bool(flip), float(rot), float(sc))]
+        out_i = augment.affine_warp(img.cuda(), params, "cubic").cpu().numpy()[0]
+        out_g = augment.affine_warp(gt.cuda(), params, "nearest").cpu().numpy()[0, 0]
+        assert np.array_equal(out_g, fx[f"c{k}.out_gt"]), k
+        err = np.abs(out_i.transpose(1, 2, 0) - fx[f"c{k}.out_image"]).max()
+        assert err <= 3e-4, (k, err)

@@ -680,7 +680,8 @@ def main():
     if rank == 0 and not train and "roofline" not in skip:
         rec = []
         span = {"a": None}
-        origs = {n: getattr(ops, n) for n in ("conv3x3", "stage1_fused", "side_folded", "conv_first", "tail_fwd")}
+        origs = {n: getattr(ops, n) for n in ("conv3x3", "stage1_fused", "side_folded", "side_folded_multi", "conv_first",
+                                              "tail_fwd")}
 
         def mark_first():
             if span["a"] is None:
@@ -705,6 +706,12 @@ def main():
             rec.append((2.0 * n_ * hh * ww * 16 * 9 * ci, "side_conv_kernel"))
             return origs["side_folded"](x, *a, **k)
 
+        def w_side_multi(xs, *a, **k):            # the four scales' folded side convs in one launch: all their flops
+            mark_first()
+            rec.append((sum(2.0 * x.shape[0] * x.shape[1] * x.shape[2] * 16 * 9 * x.shape[3] for x in xs),
+                        f"side_conv_kernel ({len(xs)} scales in one launch)"))
+            return origs["side_folded_multi"](xs, *a, **k)
+
         def w_first(x, *a, **k):                  # separate conv1_1 (training / fast mode): inside the span, flops counted
             mark_first()
             n_, _, hh, ww = x.shape
@@ -718,6 +725,7 @@ def main():
             span["a"] = None
             return origs["tail_fwd"](*a, **k)
         ops.conv3x3, ops.stage1_fused, ops.side_folded, ops.conv_first, ops.tail_fwd = w_conv3x3, w_stage1, w_side, w_first, w_tail
+        ops.side_folded_multi = w_side_multi
         net._engine.use_cuda_graph = False          # the span events need the eager path
         reps = min(steps, 10)
         for i in range(3):                          # eager warm-up passes, not counted

@@ -134,6 +134,24 @@ OSVOS_API int osvos_conv3x3(const osvos_conv3x3_args* args /* host */, osvos_str
 OSVOS_API int osvos_fold_side_weights(const float* side_w /* [16,cin,3,3] */, const float* side_b /* [16] or NULL */,
                                       const float* proj_w /* [32] */, const float* proj_b /* [1] or NULL */, void* packed,
                                       float* bias2 /* [2] */, int cin, osvos_stream_t stream);
+/* The folded side convolutions (cout == 2 calls of osvos_conv3x3) of up to four scales in ONE launch: `args` is an array
+ * of `count` argument blocks, each exactly what the single call takes; results are identical.  Inference runs the four
+ * scales this way after the last trunk convolution (networks/vgg_osvos.py:67,69,72 for all four stages at once). */
+OSVOS_API int osvos_side_folded_multi(const osvos_conv3x3_args* args /* host array */, int count, osvos_stream_t stream);
+
+/* The same fold for up to four scales in ONE launch (training re-folds after every optimizer step), optionally with an
+ * fp32 copy of W' in [tap][o][ci] order (18 * cin floats) - the operand of the folded backward below.              */
+typedef struct {
+  const float* side_w;   /* [16,cin,3,3] */
+  const float* side_b;   /* [16] or NULL */
+  const float* proj_w;   /* [32]: score_dsn.weight | this scale's slice of fuse.weight */
+  const float* proj_b;   /* [1] or NULL */
+  void* packed;          /* osvos_packed_weight_bytes(2, cin) bytes */
+  float* bias2;          /* [2] */
+  float* folded_f32;     /* [9][2][cin] or NULL */
+  int cin;
+} osvos_fold_item;
+OSVOS_API int osvos_fold_side_weights_multi(const osvos_fold_item* items /* host */, int count, osvos_stream_t stream);
 /* Same contract on CUDA cores (fp32 FMA over hi+lo); debugging cross-check only. */
 OSVOS_API int osvos_conv3x3_simt(const osvos_conv3x3_args* args /* host */, osvos_stream_t stream);
 
@@ -289,6 +307,45 @@ OSVOS_API int osvos_unpool_add_mask(const void* dpool_hi, const void* dpool_lo, 
                                     const float* dside /* [n,h,w,c] fp32 or NULL */, void* dz_hi, void* dz_lo,
                                     float* colsum /* [c] accumulated per-channel sum of dz, or NULL */, int n,
                                     int h, int w, int c, osvos_stream_t stream);
+
+/* ---- side branch backward in folded (rank-2) form -------------------------------------------------------------
+ * Autograd of networks/vgg_osvos.py:67,69,72 (side_prep -> score_dsn / fuse slice) expressed on the folded 3x3
+ * convolution C -> 2 (see osvos_fold_side_weights): the branch's backward only sees the two gradient channels
+ * dpq = (dL/dp, dL/dq).
+ *   osvos_side_folded_wgrad:  g[t][o][c] += sum_px dpq[px - t][o] * x[px][c]  (t = 3r + s <-> offset (r-1, s-1)),
+ *                             g[18 c + o] += sum_px dpq[px][o];   g: osvos_side_folded_wgrad_floats(c) floats, PRE-ZEROED,
+ *                             16-byte aligned; c a multiple of 128.
+ *   osvos_side_grads_finish:  every parameter gradient of up to four scales from g, one launch:
+ *                             d side_prep.weight[f][c][t] = proj[f] g[t][0][c] + proj[16+f] g[t][1][c],
+ *                             d side_prep.bias[f] = proj[f] S0 + proj[16+f] S1,
+ *                             d score_dsn.weight[f] = <side_w[f], g[.][0][.]> + side_b[f] S0, d score_dsn.bias = S0,
+ *                             d fuse.weight slice[f] = <side_w[f], g[.][1][.]> + side_b[f] S1
+ *                             (NULL outputs are skipped; accumulate: add to the destinations instead of overwriting).
+ *   osvos_unpool_side_mask:   dz = ReLU'(x) * (unpool(dpool) + dX),  dX[px][c] = sum_{t,o} wfold[t][o][c] dpq[px - t][o]
+ *                             - osvos_unpool_add_mask with the side gradient computed on the fly from dpq and the fp32
+ *                             folded weights (osvos_fold_side_weights_multi) instead of read from an fp32 map;
+ *                             dpool_hi NULL: no pooling consumer (deepest stage).                                    */
+OSVOS_API size_t osvos_side_folded_wgrad_floats(int c);
+OSVOS_API int osvos_side_folded_wgrad(const void* x_hi, const void* x_lo /* or NULL */, const float* dpq /* [n,h,w,2] */,
+                                      float* g, int n, int h, int w, int c, osvos_stream_t stream);
+typedef struct {
+  const float* g;        /* as filled by osvos_side_folded_wgrad */
+  const float* side_w;   /* [16,c,3,3] */
+  const float* side_b;   /* [16] or NULL */
+  const float* proj_w;   /* [32] */
+  float* d_side_w;       /* [16,c,3,3] */
+  float* d_side_b;       /* [16] */
+  float* d_score_w;      /* [16] or NULL */
+  float* d_score_b;      /* [1] or NULL */
+  float* d_fuse_w;       /* [16] (this scale's slice) or NULL */
+  int c;
+  int accumulate;
+} osvos_side_grads_item;
+OSVOS_API int osvos_side_grads_finish(const osvos_side_grads_item* items /* host */, int count, osvos_stream_t stream);
+OSVOS_API int osvos_unpool_side_mask(const void* dpool_hi /* or NULL */, const void* dpool_lo, const void* x_hi,
+                                     const void* x_lo, const float* dpq /* [n,h,w,2] */,
+                                     const float* wfold /* [9][2][c] fp32 */, void* dz_hi, void* dz_lo,
+                                     float* colsum /* or NULL */, int n, int h, int w, int c, osvos_stream_t stream);
 
 /* ---- bias gradient: out[c] = sum over pixels of an act ----------------------------- */
 OSVOS_API int osvos_channel_sum(const void* act_hi, const void* act_lo, float* out, size_t npix, int c,

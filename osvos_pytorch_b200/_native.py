@@ -65,6 +65,19 @@ class WgradFinishItem(Structure):
                 ("swapped", c_int), ("accumulate", c_int), ("scale", c_float)]
 
 
+class FoldItem(Structure):
+    """osvos_fold_item (include/osvos_b200.h)."""
+    _fields_ = [("side_w", c_void_p), ("side_b", c_void_p), ("proj_w", c_void_p), ("proj_b", c_void_p),
+                ("packed", c_void_p), ("bias2", c_void_p), ("folded_f32", c_void_p), ("cin", c_int)]
+
+
+class SideGradsItem(Structure):
+    """osvos_side_grads_item (include/osvos_b200.h)."""
+    _fields_ = [("g", c_void_p), ("side_w", c_void_p), ("side_b", c_void_p), ("proj_w", c_void_p),
+                ("d_side_w", c_void_p), ("d_side_b", c_void_p), ("d_score_w", c_void_p), ("d_score_b", c_void_p),
+                ("d_fuse_w", c_void_p), ("c", c_int), ("accumulate", c_int)]
+
+
 class TailBwdArgs(Structure):
     _fields_ = [("grad_out", c_void_p * 5), ("dpq", c_void_p * 4), ("n", c_int), ("h", c_int), ("w", c_int)]
 
@@ -94,6 +107,8 @@ SIGNATURES = {
     "osvos_stage1_fused": (c_int, [POINTER(Stage1Args), c_void_p]),
     "osvos_set_pdl": (c_int, [c_int]),
     "osvos_fold_side_weights": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "osvos_side_folded_multi": (c_int, [POINTER(Conv3x3Args), c_int, c_void_p]),
+    "osvos_fold_side_weights_multi": (c_int, [POINTER(FoldItem), c_int, c_void_p]),
     "osvos_conv3x3_simt": (c_int, [POINTER(Conv3x3Args), c_void_p]),
     "osvos_maxpool2x2_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "osvos_tail_fwd": (c_int, [POINTER(TailFwdArgs), c_void_p]),
@@ -109,6 +124,11 @@ SIGNATURES = {
                                c_int, c_void_p]),
     "osvos_unpool_add_mask": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                       c_int, c_int, c_int, c_int, c_void_p]),
+    "osvos_side_folded_wgrad_floats": (c_size_t, [c_int]),
+    "osvos_side_folded_wgrad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "osvos_side_grads_finish": (c_int, [POINTER(SideGradsItem), c_int, c_void_p]),
+    "osvos_unpool_side_mask": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                       c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "osvos_channel_sum": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
     "osvos_conv_first_bwd_workspace_bytes": (c_size_t, []),
     "osvos_conv_first_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,

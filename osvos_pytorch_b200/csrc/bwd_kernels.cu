@@ -130,39 +130,97 @@ __device__ __forceinline__ void load_pair8(const __nv_bfloat16* hi, const __nv_b
   }
 }
 
-__global__ void __launch_bounds__(256, 4)
+// dz = ReLU'(x) * (unpool(dpool) + side-branch gradient), + fused bias gradient (column sums).
+// The side-branch gradient comes in one of two forms:
+//   SIDE = false: `dside`, an fp32 map [n,h,w,c] (or none: stage 1 has no side branch);
+//   SIDE = true:  the FOLDED form (side_bwd_folded.cu, eq. 2): dX[px][c] = sum_{t,o} W'[t][o][c] * dpq[px - t][o], formed on
+//   the fly from the two projection gradients and the fp32 folded weights [9][2][c] - no map of the stage's size is written
+//   or read for the side branch.  A thread owns 8 channels of the (up to) four pixels of a pooling window: the 4 x 4
+//   window of dpq around them is loaded once (16 float2), and for each of the nine taps the 2 x 8 weights are fetched
+//   ONCE and applied to all four pixels (64 FMAs per 4 vector loads).  `wsrc` is the table in shared memory when a block
+//   has enough tiles to amortise copying it (18 c floats), else the table in global memory through L1.
+// POOL = false: the deepest stage, whose output has no pooling consumer (dz = ReLU' * side gradient only).
+template <bool POOL, bool SIDE>
+__global__ void __launch_bounds__(256, SIDE ? 2 : 4)
 unpool_add_mask_kernel(const __nv_bfloat16* __restrict__ dp_hi, const __nv_bfloat16* __restrict__ dp_lo,
                        const __nv_bfloat16* __restrict__ x_hi, const __nv_bfloat16* __restrict__ x_lo,
-                       const float* __restrict__ dside, __nv_bfloat16* __restrict__ dz_hi,
-                       __nv_bfloat16* __restrict__ dz_lo, float* __restrict__ colsum, int n, int h, int w, int c,
-                       int oh, int ow) {
-  extern __shared__ float cs[];  // [c] block-local channel sums (fused bias gradient)
+                       const float* __restrict__ dside, const float* __restrict__ dpq, const float* __restrict__ wfold,
+                       __nv_bfloat16* __restrict__ dz_hi, __nv_bfloat16* __restrict__ dz_lo, float* __restrict__ colsum,
+                       int n, int h, int w, int c, int oh, int ow, int wf_in_smem) {
+  extern __shared__ float cs[];  // [c] block-local channel sums (fused bias gradient), then [18][c] folded weights
+  float* wf = cs + c;
   if (colsum) {
     for (int i = threadIdx.x; i < c; i += blockDim.x) cs[i] = 0.f;
-    __syncthreads();
   }
-  pdl_wait();               // dpool / dside are the previous kernels' outputs (ptx.cuh)
+  if (SIDE && wf_in_smem) {        // parameters, not the predecessor's output: may be read before pdl_wait
+    for (int i = threadIdx.x; i < 18 * c; i += blockDim.x) wf[i] = __ldg(wfold + i);
+  }
+  __syncthreads();
+  pdl_wait();               // dpool / dside / dpq are the previous kernels' outputs (ptx.cuh)
   pdl_launch_dependents();
+  const float* wsrc = (SIDE && wf_in_smem) ? wf : wfold;
   const int groups = c / 8;
   // blockDim (256) is a multiple of `groups`: a thread keeps the same channel group over the whole loop, and a block
-  // iteration covers 256 / groups consecutive pooled pixels of one pooled row (32-bit index math only)
+  // iteration covers 256 / groups consecutive (pooled) pixels of one row (32-bit index math only)
   const int g = static_cast<int>(threadIdx.x % groups);
   const int pl = static_cast<int>(threadIdx.x / groups);
   const int ppb = 256 / groups;
   const int tiles_x = (ow + ppb - 1) / ppb;
   const int total_tiles = n * oh * tiles_x;
+  constexpr int kPos = POOL ? 4 : 1;
+  constexpr int kWin = POOL ? 4 : 3;
   float csum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
     const int tx = tile % tiles_x, row = tile / tiles_x;
     const int oy = row % oh, nn = row / oh;
     const int ox = tx * ppb + pl;
     if (ox >= ow) continue;
-    // pass 1: argmax (first maximum in (dy, dx) scan order) and positivity of the four window elements
+    const int by = POOL ? 2 * oy : oy, bx = POOL ? 2 * ox : ox;     // first pixel of the window
+    float ds[kPos][8];
+#pragma unroll
+    for (int q = 0; q < kPos; ++q)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ds[q][j] = 0.f;
+    if (SIDE) {
+      // dwin[u][v] = dpq[(by - 1 + u, bx - 1 + v)]; pixel (a, b) of the window and tap (r, s) meet at u = a + 2 - r,
+      // v = b + 2 - s  (dpq[px - t], t = (r - 1, s - 1))
+      float2 dwin[kWin][kWin];
+      const float2* dq = reinterpret_cast<const float2*>(dpq) + static_cast<size_t>(nn) * h * w;
+#pragma unroll
+      for (int u = 0; u < kWin; ++u)
+#pragma unroll
+        for (int v = 0; v < kWin; ++v) {
+          const int yy = by - 1 + u, xx = bx - 1 + v;
+          dwin[u][v] = make_float2(0.f, 0.f);
+          if (yy >= 0 && yy < h && xx >= 0 && xx < w) dwin[u][v] = __ldg(dq + yy * w + xx);
+        }
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int s3 = 0; s3 < 3; ++s3) {
+          const float* w0 = wsrc + (2 * (3 * r + s3)) * c + g * 8;
+          const float4 a0 = *reinterpret_cast<const float4*>(w0), a1 = *reinterpret_cast<const float4*>(w0 + 4);
+          const float4 b0 = *reinterpret_cast<const float4*>(w0 + c), b1 = *reinterpret_cast<const float4*>(w0 + c + 4);
+#pragma unroll
+          for (int q = 0; q < kPos; ++q) {
+            const float2 d = dwin[(q >> 1) + 2 - r][(q & 1) + 2 - s3];
+            ds[q][0] = fmaf(a0.x, d.x, fmaf(b0.x, d.y, ds[q][0]));
+            ds[q][1] = fmaf(a0.y, d.x, fmaf(b0.y, d.y, ds[q][1]));
+            ds[q][2] = fmaf(a0.z, d.x, fmaf(b0.z, d.y, ds[q][2]));
+            ds[q][3] = fmaf(a0.w, d.x, fmaf(b0.w, d.y, ds[q][3]));
+            ds[q][4] = fmaf(a1.x, d.x, fmaf(b1.x, d.y, ds[q][4]));
+            ds[q][5] = fmaf(a1.y, d.x, fmaf(b1.y, d.y, ds[q][5]));
+            ds[q][6] = fmaf(a1.z, d.x, fmaf(b1.z, d.y, ds[q][6]));
+            ds[q][7] = fmaf(a1.w, d.x, fmaf(b1.w, d.y, ds[q][7]));
+          }
+        }
+    }
+    // pass 1: argmax (first maximum in (dy, dx) scan order) and positivity of the window elements
     float best[8];
     uint32_t arg = 0, pos = 0;  // arg: 2 bits per channel; pos: bit (q * 8 + j) = x[q][j] > 0
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int iy = 2 * oy + (q >> 1), ix = 2 * ox + (q & 1);
+    for (int q = 0; q < kPos; ++q) {
+      const int iy = by + (q >> 1), ix = bx + (q & 1);
       if (iy >= h || ix >= w) continue;
       float v[8];
       load_pair8(x_hi, x_lo, ((static_cast<size_t>(nn) * h + iy) * w + ix) * c + g * 8, v);
@@ -175,25 +233,25 @@ unpool_add_mask_kernel(const __nv_bfloat16* __restrict__ dp_hi, const __nv_bfloa
         if (v[j] > 0.f) pos |= 1u << (q * 8 + j);
       }
     }
-    float dpv[8];
-    load_pair8(dp_hi, dp_lo, ((static_cast<size_t>(nn) * oh + oy) * ow + ox) * c + g * 8, dpv);
-    // pass 2: gradients of the four positions
+    float dpv[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (POOL) load_pair8(dp_hi, dp_lo, ((static_cast<size_t>(nn) * oh + oy) * ow + ox) * c + g * 8, dpv);
+    // pass 2: gradients of the window positions
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int iy = 2 * oy + (q >> 1), ix = 2 * ox + (q & 1);
+    for (int q = 0; q < kPos; ++q) {
+      const int iy = by + (q >> 1), ix = bx + (q & 1);
       if (iy >= h || ix >= w) continue;
       const size_t dst = ((static_cast<size_t>(nn) * h + iy) * w + ix) * c + g * 8;
-      float ds[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      if (dside) {
+      if (!SIDE && dside) {
         const float4 a = __ldg(reinterpret_cast<const float4*>(dside + dst));
         const float4 b = __ldg(reinterpret_cast<const float4*>(dside + dst) + 1);
-        ds[0] = a.x, ds[1] = a.y, ds[2] = a.z, ds[3] = a.w, ds[4] = b.x, ds[5] = b.y, ds[6] = b.z, ds[7] = b.w;
+        ds[q][0] = a.x, ds[q][1] = a.y, ds[q][2] = a.z, ds[q][3] = a.w;
+        ds[q][4] = b.x, ds[q][5] = b.y, ds[q][6] = b.z, ds[q][7] = b.w;
       }
       uint32_t hi[4], lo[4];
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
-        float v0 = ds[2 * t] + (((arg >> (4 * t)) & 3u) == static_cast<uint32_t>(q) ? dpv[2 * t] : 0.f);
-        float v1 = ds[2 * t + 1] + (((arg >> (4 * t + 2)) & 3u) == static_cast<uint32_t>(q) ? dpv[2 * t + 1] : 0.f);
+        float v0 = ds[q][2 * t] + (((arg >> (4 * t)) & 3u) == static_cast<uint32_t>(q) ? dpv[2 * t] : 0.f);
+        float v1 = ds[q][2 * t + 1] + (((arg >> (4 * t + 2)) & 3u) == static_cast<uint32_t>(q) ? dpv[2 * t + 1] : 0.f);
         if (!((pos >> (q * 8 + 2 * t)) & 1u)) v0 = 0.f;
         if (!((pos >> (q * 8 + 2 * t + 1)) & 1u)) v1 = 0.f;
         csum[2 * t] += v0;
@@ -494,21 +552,50 @@ extern "C" int osvos_side_bwd(const float* feat, const float* dpq, const float* 
   return OSVOS_OK;
 }
 
+template <bool POOL, bool SIDE>
+static int launch_unpool(const void* dpool_hi, const void* dpool_lo, const void* x_hi, const void* x_lo, const float* dside,
+                         const float* dpq, const float* wfold, void* dz_hi, void* dz_lo, float* colsum, int n, int h, int w,
+                         int c, cudaStream_t stream) {
+  const int oh = POOL ? (h + 1) / 2 : h, ow = POOL ? (w + 1) / 2 : w;
+  const int ppb = 256 / (c / 8);
+  const size_t tiles = static_cast<size_t>(n) * oh * ((ow + ppb - 1) / ppb);
+  OSVOS_CHECK_ARG(tiles < (static_cast<size_t>(1) << 31));
+  const int grid = grid_cap(tiles, SIDE ? 2 : 4);
+  // the folded weights go to shared memory when every block has tiles enough to amortise the copy
+  const int wf_in_smem = (SIDE && tiles >= static_cast<size_t>(grid) * 4) ? 1 : 0;
+  const size_t smem = static_cast<size_t>(c) * sizeof(float) * (wf_in_smem ? 19 : 1);
+  auto kern = unpool_add_mask_kernel<POOL, SIDE>;
+  static uint64_t attr_done = 0;
+  if (smem > 48 * 1024) OSVOS_CHECK_CUDA(ensure_dynamic_smem(kern, 19 * 2048 * sizeof(float), &attr_done));
+  OSVOS_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(256), smem, stream,
+                              static_cast<const __nv_bfloat16*>(dpool_hi), static_cast<const __nv_bfloat16*>(dpool_lo),
+                              static_cast<const __nv_bfloat16*>(x_hi), static_cast<const __nv_bfloat16*>(x_lo), dside, dpq,
+                              wfold, static_cast<__nv_bfloat16*>(dz_hi), static_cast<__nv_bfloat16*>(dz_lo), colsum, n, h, w,
+                              c, oh, ow, wf_in_smem));
+  return OSVOS_OK;
+}
+
 extern "C" int osvos_unpool_add_mask(const void* dpool_hi, const void* dpool_lo, const void* x_hi, const void* x_lo,
                                      const float* dside, void* dz_hi, void* dz_lo, float* colsum, int n, int h, int w,
                                      int c, osvos_stream_t stream_) {
   OSVOS_CHECK_ARG(dpool_hi != nullptr && x_hi != nullptr && dz_hi != nullptr && n > 0 && h > 0 && w > 0 && c % 8 == 0);
-  const int oh = (h + 1) / 2, ow = (w + 1) / 2;
   OSVOS_CHECK_ARG(c <= 2048 && 256 % (c / 8) == 0);
-  const int ppb = 256 / (c / 8);
-  const size_t tiles = static_cast<size_t>(n) * oh * ((ow + ppb - 1) / ppb);
-  OSVOS_CHECK_ARG(tiles < (static_cast<size_t>(1) << 31));
-  OSVOS_CHECK_CUDA(launch_pdl(unpool_add_mask_kernel, dim3(grid_cap(tiles, 4)), dim3(256), c * sizeof(float),
-                              static_cast<cudaStream_t>(stream_), static_cast<const __nv_bfloat16*>(dpool_hi),
-                              static_cast<const __nv_bfloat16*>(dpool_lo), static_cast<const __nv_bfloat16*>(x_hi),
-                              static_cast<const __nv_bfloat16*>(x_lo), dside, static_cast<__nv_bfloat16*>(dz_hi),
-                              static_cast<__nv_bfloat16*>(dz_lo), colsum, n, h, w, c, oh, ow));
-  return OSVOS_OK;
+  return launch_unpool<true, false>(dpool_hi, dpool_lo, x_hi, x_lo, dside, nullptr, nullptr, dz_hi, dz_lo, colsum, n, h, w, c,
+                             static_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int osvos_unpool_side_mask(const void* dpool_hi, const void* dpool_lo, const void* x_hi, const void* x_lo,
+                                      const float* dpq, const float* wfold, void* dz_hi, void* dz_lo, float* colsum, int n,
+                                      int h, int w, int c, osvos_stream_t stream_) {
+  OSVOS_CHECK_ARG(x_hi != nullptr && dz_hi != nullptr && dpq != nullptr && wfold != nullptr && n > 0 && h > 0 && w > 0 &&
+                  c % 8 == 0);
+  OSVOS_CHECK_ARG(c <= 2048 && 256 % (c / 8) == 0);
+  OSVOS_CHECK_ARG(static_cast<long>(h) * w < (1l << 30));
+  OSVOS_CHECK_ARG((reinterpret_cast<uintptr_t>(wfold) & 15) == 0);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (dpool_hi != nullptr)
+    return launch_unpool<true, true>(dpool_hi, dpool_lo, x_hi, x_lo, nullptr, dpq, wfold, dz_hi, dz_lo, colsum, n, h, w, c, stream);
+  return launch_unpool<false, true>(nullptr, nullptr, x_hi, x_lo, nullptr, dpq, wfold, dz_hi, dz_lo, colsum, n, h, w, c, stream);
 }
 
 extern "C" int osvos_channel_sum(const void* act_hi, const void* act_lo, float* out, size_t npix, int c,

@@ -412,6 +412,26 @@ static int check_conv_args(const osvos_conv3x3_args* a) {
 
 using namespace osvos;
 
+extern "C" int osvos_side_folded_multi(const osvos_conv3x3_args* args, int count, osvos_stream_t stream_) {
+  OSVOS_CHECK_ARG(args != nullptr && count > 0 && count <= 4);
+  const osvos_conv3x3_args* order[4];
+  for (int k = 0; k < count; ++k) {
+    int rc = check_conv_args(&args[k]);
+    if (rc) return rc;
+    OSVOS_CHECK_ARG(args[k].cout == 2);
+    OSVOS_CHECK_ARG((args[k].flags & OSVOS_FLAG_FAST) == (args[0].flags & OSVOS_FLAG_FAST));
+    order[k] = &args[k];
+  }
+  // deepest scale first: its tiles hold the most channel chunks, and the round-robin deal balances better that way
+  for (int i = 1; i < count; ++i)
+    for (int j = i; j > 0 && order[j]->cin > order[j - 1]->cin; --j) {
+      const osvos_conv3x3_args* t = order[j];
+      order[j] = order[j - 1];
+      order[j - 1] = t;
+    }
+  return side_conv_multi_dispatch(order, count, static_cast<cudaStream_t>(stream_));
+}
+
 extern "C" int osvos_conv3x3(const osvos_conv3x3_args* a, osvos_stream_t stream_) {
   int rc = check_conv_args(a);
   if (rc) return rc;

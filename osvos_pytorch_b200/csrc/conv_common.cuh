@@ -488,6 +488,7 @@ static inline int encode_weight_maps(CUtensorMap* hi, CUtensorMap* lo, const osv
 int conv_first_tc_launch(const float* x, const float* w_oihw, const float* bias, void* y_hi, void* y_lo, int n, int h,
                          int w, int flags, cudaStream_t stream);
 int side_conv_dispatch(const osvos_conv3x3_args* a, cudaStream_t stream);
+int side_conv_multi_dispatch(const osvos_conv3x3_args* const* args, int count, cudaStream_t stream);
 int conv3x3_halo_dispatch(const osvos_conv3x3_args* a, cudaStream_t stream);
 
 }  // namespace osvos

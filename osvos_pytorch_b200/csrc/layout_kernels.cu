@@ -67,6 +67,52 @@ __global__ void fold_side_weights_kernel(const float* __restrict__ w_side, const
   }
 }
 
+// All scales of the side branch in ONE launch (training re-folds after every optimizer step), optionally with an fp32
+// copy of W' in the same [tap][o][ci] order for the folded backward (side_bwd_folded.cu, bwd_kernels.cu).
+struct FoldScale {
+  const float* side_w;
+  const float* side_b;
+  const float* proj_w;
+  const float* proj_b;
+  __nv_bfloat16* packed;
+  float* bias2;
+  float* folded_f32;
+  int cin;
+  int begin;      // first index of this scale in the concatenated [18 * cin] index space
+};
+struct FoldTable {
+  FoldScale s[4];
+  int count;
+  int total;
+};
+__global__ void fold_side_weights_multi_kernel(const __grid_constant__ FoldTable t) {
+  for (int gi = blockIdx.x * blockDim.x + threadIdx.x; gi < t.total; gi += gridDim.x * blockDim.x) {
+    int k = 0;
+    while (k + 1 < t.count && gi >= t.s[k + 1].begin) ++k;
+    const FoldScale& L = t.s[k];
+    const int i = gi - L.begin, cin = L.cin, plane = 18 * cin;
+    const int ci = i % cin;
+    const int o = (i / cin) & 1;
+    const int tap = i / (2 * cin);
+    float v = 0.f;
+#pragma unroll
+    for (int co = 0; co < 16; ++co)
+      v = fmaf(__ldg(L.proj_w + 16 * o + co), __ldg(L.side_w + (static_cast<size_t>(co) * cin + ci) * 9 + tap), v);
+    __nv_bfloat16 hi, lo;
+    split_bf16(v, hi, lo);
+    L.packed[i] = hi;
+    L.packed[plane + i] = lo;
+    if (L.folded_f32) L.folded_f32[i] = v;
+    if (i < 2) {
+      float b = (i == 0 && L.proj_b) ? __ldg(L.proj_b) : 0.f;
+      if (L.side_b) {
+        for (int co = 0; co < 16; ++co) b = fmaf(__ldg(L.proj_w + 16 * i + co), __ldg(L.side_b + co), b);
+      }
+      L.bias2[i] = b;
+    }
+  }
+}
+
 // ------------------------------------------------------------ NCHW <-> act
 __global__ void nchw_to_act_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
                                    __nv_bfloat16* __restrict__ lo, int n, int c, int h, int w) {
@@ -340,6 +386,33 @@ extern "C" int osvos_fold_side_weights(const float* side_w, const float* side_b,
   OSVOS_CHECK_ARG(cin >= 64 && cin % 64 == 0);
   fold_side_weights_kernel<<<grid_for(static_cast<size_t>(18) * cin, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       side_w, side_b, proj_w, proj_b, static_cast<__nv_bfloat16*>(packed), bias2, cin);
+  OSVOS_CHECK_CUDA(cudaGetLastError());
+  return OSVOS_OK;
+}
+
+extern "C" int osvos_fold_side_weights_multi(const osvos_fold_item* items, int count, osvos_stream_t stream) {
+  OSVOS_CHECK_ARG(items != nullptr && count > 0 && count <= 4);
+  FoldTable t;
+  t.count = count;
+  int total = 0;
+  for (int k = 0; k < count; ++k) {
+    const osvos_fold_item& it = items[k];
+    OSVOS_CHECK_ARG(it.side_w != nullptr && it.proj_w != nullptr && it.packed != nullptr && it.bias2 != nullptr);
+    OSVOS_CHECK_ARG(it.cin >= 64 && it.cin % 64 == 0 && it.cin <= 4096);
+    FoldScale& L = t.s[k];
+    L.side_w = it.side_w;
+    L.side_b = it.side_b;
+    L.proj_w = it.proj_w;
+    L.proj_b = it.proj_b;
+    L.packed = static_cast<__nv_bfloat16*>(it.packed);
+    L.bias2 = it.bias2;
+    L.folded_f32 = it.folded_f32;
+    L.cin = it.cin;
+    L.begin = total;
+    total += 18 * it.cin;
+  }
+  t.total = total;
+  fold_side_weights_multi_kernel<<<grid_for(static_cast<size_t>(total), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(t);
   OSVOS_CHECK_CUDA(cudaGetLastError());
   return OSVOS_OK;
 }

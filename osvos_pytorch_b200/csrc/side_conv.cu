@@ -17,6 +17,8 @@
 // N = 32 (18 used) instead of 144: 1/8 of the accumulator columns to exchange, 1/4.5 of the weight bytes to stream,
 // a third less tensor time - the side branch was bound by exactly those (shared-memory bandwidth: the N = 144 MMA alone
 // reads 120 B/clk of operands).  Training keeps NCO = 16: its backward needs the 16 features.
+#include <string.h>
+
 #include "conv_common.cuh"
 
 namespace osvos {
@@ -27,15 +29,28 @@ constexpr int kSideThreads = 192;                           // warp 0 TMA, warp 
 constexpr int kSideABox = kSideHaloW * kSideHaloH * 128;    // 15360 B
 constexpr int kSideAPlane = 128 * 128;                      // the MMA reads 128 rows
 
-struct SideParams {
+// One launch serves up to four SCALES (inference: the folded side convolutions of stages 2-5 after the last trunk conv -
+// one fill / drain and one launch instead of four, and the 21- and 84-tile scales no longer leave most SMs idle).  Tiles
+// are numbered scale after scale, deepest (most channel chunks per tile) first, and dealt round-robin.
+constexpr int kSideMaxScales = 4;
+struct SideScale {
   const float* bias;
   float* y_f32;
   const float* proj_w;
   const float* proj_b;
   float* pq;
   int n, h, w, cin;
-  int tiles_x, tiles_y, total_tiles, k_chunks;
+  int tiles_x, tiles_y, k_chunks;
+  int tile_begin;    // first tile index of this scale
   int relu;
+};
+struct SideParams {
+  SideScale sc[kSideMaxScales];
+  int count;
+  int total_tiles;
+};
+struct SideMaps {
+  CUtensorMap x_hi[kSideMaxScales], x_lo[kSideMaxScales], w_hi[kSideMaxScales], w_lo[kSideMaxScales];
 };
 
 template <int PLANES, int NCO>
@@ -56,18 +71,20 @@ struct SideCfg {
   static constexpr int kSmem = kAStages * kAStage + kBStages * kBStage + kYBuf + 1024 + 256;
 };
 
-__device__ __forceinline__ void side_decode(const SideParams& p, int tile, int& tx, int& ty, int& img) {
-  tx = tile % p.tiles_x;
-  const int t = tile / p.tiles_x;
-  ty = t % p.tiles_y;
-  img = t / p.tiles_y;
+__device__ __forceinline__ void side_decode(const SideParams& p, int tile, int& sc, int& tx, int& ty, int& img) {
+  sc = 0;
+  while (sc + 1 < p.count && tile >= p.sc[sc + 1].tile_begin) ++sc;
+  const SideScale& L = p.sc[sc];
+  const int local = tile - L.tile_begin;
+  tx = local % L.tiles_x;
+  const int t = local / L.tiles_x;
+  ty = t % L.tiles_y;
+  img = t / L.tiles_y;
 }
 
 template <int PLANES, int NCO>
 __global__ void __launch_bounds__(kSideThreads, 1)
-side_conv_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo,
-                 const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
-                 const SideParams p) {
+side_conv_kernel(const __grid_constant__ SideMaps maps, const __grid_constant__ SideParams p) {
   using Cfg = SideCfg<PLANES, NCO>;
   constexpr int kSideAStages = Cfg::kAStages, kSideBStages = Cfg::kBStages, kSideBPlane = Cfg::kBPlane, kSideN = Cfg::kN, kSideYBuf = Cfg::kYBuf;
   extern __shared__ uint8_t smem_raw[];
@@ -88,8 +105,10 @@ side_conv_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    tma_prefetch_desc(&map_x_hi);
-    tma_prefetch_desc(&map_w_hi);
+    for (int i = 0; i < p.count; ++i) {
+      tma_prefetch_desc(&maps.x_hi[i]);
+      tma_prefetch_desc(&maps.w_hi[i]);
+    }
     for (int i = 0; i < kSideAStages; ++i) {
       mbar_init(&a_full[i], 1);
       mbar_init(&a_empty[i], 1);
@@ -118,22 +137,27 @@ side_conv_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
     int a_stage = 0, b_stage = 0;
     uint32_t a_phase = 0, b_phase = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      int tx, ty, img;
-      side_decode(p, tile, tx, ty, img);
-      for (int kc = 0; kc < p.k_chunks; ++kc) {
+      int sc, tx, ty, img;
+      side_decode(p, tile, sc, tx, ty, img);
+      const int k_chunks = p.sc[sc].k_chunks;
+      const CUtensorMap* mx_hi = &maps.x_hi[sc];
+      const CUtensorMap* mx_lo = &maps.x_lo[sc];
+      const CUtensorMap* mw_hi = &maps.w_hi[sc];
+      const CUtensorMap* mw_lo = &maps.w_lo[sc];
+      for (int kc = 0; kc < k_chunks; ++kc) {
         mbar_wait(&a_empty[a_stage], a_phase ^ 1);
         mbar_wait(&b_empty[b_stage], b_phase ^ 1);
         {
           uint8_t* sa = smem_a + a_stage * Cfg::kAStage;
           uint8_t* sb = smem_b + b_stage * Cfg::kBStage;
           mbar_arrive_expect_tx(&a_full[a_stage], PLANES * kSideABox);
-          tma_load_4d(&map_x_hi, &a_full[a_stage], sa, kc * 64, tx * kSideTileW - 1, ty * kSideTileH - 1, img);
+          tma_load_4d(mx_hi, &a_full[a_stage], sa, kc * 64, tx * kSideTileW - 1, ty * kSideTileH - 1, img);
           if (PLANES == 2)
-            tma_load_4d(&map_x_lo, &a_full[a_stage], sa + kSideAPlane, kc * 64, tx * kSideTileW - 1,
+            tma_load_4d(mx_lo, &a_full[a_stage], sa + kSideAPlane, kc * 64, tx * kSideTileW - 1,
                         ty * kSideTileH - 1, img);
           mbar_arrive_expect_tx(&b_full[b_stage], PLANES * Cfg::kBBox);
-          tma_load_3d(&map_w_hi, &b_full[b_stage], sb, kc * 64, 0, 0);
-          if (PLANES == 2) tma_load_3d(&map_w_lo, &b_full[b_stage], sb + kSideBPlane, kc * 64, 0, 0);
+          tma_load_3d(mw_hi, &b_full[b_stage], sb, kc * 64, 0, 0);
+          if (PLANES == 2) tma_load_3d(mw_lo, &b_full[b_stage], sb + kSideBPlane, kc * 64, 0, 0);
         }
         if (++a_stage == kSideAStages) {
           a_stage = 0;
@@ -160,7 +184,10 @@ side_conv_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
       mbar_wait(&tempty_bar[as], aph ^ 1);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + as * 256;
-      for (int kc = 0; kc < p.k_chunks; ++kc) {
+      int sc, tx_, ty_, img_;
+      side_decode(p, tile, sc, tx_, ty_, img_);
+      const int k_chunks = p.sc[sc].k_chunks;
+      for (int kc = 0; kc < k_chunks; ++kc) {
         mbar_wait(&a_full[a_stage], a_phase);
         mbar_wait(&b_full[b_stage], b_phase);
         tc_fence_after();
@@ -184,7 +211,7 @@ side_conv_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
           }
           umma_commit(&a_empty[a_stage]);
           umma_commit(&b_empty[b_stage]);
-          if (kc == p.k_chunks - 1) umma_commit(&tfull_bar[as]);
+          if (kc == k_chunks - 1) umma_commit(&tfull_bar[as]);
         }
         if (++a_stage == kSideAStages) {
           a_stage = 0;
@@ -205,8 +232,9 @@ side_conv_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
     const int oy = row / kSideTileW, ox = row % kSideTileW;   // as an OUTPUT pixel of the tile (row < 80)
     int it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-      int tx, ty, img;
-      side_decode(p, tile, tx, ty, img);
+      int sc, tx, ty, img;
+      side_decode(p, tile, sc, tx, ty, img);
+      const SideScale& L = p.sc[sc];
       const int as = it & 1;
       const uint32_t aph = (it >> 1) & 1;
       mbar_wait(&tfull_bar[as], aph);
@@ -226,22 +254,22 @@ side_conv_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
           yb[tap * 128 + row] = make_float2(__uint_as_float(v[2 * tap]), __uint_as_float(v[2 * tap + 1]));
         asm volatile("bar.sync 1, 128;" ::: "memory");
         const int y = ty * kSideTileH + oy, x = tx * kSideTileW + ox;
-        if (row < kSideTileW * kSideTileH && y < p.h && x < p.w) {
-          float sp = p.bias ? __ldg(p.bias) : 0.f, sq = p.bias ? __ldg(p.bias + 1) : 0.f;
+        if (row < kSideTileW * kSideTileH && y < L.h && x < L.w) {
+          float sp = L.bias ? __ldg(L.bias) : 0.f, sq = L.bias ? __ldg(L.bias + 1) : 0.f;
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
             const float2 t = yb[tap * 128 + (oy + tap / 3) * kSideHaloW + ox + tap % 3];
             sp += t.x;
             sq += t.y;
           }
-          const size_t pix = (static_cast<size_t>(img) * p.h + y) * p.w + x;
-          *reinterpret_cast<float2*>(p.pq + pix * 2) = make_float2(sp, sq);
+          const size_t pix = (static_cast<size_t>(img) * L.h + y) * L.w + x;
+          *reinterpret_cast<float2*>(L.pq + pix * 2) = make_float2(sp, sq);
         }
         continue;
       }
       float acc[16];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) acc[j] = p.bias ? __ldg(p.bias + j) : 0.f;
+      for (int j = 0; j < 16; ++j) acc[j] = L.bias ? __ldg(L.bias + j) : 0.f;
 #pragma unroll 1
       for (int r = 0; r < 3; ++r) {
         // (1) every halo-pixel thread publishes its three taps of row r: ybuf[s][co][pixel]
@@ -268,25 +296,25 @@ side_conv_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
       tc_fence_before();
       mbar_arrive(&tempty_bar[as]);
       const int y = ty * kSideTileH + oy, x = tx * kSideTileW + ox;
-      if (row < kSideTileW * kSideTileH && y < p.h && x < p.w) {
-        const size_t pix = (static_cast<size_t>(img) * p.h + y) * p.w + x;
-        if (p.relu) {
+      if (row < kSideTileW * kSideTileH && y < L.h && x < L.w) {
+        const size_t pix = (static_cast<size_t>(img) * L.h + y) * L.w + x;
+        if (L.relu) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) acc[j] = fmaxf(acc[j], 0.f);
         }
-        if (p.y_f32) {
-          float4* dst = reinterpret_cast<float4*>(p.y_f32 + pix * 16);
+        if (L.y_f32) {
+          float4* dst = reinterpret_cast<float4*>(L.y_f32 + pix * 16);
 #pragma unroll
           for (int j = 0; j < 4; ++j) dst[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
         }
-        if (p.pq) {
-          float sp = p.proj_b ? __ldg(p.proj_b) : 0.f, sq = 0.f;
+        if (L.pq) {
+          float sp = L.proj_b ? __ldg(L.proj_b) : 0.f, sq = 0.f;
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            sp = fmaf(acc[j], __ldg(p.proj_w + j), sp);
-            sq = fmaf(acc[j], __ldg(p.proj_w + 16 + j), sq);
+            sp = fmaf(acc[j], __ldg(L.proj_w + j), sp);
+            sq = fmaf(acc[j], __ldg(L.proj_w + 16 + j), sq);
           }
-          *reinterpret_cast<float2*>(p.pq + pix * 2) = make_float2(sp, sq);
+          *reinterpret_cast<float2*>(L.pq + pix * 2) = make_float2(sp, sq);
         }
       }
     }
@@ -301,61 +329,83 @@ side_conv_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
 }
 
 template <int PLANES, int NCO>
-static int launch_side(const osvos_conv3x3_args* a, cudaStream_t stream) {
+static int launch_side(const osvos_conv3x3_args* const* args, int count, cudaStream_t stream) {
   using Cfg = SideCfg<PLANES, NCO>;
   SideParams p;
-  p.bias = a->bias;
-  p.y_f32 = a->y_f32;
-  p.proj_w = a->proj_w;
-  p.proj_b = a->proj_b;
-  p.pq = a->pq;
-  p.n = a->n;
-  p.h = a->h;
-  p.w = a->w;
-  p.cin = a->cin;
-  p.tiles_x = (a->w + kSideTileW - 1) / kSideTileW;
-  p.tiles_y = (a->h + kSideTileH - 1) / kSideTileH;
-  p.total_tiles = p.tiles_x * p.tiles_y * a->n;
-  p.k_chunks = a->cin / 64;
-  p.relu = (a->flags & OSVOS_FLAG_RELU) ? 1 : 0;
-  CUtensorMap mx_hi, mx_lo, mw_hi, mw_lo;
-  {
-    const uint64_t dims[4] = {(uint64_t)a->cin, (uint64_t)a->w, (uint64_t)a->h, (uint64_t)a->n};
-    const uint64_t strides[3] = {(uint64_t)a->cin * 2, (uint64_t)a->w * a->cin * 2, (uint64_t)a->h * a->w * a->cin * 2};
-    const uint32_t box[4] = {64, kSideHaloW, kSideHaloH, 1};
-    int rc = encode_tensor_map(&mx_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 4, a->x_hi, dims, strides, box,
-                               CU_TENSOR_MAP_SWIZZLE_128B);
-    if (rc) return rc;
-    rc = encode_tensor_map(&mx_lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 4, PLANES == 2 ? a->x_lo : a->x_hi, dims, strides,
-                           box, CU_TENSOR_MAP_SWIZZLE_128B);
-    if (rc) return rc;
+  SideMaps maps;
+  memset(&p, 0, sizeof(p));
+  p.count = count;
+  int total = 0;
+  for (int k = 0; k < count; ++k) {
+    const osvos_conv3x3_args* a = args[k];
+    SideScale& L = p.sc[k];
+    L.bias = a->bias;
+    L.y_f32 = a->y_f32;
+    L.proj_w = a->proj_w;
+    L.proj_b = a->proj_b;
+    L.pq = a->pq;
+    L.n = a->n;
+    L.h = a->h;
+    L.w = a->w;
+    L.cin = a->cin;
+    L.tiles_x = (a->w + kSideTileW - 1) / kSideTileW;
+    L.tiles_y = (a->h + kSideTileH - 1) / kSideTileH;
+    L.k_chunks = a->cin / 64;
+    L.relu = (a->flags & OSVOS_FLAG_RELU) ? 1 : 0;
+    L.tile_begin = total;
+    total += L.tiles_x * L.tiles_y * a->n;
+    {
+      const uint64_t dims[4] = {(uint64_t)a->cin, (uint64_t)a->w, (uint64_t)a->h, (uint64_t)a->n};
+      const uint64_t strides[3] = {(uint64_t)a->cin * 2, (uint64_t)a->w * a->cin * 2, (uint64_t)a->h * a->w * a->cin * 2};
+      const uint32_t box[4] = {64, kSideHaloW, kSideHaloH, 1};
+      int rc = encode_tensor_map(&maps.x_hi[k], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 4, a->x_hi, dims, strides, box,
+                                 CU_TENSOR_MAP_SWIZZLE_128B);
+      if (rc) return rc;
+      rc = encode_tensor_map(&maps.x_lo[k], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 4, PLANES == 2 ? a->x_lo : a->x_hi, dims,
+                             strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+      if (rc) return rc;
+    }
+    {
+      const size_t plane = static_cast<size_t>(9) * NCO * a->cin;
+      const uint64_t dims[3] = {(uint64_t)a->cin, NCO, 9};
+      const uint64_t strides[2] = {(uint64_t)a->cin * 2, (uint64_t)NCO * a->cin * 2};
+      const uint32_t box[3] = {64, NCO, 9};
+      const __nv_bfloat16* wp = static_cast<const __nv_bfloat16*>(a->w_packed);
+      int rc = encode_tensor_map(&maps.w_hi[k], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 3, wp, dims, strides, box,
+                                 CU_TENSOR_MAP_SWIZZLE_128B);
+      if (rc) return rc;
+      rc = encode_tensor_map(&maps.w_lo[k], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 3, wp + plane, dims, strides, box,
+                             CU_TENSOR_MAP_SWIZZLE_128B);
+      if (rc) return rc;
+    }
   }
-  {
-    const size_t plane = static_cast<size_t>(9) * NCO * a->cin;
-    const uint64_t dims[3] = {(uint64_t)a->cin, NCO, 9};
-    const uint64_t strides[2] = {(uint64_t)a->cin * 2, (uint64_t)NCO * a->cin * 2};
-    const uint32_t box[3] = {64, NCO, 9};
-    const __nv_bfloat16* wp = static_cast<const __nv_bfloat16*>(a->w_packed);
-    int rc = encode_tensor_map(&mw_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 3, wp, dims, strides, box,
-                               CU_TENSOR_MAP_SWIZZLE_128B);
-    if (rc) return rc;
-    rc = encode_tensor_map(&mw_lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 3, wp + plane, dims, strides, box,
-                           CU_TENSOR_MAP_SWIZZLE_128B);
-    if (rc) return rc;
+  for (int k = count; k < kSideMaxScales; ++k) {   // unused slots: valid descriptors (never dereferenced)
+    maps.x_hi[k] = maps.x_hi[0];
+    maps.x_lo[k] = maps.x_lo[0];
+    maps.w_hi[k] = maps.w_hi[0];
+    maps.w_lo[k] = maps.w_lo[0];
   }
+  p.total_tiles = total;
   auto kern = side_conv_kernel<PLANES, NCO>;
   static uint64_t attr_done = 0;   // per instantiation: bit d = device d has the shared-memory opt-in
   OSVOS_CHECK_CUDA(ensure_dynamic_smem(kern, Cfg::kSmem, &attr_done));
   const int sms = device_sm_count();
   const int grid = p.total_tiles < sms ? p.total_tiles : sms;
-  OSVOS_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(kSideThreads), Cfg::kSmem, stream, mx_hi, mx_lo, mw_hi, mw_lo, p));
+  OSVOS_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(kSideThreads), Cfg::kSmem, stream, maps, p));
   return OSVOS_OK;
 }
 
 int side_conv_dispatch(const osvos_conv3x3_args* a, cudaStream_t stream) {
+  const osvos_conv3x3_args* one[1] = {a};
   if (a->cout == 2)   // folded projections (osvos_fold_side_weights): pq only
-    return (a->flags & OSVOS_FLAG_FAST) ? launch_side<1, 2>(a, stream) : launch_side<2, 2>(a, stream);
-  return (a->flags & OSVOS_FLAG_FAST) ? launch_side<1, 16>(a, stream) : launch_side<2, 16>(a, stream);
+    return (a->flags & OSVOS_FLAG_FAST) ? launch_side<1, 2>(one, 1, stream) : launch_side<2, 2>(one, 1, stream);
+  return (a->flags & OSVOS_FLAG_FAST) ? launch_side<1, 16>(one, 1, stream) : launch_side<2, 16>(one, 1, stream);
+}
+
+// Folded side convolutions of several scales in one launch; `args` sorted deepest (most input channels) first.
+int side_conv_multi_dispatch(const osvos_conv3x3_args* const* args, int count, cudaStream_t stream) {
+  const bool fast = (args[0]->flags & OSVOS_FLAG_FAST) != 0;
+  return fast ? launch_side<1, 2>(args, count, stream) : launch_side<2, 2>(args, count, stream);
 }
 
 }  // namespace osvos

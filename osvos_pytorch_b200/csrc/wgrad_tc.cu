@@ -22,6 +22,8 @@
 //
 // Replaces autograd's weight gradient of nn.Conv2d(k=3, p=1)
 // (reference networks/vgg_osvos.py:41,142; backward triggered at train_online.py:141).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -41,7 +43,8 @@ struct WgradParams {
   int total_items;
   int p_shifted;  // 1: P is the shifted operand, 0: Q is
   int tap_pairs;  // 1: Q has 64 channels and the two 64-wide N atoms of a 128-wide item are TWO TAPS (2g, 2g+1)
-  int tap_items;  // 9, or 5 tap groups in tap_pairs mode
+  int tap_rows;   // 1: P AND Q have 64 channels (conv1_2): an item is one tap ROW - see launch_wgrad
+  int tap_items;  // 9, 5 tap groups in tap_pairs mode, or 3 tap rows in tap_rows mode
 };
 
 template <int BLOCK_N, int PLANES>
@@ -146,8 +149,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_p_hi, const __grid_const
               const CUtensorMap* mp = pl == 0 ? &map_p_hi : &map_p_lo;
               uint8_t* sp = st + pl * Cfg::kPBytes;
 #pragma unroll
-              for (int j = 0; j < 2; ++j)
-                tma_load_4d(mp, &full_bar[stage], sp + j * kWgBoxBytes, c_p + j * 64, x0 + pdx, y0 + pdy, img);
+              for (int j = 0; j < 2; ++j) {
+                if (p.tap_rows)   // M atom j = the single 64-channel block of dz shifted by (0, +j)
+                  tma_load_4d(mp, &full_bar[stage], sp + j * kWgBoxBytes, 0, x0 + j, y0, img);
+                else
+                  tma_load_4d(mp, &full_bar[stage], sp + j * kWgBoxBytes, c_p + j * 64, x0 + pdx, y0 + pdy, img);
+              }
             }
           } else {
             mbar_arrive_expect_tx(&full_bar[stage], PLANES * Cfg::kQBytes);
@@ -157,7 +164,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_p_hi, const __grid_const
               uint8_t* sq = st + PLANES * Cfg::kPBytes + pl * Cfg::kQBytes;
 #pragma unroll
               for (int j = 0; j < BLOCK_N / 64; ++j) {
-                if (p.tap_pairs)   // atom j = tap (2g + j) of the single 64-channel block
+                if (p.tap_rows)    // N atom j = the single 64-channel block of x shifted by (row - 1, +j)
+                  tma_load_4d(mq, &full_bar[stage], sq + j * kWgBoxBytes, 0, x0 + j, y0 + tap - 1, img);
+                else if (p.tap_pairs)   // atom j = tap (2g + j) of the single 64-channel block
                   tma_load_4d(mq, &full_bar[stage], sq + j * kWgBoxBytes, 0, x0 + (j ? dx1 : dx), y0 + (j ? dy1 : dy), img);
                 else
                   tma_load_4d(mq, &full_bar[stage], sq + j * kWgBoxBytes, c_q + j * 64, x0 + qdx, y0 + qdy, img);
@@ -250,16 +259,25 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_p_hi, const __grid_const
       const uint32_t taddr = tmem_base + as * Cfg::kAccCols + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
       for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-        // destination of this 32-column chunk: channel block nb, or (tap_pairs) tap 2g + c0/64 of the 64 channels
-        const int tap_c = p.tap_pairs ? 2 * tap + (c0 >> 6) : tap;
-        const bool chunk_ok = tap_c < 9;
-        float* dst = p.ws + (static_cast<size_t>(chunk_ok ? tap_c : 0) * p.m_total + m) * p.n_total +
-                     (p.tap_pairs ? -(c0 & ~63) : nb * BLOCK_N);
+        // destination of this 32-column chunk: channel block nb, or (tap_pairs) tap 2g + c0/64 of the 64 channels, or
+        // (tap_rows) the tap = shift of the N atom minus shift of the M atom: (M0,N0) -> s = 1, (M0,N1) -> s = 2,
+        // (M1,N0) -> s = 0, (M1,N1) -> s = 1 again (discarded)
+        int tap_c = p.tap_pairs ? 2 * tap + (c0 >> 6) : tap;
+        bool chunk_ok = tap_c < 9;
+        int m_out = m;
+        if (p.tap_rows) {
+          const int pj = row >> 6, qj = c0 >> 6;
+          chunk_ok = !(pj && qj);
+          tap_c = 3 * tap + (pj ? 0 : 1 + qj);
+          m_out = row & 63;
+        }
+        float* dst = p.ws + (static_cast<size_t>(chunk_ok ? tap_c : 0) * p.m_total + m_out) * p.n_total +
+                     ((p.tap_pairs || p.tap_rows) ? -(c0 & ~63) : nb * BLOCK_N);
         uint32_t v[32], v2[32];
         tmem_ld32(taddr + c0, v);
         if (Cfg::kSplitAcc) tmem_ld32(taddr + BLOCK_N + c0, v2);
         tmem_ld_wait();
-        if (m < p.m_valid && chunk_ok) {
+        if ((m < p.m_valid || p.tap_rows) && chunk_ok) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             float4 val = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
@@ -404,9 +422,20 @@ static int launch_wgrad(const osvos_wgrad_args* a, cudaStream_t stream) {
   p.m_blocks = (cp + 127) / 128;
   // Cin = 64 trunk layers (conv1_2, conv2_1): the 128-wide item holds two TAPS of the single 64-channel block, which
   // halves the number of tcgen05.mma (the ~85-cycle instruction floor makes N = 64 items twice as expensive per flop)
-  p.tap_pairs = (!swapped && cq == 64 && BLOCK_N == 128) ? 1 : 0;
-  p.tap_items = p.tap_pairs ? 5 : 9;
-  p.n_blocks = p.tap_pairs ? 1 : cq / BLOCK_N;
+  // Cin = Cout = 64 (conv1_2): an item is a tap ROW r.  M = [dz | dz shifted by (0,+1)], N = [x shifted by (r-1, 0) |
+  // x shifted by (r-1, +1)]: the four 64 x 64 quadrants are the taps s = 1, 2, 0 and 1 again - three of four useful
+  // instead of the two of four of tap pairs under a half-empty M (a tcgen05.mma costs max(M, 128) rows either way).
+  // Exact at the borders: the terms dz[u] x[u + (., -1)] the shifted M atom cannot reach (u.x = 0) multiply the zero
+  // padding of x, and everything out of the image is zero-filled by TMA on both operands.
+  static int rows_on = -1;   // OSVOS_WGRAD_ROWS=0: tap pairs instead (A/B; read once)
+  if (rows_on < 0) {
+    const char* e = getenv("OSVOS_WGRAD_ROWS");
+    rows_on = (e == nullptr || atoi(e) != 0) ? 1 : 0;
+  }
+  p.tap_rows = (rows_on && !swapped && cq == 64 && cp == 64 && BLOCK_N == 128) ? 1 : 0;
+  p.tap_pairs = (!swapped && cq == 64 && BLOCK_N == 128 && !p.tap_rows) ? 1 : 0;
+  p.tap_items = p.tap_rows ? 3 : p.tap_pairs ? 5 : 9;
+  p.n_blocks = (p.tap_pairs || p.tap_rows) ? 1 : cq / BLOCK_N;
   p.patches_x = (a->w + kWgPatchW - 1) / kWgPatchW;
   p.patches_y = (a->h + kWgPatchH - 1) / kWgPatchH;
   p.patches_total = p.patches_x * p.patches_y * a->n;

@@ -32,6 +32,9 @@ class OSVOSEngine:
         # inference only: fold side_prep with its two 1x1 projections into one 3x3 conv C -> 2 (OSVOS_FOLD_SIDE=0, read per
         # eager pass, switches it off for A/B runs)
         self.fold_side_branch = True
+        # training: the side branch as the folded conv C -> 2 forward and its rank-2 backward (csrc/side_bwd_folded.cu);
+        # False / OSVOS_SIDE_BWD=literal keeps the literal 16-feature route (cross-check, tests/test_gpu_side_folded.py)
+        self.folded_side_backward = os.environ.get("OSVOS_SIDE_BWD", "folded") != "literal"
 
     def direct_grad_accumulation(self):
         """Context manager enabling in-place gradient accumulation for the backward passes run inside it."""
@@ -115,11 +118,19 @@ class OSVOSEngine:
                                                fu.weight.detach().reshape(64)[16 * i:16 * i + 16]]).float().contiguous())
 
     def _folded_side(self, i):
-        """(packed [2,C,3,3] operand, bias2) of side_prep[i] folded with score_dsn[i] and fuse's slice (inference)."""
+        """(packed [2,C,3,3] operand, bias2) of side_prep[i] folded with score_dsn[i] and fuse's slice."""
+        return self._folded_side_all()[i][:2]
+
+    def _folded_side_all(self):
+        """[(packed operand, bias2, fp32 W' [9,2,C])] of the four side scales, folded by ONE launch and cached on the
+        versions of every parameter that enters (training re-folds after each optimizer step)."""
         m = self.m
-        sp, sd = m.side_prep[i], m.score_dsn[i]
-        return self._cached(("fold", i), [sp.weight, sp.bias, sd.weight, sd.bias, m.fuse.weight],
-                            lambda: ops.fold_side_weights(sp.weight, sp.bias.detach(), self._proj(i), sd.bias.detach()))
+        deps = [m.fuse.weight]
+        for i in range(4):
+            deps += [m.side_prep[i].weight, m.side_prep[i].bias, m.score_dsn[i].weight, m.score_dsn[i].bias]
+        return self._cached(("fold_all",), deps, lambda: ops.fold_side_weights_multi(
+            [(m.side_prep[i].weight, m.side_prep[i].bias.detach(), self._proj(i), m.score_dsn[i].bias.detach())
+             for i in range(4)]))
 
     def _check_deconvs(self):
         """The native tail implements the bilinear deconvolution in closed form; both entry points of
@@ -241,6 +252,12 @@ class OSVOSEngine:
         if return_intermediates:
             inter["stage0"] = full
         pqs = []
+        fold = not simt and not return_intermediates and self.fold_side_branch and \
+            os.environ.get("OSVOS_FOLD_SIDE", "1") != "0"
+        # folded side branches of the four scales in ONE launch after the last trunk conv (OSVOS_SIDE_MULTI=0: one launch
+        # per scale, right after its stage)
+        multi = fold and os.environ.get("OSVOS_SIDE_MULTI", "1") != "0"
+        stage_outs = []
         for i in range(1, 5):
             convs = [c for c in m.stages[i] if isinstance(c, nn.Conv2d)]
             for j, conv in enumerate(convs):
@@ -260,7 +277,10 @@ class OSVOSEngine:
                 _, feat, _ = ops.conv3x3(full, self._packed(sp, f"sp{i}"), sp.bias.detach(), 16, relu=False, fast=fast,
                                          out_act=False, out_f32=True, simt=True)
                 pq = ops.side_project(feat, self._proj(i - 1), m.score_dsn[i - 1].bias.detach())
-            elif not return_intermediates and self.fold_side_branch and os.environ.get("OSVOS_FOLD_SIDE", "1") != "0":
+            elif multi:
+                stage_outs.append(full)
+                continue
+            elif fold:
                 # inference: side_prep o (score_dsn, fuse slice) folded into one 3x3 conv C -> 2 (include/osvos_b200.h)
                 feat = None
                 pq = ops.side_folded(full, *self._folded_side(i - 1), fast=fast)
@@ -272,6 +292,8 @@ class OSVOSEngine:
                 inter[f"side{i}"] = feat
                 inter[f"pq{i}"] = pq
             pqs.append(pq)
+        if multi:
+            pqs = ops.side_folded_multi(stage_outs, self._folded_side_all(), fast=fast)
         out, _ = ops.tail_fwd(pqs, m.fuse.bias.detach(), n, h, w)
         outs = [out[k] for k in range(5)]
         if return_intermediates:

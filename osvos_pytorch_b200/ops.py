@@ -110,6 +110,30 @@ def fold_side_weights(side_w, side_b, proj_w, proj_b):
     return packed, bias2
 
 
+def fold_side_weights_multi(entries, want_f32=True):
+    """All side scales folded in ONE launch.  entries: [(side_w, side_b, proj_w [32], proj_b)] ->
+    [(packed, bias2, folded_f32 [9, 2, cin] | None)]; see include/osvos_b200.h (osvos_fold_side_weights_multi)."""
+    lib = nat.load()
+    items = (nat.FoldItem * len(entries))()
+    outs, keep = [], []
+    for k, (side_w, side_b, proj_w, proj_b) in enumerate(entries):
+        side_w = side_w.detach().contiguous().float()
+        cin = int(side_w.shape[1])
+        dev = side_w.device
+        packed = torch.empty(lib.osvos_packed_weight_bytes(2, cin) // 2, dtype=torch.bfloat16, device=dev)
+        bias2 = torch.empty(2, dtype=torch.float32, device=dev)
+        f32 = torch.empty((9, 2, cin), dtype=torch.float32, device=dev) if want_f32 else None
+        it = items[k]
+        it.side_w, it.side_b = side_w.data_ptr(), nat.ptr(side_b)
+        it.proj_w, it.proj_b = proj_w.data_ptr(), nat.ptr(proj_b)
+        it.packed, it.bias2, it.folded_f32, it.cin = packed.data_ptr(), bias2.data_ptr(), nat.ptr(f32), cin
+        keep.append(side_w)
+        outs.append((packed, bias2, f32))
+    _count()
+    nat.check(lib.osvos_fold_side_weights_multi(items, len(entries), _stream()), "osvos_fold_side_weights_multi")
+    return outs
+
+
 def stage1_fused(x, w1, b1, w2_packed, b2, pool=True, out_act=False):
     """conv1_1 + ReLU + conv1_2 + ReLU (+ fused 2x2 ceil-mode max pool) of an fp32 NCHW frame in ONE kernel (exact
     mode, inference): -> (full-resolution Act | None, pooled Act | None).  See include/osvos_b200.h."""
@@ -145,6 +169,26 @@ def side_folded(x, packed, bias2, fast=False):
     _count()
     nat.check(lib.osvos_conv3x3(byref(a), _stream()), "osvos_conv3x3 (folded side branch)")
     return pq
+
+
+def side_folded_multi(xs, folded, fast=False):
+    """The folded side branches of several scales in ONE launch: xs = stage outputs (Acts), folded = [(packed, bias2, ...)]
+    per scale -> list of pq [n,h,w,2] in the same order (osvos_side_folded_multi)."""
+    lib = nat.load()
+    arr = (nat.Conv3x3Args * len(xs))()
+    pqs = []
+    for k, (x, f) in enumerate(zip(xs, folded)):
+        n, h, w, cin = x.shape
+        pq = torch.empty((n, h, w, 2), dtype=torch.float32, device=x.hi.device)
+        a = arr[k]
+        a.x_hi, a.x_lo = x.hi.data_ptr(), nat.ptr(x.lo)
+        a.w_packed, a.bias, a.pq = f[0].data_ptr(), f[1].data_ptr(), pq.data_ptr()
+        a.n, a.h, a.w, a.cin, a.cout = n, h, w, cin, 2
+        a.flags = nat.FLAG_FAST if fast else 0
+        pqs.append(pq)
+    _count()
+    nat.check(lib.osvos_side_folded_multi(arr, len(xs), _stream()), "osvos_side_folded_multi")
+    return pqs
 
 
 def conv3x3(x, w_packed, bias, cout, relu=False, fast=False, out_act=True, out_f32=False, mask=None,
@@ -370,6 +414,51 @@ def unpool_add_mask(dpool, x, dside, colsum=None):
                                         _stream()),
               "osvos_unpool_add_mask")
     return dz
+
+
+def unpool_side_mask(dpool, x, dpq, wfold, colsum=None):
+    """dz = ReLU'(x) * (unpool(dpool) + folded side gradient of dpq); dpool None: no pooling consumer."""
+    lib = nat.load()
+    n, h, w, c = x.shape
+    dz = Act.empty(n, h, w, c, x.hi.device, x.lo is None)
+    _count()
+    nat.check(lib.osvos_unpool_side_mask(dpool.hi.data_ptr() if dpool is not None else None,
+                                         nat.ptr(dpool.lo) if dpool is not None else None, x.hi.data_ptr(), nat.ptr(x.lo),
+                                         dpq.data_ptr(), wfold.data_ptr(), dz.hi.data_ptr(), nat.ptr(dz.lo),
+                                         nat.ptr(colsum), n, h, w, c, _stream()),
+              "osvos_unpool_side_mask")
+    return dz
+
+
+def side_folded_wgrad_floats(c):
+    return int(nat.load().osvos_side_folded_wgrad_floats(c))
+
+
+def side_folded_wgrad(x, dpq, g):
+    """g ([18 c + 2] fp32, PRE-ZEROED) += folded weight gradient of the side branch (include/osvos_b200.h)."""
+    lib = nat.load()
+    n, h, w, c = x.shape
+    _count()
+    nat.check(lib.osvos_side_folded_wgrad(x.hi.data_ptr(), nat.ptr(x.lo), dpq.data_ptr(), g.data_ptr(), n, h, w, c,
+                                          _stream()), "osvos_side_folded_wgrad")
+    return g
+
+
+def side_grads_finish(entries, accumulate):
+    """entries: dicts with g, side_w, side_b, proj_w, d_side_w, d_side_b, d_score_w, d_score_b, d_fuse_w (tensors or
+    None), c.  One launch for all scales."""
+    lib = nat.load()
+    items = (nat.SideGradsItem * len(entries))()
+    for k, e in enumerate(entries):
+        it = items[k]
+        it.g, it.side_w, it.side_b, it.proj_w = e["g"].data_ptr(), e["side_w"].data_ptr(), nat.ptr(e["side_b"]), \
+            e["proj_w"].data_ptr()
+        it.d_side_w, it.d_side_b = e["d_side_w"].data_ptr(), e["d_side_b"].data_ptr()
+        it.d_score_w, it.d_score_b, it.d_fuse_w = nat.ptr(e.get("d_score_w")), nat.ptr(e.get("d_score_b")), \
+            nat.ptr(e.get("d_fuse_w"))
+        it.c, it.accumulate = int(e["c"]), 1 if accumulate else 0
+    _count()
+    nat.check(lib.osvos_side_grads_finish(items, len(entries), _stream()), "osvos_side_grads_finish")
 
 
 def channel_sum(a):

@@ -38,7 +38,7 @@ def dev():
     return torch.device("cuda:0")
 
 
-@pytest.mark.parametrize("n,h,w,cin,cout", [(1, 8, 8, 64, 64), (1, 20, 13, 64, 64), (2, 17, 9, 128, 128),
+@pytest.mark.parametrize("n,h,w,cin,cout", [(1, 8, 8, 64, 64), (1, 20, 13, 64, 64), (2, 16, 24, 64, 64), (2, 17, 9, 128, 128),
                                             (1, 9, 11, 256, 128), (1, 33, 45, 64, 128), (1, 5, 3, 512, 512)])
 @pytest.mark.parametrize("fast", [False, True])
 def test_wgrad_tensor_core(dev, n, h, w, cin, cout, fast):

@@ -144,6 +144,35 @@ def test_side_branch_folded_into_one_conv(dev):
         assert maxrel(pqf, want) < FAST_TOL
 
 
+def test_side_branch_folded_multi_scale_launch(dev):
+    """osvos_side_folded_multi: the folded side convs of several scales in one launch give bit-identical pq to one launch
+    per scale (same tiles, same arithmetic; only the tile -> CTA assignment differs), in any order of the scales."""
+    from osvos_pytorch_b200 import ops
+    g = torch.Generator().manual_seed(21)
+    shapes = [(1, 30, 53, 128), (1, 15, 27, 256), (1, 8, 14, 512), (1, 4, 7, 512)]
+    for fast in (False, True):
+        acts, folded, single = [], [], []
+        for n, h, w, cin in shapes:
+            x = torch.randn(n, cin, h, w, generator=g) * 2.0
+            wt = torch.randn(16, cin, 3, 3, generator=g) * math.sqrt(2.0 / (9 * cin))
+            bs = torch.randn(16, generator=g) * 0.1
+            proj = torch.randn(32, generator=g) * 0.3
+            pb = torch.randn(1, generator=g)
+            a = ops.nchw_to_act(x.to(dev), fast)
+            (f,) = ops.fold_side_weights_multi([(wt.to(dev), bs.to(dev), proj.to(dev), pb.to(dev))])
+            acts.append(a)
+            folded.append(f)
+            single.append(ops.side_folded(a, f[0], f[1], fast=fast))
+        multi = ops.side_folded_multi(acts, folded, fast=fast)
+        for k in range(len(shapes)):
+            assert torch.equal(multi[k], single[k]), (fast, k)
+        rev = ops.side_folded_multi(acts[::-1], folded[::-1], fast=fast)[::-1]
+        for k in range(len(shapes)):
+            assert torch.equal(rev[k], single[k]), (fast, k)
+        two = ops.side_folded_multi(acts[1:3], folded[1:3], fast=fast)
+        assert torch.equal(two[0], single[1]) and torch.equal(two[1], single[2])
+
+
 def test_conv3x3_relu_mask_and_projection(dev):
     from osvos_pytorch_b200 import ops
     g = torch.Generator().manual_seed(7)

@@ -229,9 +229,8 @@ OSVOS_API int osvos_cbce_bwd(const float* output, const float* label, const doub
  * Replaces autograd's weight gradient of nn.Conv2d(k=3,p=1) (reference
  * networks/vgg_osvos.py:41,142; backward at train_online.py:141 / train_parent.py:164):
  *   dw[co][ci][r][s] = sum_px dz[px][co] * x[px + (r-1, s-1)][ci]
- * swapped == 0: trunk conv, dz has `cout` channels (dz_channels == cout, a multiple of 64).
- * swapped == 1: side_prep, dz is the 16-channel feature gradient stored with
- *               dz_channels == 64 (channels >= cout are zero).
+ * dz has `cout` channels (dz_channels == cout, a multiple of 64).  (side_prep's weight gradient does not come through
+ * here: osvos_side_folded_wgrad / osvos_side_grads_finish.)
  * workspace: osvos_wgrad_workspace_bytes(dz_channels, cin) bytes, contents destroyed.  */
 typedef struct {
   const void* x_hi;   /* layer input act [n,h,w,cin]        */
@@ -241,7 +240,6 @@ typedef struct {
   float* dw;          /* [cout][cin][3][3] fp32, overwritten */
   float* workspace;
   int n, h, w, cin, cout, dz_channels;
-  int swapped;
   int flags;          /* OSVOS_FLAG_FAST | OSVOS_FLAG_DEFER_FINISH (then dw may be NULL) */
 } osvos_wgrad_args;
 OSVOS_API size_t osvos_wgrad_workspace_bytes(int dz_channels, int cin);
@@ -254,7 +252,7 @@ OSVOS_API int osvos_conv3x3_wgrad(const osvos_wgrad_args* args /* host */, osvos
 typedef struct {
   const float* workspace;  /* as passed to osvos_conv3x3_wgrad with OSVOS_FLAG_DEFER_FINISH */
   float* dw;               /* [cout][cin][3][3] */
-  int cout, cin, dz_channels, swapped;
+  int cout, cin, dz_channels;
   int accumulate;
   float scale;
 } osvos_wgrad_finish_item;
@@ -292,15 +290,6 @@ OSVOS_API int osvos_tail_loss_bwd(const osvos_tail_loss_bwd_args* args /* host *
 
 /* out[0] = sum(x[0:n]) (fuse.bias gradient); scratch: 2 doubles (total, arrival counter).  */
 OSVOS_API int osvos_sum_f32(const float* x, size_t n, double* scratch, float* out, osvos_stream_t stream);
-
-/* ---- backward of score_dsn / the fuse slice (1x1 convs, networks/vgg_osvos.py:44,54) --
- * dfeat = dp*w_score + dq*w_fuse_slice as an act with 64 channels (16..63 zero);
- * param_grads[0:16] = d score_dsn.weight, [16] = d score_dsn.bias,
- * [17:33] = d fuse.weight slice, [33] = sum dq, [34:50] = d side_prep.bias (= w_score*sum dp +
- * w_fuse*sum dq).  param_grads: 50 floats; scratch: 35 doubles.  feat may be NULL (then only
- * dfeat, the plain sums and the bias gradient are produced).                              */
-OSVOS_API int osvos_side_bwd(const float* feat, const float* dpq, const float* proj_w, void* dfeat_hi, void* dfeat_lo,
-                             double* scratch, float* param_grads, int n, int h, int w, osvos_stream_t stream);
 
 /* ---- max-unpool + side-branch add + ReLU mask (autograd of networks/vgg_osvos.py:140,143) */
 OSVOS_API int osvos_unpool_add_mask(const void* dpool_hi, const void* dpool_lo, const void* x_hi, const void* x_lo,

@@ -57,12 +57,12 @@ class TailLossBwdArgs(Structure):
 class WgradArgs(Structure):
     _fields_ = [("x_hi", c_void_p), ("x_lo", c_void_p), ("dz_hi", c_void_p), ("dz_lo", c_void_p), ("dw", c_void_p),
                 ("workspace", c_void_p), ("n", c_int), ("h", c_int), ("w", c_int), ("cin", c_int), ("cout", c_int),
-                ("dz_channels", c_int), ("swapped", c_int), ("flags", c_int)]
+                ("dz_channels", c_int), ("flags", c_int)]
 
 
 class WgradFinishItem(Structure):
     _fields_ = [("workspace", c_void_p), ("dw", c_void_p), ("cout", c_int), ("cin", c_int), ("dz_channels", c_int),
-                ("swapped", c_int), ("accumulate", c_int), ("scale", c_float)]
+                ("accumulate", c_int), ("scale", c_float)]
 
 
 class FoldItem(Structure):
@@ -120,8 +120,6 @@ SIGNATURES = {
     "osvos_tail_bwd": (c_int, [POINTER(TailBwdArgs), c_void_p]),
     "osvos_tail_loss_bwd": (c_int, [POINTER(TailLossBwdArgs), c_void_p]),
     "osvos_sum_f32": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
-    "osvos_side_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
-                               c_int, c_void_p]),
     "osvos_unpool_add_mask": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                       c_int, c_int, c_int, c_int, c_void_p]),
     "osvos_side_folded_wgrad_floats": (c_size_t, [c_int]),

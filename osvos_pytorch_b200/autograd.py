@@ -38,8 +38,6 @@ class _OSVOSFunction(torch.autograd.Function):
                               fast=fast, pool=True)               # 2x2 max pool fused into the epilogue
         stage_acts.append(full)
         acts.append(stage_acts)
-        feats, pqs = [], []
-        folded = bool(getattr(engine, "folded_side_backward", True))
         for i in range(1, 5):
             pooled.append(a)
             stage_acts = []
@@ -53,29 +51,18 @@ class _OSVOSFunction(torch.autograd.Function):
                     full = a
                 stage_acts.append(full)
             acts.append(stage_acts)
-            if folded:
-                continue             # the four scales' folded side convs run as one launch below
-            sp = m.side_prep[i - 1]
-            _, feat, pq = ops.conv3x3(full, engine._packed(sp, f"sp{i}"), sp.bias.detach(), 16, relu=False, fast=fast,
-                                      out_act=False, out_f32=True, proj_w=engine._proj(i - 1),
-                                      proj_b=m.score_dsn[i - 1].bias.detach())
-            feats.append(feat)
-            pqs.append(pq)
-        if folded:
-            # side_prep has no ReLU: side_prep o (score_dsn, fuse slice) is ONE 3x3 conv C -> 2 (csrc/side_conv.cu), all four
-            # scales in one launch; its backward needs neither the 16 features nor their gradient (csrc/side_bwd_folded.cu)
-            pqs = ops.side_folded_multi([acts[i][-1] for i in range(1, 5)], engine._folded_side_all(), fast=fast)
-            feats = [None] * 4
+        # side_prep has no ReLU: side_prep o (score_dsn, fuse slice) is ONE 3x3 conv C -> 2 (csrc/side_conv.cu), all four
+        # scales in one launch; its backward needs neither the 16 features nor their gradient (csrc/side_bwd_folded.cu)
+        pqs = ops.side_folded_multi([acts[i][-1] for i in range(1, 5)], engine._folded_side_all(), fast=fast)
         ctx.engine = engine
         ctx.dims = (n, h, w)
         ctx.fast = fast
-        ctx.folded = folded
         if getattr(engine, "debug_capture", None) is not None:      # tests: the saved activations of this pass
-            engine.debug_capture.update(acts=acts, pooled=pooled, feats=feats)
+            engine.debug_capture.update(acts=acts, pooled=pooled)
         if objective is None:
             out, _ = ops.tail_fwd(pqs, m.fuse.bias.detach(), n, h, w)
             ctx.objective = None
-            ctx.saved = (xin, acts, pooled, feats)
+            ctx.saved = (xin, acts, pooled)
             return tuple(out[k] for k in range(5))
         label, weights, divisor = objective
         label = label.detach().to(xin.device).contiguous().float()
@@ -85,7 +72,7 @@ class _OSVOSFunction(torch.autograd.Function):
         out, sums, losses = ops.tail_fwd(pqs, m.fuse.bias.detach(), n, h, w, label=label, loss_weights=weights,
                                          divisor=divisor)
         ctx.objective = (out, label, sums, weights, float(divisor))
-        ctx.saved = (xin, acts, pooled, feats)
+        ctx.saved = (xin, acts, pooled)
         maps = tuple(out[k] for k in range(5))
         total = losses[5:6].reshape(())          # 0-dim view of the weighted total
         per_map = losses[0:5]
@@ -97,7 +84,7 @@ class _OSVOSFunction(torch.autograd.Function):
         engine = ctx.engine
         m = engine.m
         fast = ctx.fast
-        xin, acts, pooled, feats = ctx.saved
+        xin, acts, pooled = ctx.saved
         n, h, w = ctx.dims
         convs = _trunk_convs(m)
         pg = {}                                   # parameter -> gradient tensor
@@ -120,12 +107,10 @@ class _OSVOSFunction(torch.autograd.Function):
                     and g.is_contiguous() and g.device == xin.device:
                 return g
             return None
-        folded = ctx.folded
-        wconvs = [c for stage in convs for c in stage][1:] + ([] if folded else list(m.side_prep))
-        ws_sizes = [ops.wgrad_workspace_floats(64 if c.out_channels == 16 else c.out_channels, c.in_channels)
-                    for c in wconvs]
-        # folded side branch: G [18 C + 2] per scale (rounded up to 16 bytes) behind the wgrad workspaces
-        g_sizes = [(ops.side_folded_wgrad_floats(sp.in_channels) + 3) // 4 * 4 for sp in m.side_prep] if folded else []
+        wconvs = [c for stage in convs for c in stage][1:]
+        ws_sizes = [ops.wgrad_workspace_floats(c.out_channels, c.in_channels) for c in wconvs]
+        # side branch: G [18 C + 2] per scale (rounded up to 16 bytes) behind the wgrad workspaces
+        g_sizes = [(ops.side_folded_wgrad_floats(sp.in_channels) + 3) // 4 * 4 for sp in m.side_prep]
         arena = torch.zeros(sum(ws_sizes) + sum(g_sizes), dtype=torch.float32, device=xin.device)
         ws_of, off = {}, 0
         for c, sz in zip(wconvs, ws_sizes):
@@ -139,9 +124,9 @@ class _OSVOSFunction(torch.autograd.Function):
         fresh_buf = torch.empty(sum(c.weight.numel() for c in fresh), dtype=torch.float32, device=xin.device)
         finish_items, off = [], 0
 
-        def wgrad(conv, inp, dz_act, swapped=False):
+        def wgrad(conv, inp, dz_act):
             nonlocal off
-            it = ops.conv3x3_wgrad(inp, dz_act, conv.out_channels, swapped=swapped, fast=fast, deferred_ws=ws_of[conv])
+            it = ops.conv3x3_wgrad(inp, dz_act, conv.out_channels, fast=fast, deferred_ws=ws_of[conv])
             tgt = grad_target(conv.weight)
             if tgt is not None:
                 it["dw"], it["accumulate"] = tgt, True
@@ -165,7 +150,6 @@ class _OSVOSFunction(torch.autograd.Function):
             dpq = ops.tail_bwd(list(grads), n, h, w)
             if grads[4] is not None:
                 pg[m.fuse.bias] = ops.sum_f32(grads[4]).reshape(m.fuse.bias.shape)
-        fuse_w_grad = torch.zeros(64, dtype=torch.float32, device=xin.device) if grads[4] is not None else None
         # one zeroed buffer for all 13 trunk bias gradients; the dgrad / unpool epilogues accumulate into its slices
         flat_convs = [c for stage in convs for c in stage]
         bias_buf = torch.zeros(sum(c.out_channels for c in flat_convs), dtype=torch.float32, device=xin.device)
@@ -179,86 +163,58 @@ class _OSVOSFunction(torch.autograd.Function):
 
         def bias_grad(c):                              # None: already accumulated into c.bias.grad
             return None if c in bias_direct else bias_slices[c]
-        dfeats = []
-        if folded:
-            # every parameter gradient of the side branch from G[t][o][c] = sum_px dpq[px - t][o] x[px][c] (one pass over
-            # the stage output per scale) and one finish launch for the four scales
-            fold = engine._folded_side_all()
-            side_params = [m.fuse.weight] if grads[4] is not None else []
-            for i in range(4):
-                side_params += [m.side_prep[i].weight, m.side_prep[i].bias]
+        # every parameter gradient of the side branch from G[t][o][c] = sum_px dpq[px - t][o] x[px][c] (one pass over
+        # the stage output per scale) and one finish launch for the four scales
+        fold = engine._folded_side_all()
+        side_params = [m.fuse.weight] if grads[4] is not None else []
+        for i in range(4):
+            side_params += [m.side_prep[i].weight, m.side_prep[i].bias]
+            if grads[i] is not None:
+                side_params += [m.score_dsn[i].weight, m.score_dsn[i].bias]
+        in_place = all(grad_target(p) is not None for p in side_params)
+        if not in_place:
+            fresh_small = torch.zeros(4 * 34 + 64, dtype=torch.float32, device=xin.device)
+            fresh_side = torch.empty(sum(sp.weight.numel() for sp in m.side_prep), dtype=torch.float32,
+                                     device=xin.device)
+        entries, off_side = [], 0
+        for i in range(4):
+            sp, sd = m.side_prep[i], m.score_dsn[i]
+            ops.side_folded_wgrad(acts[i + 1][-1], dpq[i], g_of[i])
+            e = {"g": g_of[i], "side_w": sp.weight.detach(), "side_b": sp.bias.detach(), "proj_w": engine._proj(i),
+                 "c": sp.in_channels}
+            if in_place:
+                e["d_side_w"], e["d_side_b"] = sp.weight.grad, sp.bias.grad
+                pg[sp.weight] = pg[sp.bias] = None
                 if grads[i] is not None:
-                    side_params += [m.score_dsn[i].weight, m.score_dsn[i].bias]
-            in_place = all(grad_target(p) is not None for p in side_params)
-            if not in_place:
-                fresh_small = torch.zeros(4 * 34 + 64, dtype=torch.float32, device=xin.device)
-                fresh_side = torch.empty(sum(sp.weight.numel() for sp in m.side_prep), dtype=torch.float32,
-                                         device=xin.device)
-            entries, off_side = [], 0
-            for i in range(4):
-                sp, sd = m.side_prep[i], m.score_dsn[i]
-                ops.side_folded_wgrad(acts[i + 1][-1], dpq[i], g_of[i])
-                e = {"g": g_of[i], "side_w": sp.weight.detach(), "side_b": sp.bias.detach(), "proj_w": engine._proj(i),
-                     "c": sp.in_channels}
-                if in_place:
-                    e["d_side_w"], e["d_side_b"] = sp.weight.grad, sp.bias.grad
-                    pg[sp.weight] = pg[sp.bias] = None
-                    if grads[i] is not None:
-                        e["d_score_w"], e["d_score_b"] = sd.weight.grad, sd.bias.grad
-                        pg[sd.weight] = pg[sd.bias] = None
-                    if grads[4] is not None:
-                        e["d_fuse_w"] = m.fuse.weight.grad.view(-1)[16 * i:16 * i + 16]
-                        pg[m.fuse.weight] = None
-                else:
-                    nel = sp.weight.numel()
-                    e["d_side_w"] = fresh_side[off_side:off_side + nel].view(sp.weight.shape)
-                    off_side += nel
-                    small = fresh_small[34 * i:34 * i + 34]
-                    e["d_side_b"] = small[0:16]
-                    pg[sp.weight], pg[sp.bias] = e["d_side_w"], e["d_side_b"]
-                    if grads[i] is not None:
-                        e["d_score_w"], e["d_score_b"] = small[16:32], small[32:33]
-                        pg[sd.weight] = e["d_score_w"].view(sd.weight.shape)
-                        pg[sd.bias] = e["d_score_b"].view(sd.bias.shape)
-                    if grads[4] is not None:
-                        e["d_fuse_w"] = fresh_small[136 + 16 * i:136 + 16 * i + 16]
-                entries.append(e)
-            if not in_place and grads[4] is not None:
-                pg[m.fuse.weight] = fresh_small[136:200].view(m.fuse.weight.shape)
-            ops.side_grads_finish(entries, accumulate=in_place)
-        else:
-            for i in range(4):
-                d, g50 = ops.side_bwd(feats[i], dpq[i], engine._proj(i), fast)
-                dfeats.append(d)
+                    e["d_score_w"], e["d_score_b"] = sd.weight.grad, sd.bias.grad
+                    pg[sd.weight] = pg[sd.bias] = None
+                if grads[4] is not None:
+                    e["d_fuse_w"] = m.fuse.weight.grad.view(-1)[16 * i:16 * i + 16]
+                    pg[m.fuse.weight] = None
+            else:
+                nel = sp.weight.numel()
+                e["d_side_w"] = fresh_side[off_side:off_side + nel].view(sp.weight.shape)
+                off_side += nel
+                small = fresh_small[34 * i:34 * i + 34]
+                e["d_side_b"] = small[0:16]
+                pg[sp.weight], pg[sp.bias] = e["d_side_w"], e["d_side_b"]
                 if grads[i] is not None:
-                    pg[m.score_dsn[i].weight] = g50[0:16].reshape(m.score_dsn[i].weight.shape)
-                    pg[m.score_dsn[i].bias] = g50[16:17].reshape(m.score_dsn[i].bias.shape)
-                if fuse_w_grad is not None:
-                    fuse_w_grad[16 * i:16 * i + 16] = g50[17:33]           # slice copy (plumbing)
-                sp = m.side_prep[i]
-                wgrad(sp, acts[i + 1][-1], d, swapped=True)
-                pg[sp.bias] = g50[34:50]
-            if fuse_w_grad is not None:
-                pg[m.fuse.weight] = fuse_w_grad.reshape(m.fuse.weight.shape)
-
+                    e["d_score_w"], e["d_score_b"] = small[16:32], small[32:33]
+                    pg[sd.weight] = e["d_score_w"].view(sd.weight.shape)
+                    pg[sd.bias] = e["d_score_b"].view(sd.bias.shape)
+                if grads[4] is not None:
+                    e["d_fuse_w"] = fresh_small[136 + 16 * i:136 + 16 * i + 16]
+            entries.append(e)
+        if not in_place and grads[4] is not None:
+            pg[m.fuse.weight] = fresh_small[136:200].view(m.fuse.weight.shape)
+        ops.side_grads_finish(entries, accumulate=in_place)
         dpool = None
         for i in range(4, 0, -1):
             s_out = acts[i][-1]
-            sp = m.side_prep[i - 1]
-            wt_side = None if folded else engine._packed(sp, f"sp{i}", transpose_flip=True, col_pad=64)
-            cst = s_out.shape[3]
             last_bias = bias_slices[convs[i][-1]]
-            if folded:
-                # ReLU'(x) * (unpool(dpool) + side gradient), the latter formed on the fly from dpq and the fp32 folded
-                # weights (18 FMAs per element); deepest stage: dpool None, the side branch is the only consumer
-                dz = ops.unpool_side_mask(dpool, s_out, dpq[i - 1], fold[i - 1][2], colsum=last_bias)
-            elif dpool is None:        # deepest stage: the side branch is the only consumer
-                dz, _, _ = ops.conv3x3(dfeats[i - 1], wt_side, None, cst, fast=fast, mask=s_out.hi, colsum=last_bias,
-                                       k_valid=16)
-            else:
-                _, dside, _ = ops.conv3x3(dfeats[i - 1], wt_side, None, cst, fast=fast, out_act=False, out_f32=True,
-                                          k_valid=16)
-                dz = ops.unpool_add_mask(dpool, s_out, dside, colsum=last_bias)
+            # ReLU'(x) * (unpool(dpool) + side gradient), the latter formed on the fly from dpq and the fp32 folded weights
+            # (18 FMAs per element); deepest stage: dpool None, the side branch is the only consumer
+            dz = ops.unpool_side_mask(dpool, s_out, dpq[i - 1], fold[i - 1][2], colsum=last_bias)
             for j in range(len(convs[i]) - 1, -1, -1):
                 conv = convs[i][j]
                 inp = acts[i][j - 1] if j > 0 else pooled[i]

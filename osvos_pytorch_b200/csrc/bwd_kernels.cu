@@ -1,6 +1,6 @@
 // Bandwidth-bound backward kernels around the tensor-core dgrad / wgrad GEMMs:
-// adjoint of the bilinear tail, side-branch 1x1 backward, max-unpool + ReLU
-// mask, per-channel bias-gradient sums and the conv1_1 (Cin = 3) backward.
+// max-unpool + ReLU mask (+ the side branch's folded gradient), per-channel
+// bias-gradient sums and the conv1_1 (Cin = 3) backward.
 // They replace the autograd graph PyTorch builds for reference
 // networks/vgg_osvos.py:59-74 (triggered at train_online.py:141, train_parent.py:164).
 #include "common.cuh"
@@ -31,92 +31,6 @@ __global__ void __launch_bounds__(256) sum_f32_kernel(const float* __restrict__ 
   if (last_block_arrives(reinterpret_cast<unsigned int*>(out + 1)) && threadIdx.x == 0)
     result[0] = static_cast<float>(__ldcg(out));
 }
-// ------------------------------------------------------------------ side bwd
-// feat [npix][16] fp32, dpq [npix][2], pw[32] = {score_dsn w, fuse slice}:
-//   dfeat[px][c] = dp*pw[c] + dq*pw[16+c]  -> act with 64 channels (16..63 zero)
-//   acc[0:16] += dp*feat, acc[16] += dp, acc[17:33] += dq*feat, acc[33] += dq   (fp64 atomics)
-__global__ void __launch_bounds__(256)
-side_bwd_kernel(const float* __restrict__ feat, const float* __restrict__ dpq, const float* __restrict__ pw,
-                __nv_bfloat16* __restrict__ d_hi, __nv_bfloat16* __restrict__ d_lo, double* __restrict__ acc,
-                float* __restrict__ out, size_t npix) {
-  float a[34];
-#pragma unroll
-  for (int j = 0; j < 34; ++j) a[j] = 0.f;
-  float w[32];
-#pragma unroll
-  for (int j = 0; j < 32; ++j) w[j] = __ldg(pw + j);
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < npix;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const float2 g = __ldg(reinterpret_cast<const float2*>(dpq) + i);
-    float f[16];
-    if (feat) {
-      const float4* fp = reinterpret_cast<const float4*>(feat + i * 16);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float4 v = __ldg(fp + j);
-        f[4 * j] = v.x, f[4 * j + 1] = v.y, f[4 * j + 2] = v.z, f[4 * j + 3] = v.w;
-      }
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        a[j] = fmaf(g.x, f[j], a[j]);
-        a[17 + j] = fmaf(g.y, f[j], a[17 + j]);
-      }
-    }
-    a[16] += g.x;
-    a[33] += g.y;
-    uint32_t hi[8], lo[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float v0 = fmaf(g.x, w[2 * j], g.y * w[16 + 2 * j]);
-      const float v1 = fmaf(g.x, w[2 * j + 1], g.y * w[16 + 2 * j + 1]);
-      __nv_bfloat16 h0, l0, h1, l1;
-      split_bf16(v0, h0, l0);
-      split_bf16(v1, h1, l1);
-      hi[j] = pack_bf16x2(h0, h1);
-      lo[j] = pack_bf16x2(l0, l1);
-    }
-    uint4* dh = reinterpret_cast<uint4*>(d_hi + i * 64);
-    dh[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    dh[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-    const uint4 z = make_uint4(0, 0, 0, 0);
-#pragma unroll
-    for (int j = 2; j < 8; ++j) dh[j] = z;
-    if (d_lo) {
-      uint4* dl = reinterpret_cast<uint4*>(d_lo + i * 64);
-      dl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-      dl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
-#pragma unroll
-      for (int j = 2; j < 8; ++j) dl[j] = z;
-    }
-  }
-  __shared__ float red[8][34];
-#pragma unroll
-  for (int j = 0; j < 34; ++j) {
-    float v = a[j];
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][j] = v;
-  }
-  __syncthreads();
-  if (threadIdx.x < 34) {
-    double t = 0.0;
-    for (int i = 0; i < 8; ++i) t += static_cast<double>(red[i][threadIdx.x]);
-    atomicAdd(acc + threadIdx.x, t);
-  }
-  // finalize in the last block to arrive (acc[34] holds the arrival counter):
-  // out[0:34] = sums; out[34+c] = d side_prep.bias[c] = w_score[c]*sum(dp) + w_fuse[c]*sum(dq)
-  if (last_block_arrives(reinterpret_cast<unsigned int*>(acc + 34))) {
-    const int i = threadIdx.x;
-    if (i < 34) out[i] = static_cast<float>(__ldcg(acc + i));
-    else if (i < 50) out[i] = static_cast<float>(static_cast<double>(pw[i - 34]) * __ldcg(acc + 16) +
-                                                 static_cast<double>(pw[i - 18]) * __ldcg(acc + 33));
-  }
-}
-
-// ------------------------------------------------- max-unpool + add + ReLU mask
-// dz[n,h,w,c] = (x > 0) * (dside + (pixel is the argmax of its 2x2 window ? dpool : 0))
-// One thread per (pooled pixel, 8 channels).  Pass 1 reads the four activations and keeps only the argmax index and
-// the sign bits (a few registers, so that many threads / loads are in flight); pass 2 streams dside / dpool and writes.
 __device__ __forceinline__ void load_pair8(const __nv_bfloat16* hi, const __nv_bfloat16* lo, size_t off, float (&v)[8]) {
   const uint4 vh = __ldg(reinterpret_cast<const uint4*>(hi + off));
   uint4 vl = make_uint4(0, 0, 0, 0);
@@ -534,20 +448,6 @@ extern "C" int osvos_sum_f32(const float* x, size_t n, double* scratch, float* o
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   OSVOS_CHECK_CUDA(cudaMemsetAsync(scratch, 0, 2 * sizeof(double), stream));
   sum_f32_kernel<<<grid_cap((n + 255) / 256, 4), 256, 0, stream>>>(x, n, scratch, out);
-  OSVOS_CHECK_CUDA(cudaGetLastError());
-  return OSVOS_OK;
-}
-
-extern "C" int osvos_side_bwd(const float* feat, const float* dpq, const float* proj_w, void* dfeat_hi, void* dfeat_lo,
-                              double* scratch, float* param_grads, int n, int h, int w, osvos_stream_t stream_) {
-  OSVOS_CHECK_ARG(dpq != nullptr && proj_w != nullptr && dfeat_hi != nullptr && scratch != nullptr &&
-                  param_grads != nullptr && n > 0 && h > 0 && w > 0);
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  const size_t npix = static_cast<size_t>(n) * h * w;
-  OSVOS_CHECK_CUDA(cudaMemsetAsync(scratch, 0, 35 * sizeof(double), stream));
-  side_bwd_kernel<<<grid_cap((npix + 255) / 256, 4), 256, 0, stream>>>(
-      feat, dpq, proj_w, static_cast<__nv_bfloat16*>(dfeat_hi), static_cast<__nv_bfloat16*>(dfeat_lo), scratch,
-      param_grads, npix);
   OSVOS_CHECK_CUDA(cudaGetLastError());
   return OSVOS_OK;
 }

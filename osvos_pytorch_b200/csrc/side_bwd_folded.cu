@@ -26,92 +26,138 @@
 
 namespace osvos {
 
-constexpr int kSwThreads = 256;     // 8 warps; a warp owns a 128-channel slab (4 channels per lane) of a row segment
 constexpr int kSwSlab = 128;
 
-// G[t][o][c] (+ S[2] behind it), t = 3 r + s.  Work item = (image, row, segment of `seg` pixels); a block's eight warps
-// share one 128-channel slab (blockIdx % slabs) and walk items together, so that ONE shared-memory reduction per block
-// precedes the global atomics (18 x 128 floats per block).  Per item the 3 x (seg + 2) window of dpq goes to shared memory
-// once (coalesced), and the lane's four channels of the next FOUR pixels are always in flight: the first version loaded a
-// dpq column and one pixel per iteration and waited for both (54 us for the 52 MB stage-2 map, 1 TB/s).
-constexpr int kSwMaxSeg = 32;
-__global__ void __launch_bounds__(kSwThreads, 2)
-side_folded_wgrad_kernel(const __nv_bfloat16* __restrict__ x_hi, const __nv_bfloat16* __restrict__ x_lo,
-                         const float* __restrict__ dpq, float* __restrict__ g, int n, int h, int w, int c, int seg) {
-  __shared__ __align__(16) float red[18 * kSwSlab];
-  __shared__ float red_s[2];
-  __shared__ float2 win_all[kSwThreads / 32][3][kSwMaxSeg + 2];
+// G[t][o][c] (+ S[2] behind it), t = 3 r + s.
+// Work item = a CHUNK of 28 consecutive pixels of one image row x one 128-channel slab.  A block (seven compute warps + one
+// producer warp; two blocks per SM) owns one slab (blockIdx % slabs) and walks the chunks of that slab round-robin, so that neighbouring
+// blocks read neighbouring 7 KiB pieces of the map.  The producer warp streams the chunks through a four-stage ring: the
+// 28 x 128-channel tile of each bf16 plane by ONE 2-D TMA box (the map is a [pixels, C] matrix), the 3 x 30 window of
+// dpq by 8-byte cp.async copies that arrive on the same barrier.  Compute warp w takes pixels 4w .. 4w+3 of the chunk: its lane holds four
+// channels x 18 accumulators; per pixel it reads 8 + 8 bytes of x and nine float2 of the window from shared memory.
+// (History, stage-2 map of 52 MB at 480p: per-warp row segments with register prefetch, a dpq column and one pixel
+// loaded per iteration: 54 us; window in shared memory + the next four pixels in flight: 44 us - 4,700 concurrent
+// 256-byte streams kept DRAM at 1.3 TB/s with 2.5 us of load latency (profiles/r02l_ncu_side_folded_wgrad_v2.txt).)
+constexpr int kSwChunk = 28;                       // pixels per chunk: four per compute warp
+constexpr int kSwStages = 4;
+constexpr int kSwTileBytes = kSwChunk * kSwSlab * 2;          // one plane: 8 KiB
+constexpr int kSwWinBytes = 1024;                  // 3 x 30 float2 = 720 B
+constexpr int kSwStageBytes = 2 * kSwTileBytes + kSwWinBytes;
+static_assert(kSwTileBytes % 128 == 0 && kSwStageBytes % 128 == 0, "TMA destinations stay 128-byte aligned");
+constexpr int kSwComputeWarps = 7;                  // + 1 producer warp = 256 threads: 128 registers at two blocks per SM
+constexpr int kSwKernelThreads = (kSwComputeWarps + 1) * 32;
+constexpr int kSwWinPerLane = (3 * (kSwChunk + 2) + 31) / 32;
+static_assert(kSwComputeWarps * 4 == kSwChunk, "four pixels of a chunk per compute warp");
+static_assert(3 * (kSwChunk + 2) * 8 <= kSwWinBytes, "window area");
+constexpr int kSwPartBytes = kSwComputeWarps * 18 * kSwSlab * 4;            // 63 KiB of partial sums at the end
+constexpr int kSwRingBytes = kSwStages * kSwStageBytes;
+constexpr int kSwDataBytes = kSwPartBytes > kSwRingBytes ? kSwPartBytes : kSwRingBytes;
+constexpr int kSwSmemBytes = kSwDataBytes + (2 * kSwComputeWarps + 2) * 4 + 2 * kSwStages * 8 + 128;
+static_assert(kSwDataBytes % 8 == 0 && ((2 * kSwComputeWarps + 2) * 4) % 8 == 0, "mbarrier alignment");
+
+__global__ void __launch_bounds__(kSwKernelThreads, 2)
+side_folded_wgrad_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
+                         const float* __restrict__ dpq, float* __restrict__ g, int n, int h, int w, int c, int has_lo) {
+  extern __shared__ uint8_t sw_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(sw_smem_raw) + 127) & ~uintptr_t(127));
+  // after the last chunk the ring (+ the slack behind it) is reused for the warps' partial sums: [warp][18][128] floats
+  float* part = reinterpret_cast<float*>(smem);
+  float* part_s = reinterpret_cast<float*>(smem + kSwPartBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(part_s + 2 * kSwComputeWarps + 2);
+  uint64_t* empty_bar = full_bar + kSwStages;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float2 (*win)[kSwMaxSeg + 2] = win_all[warp];
   const int slabs = c / kSwSlab;
   const int slab = static_cast<int>(blockIdx.x) % slabs;
   const int blk = static_cast<int>(blockIdx.x) / slabs, nblk = (static_cast<int>(gridDim.x) + slabs - 1 - slab) / slabs;
-  const int c0 = slab * kSwSlab + lane * 4;
-  for (int i = threadIdx.x; i < 18 * kSwSlab; i += kSwThreads) red[i] = 0.f;
-  if (threadIdx.x < 2) red_s[threadIdx.x] = 0.f;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map_hi);
+    if (has_lo) tma_prefetch_desc(&map_lo);
+    for (int i = 0; i < kSwStages; ++i) {
+      mbar_init(&full_bar[i], 1 + 32);          // the TMA transaction + the 32 producer lanes' window copies
+      mbar_init(&empty_bar[i], kSwComputeWarps);
+    }
+    fence_barrier_init();
+  }
   __syncthreads();
   pdl_wait();               // dpq / x are outputs of earlier kernels of the stream (ptx.cuh)
   pdl_launch_dependents();
 
-  float acc[9][2][4];
-#pragma unroll
-  for (int t = 0; t < 9; ++t)
-#pragma unroll
-    for (int o = 0; o < 2; ++o)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[t][o][j] = 0.f;
-  float s0 = 0.f, s1 = 0.f;
+  const int cpr = (w + kSwChunk - 1) / kSwChunk;                 // chunks per image row
+  const int chunks = n * h * cpr;
 
-  const int segs_x = (w + seg - 1) / seg;
-  const int items = n * h * segs_x;
-  const bool has_lo = x_lo != nullptr;
-  for (int item = blk * 8 + warp; item < items; item += nblk * 8) {
-    const int sx = item % segs_x, row = item / segs_x;
-    const int y = row % h, img = row / h;
-    const int x0 = sx * seg;
-    const int x1 = min(x0 + seg, w);
-    // window: win[r][k] = dpq[(y + 1 - r, x0 - 1 + k)], zero outside the image (= dpq[px - t] for t = (r - 1, s - 1) at
-    // k = (x - x0) + 2 - s)
-    __syncwarp();
-    for (int idx = lane; idx < 3 * (seg + 2); idx += 32) {
-      const int r = idx / (seg + 2), k = idx - r * (seg + 2);
-      const int yy = y + 1 - r, xx = x0 - 1 + k;
-      float2 v = make_float2(0.f, 0.f);
-      if (yy >= 0 && yy < h && xx >= 0 && xx < w)
-        v = __ldg(reinterpret_cast<const float2*>(dpq) + (static_cast<size_t>(img) * h + yy) * w + xx);
-      win[r][k] = v;
-    }
-    const size_t rowbase = (static_cast<size_t>(img) * h + y) * w;
-    uint2 rh[4], rl[4];
+  if (warp == kSwComputeWarps) {
+    // ------------------------------------------------------------------ producer warp
+    // Per chunk and stage: the 3 x 30 window of dpq by 8-byte cp.async with zero fill outside the image (window entry
+    // idx = r * 30 + k <-> dpq[(y + 1 - r, x0 - 1 + k)]; up to kSwWinPerLane entries per lane), each lane's copies arriving
+    // on the stage's full barrier when they land, and the two x tiles by TMA - nothing here waits for memory, so all four
+    // stages are in flight.  (With the window prefetched ONE chunk ahead into registers the producer handed over one chunk
+    // per load latency: 34 us for the stage-2 map.)
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int ci = blk; ci < chunks; ci += nblk) {
+      const int cx = ci % cpr, row = ci / cpr;
+      const int y = row % h, img = row / h, x0 = cx * kSwChunk;
+      mbar_wait(&empty_bar[stage], phase ^ 1);
+      uint8_t* st = smem + stage * kSwStageBytes;
+      float2* win = reinterpret_cast<float2*>(st + 2 * kSwTileBytes);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      rh[u] = rl[u] = make_uint2(0, 0);
-      if (x0 + u < x1) {
-        rh[u] = __ldg(reinterpret_cast<const uint2*>(x_hi + (rowbase + x0 + u) * c + c0));
-        if (has_lo) rl[u] = __ldg(reinterpret_cast<const uint2*>(x_lo + (rowbase + x0 + u) * c + c0));
+      for (int j = 0; j < kSwWinPerLane; ++j) {
+        const int idx = lane + 32 * j;
+        if (idx < 3 * (kSwChunk + 2)) {
+          const int r = idx / (kSwChunk + 2), k = idx - r * (kSwChunk + 2);
+          const int yy = y + 1 - r, xx = x0 - 1 + k;
+          const bool in = yy >= 0 && yy < h && xx >= 0 && xx < w;
+          const float2* src = reinterpret_cast<const float2*>(dpq) + (in ? (static_cast<size_t>(img) * h + yy) * w + xx : 0);
+          cp_async_8_zfill(win + idx, src, in ? 8u : 0u);
+        }
+      }
+      cp_async_mbar_arrive_noinc(&full_bar[stage]);
+      if (lane == 0) {
+        const int pix0 = row * w + x0;                                // flat pixel index of the chunk's first pixel
+        mbar_arrive_expect_tx(&full_bar[stage], (has_lo ? 2 : 1) * kSwTileBytes);
+        tma_load_2d(&map_hi, &full_bar[stage], st, slab * kSwSlab, pix0);
+        if (has_lo) tma_load_2d(&map_lo, &full_bar[stage], st + kSwTileBytes, slab * kSwSlab, pix0);
+      }
+      if (++stage == kSwStages) {
+        stage = 0;
+        phase ^= 1;
       }
     }
-    __syncwarp();
-    for (int xb = x0; xb < x1; xb += 4) {
+  } else {
+    // ------------------------------------------------------------------ compute warps
+    float acc[9][2][4];
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int o = 0; o < 2; ++o)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[t][o][j] = 0.f;
+    float s0 = 0.f, s1 = 0.f;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int ci = blk; ci < chunks; ci += nblk) {
+      const int cx = ci % cpr;
+      const int valid = min(kSwChunk, w - cx * kSwChunk);            // pixels of this chunk inside the row
+      mbar_wait(&full_bar[stage], phase);
+      const uint8_t* st = smem + stage * kSwStageBytes;
+      const float2* win = reinterpret_cast<const float2*>(st + 2 * kSwTileBytes);
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const int xx = xb + u;
-        if (xx < x1) {
+        const int px = warp * 4 + u;
+        if (px < valid) {
+          const uint2 rh = *reinterpret_cast<const uint2*>(st + px * (kSwSlab * 2) + lane * 8);
+          uint2 rl = make_uint2(0, 0);
+          if (has_lo) rl = *reinterpret_cast<const uint2*>(st + kSwTileBytes + px * (kSwSlab * 2) + lane * 8);
           float v[4];
-          v[0] = bf16_lo_to_float(rh[u].x) + bf16_lo_to_float(rl[u].x);
-          v[1] = bf16_hi_to_float(rh[u].x) + bf16_hi_to_float(rl[u].x);
-          v[2] = bf16_lo_to_float(rh[u].y) + bf16_lo_to_float(rl[u].y);
-          v[3] = bf16_hi_to_float(rh[u].y) + bf16_hi_to_float(rl[u].y);
-          if (xx + 4 < x1) {          // this slot's next tenant: four pixels ahead
-            rh[u] = __ldg(reinterpret_cast<const uint2*>(x_hi + (rowbase + xx + 4) * c + c0));
-            if (has_lo) rl[u] = __ldg(reinterpret_cast<const uint2*>(x_lo + (rowbase + xx + 4) * c + c0));
-          }
-          const int k0 = xx - x0 + 2;
+          v[0] = bf16_lo_to_float(rh.x) + bf16_lo_to_float(rl.x);
+          v[1] = bf16_hi_to_float(rh.x) + bf16_hi_to_float(rl.x);
+          v[2] = bf16_lo_to_float(rh.y) + bf16_lo_to_float(rl.y);
+          v[3] = bf16_hi_to_float(rh.y) + bf16_hi_to_float(rl.y);
 #pragma unroll
           for (int r = 0; r < 3; ++r)
 #pragma unroll
             for (int s = 0; s < 3; ++s) {
-              const float2 d = win[r][k0 - s];
+              const float2 d = win[r * (kSwChunk + 2) + px + 2 - s];       // dpq[px - t], t = (r - 1, s - 1)
               if (r == 1 && s == 1) {
                 s0 += d.x;
                 s1 += d.y;
@@ -124,26 +170,46 @@ side_folded_wgrad_kernel(const __nv_bfloat16* __restrict__ x_hi, const __nv_bflo
             }
         }
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[stage]);
+      if (++stage == kSwStages) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+    // every compute warp is through with the ring: its memory now holds the warps' partial sums (see below)
+    asm volatile("bar.sync 1, %0;" ::"n"(kSwComputeWarps * 32) : "memory");
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int o = 0; o < 2; ++o)
+        *reinterpret_cast<float4*>(part + (warp * 18 + 2 * t + o) * kSwSlab + lane * 4) =
+            make_float4(acc[t][o][0], acc[t][o][1], acc[t][o][2], acc[t][o][3]);
+    if (lane == 0) {   // every lane of a warp saw the same dpq: one lane counts
+      part_s[2 * warp] = s0;
+      part_s[2 * warp + 1] = s1;
     }
   }
-  // block reduction in shared memory, then one vector atomic per (tap, o, 4 channels)
-#pragma unroll
-  for (int t = 0; t < 9; ++t)
-#pragma unroll
-    for (int o = 0; o < 2; ++o)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) atomicAdd(&red[(2 * t + o) * kSwSlab + lane * 4 + j], acc[t][o][j]);
-  if (slab == 0 && lane == 0) {   // every lane of a warp saw the same dpq: one lane counts
-    atomicAdd(&red_s[0], s0);
-    atomicAdd(&red_s[1], s1);
-  }
   __syncthreads();
-  for (int i = threadIdx.x; i < 18 * (kSwSlab / 4); i += kSwThreads) {
+  // Block reduction over the seven warps' partials (plain loads in a fixed order - the float atomicAdd on shared memory the
+  // first versions used is a compare-and-swap loop, 72 of them per thread under 7-way contention), then one vector atomic
+  // per (tap, o, 4 channels) and block.
+  for (int i = threadIdx.x; i < 18 * (kSwSlab / 4); i += kSwKernelThreads) {
+    float4 val = *reinterpret_cast<const float4*>(part + i * 4);
+#pragma unroll
+    for (int wv = 1; wv < kSwComputeWarps; ++wv) {
+      const float4 v = *reinterpret_cast<const float4*>(part + wv * 18 * kSwSlab + i * 4);
+      val.x += v.x, val.y += v.y, val.z += v.z, val.w += v.w;
+    }
     const int to = i / (kSwSlab / 4), c4 = i % (kSwSlab / 4);
-    const float4 val = *reinterpret_cast<const float4*>(&red[to * kSwSlab + c4 * 4]);
     atomicAdd(reinterpret_cast<float4*>(g + static_cast<size_t>(to) * c + slab * kSwSlab + c4 * 4), val);
   }
-  if (slab == 0 && threadIdx.x < 2) atomicAdd(g + static_cast<size_t>(18) * c + threadIdx.x, red_s[threadIdx.x]);
+  if (slab == 0 && threadIdx.x < 2) {
+    float v = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < kSwComputeWarps; ++wv) v += part_s[2 * wv + threadIdx.x];
+    atomicAdd(g + static_cast<size_t>(18) * c + threadIdx.x, v);
+  }
 }
 
 // Parameter gradients of the side branch of up to four scales from G / S: one block per (scale, feature f).
@@ -231,22 +297,32 @@ extern "C" int osvos_side_folded_wgrad(const void* x_hi, const void* x_lo, const
                                        int w, int c, osvos_stream_t stream_) {
   OSVOS_CHECK_ARG(x_hi != nullptr && dpq != nullptr && g != nullptr && n > 0 && h > 0 && w > 0);
   OSVOS_CHECK_ARG(c >= kSwSlab && c % kSwSlab == 0);
-  OSVOS_CHECK_ARG((reinterpret_cast<uintptr_t>(g) & 15) == 0);
+  OSVOS_CHECK_ARG((reinterpret_cast<uintptr_t>(g) & 15) == 0 && (reinterpret_cast<uintptr_t>(x_hi) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(x_lo) & 15) == 0);
   const int slabs = c / kSwSlab;
-  const long rows = static_cast<long>(n) * h;
-  const long blocks_cap = static_cast<long>(device_sm_count()) * 2 / slabs > 0 ? static_cast<long>(device_sm_count()) * 2 / slabs : 1;
-  // segment length: the longest of 32 / 16 / 8 pixels that still leaves ~2.5 items per warp of the slab (balance of the
-  // static item assignment against the per-item window load)
-  int seg = kSwMaxSeg;
-  while (seg > 8 && rows * ((w + seg - 1) / seg) * 2 < blocks_cap * 8 * 5) seg >>= 1;
-  const long items = rows * ((w + seg - 1) / seg);
-  OSVOS_CHECK_ARG(items < (1l << 30));
-  long blocks_per_slab = (items + 7) / 8;
-  if (blocks_per_slab > blocks_cap) blocks_per_slab = blocks_cap;
+  const long npix = static_cast<long>(n) * h * w;
+  const long chunks = static_cast<long>(n) * h * ((w + kSwChunk - 1) / kSwChunk);
+  OSVOS_CHECK_ARG(npix < (1l << 31) && chunks < (1l << 30));
+  CUtensorMap map_hi, map_lo;
+  {
+    const uint64_t dims[2] = {(uint64_t)c, (uint64_t)npix};
+    const uint64_t strides[1] = {(uint64_t)c * 2};
+    const uint32_t box[2] = {kSwSlab, kSwChunk};
+    int rc = encode_tensor_map(&map_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 2, x_hi, dims, strides, box,
+                               CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (rc) return rc;
+    rc = encode_tensor_map(&map_lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 2, x_lo ? x_lo : x_hi, dims, strides, box,
+                           CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (rc) return rc;
+  }
+  long blocks_per_slab = static_cast<long>(device_sm_count()) * 2 / slabs;
+  if (blocks_per_slab < 1) blocks_per_slab = 1;
+  if (blocks_per_slab > chunks) blocks_per_slab = chunks;
   const unsigned grid = static_cast<unsigned>(blocks_per_slab * slabs);
-  OSVOS_CHECK_CUDA(launch_pdl(side_folded_wgrad_kernel, dim3(grid), dim3(kSwThreads), 0, static_cast<cudaStream_t>(stream_),
-                              static_cast<const __nv_bfloat16*>(x_hi), static_cast<const __nv_bfloat16*>(x_lo), dpq, g, n,
-                              h, w, c, seg));
+  static uint64_t attr_done = 0;
+  OSVOS_CHECK_CUDA(ensure_dynamic_smem(side_folded_wgrad_kernel, kSwSmemBytes, &attr_done));
+  OSVOS_CHECK_CUDA(launch_pdl(side_folded_wgrad_kernel, dim3(grid), dim3(kSwKernelThreads), kSwSmemBytes,
+                              static_cast<cudaStream_t>(stream_), map_hi, map_lo, dpq, g, n, h, w, c, x_lo != nullptr ? 1 : 0));
   return OSVOS_OK;
 }
 

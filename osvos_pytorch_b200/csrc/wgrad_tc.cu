@@ -3,10 +3,9 @@
 //
 //   ws[tap][m][n] += sum_px P[px (+tap)][m] * Q[px (+tap)][n]
 //
-// For a trunk conv P = dZ (gradient of the conv output, unshifted, m = co) and
-// Q = the layer's input activation shifted by the tap (n = ci); for side_prep the
-// roles are swapped (P = shifted input, m = ci; Q = the 16-channel feature
-// gradient padded to 64, n = co) so that M stays 128-wide.  Both operands are
+// P = dZ (gradient of the conv output, unshifted, m = co) and Q = the layer's input
+// activation shifted by the tap (n = ci).  (side_prep's weight gradient is not a GEMM
+// of this shape any more: side_bwd_folded.cu.)  Both operands are
 // NHWC acts, i.e. the reduction index (pixel) is the strided one: they are
 // "MN-major" UMMA operands.  A K block is a patch of 8 x 8 pixels; its TMA box
 // {64 ch, 8 px, 8 rows, 1} lands as 64 rows x 128 B (SWIZZLE_128B), which is the
@@ -41,7 +40,6 @@ struct WgradParams {
   int m_blocks, n_blocks, splits;
   int patches_x, patches_y, patches_total, patches_per_split;
   int total_items;
-  int p_shifted;  // 1: P is the shifted operand, 0: Q is
   int tap_pairs;  // 1: Q has 64 channels and the two 64-wide N atoms of a 128-wide item are TWO TAPS (2g, 2g+1)
   int tap_rows;   // 1: P AND Q have 64 channels (conv1_2): an item is one tap ROW - see launch_wgrad
   int tap_items;  // 9, 5 tap groups in tap_pairs mode, or 3 tap rows in tap_rows mode
@@ -129,8 +127,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_p_hi, const __grid_const
         const int tap1 = (p.tap_pairs && tap0 + 1 < 9) ? tap0 + 1 : tap0;   // second N atom (tap 8 is alone: repeated, unused)
         const int dy = tap0 / 3 - 1, dx = tap0 % 3 - 1;
         const int dy1 = tap1 / 3 - 1, dx1 = tap1 % 3 - 1;
-        const int pdy = p.p_shifted ? dy : 0, pdx = p.p_shifted ? dx : 0;
-        const int qdy = p.p_shifted ? 0 : dy, qdx = p.p_shifted ? 0 : dx;
+        const int qdy = dy, qdx = dx;      // Q is the shifted operand (zero-filled outside the image = conv padding)
         const int pb = split * p.patches_per_split;
         int pe = pb + p.patches_per_split;
         if (pe > p.patches_total) pe = p.patches_total;
@@ -153,7 +150,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_p_hi, const __grid_const
                 if (p.tap_rows)   // M atom j = the single 64-channel block of dz shifted by (0, +j)
                   tma_load_4d(mp, &full_bar[stage], sp + j * kWgBoxBytes, 0, x0 + j, y0, img);
                 else
-                  tma_load_4d(mp, &full_bar[stage], sp + j * kWgBoxBytes, c_p + j * 64, x0 + pdx, y0 + pdy, img);
+                  tma_load_4d(mp, &full_bar[stage], sp + j * kWgBoxBytes, c_p + j * 64, x0, y0, img);
               }
             }
           } else {
@@ -305,28 +302,25 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_p_hi, const __grid_const
   }
 }
 
-// ws[tap][a][b] (+ optional existing grad) -> OIHW gradient.
-//   swapped == 0: a = co, b = ci ; swapped == 1: a = ci, b = co (b padded to ld_b)
+// ws[tap][co][ci] -> OIHW gradient (the immediate, non-deferred form of one layer).
 __global__ void wgrad_finish_kernel(const float* __restrict__ ws, float* __restrict__ dw, int cout, int cin, int ld_a,
-                                    int ld_b, int swapped, float scale, int accumulate) {
+                                    int ld_b) {
   const int total = cout * cin * 9;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int tap = i % 9;
     const int ci = (i / 9) % cin;
     const int co = i / (9 * cin);
-    const int a = swapped ? ci : co, b = swapped ? co : ci;
-    const float v = ws[(static_cast<size_t>(tap) * ld_a + a) * ld_b + b] * scale;
-    dw[i] = accumulate ? dw[i] + v : v;
+    dw[i] = ws[(static_cast<size_t>(tap) * ld_a + co) * ld_b + ci];
   }
 }
 
 // Deferred finish of many layers in one launch.  A work item is one output row (co) x 64 input channels x 9 taps
 // = 576 contiguous OIHW floats: the nine workspace rows are read coalesced (256 B each), transposed through shared
-// memory and written coalesced.  The thin side_prep gradients (swapped roles, 16 x C x 9) take the element-wise path.
+// memory and written coalesced.
 struct FinishLayer {
   const float* ws;
   float* dw;
-  int cout, cin, ld_a, ld_b, swapped, accumulate;
+  int cout, cin, ld_a, ld_b, accumulate;
   float scale;
   int items;
 };
@@ -352,17 +346,6 @@ wgrad_finish_multi_kernel(const __grid_constant__ FinishTable t) {
     }
     const FinishLayer& L = t.layer[li];
     const int item = work - base;
-    if (L.swapped) {
-      const int total = L.cout * L.cin * 9;
-      for (int i = item * kFinishChunk + threadIdx.x; i < min(total, (item + 1) * kFinishChunk); i += kFinishThreads) {
-        const int tap = i % 9;
-        const int ci = (i / 9) % L.cin;
-        const int co = i / (9 * L.cin);
-        const float v = L.ws[(static_cast<size_t>(tap) * L.ld_a + ci) * L.ld_b + co] * L.scale;
-        L.dw[i] = L.accumulate ? L.dw[i] + v : v;
-      }
-      continue;
-    }
     const int chunks = L.cin / 64;
     const int co = item / chunks, ci0 = (item - co * chunks) * 64;
     __syncthreads();   // previous item's readers of `tile` are done
@@ -400,14 +383,13 @@ wgrad_finish_multi_kernel(const __grid_constant__ FinishTable t) {
 template <int BLOCK_N, int PLANES>
 static int launch_wgrad(const osvos_wgrad_args* a, cudaStream_t stream) {
   using Cfg = WgCfg<BLOCK_N, PLANES>;
-  const bool swapped = a->swapped != 0;
   // operand roles
-  const void* p_hi = swapped ? a->x_hi : a->dz_hi;
-  const void* p_lo = swapped ? a->x_lo : a->dz_lo;
-  const void* q_hi = swapped ? a->dz_hi : a->x_hi;
-  const void* q_lo = swapped ? a->dz_lo : a->x_lo;
-  const int cp = swapped ? a->cin : a->dz_channels;   // channels of the P tensor
-  const int cq = swapped ? a->dz_channels : a->cin;   // channels of the Q tensor
+  const void* p_hi = a->dz_hi;
+  const void* p_lo = a->dz_lo;
+  const void* q_hi = a->x_hi;
+  const void* q_lo = a->x_lo;
+  const int cp = a->dz_channels;   // channels of the P tensor
+  const int cq = a->cin;           // channels of the Q tensor
 
   WgradParams p;
   p.ws = a->workspace;
@@ -432,8 +414,8 @@ static int launch_wgrad(const osvos_wgrad_args* a, cudaStream_t stream) {
     const char* e = getenv("OSVOS_WGRAD_ROWS");
     rows_on = (e == nullptr || atoi(e) != 0) ? 1 : 0;
   }
-  p.tap_rows = (rows_on && !swapped && cq == 64 && cp == 64 && BLOCK_N == 128) ? 1 : 0;
-  p.tap_pairs = (!swapped && cq == 64 && BLOCK_N == 128 && !p.tap_rows) ? 1 : 0;
+  p.tap_rows = (rows_on && cq == 64 && cp == 64 && BLOCK_N == 128) ? 1 : 0;
+  p.tap_pairs = (cq == 64 && BLOCK_N == 128 && !p.tap_rows) ? 1 : 0;
   p.tap_items = p.tap_rows ? 3 : p.tap_pairs ? 5 : 9;
   p.n_blocks = (p.tap_pairs || p.tap_rows) ? 1 : cq / BLOCK_N;
   p.patches_x = (a->w + kWgPatchW - 1) / kWgPatchW;
@@ -441,14 +423,39 @@ static int launch_wgrad(const osvos_wgrad_args* a, cudaStream_t stream) {
   p.patches_total = p.patches_x * p.patches_y * a->n;
   const int tiles = p.m_blocks * p.n_blocks * p.tap_items;
   const int sms = device_sm_count();
-  int splits = (2 * sms + tiles - 1) / tiles;
+  // Pixel-range splits: items are dealt round-robin to the persistent CTAs, so the kernel lasts as long as the CTA with
+  // the most items - ROUNDS x K blocks per item.  Pick the split count that minimises that (plus ~2 K-block times per
+  // item for the accumulator flush that is not hidden behind the next item's MMAs).  The first rule, ceil(2 SMs /
+  // tiles), landed just ABOVE two full rounds for most layers (297 items on 148 CTAs: a third round for one item,
+  // 67 % of the tensor time) - profiles/r02l_*.
   const int max_splits = (p.patches_total + 3) / 4;
+  static int split_rule = -1;   // OSVOS_WGRAD_SPLITS=legacy: the first rule (A/B; read once)
+  if (split_rule < 0) {
+    const char* e = getenv("OSVOS_WGRAD_SPLITS");
+    split_rule = (e != nullptr && strcmp(e, "legacy") == 0) ? 1 : 0;
+  }
+  int splits = 1;
+  if (split_rule == 1) {
+    splits = (2 * sms + tiles - 1) / tiles;
+  } else {
+    long best = -1;
+    const int s_hi = 4 * sms / tiles + 1;
+    for (int s = 1; s <= s_hi && s <= max_splits; ++s) {
+      const long pps = (p.patches_total + s - 1) / s;
+      const long se = (p.patches_total + pps - 1) / pps;
+      const long rounds = (static_cast<long>(tiles) * se + sms - 1) / sms;
+      const long cost = rounds * (pps + 2) + 4;
+      if (best < 0 || cost < best) {
+        best = cost;
+        splits = s;
+      }
+    }
+  }
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
   p.patches_per_split = (p.patches_total + splits - 1) / splits;
   p.splits = (p.patches_total + p.patches_per_split - 1) / p.patches_per_split;
   p.total_items = tiles * p.splits;
-  p.p_shifted = swapped ? 1 : 0;
 
   CUtensorMap mp_hi, mp_lo, mq_hi, mq_lo;
   auto enc = [&](CUtensorMap* m, const void* base, int c) {
@@ -478,8 +485,7 @@ static int launch_wgrad(const osvos_wgrad_args* a, cudaStream_t stream) {
   kern<<<grid, kWgThreads, Cfg::kSmemBytes, stream>>>(mp_hi, mp_lo, mq_hi, mq_lo, p);
   OSVOS_CHECK_CUDA(cudaGetLastError());
   const int total = a->cout * a->cin * 9;
-  wgrad_finish_kernel<<<(total + 255) / 256, 256, 0, stream>>>(a->workspace, a->dw, a->cout, a->cin, p.m_total,
-                                                                p.n_total, swapped ? 1 : 0, 1.0f, 0);
+  wgrad_finish_kernel<<<(total + 255) / 256, 256, 0, stream>>>(a->workspace, a->dw, a->cout, a->cin, p.m_total, p.n_total);
   OSVOS_CHECK_CUDA(cudaGetLastError());
   return OSVOS_OK;
 }
@@ -500,18 +506,17 @@ extern "C" int osvos_wgrad_finish(const osvos_wgrad_finish_item* items, int coun
   for (int i = 0; i < count; ++i) {
     const osvos_wgrad_finish_item& it = items[i];
     OSVOS_CHECK_ARG(it.workspace != nullptr && it.dw != nullptr && it.cout > 0 && it.cin > 0 && it.cin % 64 == 0);
-    OSVOS_CHECK_ARG(it.dz_channels % 64 == 0 && it.cout <= it.dz_channels);
+    OSVOS_CHECK_ARG(it.dz_channels % 64 == 0 && it.cout == it.dz_channels);
     FinishLayer& L = t.layer[i];
     L.ws = it.workspace;
     L.dw = it.dw;
     L.cout = it.cout;
     L.cin = it.cin;
-    L.swapped = it.swapped ? 1 : 0;
-    L.ld_a = it.swapped ? it.cin : it.dz_channels;
-    L.ld_b = it.swapped ? it.dz_channels : it.cin;
+    L.ld_a = it.dz_channels;
+    L.ld_b = it.cin;
     L.accumulate = it.accumulate ? 1 : 0;
     L.scale = it.scale;
-    L.items = it.swapped ? (it.cout * it.cin * 9 + kFinishChunk - 1) / kFinishChunk : it.cout * (it.cin / 64);
+    L.items = it.cout * (it.cin / 64);
     total_items += L.items;
   }
   OSVOS_CHECK_ARG(total_items < (1ll << 31));
@@ -527,14 +532,10 @@ extern "C" int osvos_conv3x3_wgrad(const osvos_wgrad_args* a, osvos_stream_t str
   OSVOS_CHECK_ARG(a != nullptr && a->x_hi != nullptr && a->dz_hi != nullptr && a->workspace != nullptr);
   OSVOS_CHECK_ARG(a->dw != nullptr || (a->flags & OSVOS_FLAG_DEFER_FINISH));
   OSVOS_CHECK_ARG(a->n > 0 && a->h > 0 && a->w > 0 && a->cin % 64 == 0 && a->dz_channels % 64 == 0);
-  OSVOS_CHECK_ARG(a->cout <= a->dz_channels);
+  OSVOS_CHECK_ARG(a->cout == a->dz_channels);
   OSVOS_CHECK_ARG((a->flags & OSVOS_FLAG_FAST) || (a->x_lo != nullptr && a->dz_lo != nullptr));
-  OSVOS_CHECK_ARG(!a->swapped || a->dz_channels == 64);
-  OSVOS_CHECK_ARG(a->swapped || a->cout == a->dz_channels);
+  OSVOS_CHECK_ARG(a->cin % 128 == 0 || a->cin == 64);     // Cin = 64: tap-pair / tap-row modes of the 128-wide kernel
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const bool fast = (a->flags & OSVOS_FLAG_FAST) != 0;
-  const int cq = a->swapped ? a->dz_channels : a->cin;
-  if (cq % 128 == 0 || (!a->swapped && cq == 64))   // Cin = 64: tap-pair mode of the 128-wide kernel
-    return fast ? launch_wgrad<128, 1>(a, stream) : launch_wgrad<128, 2>(a, stream);
-  return fast ? launch_wgrad<64, 1>(a, stream) : launch_wgrad<64, 2>(a, stream);
+  return fast ? launch_wgrad<128, 1>(a, stream) : launch_wgrad<128, 2>(a, stream);
 }

@@ -32,9 +32,6 @@ class OSVOSEngine:
         # inference only: fold side_prep with its two 1x1 projections into one 3x3 conv C -> 2 (OSVOS_FOLD_SIDE=0, read per
         # eager pass, switches it off for A/B runs)
         self.fold_side_branch = True
-        # training: the side branch as the folded conv C -> 2 forward and its rank-2 backward (csrc/side_bwd_folded.cu);
-        # False / OSVOS_SIDE_BWD=literal keeps the literal 16-feature route (cross-check, tests/test_gpu_side_folded.py)
-        self.folded_side_backward = os.environ.get("OSVOS_SIDE_BWD", "folded") != "literal"
 
     def direct_grad_accumulation(self):
         """Context manager enabling in-place gradient accumulation for the backward passes run inside it."""
@@ -65,8 +62,8 @@ class OSVOSEngine:
                             lambda: ops.pack_conv3x3_weights(conv.weight, transpose_flip, col_pad))
 
     def _tensor_core_convs(self):
-        """(conv module, cache key) of every 3x3 conv that runs on the packed tensor-core path (conv1_1 takes its
-        OIHW weights directly)."""
+        """(conv module, cache key) of every trunk 3x3 conv that runs on the packed tensor-core path (conv1_1 takes its
+        OIHW weights directly; side_prep is folded with its 1x1 projections instead)."""
         m = self.m
         out = []
         for i in range(5):
@@ -75,8 +72,7 @@ class OSVOSEngine:
                 if i == 0 and j == 0:
                     continue
                 out.append((conv, f"s{i}c{j}"))
-        out += [(m.side_prep[i - 1], f"sp{i}") for i in range(1, 5)]
-        return out
+        return out                # (side_prep runs folded with its projections: engine._folded_side_all)
 
     def packed_weight_table(self):
         """[(weight Parameter, forward layout, transposed+flipped layout)] of the tensor-core convs, packed now if

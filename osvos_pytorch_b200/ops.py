@@ -313,7 +313,7 @@ def wgrad_workspace_floats(dz_channels, cin):
     return nat.load().osvos_wgrad_workspace_bytes(dz_channels, cin) // 4
 
 
-def conv3x3_wgrad(x, dz, cout, swapped=False, fast=False, deferred_ws=None):
+def conv3x3_wgrad(x, dz, cout, fast=False, deferred_ws=None):
     """dW [cout, cin, 3, 3] of a 3x3 conv from its input act `x` and output-gradient act `dz`.
     With `deferred_ws` (a ZEROED fp32 workspace of wgrad_workspace_floats(dz.channels, cin)) only the tensor-core
     accumulation is enqueued and a finish item for ops.wgrad_finish is returned instead of dW."""
@@ -324,14 +324,13 @@ def conv3x3_wgrad(x, dz, cout, swapped=False, fast=False, deferred_ws=None):
     a = nat.WgradArgs()
     a.x_hi, a.x_lo, a.dz_hi, a.dz_lo = x.hi.data_ptr(), nat.ptr(x.lo), dz.hi.data_ptr(), nat.ptr(dz.lo)
     a.n, a.h, a.w, a.cin, a.cout, a.dz_channels = n, h, w, cin, cout, dzc
-    a.swapped = int(swapped)
     a.flags = nat.FLAG_FAST if fast else 0
     if deferred_ws is not None:
         a.dw, a.workspace = None, deferred_ws.data_ptr()
         a.flags |= nat.FLAG_DEFER_FINISH
         _count(1)
         nat.check(lib.osvos_conv3x3_wgrad(byref(a), _stream()), "osvos_conv3x3_wgrad")
-        return {"ws": deferred_ws, "cout": cout, "cin": cin, "dz_channels": dzc, "swapped": int(swapped)}
+        return {"ws": deferred_ws, "cout": cout, "cin": cin, "dz_channels": dzc}
     dw = torch.empty((cout, cin, 3, 3), dtype=torch.float32, device=dev)
     ws = torch.empty(lib.osvos_wgrad_workspace_bytes(dzc, cin) // 4, dtype=torch.float32, device=dev)
     a.dw, a.workspace = dw.data_ptr(), ws.data_ptr()
@@ -349,7 +348,7 @@ def wgrad_finish(items):
         arr = (nat.WgradFinishItem * len(part))()
         for f, it in zip(arr, part):
             f.workspace, f.dw = it["ws"].data_ptr(), it["dw"].data_ptr()
-            f.cout, f.cin, f.dz_channels, f.swapped = it["cout"], it["cin"], it["dz_channels"], it["swapped"]
+            f.cout, f.cin, f.dz_channels = it["cout"], it["cin"], it["dz_channels"]
             f.accumulate, f.scale = int(bool(it.get("accumulate"))), 1.0
         _count(1)
         nat.check(lib.osvos_wgrad_finish(arr, len(part), _stream()), "osvos_wgrad_finish")
@@ -388,20 +387,6 @@ def sum_f32(x):
     nat.check(lib.osvos_sum_f32(x.data_ptr(), x.numel(), scratch.data_ptr(), out.data_ptr(), _stream()),
               "osvos_sum_f32")
     return out
-
-
-def side_bwd(feat, dpq, proj_w, fast=False):
-    """-> (dfeat Act [n,h,w,64], param_grads [34] fp32)."""
-    lib = nat.load()
-    n, h, w, _ = (int(v) for v in dpq.shape)
-    dev = dpq.device
-    d = Act.empty(n, h, w, 64, dev, fast)
-    scratch = torch.empty(35, dtype=torch.float64, device=dev)
-    pg = torch.empty(50, dtype=torch.float32, device=dev)
-    _count(1)
-    nat.check(lib.osvos_side_bwd(nat.ptr(feat), dpq.data_ptr(), proj_w.data_ptr(), d.hi.data_ptr(), nat.ptr(d.lo),
-                                 scratch.data_ptr(), pg.data_ptr(), n, h, w, _stream()), "osvos_side_bwd")
-    return d, pg
 
 
 def unpool_add_mask(dpool, x, dside, colsum=None):

@@ -53,32 +53,6 @@ def test_wgrad_tensor_core(dev, n, h, w, cin, cout, fast):
     assert maxrel(got, wt.grad) < (3e-2 if fast else 3e-5), maxrel(got, wt.grad)
 
 
-def test_wgrad_side_prep_swapped(dev):
-    from osvos_pytorch_b200 import ops
-    g = torch.Generator().manual_seed(3)
-    n, h, w, cin = 1, 19, 21, 128
-    x = torch.randn(n, cin, h, w, generator=g)
-    dz16 = torch.randn(n, 16, h, w, generator=g) * 0.1
-    dz = torch.cat([dz16, torch.zeros(n, 48, h, w)], 1)
-    wt = torch.zeros(16, cin, 3, 3, dtype=torch.float64, requires_grad=True)
-    F.conv2d(x.double(), wt, None, padding=1).backward(dz16.double())
-    got = ops.conv3x3_wgrad(ops.nchw_to_act(x.to(dev)), ops.nchw_to_act(dz.to(dev)), 16, swapped=True)
-    assert maxrel(got, wt.grad) < 3e-5
-
-
-def test_dgrad_is_the_adjoint(dev):
-    from osvos_pytorch_b200 import ops
-    g = torch.Generator().manual_seed(4)
-    n, h, w, cin, cout = 1, 18, 11, 64, 128
-    wt = torch.randn(cout, cin, 3, 3, generator=g) * 0.05
-    dz = torch.randn(n, cout, h, w, generator=g)
-    xin = torch.zeros(n, cin, h, w, dtype=torch.float64, requires_grad=True)
-    F.conv2d(xin, wt.double(), None, padding=1).backward(dz.double())
-    wp = ops.pack_conv3x3_weights(wt.to(dev), transpose_flip=True)
-    _, dx, _ = ops.conv3x3(ops.nchw_to_act(dz.to(dev)), wp, None, cin, out_act=False, out_f32=True)
-    assert maxrel(dx.permute(0, 3, 1, 2), xin.grad) < 3e-5
-
-
 @pytest.mark.parametrize("n,h,w", [(1, 48, 70), (2, 33, 45), (1, 17, 3)])
 def test_tail_bwd_is_the_adjoint(dev, n, h, w):
     from osvos_pytorch_b200 import ops
@@ -125,26 +99,12 @@ def test_unpool_add_mask(dev, n, h, w, c, with_side):
     assert maxrel(colsum.cpu(), want.sum((0, 2, 3))) < 2e-5
 
 
-def test_channel_sum_side_bwd_and_first_layer(dev):
+def test_channel_sum_and_first_layer(dev):
     from osvos_pytorch_b200 import ops
     g = torch.Generator().manual_seed(9)
     a = split_round(torch.randn(2, 128, 13, 11, generator=g))
     got = ops.channel_sum(ops.nchw_to_act(a.to(dev))).cpu()
     assert maxrel(got, a.double().sum((0, 2, 3))) < 1e-5
-    # side_bwd
-    n, h, w = 1, 9, 14
-    feat = torch.randn(n, h, w, 16, generator=g)
-    dpq = torch.randn(n, h, w, 2, generator=g)
-    pw = torch.randn(32, generator=g)
-    d, pg = ops.side_bwd(feat.to(dev), dpq.to(dev), pw.to(dev))
-    dn = ops.act_to_nchw(d).cpu()
-    want = dpq[..., 0:1] * pw[:16] + dpq[..., 1:2] * pw[16:]
-    assert maxrel(dn[:, :16].permute(0, 2, 3, 1), want) < 2e-5 and float(dn[:, 16:].abs().max()) == 0.0
-    pg = pg.cpu()
-    assert maxrel(pg[:16], (dpq[..., 0:1] * feat).double().sum((0, 1, 2))) < 1e-5
-    assert maxrel(pg[17:33], (dpq[..., 1:2] * feat).double().sum((0, 1, 2))) < 1e-5
-    assert abs(float(pg[16]) - float(dpq[..., 0].double().sum())) < 1e-4
-    assert maxrel(pg[34:50], want.double().sum((0, 1, 2))) < 1e-5          # side_prep bias gradient
     # conv1_1 backward
     x, _ = oc.synthetic_frame(2, 13, 37, 5)
     wt = torch.randn(64, 3, 3, 3, generator=g) * 0.2

@@ -317,6 +317,15 @@ OSVOS_API int osvos_unpool_add_mask(const void* dpool_hi, const void* dpool_lo, 
 OSVOS_API size_t osvos_side_folded_wgrad_floats(int c);
 OSVOS_API int osvos_side_folded_wgrad(const void* x_hi, const void* x_lo /* or NULL */, const float* dpq /* [n,h,w,2] */,
                                       float* g, int n, int h, int w, int c, osvos_stream_t stream);
+/* The same for up to four scales in one launch (x_lo either set for all items or for none). */
+typedef struct {
+  const void* x_hi;
+  const void* x_lo;
+  const float* dpq;
+  float* g;
+  int n, h, w, c;
+} osvos_side_wgrad_item;
+OSVOS_API int osvos_side_folded_wgrad_multi(const osvos_side_wgrad_item* items /* host */, int count, osvos_stream_t stream);
 typedef struct {
   const float* g;        /* as filled by osvos_side_folded_wgrad */
   const float* side_w;   /* [16,c,3,3] */

@@ -71,6 +71,12 @@ class FoldItem(Structure):
                 ("packed", c_void_p), ("bias2", c_void_p), ("folded_f32", c_void_p), ("cin", c_int)]
 
 
+class SideWgradItem(Structure):
+    """osvos_side_wgrad_item (include/osvos_b200.h)."""
+    _fields_ = [("x_hi", c_void_p), ("x_lo", c_void_p), ("dpq", c_void_p), ("g", c_void_p), ("n", c_int), ("h", c_int),
+                ("w", c_int), ("c", c_int)]
+
+
 class SideGradsItem(Structure):
     """osvos_side_grads_item (include/osvos_b200.h)."""
     _fields_ = [("g", c_void_p), ("side_w", c_void_p), ("side_b", c_void_p), ("proj_w", c_void_p),
@@ -124,6 +130,7 @@ SIGNATURES = {
                                       c_int, c_int, c_int, c_int, c_void_p]),
     "osvos_side_folded_wgrad_floats": (c_size_t, [c_int]),
     "osvos_side_folded_wgrad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "osvos_side_folded_wgrad_multi": (c_int, [POINTER(SideWgradItem), c_int, c_void_p]),
     "osvos_side_grads_finish": (c_int, [POINTER(SideGradsItem), c_int, c_void_p]),
     "osvos_unpool_side_mask": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                        c_void_p, c_int, c_int, c_int, c_int, c_void_p]),

@@ -176,10 +176,10 @@ class _OSVOSFunction(torch.autograd.Function):
             fresh_small = torch.zeros(4 * 34 + 64, dtype=torch.float32, device=xin.device)
             fresh_side = torch.empty(sum(sp.weight.numel() for sp in m.side_prep), dtype=torch.float32,
                                      device=xin.device)
+        ops.side_folded_wgrad_multi([acts[i + 1][-1] for i in range(4)], dpq, g_of)      # G of the four scales, one launch
         entries, off_side = [], 0
         for i in range(4):
             sp, sd = m.side_prep[i], m.score_dsn[i]
-            ops.side_folded_wgrad(acts[i + 1][-1], dpq[i], g_of[i])
             e = {"g": g_of[i], "side_w": sp.weight.detach(), "side_b": sp.bias.detach(), "proj_w": engine._proj(i),
                  "c": sp.in_channels}
             if in_place:

@@ -55,9 +55,35 @@ constexpr int kSwDataBytes = kSwPartBytes > kSwRingBytes ? kSwPartBytes : kSwRin
 constexpr int kSwSmemBytes = kSwDataBytes + (2 * kSwComputeWarps + 2) * 4 + 2 * kSwStages * 8 + 128;
 static_assert(kSwDataBytes % 8 == 0 && ((2 * kSwComputeWarps + 2) * 4) % 8 == 0, "mbarrier alignment");
 
+// Up to four SCALES per launch (the backward runs the four side branches' G kernels as one): the grid is cut into one
+// block range per scale, sized by the scale's chunk count, so the fixed cost of a launch (first tile's latency, block
+// reduction, atomics: ~9 us of a 10 us launch on the 30 x 54 map) is paid once.
+constexpr int kSwMaxScales = 4;
+struct SwScale {
+  const float* dpq;
+  float* g;
+  int n, h, w, c;
+  int block_begin, blocks;       // this scale's blocks: [block_begin, block_begin + blocks), a multiple of c / 128
+};
+struct SwParams {
+  SwScale sc[kSwMaxScales];
+  int count;
+  int has_lo;
+};
+struct SwMaps {
+  CUtensorMap hi[kSwMaxScales], lo[kSwMaxScales];
+};
+
 __global__ void __launch_bounds__(kSwKernelThreads, 2)
-side_folded_wgrad_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
-                         const float* __restrict__ dpq, float* __restrict__ g, int n, int h, int w, int c, int has_lo) {
+side_folded_wgrad_kernel(const __grid_constant__ SwMaps maps, const __grid_constant__ SwParams p) {
+  int sci = 0;
+  while (sci + 1 < p.count && static_cast<int>(blockIdx.x) >= p.sc[sci + 1].block_begin) ++sci;
+  const SwScale& L = p.sc[sci];
+  const CUtensorMap& map_hi = maps.hi[sci];
+  const CUtensorMap& map_lo = maps.lo[sci];
+  const float* __restrict__ dpq = L.dpq;
+  float* __restrict__ g = L.g;
+  const int n = L.n, h = L.h, w = L.w, c = L.c, has_lo = p.has_lo;
   extern __shared__ uint8_t sw_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(sw_smem_raw) + 127) & ~uintptr_t(127));
   // after the last chunk the ring (+ the slack behind it) is reused for the warps' partial sums: [warp][18][128] floats
@@ -67,8 +93,9 @@ side_folded_wgrad_kernel(const __grid_constant__ CUtensorMap map_hi, const __gri
   uint64_t* empty_bar = full_bar + kSwStages;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int slabs = c / kSwSlab;
-  const int slab = static_cast<int>(blockIdx.x) % slabs;
-  const int blk = static_cast<int>(blockIdx.x) / slabs, nblk = (static_cast<int>(gridDim.x) + slabs - 1 - slab) / slabs;
+  const int lb = static_cast<int>(blockIdx.x) - L.block_begin;      // block index inside the scale's range
+  const int slab = lb % slabs;
+  const int blk = lb / slabs, nblk = L.blocks / slabs;
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_hi);
     if (has_lo) tma_prefetch_desc(&map_lo);
@@ -293,37 +320,80 @@ using namespace osvos;
 
 extern "C" size_t osvos_side_folded_wgrad_floats(int c) { return static_cast<size_t>(18) * c + 2; }
 
-extern "C" int osvos_side_folded_wgrad(const void* x_hi, const void* x_lo, const float* dpq, float* g, int n, int h,
-                                       int w, int c, osvos_stream_t stream_) {
-  OSVOS_CHECK_ARG(x_hi != nullptr && dpq != nullptr && g != nullptr && n > 0 && h > 0 && w > 0);
-  OSVOS_CHECK_ARG(c >= kSwSlab && c % kSwSlab == 0);
-  OSVOS_CHECK_ARG((reinterpret_cast<uintptr_t>(g) & 15) == 0 && (reinterpret_cast<uintptr_t>(x_hi) & 15) == 0 &&
-                  (reinterpret_cast<uintptr_t>(x_lo) & 15) == 0);
-  const int slabs = c / kSwSlab;
-  const long npix = static_cast<long>(n) * h * w;
-  const long chunks = static_cast<long>(n) * h * ((w + kSwChunk - 1) / kSwChunk);
-  OSVOS_CHECK_ARG(npix < (1l << 31) && chunks < (1l << 30));
-  CUtensorMap map_hi, map_lo;
-  {
-    const uint64_t dims[2] = {(uint64_t)c, (uint64_t)npix};
-    const uint64_t strides[1] = {(uint64_t)c * 2};
+extern "C" int osvos_side_folded_wgrad_multi(const osvos_side_wgrad_item* items, int count, osvos_stream_t stream_) {
+  OSVOS_CHECK_ARG(items != nullptr && count > 0 && count <= kSwMaxScales);
+  SwParams p;
+  SwMaps maps;
+  memset(&p, 0, sizeof(p));
+  p.count = count;
+  p.has_lo = items[0].x_lo != nullptr ? 1 : 0;
+  long work[kSwMaxScales], total_work = 0;
+  for (int k = 0; k < count; ++k) {
+    const osvos_side_wgrad_item& it = items[k];
+    OSVOS_CHECK_ARG(it.x_hi != nullptr && it.dpq != nullptr && it.g != nullptr && it.n > 0 && it.h > 0 && it.w > 0);
+    OSVOS_CHECK_ARG(it.c >= kSwSlab && it.c % kSwSlab == 0);
+    OSVOS_CHECK_ARG((it.x_lo != nullptr) == (p.has_lo != 0));
+    OSVOS_CHECK_ARG((reinterpret_cast<uintptr_t>(it.g) & 15) == 0 && (reinterpret_cast<uintptr_t>(it.x_hi) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(it.x_lo) & 15) == 0);
+    const long npix = static_cast<long>(it.n) * it.h * it.w;
+    const long chunks = static_cast<long>(it.n) * it.h * ((it.w + kSwChunk - 1) / kSwChunk);
+    OSVOS_CHECK_ARG(npix < (1l << 31) && chunks < (1l << 30));
+    SwScale& L = p.sc[k];
+    L.dpq = it.dpq;
+    L.g = it.g;
+    L.n = it.n;
+    L.h = it.h;
+    L.w = it.w;
+    L.c = it.c;
+    work[k] = chunks * (it.c / kSwSlab);
+    total_work += work[k];
+    const uint64_t dims[2] = {(uint64_t)it.c, (uint64_t)npix};
+    const uint64_t strides[1] = {(uint64_t)it.c * 2};
     const uint32_t box[2] = {kSwSlab, kSwChunk};
-    int rc = encode_tensor_map(&map_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 2, x_hi, dims, strides, box,
+    int rc = encode_tensor_map(&maps.hi[k], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 2, it.x_hi, dims, strides, box,
                                CU_TENSOR_MAP_SWIZZLE_NONE);
     if (rc) return rc;
-    rc = encode_tensor_map(&map_lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 2, x_lo ? x_lo : x_hi, dims, strides, box,
-                           CU_TENSOR_MAP_SWIZZLE_NONE);
+    rc = encode_tensor_map(&maps.lo[k], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 2, it.x_lo ? it.x_lo : it.x_hi, dims, strides,
+                           box, CU_TENSOR_MAP_SWIZZLE_NONE);
     if (rc) return rc;
   }
-  long blocks_per_slab = static_cast<long>(device_sm_count()) * 2 / slabs;
-  if (blocks_per_slab < 1) blocks_per_slab = 1;
-  if (blocks_per_slab > chunks) blocks_per_slab = chunks;
-  const unsigned grid = static_cast<unsigned>(blocks_per_slab * slabs);
+  for (int k = count; k < kSwMaxScales; ++k) {   // unused slots: valid descriptors (never dereferenced)
+    maps.hi[k] = maps.hi[0];
+    maps.lo[k] = maps.lo[0];
+  }
+  // blocks per scale: its share of two blocks per SM by chunk count, a multiple of its slab count, at least one block per
+  // slab and at most one block per chunk
+  const long budget = static_cast<long>(device_sm_count()) * 2;
+  int begin = 0;
+  for (int k = 0; k < count; ++k) {
+    const int slabs = p.sc[k].c / kSwSlab;
+    const long chunks = work[k] / slabs;
+    long b = (budget * work[k] + total_work / 2) / total_work / slabs;
+    if (b < 1) b = 1;
+    if (b > chunks) b = chunks;
+    p.sc[k].block_begin = begin;
+    p.sc[k].blocks = static_cast<int>(b * slabs);
+    begin += p.sc[k].blocks;
+  }
   static uint64_t attr_done = 0;
   OSVOS_CHECK_CUDA(ensure_dynamic_smem(side_folded_wgrad_kernel, kSwSmemBytes, &attr_done));
-  OSVOS_CHECK_CUDA(launch_pdl(side_folded_wgrad_kernel, dim3(grid), dim3(kSwKernelThreads), kSwSmemBytes,
-                              static_cast<cudaStream_t>(stream_), map_hi, map_lo, dpq, g, n, h, w, c, x_lo != nullptr ? 1 : 0));
+  OSVOS_CHECK_CUDA(launch_pdl(side_folded_wgrad_kernel, dim3(begin), dim3(kSwKernelThreads), kSwSmemBytes,
+                              static_cast<cudaStream_t>(stream_), maps, p));
   return OSVOS_OK;
+}
+
+extern "C" int osvos_side_folded_wgrad(const void* x_hi, const void* x_lo, const float* dpq, float* g, int n, int h,
+                                       int w, int c, osvos_stream_t stream_) {
+  osvos_side_wgrad_item it;
+  it.x_hi = x_hi;
+  it.x_lo = x_lo;
+  it.dpq = dpq;
+  it.g = g;
+  it.n = n;
+  it.h = h;
+  it.w = w;
+  it.c = c;
+  return osvos_side_folded_wgrad_multi(&it, 1, stream_);
 }
 
 extern "C" int osvos_side_grads_finish(const osvos_side_grads_item* items, int count, osvos_stream_t stream_) {

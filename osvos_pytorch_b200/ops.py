@@ -429,6 +429,18 @@ def side_folded_wgrad(x, dpq, g):
     return g
 
 
+def side_folded_wgrad_multi(xs, dpqs, gs):
+    """side_folded_wgrad of several scales in ONE launch (osvos_side_folded_wgrad_multi)."""
+    lib = nat.load()
+    arr = (nat.SideWgradItem * len(xs))()
+    for it, x, dpq, g in zip(arr, xs, dpqs, gs):
+        n, h, w, c = x.shape
+        it.x_hi, it.x_lo, it.dpq, it.g = x.hi.data_ptr(), nat.ptr(x.lo), dpq.data_ptr(), g.data_ptr()
+        it.n, it.h, it.w, it.c = n, h, w, c
+    _count()
+    nat.check(lib.osvos_side_folded_wgrad_multi(arr, len(xs), _stream()), "osvos_side_folded_wgrad_multi")
+
+
 def side_grads_finish(entries, accumulate):
     """entries: dicts with g, side_w, side_b, proj_w, d_side_w, d_side_b, d_score_w, d_score_b, d_fuse_w (tensors or
     None), c.  One launch for all scales."""

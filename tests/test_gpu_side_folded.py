@@ -87,3 +87,28 @@ def test_folded_side_backward_kernels(dev, n, h, w, c):
         got = ops.act_to_nchw(dz).cpu()
         assert maxrel(got, want) < 3e-5, (pooled, maxrel(got, want))
         assert maxrel(colsum.cpu(), want.sum((0, 2, 3))) < 3e-5
+
+
+def test_folded_wgrad_multi_scale_launch(dev):
+    """osvos_side_folded_wgrad_multi: the four scales' G in one launch (block ranges per scale) equals one launch per scale
+    up to the order of the fp32 atomics."""
+    from osvos_pytorch_b200 import ops
+    g = torch.Generator().manual_seed(31)
+    shapes = [(1, 30, 53, 128), (1, 15, 27, 256), (1, 8, 14, 512), (1, 4, 7, 512)]
+    for fast in (False, True):
+        xs, dpqs = [], []
+        for n, h, w, c in shapes:
+            xs.append(ops.nchw_to_act((torch.randn(n, c, h, w, generator=g).clamp(min=0) * 2).to(dev), fast))
+            dpqs.append(torch.randn(n, h, w, 2, generator=g).to(dev))
+        single = []
+        for x, d in zip(xs, dpqs):
+            gb = torch.zeros(ops.side_folded_wgrad_floats(x.shape[3]), device=dev)
+            ops.side_folded_wgrad(x, d, gb)
+            single.append(gb)
+        multi = [torch.zeros_like(s) for s in single]
+        ops.side_folded_wgrad_multi(xs, dpqs, multi)
+        for k in range(len(shapes)):
+            assert maxrel(multi[k], single[k]) < 1e-5, (fast, k, maxrel(multi[k], single[k]))
+        two = [torch.zeros_like(single[2]), torch.zeros_like(single[0])]
+        ops.side_folded_wgrad_multi([xs[2], xs[0]], [dpqs[2], dpqs[0]], two)
+        assert maxrel(two[0], single[2]) < 1e-5 and maxrel(two[1], single[0]) < 1e-5

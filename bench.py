@@ -795,10 +795,11 @@ def main():
                          "SequenceSegmenter: pinned host frame -> H2D -> OSVOS.forward (nn.Module API) -> D2H of the "
                          "fused logit map, legs of consecutive frames overlapped on 3 streams"), **e2e_extra},
         "gpu_launches": int(launches),
-        "memcpy_per_step": (0 if train else 2),
+        "memcpy_per_step": (0 if train else 1),
         "gpu_launches_note": ("this repo's kernels per step (libosvos_b200.so), all inside one replayed CUDA graph; around the "
-                              "replay the engine issues `memcpy_per_step` device-to-device copies through torch (frame into the "
-                              "graph's static input, the five maps out into fresh caller-owned tensors) - not counted as kernels"),
+                              "replay the engine issues `memcpy_per_step` device-to-device copy through torch (the five maps out "
+                              "into fresh caller-owned tensors; an input buffer that comes back is read in place by a graph "
+                              "captured on it, so no input copy in steady state) - not counted as kernels"),
         "clocks": clocks,
     }
     if conv_rec:

@@ -25,6 +25,7 @@ class OSVOSEngine:
         # One frame is ~22 kernel launches; replaying a graph removes the Python / launch overhead (OSVOS_CUDA_GRAPH=0
         # disables it).
         self._graphs = {}
+        self._buffers_seen = {}          # (graph key, input address) -> calls seen (engine._forward_graphed)
         self.use_cuda_graph = os.environ.get("OSVOS_CUDA_GRAPH", "1") != "0"
         # training loops of this package set this: backward adds weight / trunk-bias gradients straight into an
         # existing p.grad (and hands autograd None for them) instead of returning tensors for AccumulateGrad
@@ -148,7 +149,7 @@ class OSVOSEngine:
                 self._deconv_checked[key] = ver
 
     # ----------------------------------------------------------------- forward
-    def forward(self, x):
+    def forward(self, x, fresh_outputs=True):
         if not isinstance(x, torch.Tensor) or x.dim() != 4 or x.size(1) != 3:
             raise ValueError("OSVOS.forward expects a [N, 3, H, W] tensor")
         if not x.is_cuda:
@@ -157,12 +158,12 @@ class OSVOSEngine:
         needs_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.m.parameters()))
         if x.device != torch.device("cuda", torch.cuda.current_device()):
             with torch.cuda.device(x.device):       # kernels are enqueued on the current stream of x's device
-                return self.forward(x)
+                return self.forward(x, fresh_outputs)
         if needs_grad:
             from .autograd import osvos_apply
             return osvos_apply(self, x)
         if self.use_cuda_graph and not torch.cuda.is_current_stream_capturing():
-            return self._forward_graphed(x)
+            return self._forward_graphed(x, fresh_outputs)
         return self.forward_inference(x)
 
     def forward_objective(self, x, gts, loss_weights, size_average=False, batch_average=True):
@@ -185,33 +186,61 @@ class OSVOSEngine:
         from .autograd import osvos_apply_objective
         return osvos_apply_objective(self, x, gts, loss_weights, divisor)
 
-    def _forward_graphed(self, x):
-        """Inference through a captured CUDA graph: copy the frame into the static input, replay, hand back fresh
-        output tensors (one device copy of the five maps).  Re-captured when shapes or parameters change."""
+    def _forward_graphed(self, x, fresh_outputs=True):
+        """Inference through a captured CUDA graph.  Two kinds of entry:
+        * generic: the frame is copied into the graph's static input, the graph replayed (any input tensor);
+        * direct: an input BUFFER that comes back (same address, shape, contiguous fp32 - the second call on) gets a graph
+          captured on that buffer itself: no input copy.  A video pipeline feeds a small ring of device buffers
+          (inference.SequenceSegmenter does), so in steady state every replay is direct.
+        The five maps are handed back as fresh tensors (one device copy) unless `fresh_outputs` is False: then they are
+        views of the entry's static output, valid until the SAME entry is replayed again (the sequence pipeline reads them
+        straight into its pinned host buffers).  Re-captured when shapes or parameters change."""
         m = self.m
-        key = (tuple(x.shape), x.device.index, m.precision,
-               tuple((p.data_ptr(), p._version) for p in m.parameters()))
-        entry = self._graphs.get(key)
+        pkey = (tuple(x.shape), x.device.index, m.precision,
+                tuple((p.data_ptr(), p._version) for p in m.parameters()))
+        direct_ok = x.dtype == torch.float32 and x.is_contiguous() and not x.requires_grad
+        entry = None
+        if direct_ok:
+            dkey = pkey + (x.data_ptr(),)
+            entry = self._graphs.get(dkey)
+            if entry is None:
+                seen = self._buffers_seen.get(dkey, 0) + 1
+                if len(self._buffers_seen) > 64:
+                    self._buffers_seen.clear()
+                self._buffers_seen[dkey] = seen
+                if seen >= 2:                                    # the buffer came back: give it its own graph
+                    entry = self._capture(dkey, x, direct=True)
         if entry is None:
-            if len(self._graphs) >= 4:                       # bounded: each entry pins its activation pool
-                self._graphs.pop(next(iter(self._graphs)))
-            self.forward_inference(x)                        # eager warm-up: packs weights, sets kernel attributes
-            static_x = x.detach().contiguous().float().clone()
-            torch.cuda.synchronize(x.device)
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                outs = self.forward_inference(static_x)
-            base = outs[0]._base if outs[0]._base is not None else None
-            entry = (graph, static_x, outs, base)
-            self._graphs[key] = entry
+            entry = self._graphs.get(pkey)
+            if entry is None:
+                entry = self._capture(pkey, x, direct=False)
         graph, static_x, outs, base = entry
-        static_x.copy_(x, non_blocking=True)
+        if static_x is not None:
+            static_x.copy_(x, non_blocking=True)
         graph.replay()
+        if not fresh_outputs:
+            return list(outs)
         if base is not None:
             fresh = base.clone()
             n, _, h, w = (int(v) for v in x.shape)
             return [fresh[k, :n * h * w].view(n, 1, h, w) for k in range(5)]
         return [o.clone() for o in outs]
+
+    def _capture(self, key, x, direct):
+        """Capture the inference pass for `key`; direct: on the caller's buffer itself (no static input)."""
+        limit = 12                                               # bounded: each entry pins its activation pool
+        while len(self._graphs) >= limit:
+            self._graphs.pop(next(iter(self._graphs)))
+        self.forward_inference(x)                                # eager warm-up: packs weights, sets kernel attributes
+        static_x = None if direct else x.detach().contiguous().float().clone()
+        torch.cuda.synchronize(x.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            outs = self.forward_inference(x if direct else static_x)
+        base = outs[0]._base if outs[0]._base is not None else None
+        entry = (graph, static_x, outs, base)
+        self._graphs[key] = entry
+        return entry
 
     @torch.no_grad()
     def forward_inference(self, x, simt=False, return_intermediates=False):

@@ -49,7 +49,14 @@ class SequenceSegmenter:
         if i >= self.depth:
             cur.wait_event(self._ev_host[k])                    # previous result of this slot is on the host
         with torch.no_grad():
-            fused = self.net(self._dev_in[k])[-1]
+            eng = getattr(self.net, "_engine", None)
+            if eng is not None:
+                # the ring slot is a buffer that comes back: from its second frame on the engine replays a graph captured on
+                # the slot itself (no input copy), and the fused map is read out of the graph's static output right here on
+                # the same stream (no copy of the five maps into fresh tensors)
+                fused = eng.forward(self._dev_in[k], fresh_outputs=False)[-1]
+            else:
+                fused = self.net(self._dev_in[k])[-1]
             self._ev_consumed[k].record(cur)
             if self.output == "logits":
                 self._dev_out[k].copy_(fused)

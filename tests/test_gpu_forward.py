@@ -142,3 +142,44 @@ def test_forward_is_deterministic_and_graph_equals_eager(net):
             net._engine.use_cuda_graph = True
     for u, v, z in zip(a, b, c):
         assert torch.equal(u, v) and torch.equal(u, z)
+
+
+def test_direct_graph_on_a_returning_buffer(net):
+    """An input buffer that comes back gets a graph captured on the buffer itself (engine._forward_graphed): the replay must
+    read the buffer's CURRENT contents, give what the eager pass gives, still hand back fresh tensors, and the view form
+    (fresh_outputs=False, used by SequenceSegmenter) must alias the static output."""
+    eng = net._engine
+    was = eng.use_cuda_graph
+    try:
+        eng.use_cuda_graph = True
+        eng._graphs.clear()
+        eng._buffers_seen.clear()
+        buf = torch.empty(1, 3, 40, 56, device="cuda")
+        frames = [oc.synthetic_frame(1, 40, 56, 300 + i)[0].cuda() for i in range(4)]
+        with torch.no_grad():
+            outs = []
+            for f in frames:
+                buf.copy_(f)
+                outs.append([o.clone() for o in net(buf)])
+            direct = [k for k in eng._graphs if isinstance(k[-1], int) and k[-1] == buf.data_ptr()]
+            assert len(direct) == 1                                   # second call on: a graph bound to the buffer
+            assert eng._graphs[direct[0]][1] is None                  # ... without a static input copy
+            eng.use_cuda_graph = False
+            for f, got in zip(frames, outs):
+                want = net(f)
+                for a, b in zip(got, want):
+                    assert torch.equal(a, b)
+            eng.use_cuda_graph = True
+            buf.copy_(frames[0])
+            fresh = net(buf)
+            view = eng.forward(buf, fresh_outputs=False)
+            assert fresh[4].data_ptr() != view[4].data_ptr() and torch.equal(fresh[4], view[4])
+            buf.copy_(frames[1])
+            eng.forward(buf, fresh_outputs=False)                     # replays the same entry: the view now shows frame 1
+            assert torch.equal(view[4], outs[1][4]) and torch.equal(fresh[4], outs[0][4])
+            # a non-contiguous / other-dtype input still goes through the generic entry
+            odd = frames[2].double()
+            assert torch.equal(net(odd)[4], outs[2][4])
+    finally:
+        eng.use_cuda_graph = was
+        eng._graphs.clear()

@@ -793,7 +793,10 @@ def main():
                 "blocks": e2e_blocks,
                 "path": ("pinned host frame -> .to(cuda) -> fwd+loss+bwd -> D2H of the loss" if train else
                          "SequenceSegmenter: pinned host frame -> H2D -> OSVOS.forward (nn.Module API) -> D2H of the "
-                         "fused logit map, legs of consecutive frames overlapped on 3 streams"), **e2e_extra},
+                         "fused logit map, legs of consecutive frames overlapped on 3 streams; the pipeline reads the fused "
+                         "map out of the replayed graph's static output, so per frame it does ONE 1.6 MB device copy where the "
+                         "device-resident `value` loop (net(x): five fresh maps) does one of 8.2 MB - with the PCIe legs "
+                         "fully overlapped it can therefore come out level with or a fraction above `value`"), **e2e_extra},
         "gpu_launches": int(launches),
         "memcpy_per_step": (0 if train else 1),
         "gpu_launches_note": ("this repo's kernels per step (libosvos_b200.so), all inside one replayed CUDA graph; around the "

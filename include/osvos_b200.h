@@ -119,7 +119,7 @@ typedef struct {
   int n, h, w, cin, cout;
   int flags;
   /* 0 or 64: all input channels carry data.  16 / 32 / 48: only the first k_valid channels of every 64-channel
-   * chunk can be non-zero (the 16-channel side-branch gradient is stored padded to 64): the remaining K steps
+   * chunk can be non-zero (e.g. a 16-channel operand stored padded to 64): the remaining K steps
    * are skipped - fewer tcgen05.mma, identical result. */
   int k_valid;
 } osvos_conv3x3_args;

@@ -26,6 +26,10 @@ class OSVOSEngine:
         # disables it).
         self._graphs = {}
         self._buffers_seen = {}          # (graph key, input address) -> calls seen (engine._forward_graphed)
+        self._graphs_pver = None         # parameter versions the captured graphs belong to
+        # graphs bound to input buffers: at most this many (each pins its activation pool); once reached, further
+        # buffers go through the generic entry (one input copy) - no eviction, hence no capture / evict churn
+        self.max_direct_graphs = 12
         self.use_cuda_graph = os.environ.get("OSVOS_CUDA_GRAPH", "1") != "0"
         # training loops of this package set this: backward adds weight / trunk-bias gradients straight into an
         # existing p.grad (and hands autograd None for them) instead of returning tensors for AccumulateGrad
@@ -191,19 +195,24 @@ class OSVOSEngine:
         * generic: the frame is copied into the graph's static input, the graph replayed (any input tensor);
         * direct: an input BUFFER that comes back (same address, shape, contiguous fp32 - the second call on) gets a graph
           captured on that buffer itself: no input copy.  A video pipeline feeds a small ring of device buffers
-          (inference.SequenceSegmenter does), so in steady state every replay is direct.
+          (inference.SequenceSegmenter does), so in steady state every replay is direct.  At most `max_direct_graphs`
+          of them; all graphs are dropped when a parameter changes.
         The five maps are handed back as fresh tensors (one device copy) unless `fresh_outputs` is False: then they are
         views of the entry's static output, valid until the SAME entry is replayed again (the sequence pipeline reads them
         straight into its pinned host buffers).  Re-captured when shapes or parameters change."""
         m = self.m
-        pkey = (tuple(x.shape), x.device.index, m.precision,
-                tuple((p.data_ptr(), p._version) for p in m.parameters()))
+        pver = tuple((p.data_ptr(), p._version) for p in m.parameters())
+        if pver != self._graphs_pver:                            # parameters changed: every captured graph is stale
+            self._graphs.clear()
+            self._buffers_seen.clear()
+            self._graphs_pver = pver
+        pkey = (tuple(x.shape), x.device.index, m.precision)
         direct_ok = x.dtype == torch.float32 and x.is_contiguous() and not x.requires_grad
         entry = None
         if direct_ok:
             dkey = pkey + (x.data_ptr(),)
             entry = self._graphs.get(dkey)
-            if entry is None:
+            if entry is None and sum(1 for k in self._graphs if len(k) == 4) < self.max_direct_graphs:
                 seen = self._buffers_seen.get(dkey, 0) + 1
                 if len(self._buffers_seen) > 64:
                     self._buffers_seen.clear()
@@ -213,6 +222,9 @@ class OSVOSEngine:
         if entry is None:
             entry = self._graphs.get(pkey)
             if entry is None:
+                generic = [k for k in self._graphs if len(k) == 3]
+                if len(generic) >= 4:                            # bounded: each entry pins its activation pool
+                    self._graphs.pop(generic[0])
                 entry = self._capture(pkey, x, direct=False)
         graph, static_x, outs, base = entry
         if static_x is not None:
@@ -228,9 +240,6 @@ class OSVOSEngine:
 
     def _capture(self, key, x, direct):
         """Capture the inference pass for `key`; direct: on the caller's buffer itself (no static input)."""
-        limit = 12                                               # bounded: each entry pins its activation pool
-        while len(self._graphs) >= limit:
-            self._graphs.pop(next(iter(self._graphs)))
         self.forward_inference(x)                                # eager warm-up: packs weights, sets kernel attributes
         static_x = None if direct else x.detach().contiguous().float().clone()
         torch.cuda.synchronize(x.device)

@@ -161,7 +161,7 @@ def test_direct_graph_on_a_returning_buffer(net):
             for f in frames:
                 buf.copy_(f)
                 outs.append([o.clone() for o in net(buf)])
-            direct = [k for k in eng._graphs if isinstance(k[-1], int) and k[-1] == buf.data_ptr()]
+            direct = [k for k in eng._graphs if len(k) == 4 and k[-1] == buf.data_ptr()]
             assert len(direct) == 1                                   # second call on: a graph bound to the buffer
             assert eng._graphs[direct[0]][1] is None                  # ... without a static input copy
             eng.use_cuda_graph = False
@@ -180,6 +180,21 @@ def test_direct_graph_on_a_returning_buffer(net):
             # a non-contiguous / other-dtype input still goes through the generic entry
             odd = frames[2].double()
             assert torch.equal(net(odd)[4], outs[2][4])
+            # the number of buffer-bound graphs is capped: further buffers use the generic entry, nothing is evicted
+            eng.max_direct_graphs = 2
+            more = [frames[i].clone() for i in range(3)]
+            for _ in range(3):
+                for i, t in enumerate(more):
+                    assert torch.equal(net(t)[4], outs[i][4])
+            assert sum(1 for k in eng._graphs if len(k) == 4) == 2
+            # a parameter update drops every graph
+            with torch.no_grad():
+                net.fuse.bias.add_(1.0)
+            shifted = net(buf)
+            assert all(len(k) == 3 for k in eng._graphs) and not torch.equal(shifted[4], view[4])
+            with torch.no_grad():
+                net.fuse.bias.sub_(1.0)
     finally:
         eng.use_cuda_graph = was
+        eng.max_direct_graphs = 12
         eng._graphs.clear()

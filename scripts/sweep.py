@@ -37,9 +37,13 @@ for (h, w) in ((240, 427), (480, 854), (720, 1280), (1080, 1920)):
     with torch.no_grad():
         ms_f = timed(lambda: net(x), 30)
     net.train()
-    def fb():
-        net.zero_grad(set_to_none=False)
-        cbce(net(x)[-1], gt, size_average=False).backward()
-    ms_b = timed(fb, 10)
+    # fwd + online objective + bwd as the replayed CUDA graph the training loops use (training.GraphedTrainStep); eager
+    # launches are host-bound below ~720p (50 launches + autograd per step) and would time the Python side
+    from osvos_pytorch_b200.training import GraphedTrainStep, ONLINE_WEIGHTS
+    net._engine.drop_derived_caches()
+    gstep = GraphedTrainStep(net, ONLINE_WEIGHTS, {"image": x, "gt": gt})
+    ms_b = timed(lambda: gstep(), 20)
+    del gstep
+    net._engine.drop_derived_caches()
     tf_f, tf_b = fl / ms_f / 1e9, 3 * fl / ms_b / 1e9
     print(f"{h:>4d}x{w:<5d} {ms_f:8.3f} {1000/ms_f:8.1f} {tf_f:7.1f} {tf_f/peak:6.3f} | {ms_b:8.3f} {1000/ms_b:8.1f} {tf_b:7.1f} {tf_b/peak:6.3f}")

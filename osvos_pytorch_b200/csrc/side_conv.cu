@@ -11,12 +11,13 @@
 // Replaces side_prep[i] (+ score_dsn[i] and this scale's slice of fuse as projections), reference
 // networks/vgg_osvos.py:41,44,54 run at :67,69,72.  Same argument contract as osvos_conv3x3 with cout == 16.
 //
-// NCO = 2 - the FOLDED side branch (inference): side_prep has no ReLU, so side_prep followed by the two 1x1 projections
+// NCO = 2 - the FOLDED side branch (inference and training): side_prep has no ReLU, so side_prep followed by the two 1x1 projections
 // (score_dsn, this scale's slice of fuse) is ONE linear 3x3 convolution C -> 2 whose weights are
 // W'[o][ci][tap] = sum_co proj[o][co] * W_side[co][ci][tap] (osvos_fold_side_weights).  The same kernel then runs with
 // N = 32 (18 used) instead of 144: 1/8 of the accumulator columns to exchange, 1/4.5 of the weight bytes to stream,
 // a third less tensor time - the side branch was bound by exactly those (shared-memory bandwidth: the N = 144 MMA alone
-// reads 120 B/clk of operands).  Training keeps NCO = 16: its backward needs the 16 features.
+// reads 120 B/clk of operands).  The backward of the folded form needs no features either (side_bwd_folded.cu); NCO = 16 stays
+// for osvos_conv3x3 calls with cout == 16 (the literal side_prep op).
 #include <string.h>
 
 #include "conv_common.cuh"

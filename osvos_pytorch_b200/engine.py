@@ -34,7 +34,7 @@ class OSVOSEngine:
         # training loops of this package set this: backward adds weight / trunk-bias gradients straight into an
         # existing p.grad (and hands autograd None for them) instead of returning tensors for AccumulateGrad
         self.accumulate_param_grads_in_place = False
-        # inference only: fold side_prep with its two 1x1 projections into one 3x3 conv C -> 2 (OSVOS_FOLD_SIDE=0, read per
+        # inference: fold side_prep with its two 1x1 projections into one 3x3 conv C -> 2 (training always does; OSVOS_FOLD_SIDE=0, read per
         # eager pass, switches it off for A/B runs)
         self.fold_side_branch = True
 

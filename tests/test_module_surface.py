@@ -122,3 +122,45 @@ def test_caffe_vgg_loader_matches_the_reference_loader(tmp_path, monkeypatch):
     k, (co, ci, kh, kw) = 3, shapes[3]
     w = my_sd[oc.trunk_conv_names()[k] + ".weight"]
     assert float(w[5, 7, 1, 2]) == float(weights[0, k][2, 1, 7, 5])
+
+
+def test_torchvision_vgg_loader_matches_the_reference_loader(tmp_path, monkeypatch):
+    """`OSVOS(pretrained=1)` reads models/vgg_pytorch.pth like the reference's loader (networks/vgg_osvos.py:93-109): a
+    synthetic checkpoint of the reference's OWN `VGG` class (features + classifier, random weights) goes through both
+    loaders - the reference's (oracle/_ref, unmodified) and this package's - and every trunk tensor must be bit-identical."""
+    import contextlib
+    import io
+    import torch
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("oracle/_ref not built (bash oracle/make_ref.sh; needs /root/reference)")
+    ref = ref_loader.load()
+    vgg_structure = [64, 64, 'M', 128, 128, 'M', 256, 256, 256, 'M', 512, 512, 512, 'M', 512, 512, 512, 'M']
+    torch.manual_seed(11)
+    vgg = ref.net.VGG(ref.net.make_layers(vgg_structure))
+    with torch.no_grad():
+        for m in vgg.features:
+            if isinstance(m, torch.nn.Conv2d):
+                m.weight.normal_(0.0, 0.05)
+                m.bias.normal_(0.0, 0.1)
+    (tmp_path / "models").mkdir()
+    torch.save(vgg.state_dict(), str(tmp_path / "models" / "vgg_pytorch.pth"))
+    want = [(m.weight.detach().clone(), m.bias.detach().clone()) for m in vgg.features if isinstance(m, torch.nn.Conv2d)]
+    del vgg
+    monkeypatch.chdir(tmp_path)                       # both Path.models_dir() default to ./models
+    monkeypatch.delenv("OSVOS_MODELS_DIR", raising=False)
+    with contextlib.redirect_stdout(io.StringIO()):
+        ref_net = ref.net.OSVOS(pretrained=1)
+    from osvos_pytorch_b200.networks.vgg_osvos import OSVOS
+    mine = OSVOS(pretrained=1, verbose=False)
+    ref_sd, my_sd = ref_net.state_dict(), mine.state_dict()
+    assert list(ref_sd.keys()) == list(my_sd.keys())
+    checked = 0
+    for name in ref_sd:
+        if name.startswith("stages."):
+            assert torch.equal(ref_sd[name], my_sd[name]), name
+            checked += 1
+    assert checked == 26
+    convs = [m for stage in mine.stages for m in stage if isinstance(m, torch.nn.Conv2d)]
+    for conv, (w, b) in zip(convs, want):
+        assert torch.equal(conv.weight.detach(), w) and torch.equal(conv.bias.detach(), b)
